@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI in include/dpgo_b200.h.  There is no CPU fallback: if the native
+library is missing this module raises at import time, and every compute call fails loudly
+when no CUDA device is present."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdpgo_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(dpgo_b200 has no CPU fallback)")
+
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+class RoptParams(C.Structure):
+    _fields_ = [("method", C.c_int32), ("verbose", C.c_int32), ("gradnorm_tol", C.c_double),
+                ("RGD_stepsize", C.c_double), ("RGD_use_preconditioner", C.c_int32),
+                ("RTR_iterations", C.c_int32), ("RTR_tCG_iterations", C.c_int32),
+                ("fused", C.c_int32), ("RTR_initial_radius", C.c_double),
+                ("tcg_theta", C.c_double), ("tcg_kappa", C.c_double), ("accept_rho", C.c_double),
+                ("shrink", C.c_double), ("magnify", C.c_double)]
+
+
+class RoptResult(C.Structure):
+    _fields_ = [("success", C.c_int32), ("tcg_status", C.c_int32), ("f_init", C.c_double),
+                ("gradnorm_init", C.c_double), ("f_opt", C.c_double), ("gradnorm_opt", C.c_double),
+                ("elapsed_ms", C.c_double), ("outer_iters", C.c_int32), ("inner_iters", C.c_int32),
+                ("accepted", C.c_int32), ("rejected", C.c_int32), ("n_qx", C.c_int64),
+                ("n_precon", C.c_int64), ("n_pose_sweeps", C.c_int64), ("n_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+H = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in include/dpgo_b200.h
+SIGNATURES = {
+    "dpgo_default_params": (None, [C.POINTER(RoptParams)]),
+    "dpgo_last_error": (C.c_char_p, []),
+    "dpgo_version": (C.c_char_p, []),
+    "dpgo_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(H)]),
+    "dpgo_destroy": (C.c_int, [H]),
+    "dpgo_dims": (C.c_int, [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dpgo_sync": (C.c_int, [H]),
+    "dpgo_set_private_edges": (C.c_int, [H, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),
+    "dpgo_set_shared_edges": (C.c_int, [H, C.c_int, C.c_int, _ip, _ip, _bp, _dp, _dp, _dp, _dp, _dp]),
+    "dpgo_set_priors": (C.c_int, [H, C.c_int, _ip, _dp, C.c_double, C.c_double]),
+    "dpgo_finalize": (C.c_int, [H, C.c_int]),
+    "dpgo_update_weights": (C.c_int, [H, _dp, _dp, C.c_int]),
+    "dpgo_get_Q_bsr": (C.c_int, [H, C.POINTER(C.c_int), _ip, _ip, _dp]),
+    "dpgo_set_G": (C.c_int, [H, _dp]),
+    "dpgo_set_neighbor_poses": (C.c_int, [H, _dp]),
+    "dpgo_set_neighbor_poses_dev": (C.c_int, [H, C.c_void_p]),
+    "dpgo_get_G": (C.c_int, [H, _dp]),
+    "dpgo_qx": (C.c_int, [H, _dp, _dp]),
+    "dpgo_f": (C.c_int, [H, _dp, _dp]),
+    "dpgo_egrad": (C.c_int, [H, _dp, _dp]),
+    "dpgo_rgrad": (C.c_int, [H, _dp, _dp, _dp]),
+    "dpgo_hessvec": (C.c_int, [H, _dp, _dp, _dp]),
+    "dpgo_precon": (C.c_int, [H, _dp, _dp, _dp]),
+    "dpgo_tangent_project": (C.c_int, [H, _dp, _dp, _dp]),
+    "dpgo_retract": (C.c_int, [H, _dp, _dp, _dp]),
+    "dpgo_project_manifold": (C.c_int, [H, _dp, _dp]),
+    "dpgo_optimize": (C.c_int, [H, C.POINTER(RoptParams), _dp, _dp, C.POINTER(RoptResult)]),
+    "dpgo_slot_set": (C.c_int, [H, C.c_int, _dp]),
+    "dpgo_slot_get": (C.c_int, [H, C.c_int, _dp]),
+    "dpgo_slot_copy": (C.c_int, [H, C.c_int, C.c_int]),
+    "dpgo_nesterov_update_Y": (C.c_int, [H, C.c_double]),
+    "dpgo_nesterov_update_V": (C.c_int, [H, C.c_double]),
+    "dpgo_optimize_slot": (C.c_int, [H, C.POINTER(RoptParams), C.c_int, C.POINTER(RoptResult)]),
+    "dpgo_set_public_indices": (C.c_int, [H, C.c_int, _ip]),
+    "dpgo_pack_public_dev": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
+    "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
+    "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),
+    "dpgo_bytes_qx": (C.c_int, [H, _dp]),
+    "dpgo_bytes_precon": (C.c_int, [H, _dp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class DpgoError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise DpgoError(f"dpgo_b200 error {rc}: {lib.dpgo_last_error().decode()}")

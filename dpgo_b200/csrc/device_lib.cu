@@ -1,0 +1,1296 @@
+// C-ABI implementation: handle lifecycle, host-side construction of the block-CSR connection
+// Laplacian, dense preconditioner build (cuSOLVER potrf/potri, set-up path only), stand-alone
+// kernels (one launch per op) and the host-driven RTR/RGD solver built from them.  The
+// persistent single-kernel solver lives in fused_rtr.cu.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "device_state.h"
+#include "kernels.cuh"
+#include "rtr_logic.h"
+
+namespace dpgo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      dpgo::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,              \
+                      cudaGetErrorString(_e));                                           \
+      return DPGO_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define CUSOLVER_TRY(expr)                                                               \
+  do {                                                                                   \
+    cusolverStatus_t _s = (expr);                                                        \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                                                 \
+      dpgo::set_error("%s:%d cuSOLVER error %d in %s", __FILE__, __LINE__, (int)_s, #expr); \
+      return DPGO_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define CHECK_ARG(cond)                                                                  \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      dpgo::set_error("%s:%d contract violated: %s", __FILE__, __LINE__, #cond);         \
+      return DPGO_EINVAL;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define DPGO_TRY(expr)                                                                   \
+  do {                                                                                   \
+    int _rc = (expr);                                                                    \
+    if (_rc != DPGO_OK) return _rc;                                                      \
+  } while (0)
+
+// d in {2,3}; r in [d, d+3]
+#define DPGO_DISPATCH(h, ...)                                                            \
+  switch ((h)->d * 16 + (h)->r) {                                                        \
+    case 2 * 16 + 2: { constexpr int D = 2, R = 2; __VA_ARGS__; } break;                 \
+    case 2 * 16 + 3: { constexpr int D = 2, R = 3; __VA_ARGS__; } break;                 \
+    case 2 * 16 + 4: { constexpr int D = 2, R = 4; __VA_ARGS__; } break;                 \
+    case 2 * 16 + 5: { constexpr int D = 2, R = 5; __VA_ARGS__; } break;                 \
+    case 3 * 16 + 3: { constexpr int D = 3, R = 3; __VA_ARGS__; } break;                 \
+    case 3 * 16 + 4: { constexpr int D = 3, R = 4; __VA_ARGS__; } break;                 \
+    case 3 * 16 + 5: { constexpr int D = 3, R = 5; __VA_ARGS__; } break;                 \
+    case 3 * 16 + 6: { constexpr int D = 3, R = 6; __VA_ARGS__; } break;                 \
+    default: dpgo::set_error("unsupported (d=%d, r=%d)", (h)->d, (h)->r); return DPGO_EINVAL; \
+  }
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone kernels
+// ---------------------------------------------------------------------------------------------
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_qx(BsrView Q, const double *X, const double *G,
+                                               double *out, int n) {
+  phase_qx<R, D>(make_ctx(), Q, X, G, out, n);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_fgrad(BsrView Q, const double *X, const double *G,
+                                                  double *EG, double *grad, double *S, int n,
+                                                  double *partials) {
+  double acc[2] = {0.0, 0.0};
+  phase_fgrad<R, D>(make_ctx(), Q, X, G, EG, grad, S, n, acc);
+  block_reduce_store<2>(acc, partials + 2 * blockIdx.x);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_hess(BsrView Q, const double *Y, const double *S,
+                                                 const double *V, double *HV, const double *W,
+                                                 int n, double *partials) {
+  double acc[2] = {0.0, 0.0};
+  phase_hess<R, D>(make_ctx(), Q, Y, S, V, HV, W, n, acc);
+  block_reduce_store<2>(acc, partials + 2 * blockIdx.x);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_tangent(const double *X, const double *V, double *out,
+                                                    int n) {
+  phase_tangent<R, D>(make_ctx(), X, V, out, n);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBlock) k_precon_gemv(const double *Pinv, int ld,
+                                                        const double *vec, double *zpart, int KT,
+                                                        int nsplit) {
+  phase_precon_gemv<R>(Pinv, ld, vec, zpart, KT, nsplit);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_precon_finish(const double *zpart, int ld, int nsplit,
+                                                          const double *Y, const double *rvec,
+                                                          double *z, double *neg_out, int n,
+                                                          double *partials) {
+  double acc[1] = {0.0};
+  phase_precon_finish<R, D>(make_ctx(), zpart, ld, nsplit, Y, rvec, z, neg_out, n, acc);
+  block_reduce_store<1>(acc, partials + blockIdx.x);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_retract(const double *X, const double *Eta,
+                                                    double *Xout, int n) {
+  phase_retract<R, D>(make_ctx(), X, Eta, Xout, n);
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_polar(double ca, const double *A, double cb,
+                                                  const double *B, double cc, const double *C,
+                                                  double *out, int n) {
+  phase_polar<R, D>(make_ctx(), ca, A, cb, B, cc, C, out, n);
+}
+
+__global__ void __launch_bounds__(kBlock) k_step(double a, const double *delta, const double *Hd,
+                                                 double *eta, double *r, size_t len,
+                                                 double *partials) {
+  double acc[1] = {0.0};
+  phase_step(make_ctx(), a, delta, Hd, eta, r, len, acc);
+  block_reduce_store<1>(acc, partials + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kBlock) k_axpby(double a, const double *x, double b, double *y,
+                                                  size_t len) {
+  phase_axpby(make_ctx(), a, x, b, y, len);
+}
+
+// scalars[k] = sum_b partials[b*K + k], fixed order
+__global__ void __launch_bounds__(kBlock) k_finalize(const double *partials, int nblocks, int K,
+                                                     double *scalars) {
+  __shared__ double sm[kBlock];
+  for (int k = 0; k < K; ++k) {
+    double x = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += kBlock) x += partials[(size_t)b * K + k];
+    sm[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = kBlock / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) scalars[k] = sm[0];
+    __syncthreads();
+  }
+}
+
+// dense P = Q + shift*I from the block-CSR (one thread per scalar entry)
+__global__ void k_scatter_dense(const int *browidx, const int *colidx, const double *blocks,
+                                int nnzb, int dh, double shift, double *P, int ld) {
+  const size_t total = (size_t)nnzb * dh * dh;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t / (dh * dh));
+    const int ab = (int)(t % (dh * dh));
+    const int a = ab / dh, b = ab % dh;  // row-major within the block
+    const int i = browidx[e], j = colidx[e];
+    const size_t row = (size_t)i * dh + a, col = (size_t)j * dh + b;
+    double v = blocks[t];
+    if (row == col) v += shift;
+    P[row + col * (size_t)ld] = v;
+  }
+}
+
+// copy the lower triangle onto the upper one
+__global__ void k_symmetrize(double *P, int N, int ld) {
+  const size_t total = (size_t)N * N;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t % N, j = t / N;  // element (i,j), i fastest
+    if (i > j) P[j + i * (size_t)ld] = P[i + j * (size_t)ld];
+  }
+}
+
+__global__ void k_gather_tiles(const double *X, const int *idx, int num, int tile, double *out) {
+  const size_t total = (size_t)num * tile;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(t / tile), q = (int)(t % tile);
+    out[t] = X[(size_t)idx[p] * tile + q];
+  }
+}
+
+// max_i || p_i(A) - p_i(B) ||  -> partial max per block
+__global__ void __launch_bounds__(kBlock) k_maxdist(const double *A, const double *B, int n, int r,
+                                                    int dh, double *partials) {
+  __shared__ double sm[kBlock];
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t o = ((size_t)i * dh + (dh - 1)) * r;
+    double s = 0.0;
+    for (int q = 0; q < r; ++q) {
+      const double df = A[o + q] - B[o + q];
+      s = fma(df, df, s);
+    }
+    m = fmax(m, sqrt(s));
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+__global__ void k_finalize_max(const double *partials, int nblocks, double *out) {
+  double m = 0.0;
+  for (int b = 0; b < nblocks; ++b) m = fmax(m, partials[b]);
+  *out = m;
+}
+
+__global__ void k_flush(double *buf, size_t len, double v) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < len;
+       t += (size_t)gridDim.x * blockDim.x)
+    buf[t] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static inline int pose_grid(const dpgo_dev *h, int lanes_per_pose) {
+  // lanes_per_pose = D+1 for lane-group phases, 1 for thread-per-pose phases
+  const int gpw = 32 / lanes_per_pose;
+  const long warps = ((long)h->n + gpw - 1) / gpw;
+  long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long cap = (long)h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static inline int elem_grid(const dpgo_dev *h, size_t len) {
+  long blocks = (long)((len + kBlock - 1) / kBlock);
+  const long cap = (long)h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static inline int gemv_grid(const dpgo_dev *h) {
+  long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
+  const long cap = (long)h->num_sms * 4;
+  if (tiles > cap) tiles = cap;
+  if (tiles < 1) tiles = 1;
+  return (int)tiles;
+}
+static inline BsrView qview(const dpgo_dev *h) { return BsrView{h->d_rowptr, h->d_colidx, h->d_blocks}; }
+static inline BsrView cview(const dpgo_dev *h) { return BsrView{h->d_crowptr, h->d_ccolidx, h->d_cblocks}; }
+
+#define LAUNCH_CHECK(h)                       \
+  do {                                        \
+    (h)->launches++;                          \
+    CUDA_TRY(cudaPeekAtLastError());          \
+  } while (0)
+
+static int read_scalars(dpgo_dev *h, int nblocks, int K, double *out) {
+  k_finalize<<<1, kBlock, 0, h->stream>>>(h->d_partials, nblocks, K, h->d_scalars);
+  LAUNCH_CHECK(h);
+  CUDA_TRY(cudaMemcpyAsync(h->h_scalars, h->d_scalars, K * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < K; ++k) out[k] = h->h_scalars[k];
+  return DPGO_OK;
+}
+
+// --- op launchers (device pointers) ---
+int op_qx(dpgo_dev *h, const BsrView &Q, const double *X, const double *G, double *out) {
+  const int grid = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, k_qx<R, D><<<grid, kBlock, 0, h->stream>>>(Q, X, G, out, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+int op_fgrad(dpgo_dev *h, const double *X, double *EG, double *grad, double *S, double *f,
+             double *gn2) {
+  const int grid = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, k_fgrad<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, h->d_G, EG, grad, S,
+                                                               h->n, h->d_partials));
+  LAUNCH_CHECK(h);
+  double sc[2];
+  DPGO_TRY(read_scalars(h, grid, 2, sc));
+  *f = sc[0];
+  *gn2 = sc[1];
+  return DPGO_OK;
+}
+int op_hess(dpgo_dev *h, const double *Y, const double *S, const double *V, double *HV,
+            const double *W, double *vhv, double *vw) {
+  const int grid = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, k_hess<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), Y, S, V, HV, W, h->n,
+                                                              h->d_partials));
+  LAUNCH_CHECK(h);
+  if (vhv || vw) {
+    double sc[2];
+    DPGO_TRY(read_scalars(h, grid, 2, sc));
+    if (vhv) *vhv = sc[0];
+    if (vw) *vw = sc[1];
+  }
+  return DPGO_OK;
+}
+int op_tangent(dpgo_dev *h, const double *X, const double *V, double *out) {
+  const int grid = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, k_tangent<R, D><<<grid, kBlock, 0, h->stream>>>(X, V, out, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+int op_precon(dpgo_dev *h, const double *Y, const double *rvec, double *z, double *neg_out,
+              double *z_r) {
+  if (!h->has_precon) {
+    set_error("preconditioner not built (dpgo_finalize(h, 1))");
+    return DPGO_ESTATE;
+  }
+  const int g1 = gemv_grid(h);
+  DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, 0, h->stream>>>(h->d_Pinv, h->ld, rvec,
+                                                                 h->d_zpart, h->KT, h->nsplit));
+  LAUNCH_CHECK(h);
+  const int g2 = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, k_precon_finish<R, D><<<g2, kBlock, 0, h->stream>>>(
+                       h->d_zpart, h->ld, h->nsplit, Y, rvec, z, neg_out, h->n, h->d_partials));
+  LAUNCH_CHECK(h);
+  if (z_r) {
+    double sc[1];
+    DPGO_TRY(read_scalars(h, g2, 1, sc));
+    *z_r = sc[0];
+  }
+  return DPGO_OK;
+}
+int op_retract(dpgo_dev *h, const double *X, const double *Eta, double *Xout) {
+  const int grid = pose_grid(h, 1);
+  DPGO_DISPATCH(h, k_retract<R, D><<<grid, kBlock, 0, h->stream>>>(X, Eta, Xout, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+int op_polar(dpgo_dev *h, double ca, const double *A, double cb, const double *B, double cc,
+             const double *C, double *out) {
+  const int grid = pose_grid(h, 1);
+  DPGO_DISPATCH(h, k_polar<R, D><<<grid, kBlock, 0, h->stream>>>(ca, A, cb, B, cc, C, out, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+int op_step(dpgo_dev *h, double a, const double *delta, const double *Hd, double *eta, double *r,
+            double *r_r) {
+  const int grid = elem_grid(h, h->vlen);
+  k_step<<<grid, kBlock, 0, h->stream>>>(a, delta, Hd, eta, r, h->vlen, h->d_partials);
+  LAUNCH_CHECK(h);
+  double sc[1];
+  DPGO_TRY(read_scalars(h, grid, 1, sc));
+  *r_r = sc[0];
+  return DPGO_OK;
+}
+int op_axpby(dpgo_dev *h, double a, const double *x, double b, double *y) {
+  const int grid = elem_grid(h, h->vlen);
+  k_axpby<<<grid, kBlock, 0, h->stream>>>(a, x, b, y, h->vlen);
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+int op_copy(dpgo_dev *h, const double *src, double *dst) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, h->vlen * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return DPGO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-driven solver (one launch per op, one host read-back per scalar)
+// ---------------------------------------------------------------------------------------------
+struct SolveCtx {
+  dpgo_dev *h;
+  const dpgo_ropt_params *P;
+  dpgo_ropt_result *res;
+  double *x1, *x2, *EG, *EG2, *grad, *grad2, *S, *S2;
+  double f1, gn2;
+};
+
+static int tcg_host(SolveCtx &c, double Delta, int *status, int *inner) {
+  dpgo_dev *h = c.h;
+  const dpgo_ropt_params &P = *c.P;
+  TcgState s;
+  DPGO_TRY(op_copy(h, c.grad, h->d_r));
+  double z_r = 0.0;
+  DPGO_TRY(op_precon(h, c.x1, h->d_r, h->d_z, h->d_delta, &z_r));
+  c.res->n_precon++;
+  tcg_begin(s, c.gn2, z_r);
+  CUDA_TRY(cudaMemsetAsync(h->d_eta, 0, h->vlen * sizeof(double), h->stream));
+  int j = 0;
+  *inner = 0;
+  for (j = 0; j < P.RTR_tCG_iterations; ++j) {
+    double d_Hd = 0.0;
+    DPGO_TRY(op_hess(h, c.x1, c.S, h->d_delta, h->d_Hd, nullptr, &d_Hd, nullptr));
+    c.res->n_qx++;
+    double step = 0.0;
+    *inner = j + 1;
+    if (tcg_curvature(s, d_Hd, Delta, &step)) {
+      DPGO_TRY(op_axpby(h, step, h->d_delta, 1.0, h->d_eta));
+      break;
+    }
+    double r_r = 0.0;
+    DPGO_TRY(op_step(h, step, h->d_delta, h->d_Hd, h->d_eta, h->d_r, &r_r));
+    if (tcg_converged(s, r_r, P.tcg_theta, P.tcg_kappa)) break;
+    DPGO_TRY(op_precon(h, c.x1, h->d_r, h->d_z, nullptr, &z_r));
+    c.res->n_precon++;
+    const double beta = tcg_direction(s, z_r);
+    DPGO_TRY(op_axpby(h, -1.0, h->d_z, beta, h->d_delta));
+  }
+  *status = s.status;
+  return DPGO_OK;
+}
+
+// one outer RTR iteration from (x1, f1, grad); returns accepted flag, updates Delta
+static int rtr_outer_host(SolveCtx &c, double *Delta, double max_Delta, bool *accepted) {
+  dpgo_dev *h = c.h;
+  const dpgo_ropt_params &P = *c.P;
+  int status = TCG_MAXITER, inner = 0;
+  DPGO_TRY(tcg_host(c, *Delta, &status, &inner));
+  c.res->inner_iters += inner;
+  c.res->tcg_status = status;
+  DPGO_TRY(op_retract(h, c.x1, h->d_eta, c.x2));
+  c.res->n_pose_sweeps++;
+  double f2 = 0.0, gn2_2 = 0.0;
+  DPGO_TRY(op_fgrad(h, c.x2, c.EG2, c.grad2, c.S2, &f2, &gn2_2));
+  c.res->n_qx++;
+  double eHe = 0.0, eg = 0.0;
+  DPGO_TRY(op_hess(h, c.x1, c.S, h->d_eta, h->d_Hd, c.grad, &eHe, &eg));
+  c.res->n_qx++;
+  double rho = 0.0;
+  *accepted = rtr_accept(c.f1, f2, eg, eHe, status, P.accept_rho, P.shrink, P.magnify, max_Delta,
+                         Delta, &rho);
+  if (P.verbose)
+    printf("[dpgo_b200] RTR f=%.10g -> %.10g rho=%.4f Delta=%.4g inner=%d status=%d %s\n", c.f1, f2,
+           rho, *Delta, inner, status, *accepted ? "accepted" : "REJECTED");
+  if (*accepted) {
+    std::swap(c.x1, c.x2);
+    std::swap(c.EG, c.EG2);
+    std::swap(c.grad, c.grad2);
+    std::swap(c.S, c.S2);
+    c.f1 = f2;
+    c.gn2 = gn2_2;
+    c.res->accepted++;
+  } else {
+    c.res->rejected++;
+  }
+  c.res->outer_iters++;
+  return DPGO_OK;
+}
+
+int solve_host(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
+               dpgo_ropt_result *res) {
+  SolveCtx c;
+  c.h = h; c.P = P; c.res = res;
+  c.x1 = h->d_xa; c.x2 = h->d_xb;
+  c.EG = h->d_EG; c.EG2 = h->d_EG2; c.grad = h->d_grad; c.grad2 = h->d_grad2;
+  c.S = h->d_S; c.S2 = h->d_S2;
+  DPGO_TRY(op_copy(h, x_in, c.x1));
+  DPGO_TRY(op_fgrad(h, c.x1, c.EG, c.grad, c.S, &c.f1, &c.gn2));
+  res->n_qx++;
+  res->f_init = c.f1;
+  res->gradnorm_init = sqrt(c.gn2);
+  res->tcg_status = TCG_MAXITER;
+  if (P->method == 1) {
+    // QuadraticOptimizer::gradientDescent, ref: src/QuadraticOptimizer.cpp:110-137
+    const double *dir = c.grad;
+    if (P->RGD_use_preconditioner) {
+      DPGO_TRY(op_precon(h, c.x1, c.grad, h->d_z, nullptr, nullptr));
+      res->n_precon++;
+      dir = h->d_z;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_eta, 0, h->vlen * sizeof(double), h->stream));
+    DPGO_TRY(op_axpby(h, -P->RGD_stepsize, dir, 0.0, h->d_eta));
+    DPGO_TRY(op_retract(h, c.x1, h->d_eta, c.x2));
+    res->n_pose_sweeps++;
+    std::swap(c.x1, c.x2);
+    DPGO_TRY(op_fgrad(h, c.x1, c.EG, c.grad, c.S, &c.f1, &c.gn2));
+    res->n_qx++;
+  } else if (sqrt(c.gn2) >= P->gradnorm_tol) {
+    // QuadraticOptimizer::trustRegion, ref: src/QuadraticOptimizer.cpp:50-108
+    if (P->RTR_iterations == 1) {
+      double radius = P->RTR_initial_radius;
+      int total_steps = 0;
+      while (true) {
+        double Delta = radius;
+        bool acc = false;
+        DPGO_TRY(rtr_outer_host(c, &Delta, radius, &acc));
+        if (acc) break;
+        if (total_steps > 10) break;  // "Too many RTR rejections. Returning initial guess."
+        radius /= 4.0;
+        total_steps++;
+      }
+    } else {
+      double Delta = P->RTR_initial_radius;
+      const double max_Delta = 5.0 * P->RTR_initial_radius;
+      for (int it = 0; it < P->RTR_iterations; ++it) {
+        bool acc = false;
+        DPGO_TRY(rtr_outer_host(c, &Delta, max_Delta, &acc));
+        if (sqrt(c.gn2) < P->gradnorm_tol) break;
+      }
+    }
+  }
+  res->f_opt = c.f1;
+  res->gradnorm_opt = sqrt(c.gn2);
+  res->success = 1;
+  DPGO_TRY(op_copy(h, c.x1, x_out));
+  return DPGO_OK;
+}
+
+int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
+                dpgo_ropt_result *res);  // fused_rtr.cu
+
+// ---------------------------------------------------------------------------------------------
+// host-side graph -> block-CSR
+// ---------------------------------------------------------------------------------------------
+struct Contribution {
+  int32_t row, col;
+  int32_t src;   // index into the edge set
+  int8_t kind;   // 0: T W T^T, 1: -T W, 2: -W T^T, 3: W   (private) ; 4/5 shared out/in ; 6 prior ; 7 zero
+};
+
+static void edge_T_W(const EdgeSet &E, int k, int d, double *T, double *W) {
+  const int dh = d + 1;
+  for (int a = 0; a < dh * dh; ++a) T[a] = 0.0;
+  for (int a = 0; a < d; ++a) {
+    for (int b = 0; b < d; ++b) T[a * dh + b] = E.R[(size_t)k * d * d + a * d + b];
+    T[a * dh + d] = E.t[(size_t)k * d + a];
+  }
+  T[d * dh + d] = 1.0;
+  for (int a = 0; a < d; ++a) W[a] = E.weight[k] * E.kappa[k];
+  W[d] = E.weight[k] * E.tau[k];
+}
+
+// out (row-major dh x dh) for the 4 kinds; T row-major, W diagonal
+static void block_of_kind(int kind, const double *T, const double *W, int dh, double *out) {
+  for (int a = 0; a < dh; ++a)
+    for (int b = 0; b < dh; ++b) {
+      double v = 0.0;
+      switch (kind) {
+        case 0: for (int k = 0; k < dh; ++k) v += T[a * dh + k] * W[k] * T[b * dh + k]; break;
+        case 1: v = -T[a * dh + b] * W[b]; break;
+        case 2: v = -W[a] * T[b * dh + a]; break;
+        case 3: v = (a == b) ? W[a] : 0.0; break;
+      }
+      out[a * dh + b] = v;
+    }
+}
+
+static int build_Q_host(dpgo_dev *h) {
+  const int d = h->d, dh = d + 1, n = h->n, bs = dh * dh;
+  std::vector<Contribution> cs;
+  cs.reserve((size_t)4 * h->priv.m + h->shared.m + h->prior_idx.size() + n);
+  for (int i = 0; i < n; ++i) cs.push_back({i, i, 0, 7});
+  for (int k = 0; k < h->priv.m; ++k) {
+    const int i = h->priv.a[k], j = h->priv.b[k];
+    cs.push_back({i, i, k, 0});
+    cs.push_back({i, j, k, 1});
+    cs.push_back({j, i, k, 2});
+    cs.push_back({j, j, k, 3});
+  }
+  for (int k = 0; k < h->shared.m; ++k) {
+    const int i = h->shared.a[k];
+    cs.push_back({i, i, k, (int8_t)(h->shared.outgoing[k] ? 4 : 5)});
+  }
+  for (size_t k = 0; k < h->prior_idx.size(); ++k) cs.push_back({h->prior_idx[k], h->prior_idx[k], (int32_t)k, 6});
+  std::stable_sort(cs.begin(), cs.end(), [](const Contribution &x, const Contribution &y) {
+    return x.row != y.row ? x.row < y.row : x.col < y.col;
+  });
+  h->rowptr.assign(n + 1, 0);
+  h->colidx.clear();
+  h->blocks.clear();
+  double T[16], W[4], B[16];
+  int cur_row = -1, cur_col = -1;
+  for (const Contribution &c : cs) {
+    if (c.row != cur_row || c.col != cur_col) {
+      h->colidx.push_back(c.col);
+      h->blocks.insert(h->blocks.end(), bs, 0.0);
+      h->rowptr[c.row + 1]++;
+      cur_row = c.row;
+      cur_col = c.col;
+    }
+    double *dst = h->blocks.data() + h->blocks.size() - bs;
+    if (c.kind <= 3) {
+      edge_T_W(h->priv, c.src, d, T, W);
+      block_of_kind(c.kind, T, W, dh, B);
+    } else if (c.kind == 4 || c.kind == 5) {
+      edge_T_W(h->shared, c.src, d, T, W);
+      block_of_kind(c.kind == 4 ? 0 : 3, T, W, dh, B);  // ref: src/PoseGraph.cpp:433-434, :457
+    } else if (c.kind == 6) {
+      for (int a = 0; a < bs; ++a) B[a] = 0.0;
+      for (int a = 0; a < d; ++a) B[a * dh + a] = h->prior_kappa;  // ref: src/PoseGraph.cpp:462-469
+      B[d * dh + d] = h->prior_tau;
+    } else {
+      continue;
+    }
+    for (int a = 0; a < bs; ++a) dst[a] += B[a];
+  }
+  for (int i = 0; i < n; ++i) h->rowptr[i + 1] += h->rowptr[i];
+  h->nnzb = (int)h->colidx.size();
+  return DPGO_OK;
+}
+
+template <typename T>
+static int upload(T **dptr, const std::vector<T> &v, size_t min_elems = 1) {
+  if (*dptr) {
+    CUDA_TRY(cudaFree(*dptr));
+    *dptr = nullptr;
+  }
+  const size_t ne = std::max(v.size(), min_elems);
+  CUDA_TRY(cudaMalloc((void **)dptr, ne * sizeof(T)));
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return DPGO_OK;
+}
+
+static int upload_Q(dpgo_dev *h) {
+  DPGO_TRY(upload(&h->d_rowptr, h->rowptr));
+  DPGO_TRY(upload(&h->d_colidx, h->colidx));
+  DPGO_TRY(upload(&h->d_blocks, h->blocks));
+  std::vector<int32_t> browidx(h->nnzb);
+  for (int i = 0; i < h->n; ++i)
+    for (int e = h->rowptr[i]; e < h->rowptr[i + 1]; ++e) browidx[e] = i;
+  DPGO_TRY(upload(&h->d_browidx, browidx));
+  return DPGO_OK;
+}
+
+// cross blocks:  G = Gconst + Xnbr * C,  block row = my pose, block col = neighbour slot,
+// stored block B (row-major) with out += X_slot * B^T  =>  B = -(M)^T,
+// M = W T^T (outgoing, ref: src/PoseGraph.cpp:536) or T W (incoming, ref: :561).
+static int build_cross_host(dpgo_dev *h) {
+  const int d = h->d, dh = d + 1, n = h->n, bs = dh * dh, r = h->r;
+  std::vector<int> order(h->shared.m);
+  for (int k = 0; k < h->shared.m; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int x, int y) { return h->shared.a[x] < h->shared.a[y]; });
+  std::vector<int32_t> rowptr(n + 1, 0), colidx;
+  std::vector<double> blocks;
+  double T[16], W[4];
+  for (int k : order) {
+    const int i = h->shared.a[k];
+    rowptr[i + 1]++;
+    colidx.push_back(h->shared.b[k]);
+    edge_T_W(h->shared, k, d, T, W);
+    double B[16];
+    for (int a = 0; a < dh; ++a)
+      for (int b = 0; b < dh; ++b) {
+        // B[a][b] = -M[b][a]
+        double m;
+        if (h->shared.outgoing[k]) m = W[b] * T[a * dh + b];   // M = W T^T: M[b][a] = W[b] T[a][b]
+        else m = T[b * dh + a] * W[a];                          // M = T W  : M[b][a] = T[b][a] W[a]
+        B[a * dh + b] = -m;
+      }
+    blocks.insert(blocks.end(), B, B + bs);
+  }
+  for (int i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
+  h->cnnzb = (int)colidx.size();
+  DPGO_TRY(upload(&h->d_crowptr, rowptr));
+  DPGO_TRY(upload(&h->d_ccolidx, colidx));
+  DPGO_TRY(upload(&h->d_cblocks, blocks));
+  // constant part: priors, G_idx += -P W   (ref: src/PoseGraph.cpp:566-575)
+  std::vector<double> Gc(h->vpad, 0.0);
+  for (size_t p = 0; p < h->prior_idx.size(); ++p) {
+    const int idx = h->prior_idx[p];
+    const double *pose = h->prior_poses.data() + p * (size_t)r * dh;
+    for (int c = 0; c < dh; ++c) {
+      const double w = (c < d) ? h->prior_kappa : h->prior_tau;
+      for (int q = 0; q < r; ++q) Gc[((size_t)idx * dh + c) * r + q] += -pose[c * r + q] * w;
+    }
+  }
+  CUDA_TRY(cudaMemcpy(h->d_Gconst, Gc.data(), h->vpad * sizeof(double), cudaMemcpyHostToDevice));
+  return DPGO_OK;
+}
+
+static int build_precon(dpgo_dev *h) {
+  const int N = h->N, ld = h->ld;
+  if (!h->d_Pinv) CUDA_TRY(cudaMalloc((void **)&h->d_Pinv, (size_t)ld * ld * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(h->d_Pinv, 0, (size_t)ld * ld * sizeof(double), h->stream));
+  const int dh = h->d + 1;
+  {
+    const size_t total = (size_t)h->nnzb * dh * dh;
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
+    if (grid < 1) grid = 1;
+    k_scatter_dense<<<grid, 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
+                                                 0.1 /* ref: src/PoseGraph.cpp:603 */, h->d_Pinv, ld);
+    LAUNCH_CHECK(h);
+  }
+  if (!h->cusolver) {
+    CUSOLVER_TRY(cusolverDnCreate(&h->cusolver));
+    CUSOLVER_TRY(cusolverDnSetStream(h->cusolver, h->stream));
+  }
+  int lw1 = 0, lw2 = 0;
+  CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, &lw1));
+  CUSOLVER_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, &lw2));
+  const int lw = std::max(lw1, lw2);
+  double *work = nullptr;
+  int *info = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&work, (size_t)std::max(lw, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
+  int hinfo = 0;
+  CUSOLVER_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, work, lw, info));
+  CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (hinfo != 0) {
+    cudaFree(work); cudaFree(info);
+    set_error("Cholesky of Q + 0.1 I failed (potrf info = %d)", hinfo);
+    return DPGO_ENUMERIC;
+  }
+  CUSOLVER_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, work, lw, info));
+  CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaFree(work));
+  CUDA_TRY(cudaFree(info));
+  if (hinfo != 0) {
+    set_error("inverse of Q + 0.1 I failed (potri info = %d)", hinfo);
+    return DPGO_ENUMERIC;
+  }
+  {
+    const size_t total = (size_t)N * N;
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 32);
+    if (grid < 1) grid = 1;
+    k_symmetrize<<<grid, 256, 0, h->stream>>>(h->d_Pinv, N, ld);
+    LAUNCH_CHECK(h);
+  }
+  // tiling of the apply: at most 16 inner splits, each a multiple of 64 wide
+  int KT = ((ld / 16 + 63) / 64) * 64;
+  if (KT < 512) KT = 512;
+  h->KT = KT;
+  h->nsplit = (ld + KT - 1) / KT;
+  if (h->d_zpart) CUDA_TRY(cudaFree(h->d_zpart));
+  CUDA_TRY(cudaMalloc((void **)&h->d_zpart, (size_t)h->nsplit * h->vpad * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(h->d_zpart, 0, (size_t)h->nsplit * h->vpad * sizeof(double), h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->has_precon = true;
+  return DPGO_OK;
+}
+
+static int alloc_vec(dpgo_dev *h, double **p, size_t elems) {
+  CUDA_TRY(cudaMalloc((void **)p, elems * sizeof(double)));
+  CUDA_TRY(cudaMemset(*p, 0, elems * sizeof(double)));
+  return DPGO_OK;
+}
+
+static int copy_edges(EdgeSet &E, int m, int d, const int32_t *a, const int32_t *b,
+                      const uint8_t *outgoing, const double *R, const double *t, const double *kappa,
+                      const double *tau, const double *weight) {
+  E.m = m;
+  E.a.assign(a, a + m);
+  E.b.assign(b, b + m);
+  if (outgoing) E.outgoing.assign(outgoing, outgoing + m); else E.outgoing.assign(m, 0);
+  E.R.assign(R, R + (size_t)m * d * d);
+  E.t.assign(t, t + (size_t)m * d);
+  E.kappa.assign(kappa, kappa + m);
+  E.tau.assign(tau, tau + m);
+  if (weight) E.weight.assign(weight, weight + m); else E.weight.assign(m, 1.0);
+  return DPGO_OK;
+}
+
+}  // namespace dpgo
+
+using namespace dpgo;
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+#define H_CHECK(h)                                \
+  do {                                            \
+    CHECK_ARG((h) != nullptr);                    \
+    CUDA_TRY(cudaSetDevice((h)->device));         \
+  } while (0)
+
+extern "C" {
+
+const char *dpgo_last_error(void) { return dpgo::g_err; }
+const char *dpgo_version(void) { return "dpgo_b200 0.1 (sm_100a)"; }
+
+void dpgo_default_params(dpgo_ropt_params *p) {
+  if (!p) return;
+  p->method = 0;
+  p->verbose = 0;
+  p->gradnorm_tol = 1e-2;
+  p->RGD_stepsize = 1e-3;
+  p->RGD_use_preconditioner = 1;
+  p->RTR_iterations = 3;
+  p->RTR_tCG_iterations = 50;
+  p->fused = 1;
+  p->RTR_initial_radius = 100.0;
+  p->tcg_theta = 1.0;
+  p->tcg_kappa = 0.1;
+  p->accept_rho = 0.1;
+  p->shrink = 0.25;
+  p->magnify = 2.0;
+}
+
+int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out) {
+  CHECK_ARG(out != nullptr);
+  CHECK_ARG(n > 0);
+  CHECK_ARG(d == 2 || d == 3);
+  CHECK_ARG(r >= d && r <= d + 3);  // ref: CHECK(r >= d) src/PoseGraph.cpp:19
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no CUDA device available (%s); dpgo_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return DPGO_ECUDA;
+  }
+  CHECK_ARG(device >= 0 && device < count);
+  CUDA_TRY(cudaSetDevice(device));
+  dpgo_dev *h = new dpgo_dev();
+  h->device = device; h->n = n; h->d = d; h->r = r;
+  h->N = (d + 1) * n;
+  h->ld = ((h->N + 63) / 64) * 64;
+  h->vlen = (size_t)r * h->N;
+  h->vpad = (size_t)r * h->ld;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  if (stream) {
+    h->stream = (cudaStream_t)stream;
+  } else {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  double **vecs[] = {&h->d_slot[0], &h->d_slot[1], &h->d_slot[2], &h->d_slot[3], &h->d_xa, &h->d_xb,
+                     &h->d_EG, &h->d_EG2, &h->d_grad, &h->d_grad2, &h->d_eta, &h->d_r, &h->d_z,
+                     &h->d_delta, &h->d_Hd, &h->d_t0, &h->d_t1, &h->d_t2, &h->d_G, &h->d_Gconst};
+  for (double **p : vecs) DPGO_TRY(alloc_vec(h, p, h->vpad));
+  DPGO_TRY(alloc_vec(h, &h->d_S, (size_t)n * d * d));
+  DPGO_TRY(alloc_vec(h, &h->d_S2, (size_t)n * d * d));
+  DPGO_TRY(alloc_vec(h, &h->d_partials, (size_t)h->num_sms * 32 * 8));
+  DPGO_TRY(alloc_vec(h, &h->d_scalars, 64));
+  CUDA_TRY(cudaMallocHost((void **)&h->h_scalars, 64 * sizeof(double)));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  *out = h;
+  return DPGO_OK;
+}
+
+int dpgo_destroy(dpgo_handle h) {
+  if (!h) return DPGO_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  void *ptrs[] = {h->d_rowptr, h->d_colidx, h->d_browidx, h->d_blocks, h->d_crowptr, h->d_ccolidx,
+                  h->d_cblocks, h->d_Gconst, h->d_G, h->d_nbr, h->d_Pinv, h->d_zpart, h->d_slot[0],
+                  h->d_slot[1], h->d_slot[2], h->d_slot[3], h->d_xa, h->d_xb, h->d_EG, h->d_EG2,
+                  h->d_grad, h->d_grad2, h->d_S, h->d_S2, h->d_eta, h->d_r, h->d_z, h->d_delta,
+                  h->d_Hd, h->d_t0, h->d_t1, h->d_t2, h->d_partials, h->d_scalars, h->d_fused,
+                  h->d_public_idx, h->d_flush};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_fused) cudaFreeHost(h->h_fused);
+  if (h->cusolver) cusolverDnDestroy(h->cusolver);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DPGO_OK;
+}
+
+int dpgo_dims(dpgo_handle h, int *n, int *d, int *r) {
+  CHECK_ARG(h != nullptr);
+  if (n) *n = h->n;
+  if (d) *d = h->d;
+  if (r) *r = h->r;
+  return DPGO_OK;
+}
+
+int dpgo_sync(dpgo_handle h) {
+  H_CHECK(h);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return DPGO_OK;
+}
+
+int dpgo_set_private_edges(dpgo_handle h, int m, const int32_t *p1, const int32_t *p2,
+                           const double *R, const double *t, const double *kappa,
+                           const double *tau, const double *weight) {
+  H_CHECK(h);
+  CHECK_ARG(m >= 0);
+  CHECK_ARG(m == 0 || (p1 && p2 && R && t && kappa && tau));
+  for (int k = 0; k < m; ++k) {
+    CHECK_ARG(p1[k] >= 0 && p1[k] < h->n);
+    CHECK_ARG(p2[k] >= 0 && p2[k] < h->n);
+  }
+  h->finalized = false;
+  return copy_edges(h->priv, m, h->d, p1, p2, nullptr, R, t, kappa, tau, weight);
+}
+
+int dpgo_set_shared_edges(dpgo_handle h, int m, int num_nbr_slots, const int32_t *my_idx,
+                          const int32_t *nbr_slot, const uint8_t *outgoing, const double *R,
+                          const double *t, const double *kappa, const double *tau,
+                          const double *weight) {
+  H_CHECK(h);
+  CHECK_ARG(m >= 0 && num_nbr_slots >= 0);
+  CHECK_ARG(m == 0 || (my_idx && nbr_slot && outgoing && R && t && kappa && tau));
+  for (int k = 0; k < m; ++k) {
+    CHECK_ARG(my_idx[k] >= 0 && my_idx[k] < h->n);
+    CHECK_ARG(nbr_slot[k] >= 0 && nbr_slot[k] < num_nbr_slots);
+  }
+  h->finalized = false;
+  h->num_nbr_slots = num_nbr_slots;
+  if (h->d_nbr) { CUDA_TRY(cudaFree(h->d_nbr)); h->d_nbr = nullptr; }
+  const size_t ne = (size_t)std::max(num_nbr_slots, 1) * h->r * (h->d + 1);
+  DPGO_TRY(alloc_vec(h, &h->d_nbr, ne));
+  return copy_edges(h->shared, m, h->d, my_idx, nbr_slot, outgoing, R, t, kappa, tau, weight);
+}
+
+int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *poses,
+                    double prior_kappa, double prior_tau) {
+  H_CHECK(h);
+  CHECK_ARG(num >= 0);
+  CHECK_ARG(num == 0 || (idx && poses));
+  for (int k = 0; k < num; ++k) CHECK_ARG(idx[k] >= 0 && idx[k] < h->n);  // ref: CHECK_LT(index, n())
+  h->prior_idx.assign(idx, idx + num);
+  h->prior_poses.assign(poses, poses + (size_t)num * h->r * (h->d + 1));
+  h->prior_kappa = prior_kappa;
+  h->prior_tau = prior_tau;
+  h->finalized = false;
+  return DPGO_OK;
+}
+
+int dpgo_finalize(dpgo_handle h, int build_precon_flag) {
+  H_CHECK(h);
+  DPGO_TRY(build_Q_host(h));
+  DPGO_TRY(upload_Q(h));
+  DPGO_TRY(build_cross_host(h));
+  // G starts as its constant part (no neighbour poses yet)
+  CUDA_TRY(cudaMemcpyAsync(h->d_G, h->d_Gconst, h->vpad * sizeof(double), cudaMemcpyDeviceToDevice,
+                           h->stream));
+  h->has_precon = false;
+  if (build_precon_flag) DPGO_TRY(build_precon(h));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->finalized = true;
+  return DPGO_OK;
+}
+
+int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,
+                        int build_precon_flag) {
+  H_CHECK(h);
+  if (w_private) h->priv.weight.assign(w_private, w_private + h->priv.m);
+  if (w_shared) h->shared.weight.assign(w_shared, w_shared + h->shared.m);
+  return dpgo_finalize(h, build_precon_flag);
+}
+
+int dpgo_get_Q_bsr(dpgo_handle h, int *nnzb, int32_t *rowptr, int32_t *colidx, double *blocks) {
+  CHECK_ARG(h != nullptr);
+  if (!h->finalized) { set_error("dpgo_finalize not called"); return DPGO_ESTATE; }
+  if (nnzb) *nnzb = h->nnzb;
+  if (rowptr) memcpy(rowptr, h->rowptr.data(), h->rowptr.size() * sizeof(int32_t));
+  if (colidx) memcpy(colidx, h->colidx.data(), h->colidx.size() * sizeof(int32_t));
+  if (blocks) memcpy(blocks, h->blocks.data(), h->blocks.size() * sizeof(double));
+  return DPGO_OK;
+}
+
+#define NEED_FINAL(h)                                                   \
+  do {                                                                  \
+    if (!(h)->finalized) {                                              \
+      set_error("dpgo_finalize must be called before compute calls");   \
+      return DPGO_ESTATE;                                               \
+    }                                                                   \
+  } while (0)
+
+static int h2d(dpgo_dev *h, double *dst, const double *src) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, h->vlen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return DPGO_OK;
+}
+static int d2h(dpgo_dev *h, double *dst, const double *src) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, h->vlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return DPGO_OK;
+}
+
+int dpgo_set_G(dpgo_handle h, const double *G_host) {
+  H_CHECK(h);
+  CHECK_ARG(G_host != nullptr);
+  return h2d(h, h->d_G, G_host);
+}
+
+static int rebuild_G(dpgo_dev *h) {
+  return op_qx(h, cview(h), h->d_nbr, h->d_Gconst, h->d_G);
+}
+
+int dpgo_set_neighbor_poses(dpgo_handle h, const double *tiles_host) {
+  H_CHECK(h);
+  NEED_FINAL(h);
+  CHECK_ARG(h->num_nbr_slots == 0 || tiles_host != nullptr);
+  if (h->num_nbr_slots > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->d_nbr, tiles_host,
+                             (size_t)h->num_nbr_slots * h->r * (h->d + 1) * sizeof(double),
+                             cudaMemcpyHostToDevice, h->stream));
+  return rebuild_G(h);
+}
+
+int dpgo_set_neighbor_poses_dev(dpgo_handle h, const double *tiles_dev) {
+  H_CHECK(h);
+  NEED_FINAL(h);
+  CHECK_ARG(h->num_nbr_slots == 0 || tiles_dev != nullptr);
+  if (h->num_nbr_slots > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->d_nbr, tiles_dev,
+                             (size_t)h->num_nbr_slots * h->r * (h->d + 1) * sizeof(double),
+                             cudaMemcpyDeviceToDevice, h->stream));
+  return rebuild_G(h);
+}
+
+int dpgo_get_G(dpgo_handle h, double *G_host) {
+  H_CHECK(h);
+  CHECK_ARG(G_host != nullptr);
+  return d2h(h, G_host, h->d_G);
+}
+
+int dpgo_qx(dpgo_handle h, const double *X, double *out) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(op_qx(h, qview(h), h->d_t0, nullptr, h->d_t1));
+  return d2h(h, out, h->d_t1);
+}
+
+int dpgo_f(dpgo_handle h, const double *X, double *f) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X && f);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  double gn2;
+  return op_fgrad(h, h->d_t0, h->d_EG2, h->d_grad2, h->d_S2, f, &gn2);
+}
+
+int dpgo_egrad(dpgo_handle h, const double *X, double *out) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(op_qx(h, qview(h), h->d_t0, h->d_G, h->d_t1));
+  return d2h(h, out, h->d_t1);
+}
+
+int dpgo_rgrad(dpgo_handle h, const double *X, double *out, double *norm) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X != nullptr);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  double f, gn2;
+  DPGO_TRY(op_fgrad(h, h->d_t0, h->d_EG2, h->d_grad2, h->d_S2, &f, &gn2));
+  if (norm) *norm = sqrt(gn2);
+  if (out) return d2h(h, out, h->d_grad2);
+  return DPGO_OK;
+}
+
+int dpgo_hessvec(dpgo_handle h, const double *X, const double *V, double *out) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X && V && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(h2d(h, h->d_t1, V));
+  double f, gn2;
+  DPGO_TRY(op_fgrad(h, h->d_t0, h->d_EG2, h->d_grad2, h->d_S2, &f, &gn2));
+  DPGO_TRY(op_hess(h, h->d_t0, h->d_S2, h->d_t1, h->d_t2, nullptr, nullptr, nullptr));
+  return d2h(h, out, h->d_t2);
+}
+
+int dpgo_precon(dpgo_handle h, const double *X, const double *V, double *out) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(X && V && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(h2d(h, h->d_t1, V));
+  DPGO_TRY(op_precon(h, h->d_t0, h->d_t1, h->d_t2, nullptr, nullptr));
+  return d2h(h, out, h->d_t2);
+}
+
+int dpgo_tangent_project(dpgo_handle h, const double *X, const double *V, double *out) {
+  H_CHECK(h);
+  CHECK_ARG(X && V && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(h2d(h, h->d_t1, V));
+  DPGO_TRY(op_tangent(h, h->d_t0, h->d_t1, h->d_t2));
+  return d2h(h, out, h->d_t2);
+}
+
+int dpgo_retract(dpgo_handle h, const double *X, const double *V, double *out) {
+  H_CHECK(h);
+  CHECK_ARG(X && V && out);
+  DPGO_TRY(h2d(h, h->d_t0, X));
+  DPGO_TRY(h2d(h, h->d_t1, V));
+  DPGO_TRY(op_retract(h, h->d_t0, h->d_t1, h->d_t2));
+  return d2h(h, out, h->d_t2);
+}
+
+int dpgo_project_manifold(dpgo_handle h, const double *M, double *out) {
+  H_CHECK(h);
+  CHECK_ARG(M && out);
+  DPGO_TRY(h2d(h, h->d_t0, M));
+  DPGO_TRY(op_polar(h, 1.0, h->d_t0, 0.0, nullptr, 0.0, nullptr, h->d_t2));
+  return d2h(h, out, h->d_t2);
+}
+
+static int run_solver(dpgo_dev *h, const dpgo_ropt_params *params, const double *x_in_dev,
+                      double *x_out_dev, dpgo_ropt_result *result) {
+  dpgo_ropt_params P;
+  if (params) P = *params; else dpgo_default_params(&P);
+  CHECK_ARG(P.method == 0 || P.method == 1);
+  CHECK_ARG(P.RTR_iterations >= 0 && P.RTR_tCG_iterations >= 0);
+  if ((P.method == 0 || P.RGD_use_preconditioner) && !h->has_precon) {
+    set_error("preconditioner not built (dpgo_finalize(h, 1))");
+    return DPGO_ESTATE;
+  }
+  dpgo_ropt_result res;
+  memset(&res, 0, sizeof(res));
+  const int64_t l0 = h->launches;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  int rc;
+  if (P.fused && P.method == 0) rc = solve_fused(h, &P, x_in_dev, x_out_dev, &res);
+  else rc = solve_host(h, &P, x_in_dev, x_out_dev, &res);
+  if (rc != DPGO_OK) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  res.elapsed_ms = ms;
+  res.n_launches = h->launches - l0;
+  if (result) *result = res;
+  return DPGO_OK;
+}
+
+int dpgo_optimize(dpgo_handle h, const dpgo_ropt_params *params, const double *X0, double *Xout,
+                  dpgo_ropt_result *result) {
+  H_CHECK(h); NEED_FINAL(h);
+  if (X0) DPGO_TRY(h2d(h, h->d_slot[DPGO_SLOT_X], X0));
+  DPGO_TRY(run_solver(h, params, h->d_slot[DPGO_SLOT_X], h->d_slot[DPGO_SLOT_X], result));
+  if (Xout) return d2h(h, Xout, h->d_slot[DPGO_SLOT_X]);
+  return DPGO_OK;
+}
+
+int dpgo_optimize_slot(dpgo_handle h, const dpgo_ropt_params *params, int from,
+                       dpgo_ropt_result *result) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(from >= 0 && from < 4);
+  return run_solver(h, params, h->d_slot[from], h->d_slot[DPGO_SLOT_X], result);
+}
+
+int dpgo_slot_set(dpgo_handle h, int slot, const double *host) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4 && host);
+  return h2d(h, h->d_slot[slot], host);
+}
+int dpgo_slot_get(dpgo_handle h, int slot, double *host) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4 && host);
+  return d2h(h, host, h->d_slot[slot]);
+}
+int dpgo_slot_copy(dpgo_handle h, int dst, int src) {
+  H_CHECK(h);
+  CHECK_ARG(dst >= 0 && dst < 4 && src >= 0 && src < 4);
+  if (dst == src) return DPGO_OK;
+  return op_copy(h, h->d_slot[src], h->d_slot[dst]);
+}
+
+int dpgo_nesterov_update_Y(dpgo_handle h, double alpha) {
+  H_CHECK(h);
+  return op_polar(h, 1.0 - alpha, h->d_slot[DPGO_SLOT_X], alpha, h->d_slot[DPGO_SLOT_V], 0.0, nullptr,
+                  h->d_slot[DPGO_SLOT_Y]);
+}
+int dpgo_nesterov_update_V(dpgo_handle h, double gamma) {
+  H_CHECK(h);
+  return op_polar(h, 1.0, h->d_slot[DPGO_SLOT_V], gamma, h->d_slot[DPGO_SLOT_X], -gamma,
+                  h->d_slot[DPGO_SLOT_Y], h->d_slot[DPGO_SLOT_V]);
+}
+
+int dpgo_set_public_indices(dpgo_handle h, int num_public, const int32_t *idx) {
+  H_CHECK(h);
+  CHECK_ARG(num_public >= 0);
+  CHECK_ARG(num_public == 0 || idx);
+  for (int k = 0; k < num_public; ++k) CHECK_ARG(idx[k] >= 0 && idx[k] < h->n);
+  std::vector<int32_t> v(idx, idx + num_public);
+  h->num_public = num_public;
+  return upload(&h->d_public_idx, v);
+}
+
+int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4);
+  if (h->num_public == 0) return DPGO_OK;
+  CHECK_ARG(tiles_dev != nullptr);
+  const int tile = h->r * (h->d + 1);
+  const size_t total = (size_t)h->num_public * tile;
+  int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+  k_gather_tiles<<<grid, 256, 0, h->stream>>>(h->d_slot[slot], h->d_public_idx, h->num_public, tile,
+                                              tiles_dev);
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+
+int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out) {
+  H_CHECK(h);
+  CHECK_ARG(slot_a >= 0 && slot_a < 4 && slot_b >= 0 && slot_b < 4 && out);
+  const int grid = pose_grid(h, 1);
+  k_maxdist<<<grid, kBlock, 0, h->stream>>>(h->d_slot[slot_a], h->d_slot[slot_b], h->n, h->r,
+                                            h->d + 1, h->d_partials);
+  LAUNCH_CHECK(h);
+  k_finalize_max<<<1, 1, 0, h->stream>>>(h->d_partials, grid, h->d_scalars);
+  LAUNCH_CHECK(h);
+  CUDA_TRY(cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = h->h_scalars[0];
+  return DPGO_OK;
+}
+
+}  // extern "C"
+
+// ---- measurement helpers -------------------------------------------------------------------
+static int ensure_flush(dpgo_dev *h) {
+  if (!h->d_flush) {
+    h->flush_bytes = (size_t)512 << 20;  // > 126 MB L2
+    CUDA_TRY(cudaMalloc((void **)&h->d_flush, h->flush_bytes));
+  }
+  return DPGO_OK;
+}
+static int do_flush(dpgo_dev *h) {
+  k_flush<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_bytes / sizeof(double), 1.0);
+  CUDA_TRY(cudaPeekAtLastError());
+  return DPGO_OK;
+}
+
+template <typename F>
+static int time_launches(dpgo_dev *h, int reps, int flush, F launch, double *usec) {
+  CHECK_ARG(reps > 0 && usec);
+  if (flush) DPGO_TRY(ensure_flush(h));
+  for (int w = 0; w < 3; ++w) DPGO_TRY(launch());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  double total_ms = 0.0;
+  if (flush) {
+    for (int k = 0; k < reps; ++k) {
+      DPGO_TRY(do_flush(h));
+      CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+      DPGO_TRY(launch());
+      CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+      CUDA_TRY(cudaEventSynchronize(h->ev1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      total_ms += ms;
+    }
+  } else {
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int k = 0; k < reps; ++k) DPGO_TRY(launch());
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    total_ms = ms;
+  }
+  *usec = total_ms * 1000.0 / reps;
+  return DPGO_OK;
+}
+
+extern "C" {
+
+int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec) {
+  H_CHECK(h); NEED_FINAL(h);
+  return time_launches(h, reps, flush_l2,
+                       [&]() { return op_qx(h, qview(h), h->d_slot[0], nullptr, h->d_t1); }, usec);
+}
+
+int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
+  H_CHECK(h); NEED_FINAL(h);
+  if (!h->has_precon) { set_error("preconditioner not built"); return DPGO_ESTATE; }
+  return time_launches(h, reps, flush_l2, [&]() {
+    const int g1 = gemv_grid(h);
+    DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, 0, h->stream>>>(h->d_Pinv, h->ld, h->d_slot[0],
+                                                                   h->d_zpart, h->KT, h->nsplit));
+    LAUNCH_CHECK(h);
+    return DPGO_OK;
+  }, usec);
+}
+
+int dpgo_bytes_qx(dpgo_handle h, double *bytes) {
+  CHECK_ARG(h && bytes);
+  NEED_FINAL(h);
+  const double dh = h->d + 1;
+  // nnzb*((d+1)^2*8 + 4) + (n+1)*4 + 2*r*(d+1)*n*8
+  *bytes = (double)h->nnzb * (dh * dh * 8 + 4) + ((double)h->n + 1) * 4 + 2.0 * h->r * dh * h->n * 8;
+  return DPGO_OK;
+}
+
+int dpgo_bytes_precon(dpgo_handle h, double *bytes) {
+  CHECK_ARG(h && bytes);
+  // dense N x N inverse read once + vector read + result written
+  *bytes = (double)h->N * h->N * 8 + 2.0 * h->r * h->N * 8;
+  return DPGO_OK;
+}
+
+}  // extern "C"

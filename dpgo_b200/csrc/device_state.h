@@ -1,0 +1,78 @@
+// Internal state behind a dpgo_handle (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dpgo_b200.h"
+
+namespace dpgo {
+
+struct EdgeSet {
+  int m = 0;
+  std::vector<int32_t> a, b;  // private: p1,p2 ; shared: my_idx, nbr_slot
+  std::vector<uint8_t> outgoing;
+  std::vector<double> R, t, kappa, tau, weight;
+};
+
+void set_error(const char *fmt, ...);
+
+}  // namespace dpgo
+
+struct dpgo_dev {
+  int device = 0, n = 0, d = 0, r = 0;
+  int N = 0;       // (d+1) n
+  int ld = 0;      // N rounded up to a multiple of 64 (vector / Pinv padding)
+  size_t vlen = 0; // r * N   (doubles in a lifted pose array)
+  size_t vpad = 0; // r * ld  (allocated doubles per array)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+
+  // host-side graph (reference: PoseGraph members, include/DPGO/PoseGraph.h)
+  dpgo::EdgeSet priv, shared;
+  int num_nbr_slots = 0;
+  std::vector<int32_t> prior_idx;
+  std::vector<double> prior_poses;
+  double prior_kappa = 10000.0, prior_tau = 100.0;
+
+  // block-CSR Q (host copy + device)
+  std::vector<int32_t> rowptr, colidx;
+  std::vector<double> blocks;
+  int nnzb = 0;
+  int *d_rowptr = nullptr, *d_colidx = nullptr, *d_browidx = nullptr;
+  double *d_blocks = nullptr;
+  // cross block-CSR for G = Gconst + Xnbr * C
+  int cnnzb = 0;
+  int *d_crowptr = nullptr, *d_ccolidx = nullptr;
+  double *d_cblocks = nullptr;
+  double *d_Gconst = nullptr, *d_G = nullptr, *d_nbr = nullptr;
+
+  // dense preconditioner
+  double *d_Pinv = nullptr, *d_zpart = nullptr;
+  int KT = 0, nsplit = 0;
+  bool finalized = false, has_precon = false;
+  cusolverDnHandle_t cusolver = nullptr;
+
+  // lifted pose arrays
+  double *d_slot[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_xa = nullptr, *d_xb = nullptr;
+  double *d_EG = nullptr, *d_EG2 = nullptr, *d_grad = nullptr, *d_grad2 = nullptr;
+  double *d_S = nullptr, *d_S2 = nullptr;
+  double *d_eta = nullptr, *d_r = nullptr, *d_z = nullptr, *d_delta = nullptr, *d_Hd = nullptr;
+  double *d_t0 = nullptr, *d_t1 = nullptr, *d_t2 = nullptr;
+  double *d_partials = nullptr, *d_scalars = nullptr;
+  double *h_scalars = nullptr;  // pinned
+  void *d_fused = nullptr;      // fused-kernel parameter / result block
+  void *h_fused = nullptr;      // pinned mirror
+  int *d_public_idx = nullptr;
+  int num_public = 0;
+  double *d_flush = nullptr;
+  size_t flush_bytes = 0;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+};

@@ -1,0 +1,596 @@
+// Device-side building blocks of the RBCD local solve (sm_100a).  Every phase is a __device__
+// function over a "grid context" so that the same code runs (a) as a stand-alone kernel (one
+// launch per op: parity tests, host-driven solver) and (b) inside the persistent fused RTR
+// kernel with grid-wide barriers between phases.
+//
+// Data layout: every r x N array is column-major FP64; pose i is the contiguous tile
+// [i*TILE, (i+1)*TILE) of R*(D+1) doubles (160 B for r=5,d=3).  A pose is processed by a
+// "lane group" of D+1 adjacent lanes of a warp, lane c owning column c of the tile (R doubles in
+// registers); d x d cross-column quantities are exchanged with warp shuffles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpgo {
+
+constexpr int kBlock = 256;          // threads per CTA for every phase
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kGemvCols = 64;        // output columns per dense-precon tile (2 per lane)
+constexpr int kGemvUnroll = 8;       // k-loop unroll (loads in flight per lane)
+
+struct BsrView {
+  const int *rowptr;     // [n+1]
+  const int *colidx;     // [nnzb]
+  const double *blocks;  // [nnzb][(D+1)*(D+1)]  block (i,j) of Q, row-major
+};
+
+template <int R, int D>
+struct Geo {
+  static constexpr int DH = D + 1;
+  static constexpr int TILE = R * DH;
+  static constexpr int GPW = 32 / DH;  // pose groups per warp
+};
+
+struct Ctx {
+  int tid;      // global thread id
+  int nthreads; // threads in grid
+  int warp;     // global warp id
+  int nwarps;   // warps in grid
+  int lane;
+};
+
+__device__ __forceinline__ Ctx make_ctx() {
+  Ctx c;
+  c.tid = blockIdx.x * blockDim.x + threadIdx.x;
+  c.nthreads = gridDim.x * blockDim.x;
+  c.warp = c.tid >> 5;
+  c.nwarps = c.nthreads >> 5;
+  c.lane = threadIdx.x & 31;
+  return c;
+}
+
+struct LanePos {
+  int grp;        // pose group within the warp
+  int c;          // column of the tile owned by this lane
+  int base_lane;  // first lane of the group
+  bool ok;        // lane participates (false for the 32 % (D+1) spare lanes)
+};
+
+template <int D>
+__device__ __forceinline__ LanePos lane_pos(int lane) {
+  constexpr int DH = D + 1;
+  LanePos p;
+  p.grp = lane / DH;
+  p.c = lane - p.grp * DH;
+  p.ok = p.grp < (32 / DH);
+  p.base_lane = p.grp * DH;
+  if (!p.ok) p.base_lane = 32 - DH;  // keep shuffle sources in range
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+// Deterministic block reduction of K running sums; thread 0 stores them to out[0..K).
+template <int K>
+__device__ __forceinline__ void block_reduce_store(double (&v)[K], double *out) {
+  __shared__ double sred[K][kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sred[k][w] = x;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = (lane < kWarpsPerBlock) ? sred[k][lane] : 0.0;
+#pragma unroll
+      for (int o = kWarpsPerBlock / 2; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) out[k] = x;
+    }
+  }
+  __syncthreads();
+}
+
+// Sum per-block partials [nblocks][K] in a fixed order; every thread of the CTA gets the result.
+// (Plain loads: the partials were written by other CTAs before a grid-wide barrier.)
+template <int K>
+__device__ __forceinline__ void sum_partials(const double *partials, int nblocks, double (&out)[K]) {
+  __shared__ double sres[K];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = 0.0;
+      for (int b = lane; b < nblocks; b += 32) x += partials[(size_t)b * K + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) sres[k] = x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = sres[k];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile helpers
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void load_col(const double *p, double (&v)[R]) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) v[k] = p[k];
+}
+template <int R>
+__device__ __forceinline__ void store_col(double *p, const double (&v)[R]) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) p[k] = v[k];
+}
+template <int R>
+__device__ __forceinline__ double dot_col(const double (&a)[R], const double (&b)[R]) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < R; ++k) s = fma(a[k], b[k], s);
+  return s;
+}
+
+// One column (c) of (X * Q) for pose i: sum over the block row of Q.
+//   out[:, (i,c)] = sum_j sum_k X_j[:, k] * Q_ij[c][k]        (Q symmetric)
+// X tiles are gathered with plain (coherent) loads; Q blocks / indices through the read-only path.
+template <int R, int D>
+__device__ __forceinline__ void spmm_col(const BsrView &Q, const double *X, int i, int c,
+                                         double (&acc)[R]) {
+  constexpr int DH = D + 1, TILE = R * DH;
+  const int e0 = __ldg(Q.rowptr + i), e1 = __ldg(Q.rowptr + i + 1);
+  for (int e = e0; e < e1; ++e) {
+    const int j = __ldg(Q.colidx + e);
+    const double *m = Q.blocks + (size_t)e * (DH * DH) + c * DH;
+    const double *xj = X + (size_t)j * TILE;
+    double mk[DH];
+#pragma unroll
+    for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
+#pragma unroll
+    for (int k = 0; k < DH; ++k) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = fma(xj[k * R + q], mk[k], acc[q]);
+    }
+  }
+}
+
+// Stiefel tangent projection of one pose, column-distributed over the lane group:
+//   w_Y <- w_Y - Y sym(Y^T w_Y), translation column untouched.
+// Every lane of the warp must call this (shuffles); `valid` guards memory access only.
+// sym[a] returns S[a][c] = sym(Y^T W)[a][c] for this lane's column c (< D).
+template <int R, int D>
+__device__ __forceinline__ void group_tangent(const double *Ytile, double (&w)[R], const LanePos &lp,
+                                              bool valid, double (&sym)[D]) {
+  double y[D][R];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) y[a][q] = valid ? Ytile[a * R + q] : 0.0;
+  }
+  double mcol[D];  // M[a][c] = Y_a . w_c
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) s = fma(y[a][q], w[q], s);
+    mcol[a] = s;
+  }
+  double mt[D];  // M[c][a], fetched from lane (base + a)
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    mt[a] = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double v = __shfl_sync(0xffffffffu, mcol[k], lp.base_lane + a);
+      if (k == lp.c) mt[a] = v;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < D; ++a) sym[a] = 0.5 * (mcol[a] + mt[a]);
+  if (lp.c < D) {
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) w[q] = fma(-y[a][q], sym[a], w[q]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------------------------
+// out = X * Q (+ G if G != nullptr)
+template <int R, int D>
+__device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const double *X,
+                                         const double *G, double *out, int n) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    if (lp.ok && i < n) {
+      double acc[R];
+      const size_t off = ((size_t)i * Gm::DH + lp.c) * R;
+      if (G) load_col<R>(G + off, acc);
+      else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) acc[q] = 0.0;
+      }
+      spmm_col<R, D>(Q, X, i, lp.c, acc);
+      store_col<R>(out + off, acc);
+    }
+  }
+}
+
+// Cost, Euclidean gradient, Riemannian gradient and the per-pose S = sym(Y^T EG_Y) in one pass:
+//   EG = X Q + G; f = 0.5 <EG + G, X>; grad = Proj_X(EG); acc = {f, <grad,grad>}
+// ref: QuadraticProblem::f / EucGrad / RieGrad, src/QuadraticProblem.cpp:29-47,71-83.
+template <int R, int D>
+__device__ __forceinline__ void phase_fgrad(const Ctx &ctx, const BsrView &Q, const double *X,
+                                            const double *G, double *EG, double *grad, double *S,
+                                            int n, double (&acc)[2]) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double eg[R], g[R], x[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { eg[q] = 0.0; g[q] = 0.0; x[q] = 0.0; }
+    if (valid) {
+      load_col<R>(G + off, g);
+      load_col<R>(X + off, x);
+#pragma unroll
+      for (int q = 0; q < R; ++q) eg[q] = g[q];
+      spmm_col<R, D>(Q, X, i, lp.c, eg);
+      store_col<R>(EG + off, eg);
+      acc[0] += 0.5 * (dot_col<R>(eg, x) + dot_col<R>(g, x));
+    }
+    double sym[D];
+    group_tangent<R, D>(X + (valid ? (size_t)i * Gm::TILE : 0), eg, lp, valid, sym);
+    if (valid) {
+      store_col<R>(grad + off, eg);
+      acc[1] += dot_col<R>(eg, eg);
+      if (lp.c < D) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) S[(size_t)i * (D * D) + lp.c * D + a] = sym[a];
+      }
+    }
+  }
+}
+
+// Riemannian Hessian-vector product at Y (S = sym(Y^T EG_Y) cached by phase_fgrad):
+//   HV = Proj_Y( V Q - [V_Y S, 0] );  acc = {<V, HV>, <V, W>}  (W optional)
+// ref: QuadraticProblem::EucHessianEta src/QuadraticProblem.cpp:49-54 + Stiefel EucHvToHv.
+template <int R, int D>
+__device__ __forceinline__ void phase_hess(const Ctx &ctx, const BsrView &Q, const double *Y,
+                                           const double *S, const double *V, double *HV,
+                                           const double *W, int n, double (&acc)[2]) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double out[R], v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { out[q] = 0.0; v[q] = 0.0; }
+    if (valid) {
+      spmm_col<R, D>(Q, V, i, lp.c, out);
+      load_col<R>(V + off, v);
+      if (lp.c < D) {
+        const double *Vi = V + (size_t)i * Gm::TILE;
+        const double *Si = S + (size_t)i * (D * D) + lp.c * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double sk = Si[k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) out[q] = fma(-Vi[k * R + q], sk, out[q]);
+        }
+      }
+    }
+    double sym[D];
+    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), out, lp, valid, sym);
+    if (valid) {
+      store_col<R>(HV + off, out);
+      acc[0] += dot_col<R>(v, out);
+      if (W) {
+        double w[R];
+        load_col<R>(W + off, w);
+        acc[1] += dot_col<R>(v, w);
+      }
+    }
+  }
+}
+
+// Stand-alone tangent projection out = Proj_X(V).
+template <int R, int D>
+__device__ __forceinline__ void phase_tangent(const Ctx &ctx, const double *X, const double *V,
+                                              double *out, int n) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double w[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) w[q] = 0.0;
+    if (valid) load_col<R>(V + off, w);
+    double sym[D];
+    group_tangent<R, D>(X + (valid ? (size_t)i * Gm::TILE : 0), w, lp, valid, sym);
+    if (valid) store_col<R>(out + off, w);
+  }
+}
+
+// Dense preconditioner, part 1: partial products of the r x N array `vec` with the dense
+// symmetric inverse Pinv (ld x ld, zero padded).  Tile = kGemvCols output columns x KT inner
+// indices; the 8 warps of the CTA split the inner range, lanes own 2 adjacent output columns
+// (one 16-byte streaming load per inner index), partial sums meet in shared memory.
+//   zpart[s][:, j] = sum_{k in split s} vec[:, k] * Pinv[j, k]
+// ref: QuadraticProblem::PreConditioner, src/QuadraticProblem.cpp:56-69 (the solve).
+template <int R>
+__device__ __forceinline__ void phase_precon_gemv(const double *Pinv, int ld, const double *vec,
+                                                  double *zpart, int KT, int nsplit) {
+  __shared__ double sacc[kWarpsPerBlock][R][kGemvCols];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ncb = ld / kGemvCols;
+  const int ntiles = ncb * nsplit;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int cb = t % ncb, s = t / ncb;
+    const int k0 = s * KT;
+    const int k1 = min(ld, k0 + KT);
+    const int j = cb * kGemvCols + 2 * lane;
+    double a0[R], a1[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
+    for (int k = k0 + w * kGemvUnroll; k < k1; k += kWarpsPerBlock * kGemvUnroll) {
+      double2 p[kGemvUnroll];
+#pragma unroll
+      for (int u = 0; u < kGemvUnroll; ++u)
+        p[u] = __ldcs(reinterpret_cast<const double2 *>(Pinv + (size_t)(k + u) * ld + j));
+#pragma unroll
+      for (int u = 0; u < kGemvUnroll; ++u) {
+        const double *rv = vec + (size_t)(k + u) * R;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const double x = rv[q];
+          a0[q] = fma(p[u].x, x, a0[q]);
+          a1[q] = fma(p[u].y, x, a1[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      sacc[w][q][2 * lane] = a0[q];
+      sacc[w][q][2 * lane + 1] = a1[q];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+      const int q = o / kGemvCols, jj = o % kGemvCols;
+      double x = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+      zpart[(size_t)s * ld * R + (size_t)(cb * kGemvCols + jj) * R + q] = x;
+    }
+    __syncthreads();
+  }
+}
+
+// Dense preconditioner, part 2: z = Proj_Y( sum_s zpart[s] ); acc = {<z, rvec>};
+// optionally also writes delta = -z (first tCG direction).
+template <int R, int D>
+__device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double *zpart, int ld,
+                                                    int nsplit, const double *Y, const double *rvec,
+                                                    double *z, double *neg_out, int n,
+                                                    double (&acc)[1]) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double w[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) w[q] = 0.0;
+    if (valid) {
+      for (int s = 0; s < nsplit; ++s) {
+        const double *zp = zpart + (size_t)s * ld * R + off;
+#pragma unroll
+        for (int q = 0; q < R; ++q) w[q] += zp[q];
+      }
+    }
+    double sym[D];
+    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), w, lp, valid, sym);
+    if (valid) {
+      store_col<R>(z + off, w);
+      double rr[R];
+      load_col<R>(rvec + off, rr);
+      acc[0] += dot_col<R>(w, rr);
+      if (neg_out) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) neg_out[off + q] = -w[q];
+      }
+    }
+  }
+}
+
+// QF retraction, one thread per pose: Y+ = qf(Y + eta_Y) (Gram-Schmidt, positive diagonal),
+// p+ = p + eta_p.   ref: ProductManifold::Retraction (src/QuadraticOptimizer.cpp:134).
+template <int R, int D>
+__device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, const double *Eta,
+                                              double *Xout, int n) {
+  constexpr int TILE = R * (D + 1);
+  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
+    const double *x = X + (size_t)i * TILE;
+    const double *e = Eta + (size_t)i * TILE;
+    double *o = Xout + (size_t)i * TILE;
+    double a[D][R];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) a[k][q] = x[k * R + q] + e[k * R + q];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int p = 0; p < k; ++p) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s = fma(a[p][q], a[k][q], s);
+#pragma unroll
+        for (int q = 0; q < R; ++q) a[k][q] = fma(-s, a[p][q], a[k][q]);
+      }
+      // second orthogonalization pass (keeps Y^T Y = I to rounding even for large steps)
+#pragma unroll
+      for (int p = 0; p < k; ++p) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s = fma(a[p][q], a[k][q], s);
+#pragma unroll
+        for (int q = 0; q < R; ++q) a[k][q] = fma(-s, a[p][q], a[k][q]);
+      }
+      double nn = 0.0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) nn = fma(a[k][q], a[k][q], nn);
+      const double inv = 1.0 / sqrt(nn);
+#pragma unroll
+      for (int q = 0; q < R; ++q) a[k][q] *= inv;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) o[k * R + q] = a[k][q];
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) o[D * R + q] = x[D * R + q] + e[D * R + q];
+  }
+}
+
+// Polar projection of the Stiefel block (U V^T of the thin SVD) by one-sided Jacobi, one
+// thread per pose, of the combination M = ca*A + cb*B + cc*C (B, C optional); translation is
+// the same combination, unprojected.
+// ref: LiftedSEManifold::project src/manifold/LiftedSEManifold.cpp:34-45,
+//      projectToStiefelManifold src/DPGO_utils.cpp:480-486, PGOAgent::updateY/updateV
+//      src/PGOAgent.cpp:922-936.
+template <int R, int D>
+__device__ __forceinline__ void phase_polar(const Ctx &ctx, double ca, const double *A, double cb,
+                                            const double *B, double cc, const double *C,
+                                            double *out, int n) {
+  constexpr int TILE = R * (D + 1);
+  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
+    const size_t o = (size_t)i * TILE;
+    double a[D][R], v[D][D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        double m = ca * A[o + k * R + q];
+        if (B) m = fma(cb, B[o + k * R + q], m);
+        if (C) m = fma(cc, C[o + k * R + q], m);
+        a[k][q] = m;
+      }
+#pragma unroll
+      for (int l = 0; l < D; ++l) v[k][l] = (k == l) ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      double offmax = 0.0;
+#pragma unroll
+      for (int p = 0; p < D - 1; ++p) {
+#pragma unroll
+        for (int q2 = p + 1; q2 < D; ++q2) {
+          double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            al = fma(a[p][q], a[p][q], al);
+            be = fma(a[q2][q], a[q2][q], be);
+            ga = fma(a[p][q], a[q2][q], ga);
+          }
+          const double lim = sqrt(al * be);
+          const double rel = (lim > 0.0) ? fabs(ga) / lim : 0.0;
+          offmax = fmax(offmax, rel);
+          if (rel > 1e-16) {
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              const double xp = a[p][q], xq = a[q2][q];
+              a[p][q] = cs * xp - sn * xq;
+              a[q2][q] = sn * xp + cs * xq;
+            }
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+              const double vp = v[p][l], vq = v[q2][l];
+              v[p][l] = cs * vp - sn * vq;
+              v[q2][l] = sn * vp + cs * vq;
+            }
+          }
+        }
+      }
+      if (offmax <= 1e-15) break;
+    }
+    // a[k] = sigma_k u_k (column k of A V), v[k][l] = V[l][k];  U V^T = sum_k u_k v_k^T
+    double u[D][R];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double nn = 0.0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) nn = fma(a[k][q], a[k][q], nn);
+      const double inv = (nn > 0.0) ? 1.0 / sqrt(nn) : 0.0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) u[k][q] = a[k][q] * inv;
+    }
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(u[k][q], v[k][l], s);
+        out[o + l * R + q] = s;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      double m = ca * A[o + D * R + q];
+      if (B) m = fma(cb, B[o + D * R + q], m);
+      if (C) m = fma(cc, C[o + D * R + q], m);
+      out[o + D * R + q] = m;
+    }
+  }
+}
+
+// Elementwise phases over the r x N arrays (len = R * N doubles).
+//   eta += a*delta; r += a*Hd; acc = {<r,r>}
+__device__ __forceinline__ void phase_step(const Ctx &ctx, double a, const double *delta,
+                                           const double *Hd, double *eta, double *r, size_t len,
+                                           double (&acc)[1]) {
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
+    eta[k] = fma(a, delta[k], eta[k]);
+    const double rn = fma(a, Hd[k], r[k]);
+    r[k] = rn;
+    acc[0] = fma(rn, rn, acc[0]);
+  }
+}
+//   y = a*x + b*y
+__device__ __forceinline__ void phase_axpby(const Ctx &ctx, double a, const double *x, double b,
+                                            double *y, size_t len) {
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) y[k] = fma(a, x[k], b * y[k]);
+}
+__device__ __forceinline__ void phase_copy(const Ctx &ctx, const double *x, double *y, size_t len) {
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) y[k] = x[k];
+}
+__device__ __forceinline__ void phase_zero(const Ctx &ctx, double *y, size_t len) {
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) y[k] = 0.0;
+}
+
+}  // namespace dpgo

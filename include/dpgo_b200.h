@@ -1,0 +1,182 @@
+/*
+ * dpgo_b200 -- C-ABI of the B200-native RBCD local-solve hot path.
+ *
+ * This is the drop-in boundary: everything the reference's QuadraticProblem /
+ * QuadraticOptimizer / PoseGraph data matrices / PGOAgent Nesterov step compute on the CPU
+ * (Eigen + ROPTLIB + CHOLMOD) is computed behind these entry points by hand-written sm_100a
+ * CUDA kernels.  Plain pointers and sizes only; no C++/torch types cross the boundary.
+ *
+ * Conventions
+ *   - every dense argument is FP64, column-major, r x (d+1)n ("lifted pose array",
+ *     reference layout pinned by tests/testEigenMap.cpp:12-36 and
+ *     include/DPGO/manifold/Poses.h:21-118): pose i occupies columns (d+1)i..(d+1)i+d,
+ *     first d columns = Stiefel block, last column = translation.
+ *   - "host" pointers are ordinary host memory, "dev" pointers are device memory on the
+ *     handle's device; sizes are implied by (n, d, r) of the handle.
+ *   - every function returns 0 on success, a negative DPGO_E* code otherwise; nothing throws
+ *     across the boundary; dpgo_last_error() returns a thread-local message.
+ *   - a handle is bound to one device and one stream; calls on one handle must be serialized by
+ *     the caller (PGOAgent's mutexes already do, src/PGOAgent.cpp:940-942).
+ *   - there is NO CPU fallback: every compute entry point runs CUDA kernels or fails.
+ *
+ * Citations "ref:" are file:line under the reference repository (mit-acl/dpgo @ a238090c).
+ */
+#ifndef DPGO_B200_H
+#define DPGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPGO_OK 0
+#define DPGO_EINVAL (-1)   /* bad argument / contract violation (reference: glog CHECK abort) */
+#define DPGO_ECUDA (-2)    /* CUDA runtime / cuSOLVER failure                                 */
+#define DPGO_ESTATE (-3)   /* call order violated (e.g. solve before finalize)                */
+#define DPGO_ENUMERIC (-4) /* Cholesky of Q + 0.1 I failed (ref: src/PoseGraph.cpp:606-607)   */
+
+typedef struct dpgo_dev *dpgo_handle;
+
+/* ROptParameters, ref: include/DPGO/DPGO_types.h:44-86 (+ ROPTLIB SolversTR defaults the
+ * reference leaves untouched: theta, kappa, accept_rho, shrink, magnify). */
+typedef struct dpgo_ropt_params {
+  int32_t method;                 /* 0 = RTR, 1 = RGD                          */
+  int32_t verbose;
+  double gradnorm_tol;            /* 1e-2                                      */
+  double RGD_stepsize;            /* 1e-3                                      */
+  int32_t RGD_use_preconditioner; /* 1                                         */
+  int32_t RTR_iterations;         /* 3                                         */
+  int32_t RTR_tCG_iterations;     /* 50                                        */
+  int32_t fused;                  /* 1 = single persistent kernel (default), 0 = one launch per op */
+  double RTR_initial_radius;      /* 100                                       */
+  double tcg_theta;               /* 1                                         */
+  double tcg_kappa;               /* 0.1                                       */
+  double accept_rho;              /* 0.1                                       */
+  double shrink;                  /* 0.25                                      */
+  double magnify;                 /* 2                                         */
+} dpgo_ropt_params;
+
+/* ROPTResult, ref: include/DPGO/DPGO_types.h:91-107, plus work counters. */
+typedef struct dpgo_ropt_result {
+  int32_t success;
+  int32_t tcg_status;  /* 0 LCON, 1 SCON, 2 NEGCURVTURE, 3 EXCREGION, 4 MAXITER (ROPTLIB tCGstatusSet) */
+  double f_init, gradnorm_init, f_opt, gradnorm_opt;
+  double elapsed_ms;   /* device time of the solve (CUDA events on the handle's stream) */
+  int32_t outer_iters, inner_iters, accepted, rejected;
+  /* work actually executed on the device (for the roofline accounting) */
+  int64_t n_qx;        /* block-CSR SpMM passes (Q applied to an r x N array)  */
+  int64_t n_precon;    /* dense (Q+0.1I)^-1 applications                       */
+  int64_t n_pose_sweeps; /* per-pose sweeps (projection / retraction / ...)    */
+  int64_t n_launches;  /* kernels launched by this call                        */
+} dpgo_ropt_result;
+
+void dpgo_default_params(dpgo_ropt_params *p);
+const char *dpgo_last_error(void);
+const char *dpgo_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* One handle = one agent's PoseGraph + QuadraticProblem + optimizer state on one GPU.
+ * ref: PoseGraph(id, r, d) src/PoseGraph.cpp:14-21; QuadraticProblem ctor
+ * src/QuadraticProblem.cpp:17-23.  `stream` is a cudaStream_t (or NULL: the library creates
+ * its own non-blocking stream). */
+int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out);
+int dpgo_destroy(dpgo_handle h);
+int dpgo_dims(dpgo_handle h, int *n, int *d, int *r);
+int dpgo_sync(dpgo_handle h);
+
+/* ---- data matrices (ref: PoseGraph::constructQ/G, constructConnectionLaplacianSE) -------- */
+/* Private (intra-robot) edges, struct-of-arrays; R is m x d x d row-major, t is m x d.
+ * ref: src/DPGO_utils.cpp:272-344, src/PoseGraph.cpp:381-391. */
+int dpgo_set_private_edges(dpgo_handle h, int m, const int32_t *p1, const int32_t *p2,
+                           const double *R, const double *t, const double *kappa,
+                           const double *tau, const double *weight);
+/* Shared (inter-robot) edges: my_idx = my pose, nbr_slot = index of the neighbour's pose in
+ * the neighbour-pose buffer (order chosen by the caller, e.g. PoseGraph::neighborPublicPoseIDs
+ * order), outgoing[k] = 1 if my pose is the tail (ref: m.r1 == id_, src/PoseGraph.cpp:409).
+ * ref: src/PoseGraph.cpp:403-458 (Q diagonal terms), :505-563 (G terms). */
+int dpgo_set_shared_edges(dpgo_handle h, int m, int num_nbr_slots, const int32_t *my_idx,
+                          const int32_t *nbr_slot, const uint8_t *outgoing, const double *R,
+                          const double *t, const double *kappa, const double *tau,
+                          const double *weight);
+/* Priors on my poses (ref: PoseGraph::setPrior src/PoseGraph.cpp:176-181, :462-469, :566-575);
+ * poses is num x r x (d+1) column-major tiles. */
+int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *poses,
+                    double prior_kappa, double prior_tau);
+/* Build the block-CSR Q on the host, upload it, build the cross blocks for G, and build the
+ * preconditioner (dense inverse of Q + 0.1 I via cuSOLVER potrf/potri; the reference uses a
+ * CHOLMOD factorization, src/PoseGraph.cpp:598-613 -- both are exact solves).
+ * build_precon = 0 skips the preconditioner (then only unpreconditioned ops are available). */
+int dpgo_finalize(dpgo_handle h, int build_precon);
+/* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
+ * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
+int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,
+                        int build_precon);
+
+/* Q as the library built it (for parity tests): nnzb, and optionally the arrays. */
+int dpgo_get_Q_bsr(dpgo_handle h, int *nnzb, int32_t *rowptr, int32_t *colidx, double *blocks);
+
+/* Linear term.  Either set G directly (host, r x N) or provide neighbour poses
+ * (num_nbr_slots tiles of r x (d+1)) and let the device build it.
+ * ref: PoseGraph::setNeighborPoses + constructG, src/PoseGraph.cpp:183-186, :493-580. */
+int dpgo_set_G(dpgo_handle h, const double *G_host);
+int dpgo_set_neighbor_poses(dpgo_handle h, const double *tiles_host);
+int dpgo_set_neighbor_poses_dev(dpgo_handle h, const double *tiles_dev);
+int dpgo_get_G(dpgo_handle h, double *G_host);
+
+/* ---- QuadraticProblem operators (host in / host out; used by parity tests and by the C++
+ *      QuadraticProblem shell).  ref: src/QuadraticProblem.cpp:29-83 ------------------------ */
+int dpgo_qx(dpgo_handle h, const double *X, double *out);                  /* X*Q            */
+int dpgo_f(dpgo_handle h, const double *X, double *f);                     /* :29-41         */
+int dpgo_egrad(dpgo_handle h, const double *X, double *out);               /* :43-47         */
+int dpgo_rgrad(dpgo_handle h, const double *X, double *out, double *norm); /* :71-83         */
+int dpgo_hessvec(dpgo_handle h, const double *X, const double *V, double *out); /* Riemannian Hess[V] at X (:49-54 + Stiefel::EucHvToHv) */
+int dpgo_precon(dpgo_handle h, const double *X, const double *V, double *out);  /* :56-69    */
+int dpgo_tangent_project(dpgo_handle h, const double *X, const double *V, double *out);
+int dpgo_retract(dpgo_handle h, const double *X, const double *V, double *out); /* QF retraction */
+int dpgo_project_manifold(dpgo_handle h, const double *M, double *out);  /* LiftedSEManifold::project, src/manifold/LiftedSEManifold.cpp:34-45 */
+
+/* ---- QuadraticOptimizer (ref: src/QuadraticOptimizer.cpp:26-137) ------------------------- */
+/* optimize(): X0/Xout are host r x N arrays; either may be NULL to use / keep the
+ * device-resident iterate of the handle (slot DPGO_SLOT_X). */
+int dpgo_optimize(dpgo_handle h, const dpgo_ropt_params *params, const double *X0,
+                  double *Xout, dpgo_ropt_result *result);
+
+/* ---- device-resident agent state (ref: PGOAgent X / Y / V / XPrev, src/PGOAgent.cpp) ----- */
+#define DPGO_SLOT_X 0
+#define DPGO_SLOT_Y 1
+#define DPGO_SLOT_V 2
+#define DPGO_SLOT_XPREV 3
+int dpgo_slot_set(dpgo_handle h, int slot, const double *host);
+int dpgo_slot_get(dpgo_handle h, int slot, double *host);
+int dpgo_slot_copy(dpgo_handle h, int dst, int src);
+/* Y = project((1-alpha) X + alpha V)  ref: PGOAgent::updateY src/PGOAgent.cpp:922-928 */
+int dpgo_nesterov_update_Y(dpgo_handle h, double alpha);
+/* V = project(V + gamma (X - Y))      ref: PGOAgent::updateV src/PGOAgent.cpp:930-936 */
+int dpgo_nesterov_update_V(dpgo_handle h, double gamma);
+/* X <- optimize(starting from slot `from`), result left in slot X.  ref: updateX :938-995 */
+int dpgo_optimize_slot(dpgo_handle h, const dpgo_ropt_params *params, int from,
+                       dpgo_ropt_result *result);
+/* Pack the public poses (indices given once) of slot `slot` into a device buffer of
+ * num_public tiles -- the payload of getSharedPoseDict / getAuxSharedPoseDict
+ * (ref: src/PGOAgent.cpp:97-110, :132-146). */
+int dpgo_set_public_indices(dpgo_handle h, int num_public, const int32_t *idx);
+int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev);
+/* max_i || p_i(a) - p_i(b) ||  (LiftedPoseArray::maxTranslationDistance, used for
+ * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
+int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* Time `reps` back-to-back launches of the Q*X kernel / preconditioner kernel on the handle's
+ * stream with CUDA events; flush_l2 != 0 streams a >L2-sized buffer between launches
+ * (outside the timed intervals).  Returns mean microseconds per launch. */
+int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec);
+int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
+/* algorithmic bytes of one Q*X / one preconditioner application (SURVEY 8(d) formula) */
+int dpgo_bytes_qx(dpgo_handle h, double *bytes);
+int dpgo_bytes_precon(dpgo_handle h, double *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPGO_B200_H */

@@ -1,0 +1,35 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_dataset(name):
+    """Fixture written by tools/make_fixtures.py from the reference's data/<name>.g2o."""
+    from oracle import pgo
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d, n = int(z["d"]), int(z["n"])
+    meas = pgo.make_measurements(d, z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"])
+    return meas, n, z
+
+
+@pytest.fixture(scope="session")
+def datasets():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = load_dataset(name)
+        return cache[name]
+    return get
