@@ -1,0 +1,213 @@
+"""GPU parity tests: every kernel of the hot path, called through the C-ABI, against the CPU
+oracle on the same inputs.  Tolerances (FP64, different summation order):
+  * per-kernel outputs: 1e-11 relative (Frobenius) -- SURVEY 8(d) asks 1e-12 "per-kernel"; the
+    dense-inverse preconditioner is looser (1e-8) because (Q+0.1I)^-1 amplifies rounding by
+    cond(Q+0.1I) ~ 1e6 in both the oracle's sparse LU and the GPU's potrf/potri.
+  * solver results: final objective relative gap < 1e-6 (north_star), iterate agreement 1e-6.
+"""
+import numpy as np
+import pytest
+
+from oracle import pgo
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def make_problem(meas, n, r, G=None, build_precon=True):
+    import dpgo_b200
+    prob = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa,
+                                               meas.tau, n, meas.d, r, build_precon=build_precon)
+    if G is not None:
+        prob.set_G(G)
+    return prob
+
+
+def oracle_problem(meas, n, r, G=None):
+    d = meas.d
+    Q = pgo.connection_laplacian(meas, n)
+    return pgo.QuadraticProblem(Q, np.zeros((r, (d + 1) * n)) if G is None else G, d)
+
+
+def random_state(n, d, r, seed):
+    rng = np.random.default_rng(seed)
+    X = pgo.manifold_project(rng.standard_normal((r, (d + 1) * n)), d)
+    V = rng.standard_normal((r, (d + 1) * n))
+    return X, V, rng
+
+
+CASES = [("tinyGrid3D", 3), ("tinyGrid3D", 5), ("smallGrid3D", 5), ("smallGrid3D", 4),
+         ("sphere2500", 5)]
+
+
+@pytest.mark.parametrize("name,r", CASES)
+def test_operator_parity(datasets, name, r):
+    meas, n, z = datasets(name)
+    d = meas.d
+    X, V, rng = random_state(n, d, r, 0)
+    G = rng.standard_normal(X.shape)
+    gp = make_problem(meas, n, r, G)
+    op = oracle_problem(meas, n, r, G)
+    # block-CSR Q as built by the library equals the oracle's Q
+    rowptr, colidx, blocks = gp.get_Q_bsr()
+    import scipy.sparse as sp
+    Qg = sp.bsr_matrix((blocks, colidx, rowptr), shape=op.Q.shape).tocsr()
+    assert abs(Qg - op.Q).max() <= 1e-12 * abs(op.Q).max()
+    # Q X, f, gradients, Hessian, projection, retraction, preconditioner
+    assert rel(gp.qx(X), op.XQ(X)) < 1e-12
+    assert abs(gp.f(X) - op.f(X)) <= 1e-12 * abs(op.f(X))
+    assert rel(gp.egrad(X), op.egrad(X)) < 1e-12
+    assert rel(gp.RieGrad(X), op.rgrad(X)) < 1e-11
+    assert abs(gp.RieGradNorm(X) - op.rgrad_norm(X)) <= 1e-11 * op.rgrad_norm(X)
+    Vt = pgo.tangent_project(X, V, d)
+    assert rel(gp.tangent_project(X, V), Vt) < 1e-12
+    assert rel(gp.hessvec(X, Vt), op.rhess(X, op.egrad(X), Vt)) < 1e-11
+    assert rel(gp.retract(X, 0.37 * Vt), pgo.retract_qf(X, 0.37 * Vt, d)) < 1e-12
+    M = X + 0.4 * V
+    assert rel(gp.project_manifold(M), pgo.manifold_project(M, d)) < 1e-12
+    assert rel(gp.precon(X, Vt), op.precondition(X, Vt)) < 1e-8
+    gp.close()
+
+
+def test_operator_parity_2d(datasets):
+    """d = 2 (city10000 sub-graph, r = 3): exercises the 3-lane pose groups."""
+    meas, n, z = datasets("city10000")
+    keep = np.where((meas.p1 < 600) & (meas.p2 < 600))[0]
+    sub = meas.subset(keep)
+    n = 600
+    r, d = 3, 2
+    X, V, rng = random_state(n, d, r, 3)
+    G = rng.standard_normal(X.shape)
+    gp = make_problem(sub, n, r, G)
+    op = oracle_problem(sub, n, r, G)
+    assert rel(gp.qx(X), op.XQ(X)) < 1e-12
+    assert rel(gp.RieGrad(X), op.rgrad(X)) < 1e-11
+    Vt = pgo.tangent_project(X, V, d)
+    assert rel(gp.hessvec(X, Vt), op.rhess(X, op.egrad(X), Vt)) < 1e-11
+    assert rel(gp.retract(X, 0.2 * Vt), pgo.retract_qf(X, 0.2 * Vt, d)) < 1e-12
+    assert rel(gp.project_manifold(X + 0.3 * V), pgo.manifold_project(X + 0.3 * V, d)) < 1e-12
+    assert rel(gp.precon(X, Vt), op.precondition(X, Vt)) < 1e-8
+    Xg, res = gp.optimize(X, None)
+    Xo, ro = pgo.optimize(op, X)
+    assert abs(res["f_opt"] - ro.fOpt) <= 1e-6 * abs(ro.fOpt)
+    gp.close()
+
+
+def test_stiefel_property():
+    """tests/testUtils.cpp:29-54: project / retraction outputs satisfy Y^T Y = I (1e-5; we get 1e-13)."""
+    import dpgo_b200
+    n, d, r = 100, 3, 5
+    rng = np.random.default_rng(5)
+    gp = dpgo_b200.DeviceProblem(n, d, r)
+    M = rng.standard_normal((r, 4 * n))
+    X = gp.project_manifold(M)
+    X2 = gp.retract(X, gp.tangent_project(X, rng.standard_normal(M.shape)))
+    for A in (X, X2):
+        for i in range(n):
+            Y = A[:, 4 * i:4 * i + 3]
+            assert np.linalg.norm(Y.T @ Y - np.eye(3)) < 1e-13
+    assert np.array_equal(X[:, 3::4], M[:, 3::4])
+    gp.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name,r", [("tinyGrid3D", 5), ("smallGrid3D", 5), ("sphere2500", 5)])
+def test_optimize_parity(datasets, name, r, fused):
+    """QuadraticOptimizer::optimize (RTR, reference defaults) from the lifted chordal
+    initialization: same statistics and the same iterate as the oracle."""
+    import dpgo_b200
+    meas, n, z = datasets(name)
+    d = meas.d
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    gp = make_problem(meas, n, r)
+    op = oracle_problem(meas, n, r)
+    prm = dpgo_b200.default_params(fused=fused)
+    Xg, res = gp.optimize(X0, prm)
+    Xo, ro = pgo.optimize(op, X0)
+    assert res["success"] == 1
+    assert abs(res["f_init"] - ro.fInit) <= 1e-12 * abs(ro.fInit)
+    assert abs(res["gradnorm_init"] - ro.gradNormInit) <= 1e-10 * ro.gradNormInit
+    assert res["outer_iters"] == ro.outer
+    assert res["inner_iters"] == ro.inner_total
+    assert res["accepted"] == ro.accepted
+    assert abs(res["f_opt"] - ro.fOpt) <= 1e-6 * abs(ro.fOpt)          # north_star tolerance
+    assert abs(res["f_opt"] - ro.fOpt) <= 1e-9 * abs(ro.fOpt)          # what we actually get
+    assert rel(Xg, Xo) < 1e-6
+    assert abs(res["f_opt"] - op.f(Xg)) <= 1e-10 * abs(ro.fOpt)
+    # per-pose rotation / translation error after rounding (north_star metric)
+    Tg, To = pgo.round_solution(Xg, d), pgo.round_solution(Xo, d)
+    dh = d + 1
+    rot_err = max(np.linalg.norm(Tg[:, i * dh:i * dh + d] - To[:, i * dh:i * dh + d]) for i in range(n))
+    tr_err = max(np.linalg.norm(Tg[:, i * dh + d] - To[:, i * dh + d]) for i in range(n))
+    assert rot_err < 1e-6 and tr_err < 1e-6
+    gp.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_triangle_and_prior_known_answers(fused):
+    """The reference's known-answer tests through the CUDA path
+    (tests/testTriangleGraph.cpp:56-61, tests/testPGO.cpp:131-190)."""
+    import dpgo_b200
+    from test_oracle import _triangle
+    meas, Ttrue = _triangle()
+    gp = make_problem(meas, 3, 3)
+    rng = np.random.default_rng(0)
+    Y0 = pgo.manifold_project(Ttrue + 0.3 * rng.standard_normal(Ttrue.shape), 3)
+    prm = dpgo_b200.default_params(RTR_iterations=50, RTR_tCG_iterations=500, gradnorm_tol=1e-8,
+                                   fused=fused)
+    Y, res = gp.optimize(Y0, prm)
+    assert res["gradnorm_opt"] < 1e-8
+    assert np.linalg.norm(pgo.round_solution(Y, 3) - Ttrue) <= 1e-4
+    gp.close()
+    # prior
+    m = pgo.make_measurements(3, [0], [1], [np.eye(3)], [np.zeros(3)], [10000.0], [100.0])
+    T = pgo.odometry_initialization(m, 2)
+    pr = pgo.project_rotation(np.array([[0.7236, 0.1817, 0.6658], [-0.6100, 0.6198, 0.4938],
+                                        [-0.3230, -0.7634, 0.5594]]))
+    P = np.hstack([pr, np.zeros((3, 1))])
+    gp = dpgo_b200.DeviceProblem(2, 3, 3)
+    gp.set_private_edges(m.p1, m.p2, m.R, m.t, m.kappa, m.tau)
+    gp.set_priors([1], [P])
+    gp.finalize(True)
+    prm = dpgo_b200.default_params(RTR_iterations=50, RTR_tCG_iterations=500, gradnorm_tol=1e-5,
+                                   fused=fused)
+    Y, res = gp.optimize(T, prm)
+    assert np.linalg.norm(Y[:, :4] - P) < 1e-6
+    assert np.linalg.norm(Y[:, 4:] - P) < 1e-6
+    gp.close()
+
+
+def test_rgd_step_parity(datasets):
+    """QuadraticOptimizer::gradientDescent (src/QuadraticOptimizer.cpp:110-137)."""
+    import dpgo_b200
+    meas, n, z = datasets("smallGrid3D")
+    d, r = 3, 5
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    gp = make_problem(meas, n, r)
+    op = oracle_problem(meas, n, r)
+    Xg, res = gp.optimize(X0, dpgo_b200.default_params(method=1))
+    Xo, ro = pgo.optimize(op, X0, pgo.ROptParameters(method="RGD"))
+    assert rel(Xg, Xo) < 1e-9
+    assert abs(res["f_opt"] - ro.fOpt) <= 1e-10 * abs(ro.fOpt)
+    gp.close()
+
+
+def test_linearity_and_symmetry_at_scale(datasets):
+    """Size-independent properties on the largest fixture (grid3D, n = 8000, no oracle run):
+    Q X is linear and symmetric (<U, Q V> = <V, Q U>), Q annihilates the translation gauge."""
+    meas, n, z = datasets("grid3D")
+    d, r = 3, 5
+    gp = make_problem(meas, n, r, build_precon=False)
+    rng = np.random.default_rng(7)
+    U = rng.standard_normal((r, 4 * n)); V = rng.standard_normal((r, 4 * n))
+    QU, QV = gp.qx(U), gp.qx(V)
+    assert rel(gp.qx(2.5 * U - 0.5 * V), 2.5 * QU - 0.5 * QV) < 1e-12
+    assert abs(np.sum(U * QV) - np.sum(V * QU)) <= 1e-11 * abs(np.sum(U * QV))
+    gauge = np.zeros((r, 4 * n)); gauge[:, 3::4] = rng.standard_normal((r, 1))
+    assert np.linalg.norm(gp.qx(gauge)) <= 1e-9 * np.linalg.norm(QU)
+    assert abs(2 * gp.f(pgo.lifting_matrix(d, r) @ z["T_chordal"]) - float(z["cost2_chordal"])) \
+        <= 1e-10 * float(z["cost2_chordal"])
+    gp.close()
