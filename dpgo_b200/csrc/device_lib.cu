@@ -109,18 +109,20 @@ __global__ void __launch_bounds__(kBlock) k_tangent(const double *X, const doubl
 
 template <int R>
 __global__ void __launch_bounds__(kBlock) k_precon_gemv(const double *Pinv, int ld,
-                                                        const double *vec, double *zpart, int KT,
-                                                        int nsplit) {
-  phase_precon_gemv<R>(Pinv, ld, vec, zpart, KT, nsplit);
+                                                        const double *vec, double *zpart,
+                                                        size_t zstride, int KT, int nsplit) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  GemvPipe pp = gemv_pipe_init(dsm);
+  phase_precon_gemv<R>(pp, Pinv, ld, vec, zpart, zstride, KT, nsplit);
 }
 
 template <int R, int D>
-__global__ void __launch_bounds__(kBlock) k_precon_finish(const double *zpart, int ld, int nsplit,
+__global__ void __launch_bounds__(kBlock) k_precon_finish(const double *zpart, size_t zstride, int nsplit,
                                                           const double *Y, const double *rvec,
                                                           double *z, double *neg_out, int n,
                                                           double *partials) {
   double acc[1] = {0.0};
-  phase_precon_finish<R, D>(make_ctx(), zpart, ld, nsplit, Y, rvec, z, neg_out, n, acc);
+  phase_precon_finish<R, D>(make_ctx(), zpart, zstride, nsplit, Y, rvec, z, neg_out, n, acc);
   block_reduce_store<1>(acc, partials + blockIdx.x);
 }
 
@@ -185,13 +187,25 @@ __global__ void k_scatter_dense(const int *browidx, const int *colidx, const dou
   }
 }
 
-// copy the lower triangle onto the upper one
-__global__ void k_symmetrize(double *P, int N, int ld) {
-  const size_t total = (size_t)N * N;
+// Re-lay the inverse (lower triangle of the col-major potri output A, leading dim lda) into the
+// stage-major tiled format the apply kernel streams (see phase_precon_gemv): symmetric, zero
+// padded to ld rows x ldk columns.
+__global__ void k_tile_layout(const double *A, int N, int lda, double *T, int ld, int ldk) {
+  const size_t total = (size_t)ld * ldk;
+  const int ncb = ld / kGemvCols;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
-    const size_t i = t % N, j = t / N;  // element (i,j), i fastest
-    if (i > j) P[j + i * (size_t)ld] = P[i + j * (size_t)ld];
+    // t enumerates the destination: ((kc * ncb + cb) * kStageK + kk) * kGemvCols + jj
+    const int jj = (int)(t % kGemvCols);
+    const size_t u = t / kGemvCols;
+    const int kk = (int)(u % kStageK);
+    const size_t v = u / kStageK;
+    const int cb = (int)(v % ncb);
+    const int kc = (int)(v / ncb);
+    const int j = cb * kGemvCols + jj, k = kc * kStageK + kk;
+    double val = 0.0;
+    if (j < N && k < N) val = (j >= k) ? A[(size_t)j + (size_t)k * lda] : A[(size_t)k + (size_t)j * lda];
+    T[t] = val;
   }
 }
 
@@ -258,15 +272,40 @@ static inline int elem_grid(const dpgo_dev *h, size_t len) {
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
-static inline int gemv_grid(const dpgo_dev *h) {
+static int gemv_occupancy(dpgo_dev *h);
+// persistent: exactly one wave of co-resident CTAs loops over the tiles
+static inline int gemv_grid(dpgo_dev *h) {
   long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
-  const long cap = (long)h->num_sms * 4;
+  const long cap = (long)h->num_sms * gemv_occupancy(h);
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
   return (int)tiles;
 }
 static inline BsrView qview(const dpgo_dev *h) { return BsrView{h->d_rowptr, h->d_colidx, h->d_blocks}; }
 static inline BsrView cview(const dpgo_dev *h) { return BsrView{h->d_crowptr, h->d_ccolidx, h->d_cblocks}; }
+
+template <int R>
+static int gemv_setup(int *occ) {
+  if (cudaFuncSetAttribute(k_precon_gemv<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvDynSmem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_precon_gemv<R>, kBlock, kGemvDynSmem) != cudaSuccess)
+    return -1;
+  return 0;
+}
+static int gemv_occupancy(dpgo_dev *h) {
+  if (h->gemv_occ > 0) return h->gemv_occ;
+  int occ = 0, rc = -1;
+  switch (h->r) {
+    case 2: rc = gemv_setup<2>(&occ); break;
+    case 3: rc = gemv_setup<3>(&occ); break;
+    case 4: rc = gemv_setup<4>(&occ); break;
+    case 5: rc = gemv_setup<5>(&occ); break;
+    case 6: rc = gemv_setup<6>(&occ); break;
+  }
+  if (rc != 0 || occ < 1) occ = 1;
+  h->gemv_occ = occ;
+  return occ;
+}
 
 #define LAUNCH_CHECK(h)                       \
   do {                                        \
@@ -330,12 +369,12 @@ int op_precon(dpgo_dev *h, const double *Y, const double *rvec, double *z, doubl
     return DPGO_ESTATE;
   }
   const int g1 = gemv_grid(h);
-  DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, 0, h->stream>>>(h->d_Pinv, h->ld, rvec,
-                                                                 h->d_zpart, h->KT, h->nsplit));
+  DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, kGemvDynSmem, h->stream>>>(
+                       h->d_Pinv, h->ld, rvec, h->d_zpart, h->vpad, h->KT, h->nsplit));
   LAUNCH_CHECK(h);
   const int g2 = pose_grid(h, h->d + 1);
   DPGO_DISPATCH(h, k_precon_finish<R, D><<<g2, kBlock, 0, h->stream>>>(
-                       h->d_zpart, h->ld, h->nsplit, Y, rvec, z, neg_out, h->n, h->d_partials));
+                       h->d_zpart, h->vpad, h->nsplit, Y, rvec, z, neg_out, h->n, h->d_partials));
   LAUNCH_CHECK(h);
   if (z_r) {
     double sc[1];
@@ -684,15 +723,17 @@ static int build_cross_host(dpgo_dev *h) {
 
 static int build_precon(dpgo_dev *h) {
   const int N = h->N, ld = h->ld;
-  if (!h->d_Pinv) CUDA_TRY(cudaMalloc((void **)&h->d_Pinv, (size_t)ld * ld * sizeof(double)));
-  CUDA_TRY(cudaMemsetAsync(h->d_Pinv, 0, (size_t)ld * ld * sizeof(double), h->stream));
+  // scratch: dense P = Q + 0.1 I, column-major N x N (leading dimension ld)
+  double *A = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&A, (size_t)ld * N * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(A, 0, (size_t)ld * N * sizeof(double), h->stream));
   const int dh = h->d + 1;
   {
     const size_t total = (size_t)h->nnzb * dh * dh;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
     if (grid < 1) grid = 1;
     k_scatter_dense<<<grid, 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                 0.1 /* ref: src/PoseGraph.cpp:603 */, h->d_Pinv, ld);
+                                                 0.1 /* ref: src/PoseGraph.cpp:603 */, A, ld);
     LAUNCH_CHECK(h);
   }
   if (!h->cusolver) {
@@ -700,43 +741,42 @@ static int build_precon(dpgo_dev *h) {
     CUSOLVER_TRY(cusolverDnSetStream(h->cusolver, h->stream));
   }
   int lw1 = 0, lw2 = 0;
-  CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, &lw1));
-  CUSOLVER_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, &lw2));
+  CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, &lw1));
+  CUSOLVER_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, &lw2));
   const int lw = std::max(lw1, lw2);
   double *work = nullptr;
   int *info = nullptr;
   CUDA_TRY(cudaMalloc((void **)&work, (size_t)std::max(lw, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
   int hinfo = 0;
-  CUSOLVER_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, work, lw, info));
+  CUSOLVER_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, work, lw, info));
   CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (hinfo != 0) {
-    cudaFree(work); cudaFree(info);
+    cudaFree(work); cudaFree(info); cudaFree(A);
     set_error("Cholesky of Q + 0.1 I failed (potrf info = %d)", hinfo);
     return DPGO_ENUMERIC;
   }
-  CUSOLVER_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, h->d_Pinv, ld, work, lw, info));
+  CUSOLVER_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, work, lw, info));
   CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaFree(work));
   CUDA_TRY(cudaFree(info));
   if (hinfo != 0) {
+    cudaFree(A);
     set_error("inverse of Q + 0.1 I failed (potri info = %d)", hinfo);
     return DPGO_ENUMERIC;
   }
+  if (!h->d_Pinv) CUDA_TRY(cudaMalloc((void **)&h->d_Pinv, (size_t)ld * h->ldk * sizeof(double)));
   {
-    const size_t total = (size_t)N * N;
+    const size_t total = (size_t)ld * h->ldk;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 32);
     if (grid < 1) grid = 1;
-    k_symmetrize<<<grid, 256, 0, h->stream>>>(h->d_Pinv, N, ld);
+    k_tile_layout<<<grid, 256, 0, h->stream>>>(A, N, ld, h->d_Pinv, ld, h->ldk);
     LAUNCH_CHECK(h);
   }
-  // tiling of the apply: at most 16 inner splits, each a multiple of 64 wide
-  int KT = ((ld / 16 + 63) / 64) * 64;
-  if (KT < 512) KT = 512;
-  h->KT = KT;
-  h->nsplit = (ld + KT - 1) / KT;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaFree(A));
   if (h->d_zpart) CUDA_TRY(cudaFree(h->d_zpart));
   CUDA_TRY(cudaMalloc((void **)&h->d_zpart, (size_t)h->nsplit * h->vpad * sizeof(double)));
   CUDA_TRY(cudaMemsetAsync(h->d_zpart, 0, (size_t)h->nsplit * h->vpad * sizeof(double), h->stream));
@@ -821,7 +861,16 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
   h->N = (d + 1) * n;
   h->ld = ((h->N + 63) / 64) * 64;
   h->vlen = (size_t)r * h->N;
-  h->vpad = (size_t)r * h->ld;
+  // tiling of the dense preconditioner apply: at most 16 inner splits, each a multiple of 64
+  // wide; arrays are zero padded to ldk = nsplit * KT columns so that every tile is full
+  {
+    int KT = ((h->ld / 16 + 63) / 64) * 64;
+    if (KT < 512) KT = 512;
+    h->KT = KT;
+    h->nsplit = (h->ld + KT - 1) / KT;
+    h->ldk = h->nsplit * KT;
+  }
+  h->vpad = (size_t)r * h->ldk;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -1270,8 +1319,8 @@ int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
   if (!h->has_precon) { set_error("preconditioner not built"); return DPGO_ESTATE; }
   return time_launches(h, reps, flush_l2, [&]() {
     const int g1 = gemv_grid(h);
-    DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, 0, h->stream>>>(h->d_Pinv, h->ld, h->d_slot[0],
-                                                                   h->d_zpart, h->KT, h->nsplit));
+    DPGO_DISPATCH(h, k_precon_gemv<R><<<g1, kBlock, kGemvDynSmem, h->stream>>>(
+                         h->d_Pinv, h->ld, h->d_slot[0], h->d_zpart, h->vpad, h->KT, h->nsplit));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }, usec);

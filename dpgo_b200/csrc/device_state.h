@@ -25,9 +25,10 @@ void set_error(const char *fmt, ...);
 struct dpgo_dev {
   int device = 0, n = 0, d = 0, r = 0;
   int N = 0;       // (d+1) n
-  int ld = 0;      // N rounded up to a multiple of 64 (vector / Pinv padding)
+  int ld = 0;      // N rounded up to a multiple of 64 (Pinv rows)
+  int ldk = 0;     // nsplit * KT >= ld (Pinv columns / vector padding)
   size_t vlen = 0; // r * N   (doubles in a lifted pose array)
-  size_t vpad = 0; // r * ld  (allocated doubles per array)
+  size_t vpad = 0; // r * ldk (allocated doubles per array)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int num_sms = 148;
@@ -54,6 +55,7 @@ struct dpgo_dev {
   // dense preconditioner
   double *d_Pinv = nullptr, *d_zpart = nullptr;
   int KT = 0, nsplit = 0;
+  int gemv_occ = 0;
   bool finalized = false, has_precon = false;
   cusolverDnHandle_t cusolver = nullptr;
 

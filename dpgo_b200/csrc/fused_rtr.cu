@@ -1,10 +1,307 @@
-// placeholder until the persistent kernel lands: route to the host-driven solver
+// Persistent fused RTR solver: the whole QuadraticOptimizer::optimize call (cost / gradient
+// statistics, Steihaug-Toint tCG with the dense preconditioner, QF retraction, ratio test, radius
+// update; ref: src/QuadraticOptimizer.cpp:26-108 + ROPTLIB RTRNewton) runs as ONE cooperative
+// kernel.  Phases are the same __device__ functions the stand-alone kernels use (kernels.cuh);
+// they are separated by grid-wide barriers, every reduction is a per-CTA partial followed by a
+// fixed-order sum that every CTA repeats, so all threads hold identical copies of the control
+// scalars (alpha, beta, rho, Delta, ...) and take identical branches: no host round trip until
+// the result block is read back.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "device_state.h"
+#include "kernels.cuh"
+#include "rtr_logic.h"
+
+namespace cg = cooperative_groups;
+
 namespace dpgo {
-int solve_host(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
-               dpgo_ropt_result *res);
+
+struct FusedOut {
+  double f_init, gn_init, f_opt, gn_opt;
+  int outer, inner, accepted, rejected, tcg_status, returned_initial;
+  long long n_qx, n_precon, n_sweeps, n_barriers;
+};
+
+struct FusedParams {
+  BsrView Q;
+  const double *G;
+  const double *Pinv;
+  double *zpart;
+  int ld, KT, nsplit, n;
+  size_t zstride;
+  const double *x_in;
+  double *x_out;
+  double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
+  double *partials;  // [2][gridDim.x][4]
+  FusedOut *out;
+  double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
+  int max_outer, max_inner;
+};
+
+struct GridReducer {
+  double *buf[2];
+  int flip;
+  long long barriers;
+  // block partials -> grid barrier -> every CTA sums all partials in the same order
+  template <int K>
+  __device__ __forceinline__ void reduce(cg::grid_group &grid, double (&acc)[K], double (&out)[K]) {
+    block_reduce_store<K>(acc, buf[flip] + (size_t)blockIdx.x * K);
+    grid.sync();
+    sum_partials<K>(buf[flip], gridDim.x, out);
+    flip ^= 1;
+    barriers++;
+  }
+  __device__ __forceinline__ void barrier(cg::grid_group &grid) {
+    grid.sync();
+    barriers++;
+  }
+};
+
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  cg::grid_group grid = cg::this_grid();
+  const Ctx ctx = make_ctx();
+  const int n = p.n;
+  GemvPipe pipe = gemv_pipe_init(dsm);
+  const size_t len = (size_t)R * (D + 1) * n;
+  GridReducer red;
+  red.buf[0] = p.partials;
+  red.buf[1] = p.partials + (size_t)gridDim.x * 4;
+  red.flip = 0;
+  red.barriers = 0;
+
+  double *x1 = p.xa, *x2 = p.xb, *EG = p.EG, *EG2 = p.EG2, *grad = p.grad, *grad2 = p.grad2;
+  double *S = p.S, *S2 = p.S2;
+  long long n_qx = 0, n_precon = 0, n_sweeps = 0;
+
+  // ---- statistics at the initial point (fInit, gradNormInit) = first f / Grad of the solver
+  phase_copy(ctx, p.x_in, x1, len);
+  red.barrier(grid);
+  double f1, gn2;
+  {
+    double acc[2] = {0.0, 0.0}, sc[2];
+    phase_fgrad<R, D>(ctx, p.Q, x1, p.G, EG, grad, S, n, acc);
+    red.reduce<2>(grid, acc, sc);
+    f1 = sc[0];
+    gn2 = sc[1];
+    n_qx++;
+  }
+  const double f_init = f1, gn_init = sqrt(gn2);
+  int outer = 0, inner_total = 0, accepted_cnt = 0, rejected_cnt = 0, last_status = TCG_MAXITER;
+  int returned_initial = 0;
+
+  const bool single = (p.max_outer == 1);  // ref: src/QuadraticOptimizer.cpp:80-98
+  double radius = p.init_radius;
+  double Delta = p.init_radius;
+  double max_Delta = single ? p.init_radius : 5.0 * p.init_radius;
+  int total_steps = 0;
+  bool run = (gn_init >= p.gradnorm_tol) && (p.max_outer > 0);
+
+  while (run) {
+    // ------------------------------------------------------------------ truncated CG
+    TcgState s;
+    phase_precon_gemv<R>(pipe, p.Pinv, p.ld, grad, p.zpart, p.zstride, p.KT, p.nsplit);
+    phase_copy(ctx, grad, p.r, len);
+    phase_zero(ctx, p.eta, len);
+    red.barrier(grid);
+    {
+      double acc[1] = {0.0}, sc[1];
+      phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, grad, p.z, p.delta, n, acc);
+      red.reduce<1>(grid, acc, sc);
+      tcg_begin(s, gn2, sc[0]);
+      n_precon++;
+    }
+    int inner = 0;
+    for (int j = 0; j < p.max_inner; ++j) {
+      double d_Hd;
+      {
+        double acc[2] = {0.0, 0.0}, sc[2];
+        phase_hess<R, D>(ctx, p.Q, x1, S, p.delta, p.Hd, nullptr, n, acc);
+        red.reduce<2>(grid, acc, sc);
+        d_Hd = sc[0];
+        n_qx++;
+      }
+      inner = j + 1;
+      double step;
+      if (tcg_curvature(s, d_Hd, Delta, &step)) {
+        phase_axpby(ctx, step, p.delta, 1.0, p.eta, len);
+        red.barrier(grid);
+        break;
+      }
+      double r_r;
+      {
+        double acc[1] = {0.0}, sc[1];
+        phase_step(ctx, step, p.delta, p.Hd, p.eta, p.r, len, acc);
+        red.reduce<1>(grid, acc, sc);
+        r_r = sc[0];
+      }
+      if (tcg_converged(s, r_r, p.theta, p.kappa)) break;
+      phase_precon_gemv<R>(pipe, p.Pinv, p.ld, p.r, p.zpart, p.zstride, p.KT, p.nsplit);
+      red.barrier(grid);
+      double z_r;
+      {
+        double acc[1] = {0.0}, sc[1];
+        phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, p.r, p.z, nullptr, n, acc);
+        red.reduce<1>(grid, acc, sc);
+        z_r = sc[0];
+        n_precon++;
+      }
+      const double beta = tcg_direction(s, z_r);
+      phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
+      red.barrier(grid);
+    }
+    inner_total += inner;
+    last_status = s.status;
+
+    // ------------------------------------------------------------------ candidate + ratio test
+    phase_retract<R, D>(ctx, x1, p.eta, x2, n);
+    n_sweeps++;
+    red.barrier(grid);
+    double f2, gn2_2, eHe, eg;
+    {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0}, sc[4];
+      double a01[2] = {0.0, 0.0}, a23[2] = {0.0, 0.0};
+      phase_fgrad<R, D>(ctx, p.Q, x2, p.G, EG2, grad2, S2, n, a01);
+      phase_hess<R, D>(ctx, p.Q, x1, S, p.eta, p.Hd, grad, n, a23);
+      acc[0] = a01[0]; acc[1] = a01[1]; acc[2] = a23[0]; acc[3] = a23[1];
+      red.reduce<4>(grid, acc, sc);
+      f2 = sc[0]; gn2_2 = sc[1]; eHe = sc[2]; eg = sc[3];
+      n_qx += 2;
+    }
+    double rho;
+    const bool acc_step = rtr_accept(f1, f2, eg, eHe, s.status, p.accept_rho, p.shrink, p.magnify,
+                                     max_Delta, &Delta, &rho);
+    if (acc_step) {
+      double *t;
+      t = x1; x1 = x2; x2 = t;
+      t = EG; EG = EG2; EG2 = t;
+      t = grad; grad = grad2; grad2 = t;
+      t = S; S = S2; S2 = t;
+      f1 = f2;
+      gn2 = gn2_2;
+      accepted_cnt++;
+    } else {
+      rejected_cnt++;
+    }
+    outer++;
+    if (single) {
+      if (acc_step) run = false;
+      else if (total_steps > 10) { run = false; returned_initial = 1; }
+      else { radius *= 0.25; total_steps++; Delta = radius; max_Delta = radius; }
+    } else {
+      run = (outer < p.max_outer) && !(sqrt(gn2) < p.gradnorm_tol);
+    }
+  }
+
+  phase_copy(ctx, x1, p.x_out, len);
+  if (ctx.tid == 0) {
+    FusedOut o;
+    o.f_init = f_init; o.gn_init = gn_init; o.f_opt = f1; o.gn_opt = sqrt(gn2);
+    o.outer = outer; o.inner = inner_total; o.accepted = accepted_cnt; o.rejected = rejected_cnt;
+    o.tcg_status = last_status; o.returned_initial = returned_initial;
+    o.n_qx = n_qx; o.n_precon = n_precon; o.n_sweeps = n_sweeps; o.n_barriers = red.barriers;
+    *p.out = o;
+  }
+}
+
+template <int R, int D>
+static int launch_fused(dpgo_dev *h, FusedParams &fp) {
+  static int occ_cache = -1;
+  if (occ_cache < 0) {
+    int occ = 0;
+    if (cudaFuncSetAttribute(k_rtr_fused<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvDynSmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D>, kBlock, kGemvDynSmem) != cudaSuccess ||
+        occ < 1) {
+      set_error("fused kernel does not fit on the device");
+      return DPGO_ECUDA;
+    }
+    occ_cache = occ;
+  }
+  const long cap = (long)h->num_sms * occ_cache;
+  // enough CTAs for the widest phase, never more than can be co-resident
+  const long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
+  const int gpw = 32 / (h->d + 1);
+  const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  long grid = std::max(tiles, pose_blocks);
+  grid = std::max(1L, std::min(grid, cap));
+  if ((size_t)grid * 8 > (size_t)h->num_sms * 32 * 8) {
+    set_error("partials buffer too small");
+    return DPGO_EINVAL;
+  }
+  void *args[] = {&fp};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_rtr_fused<R, D>, dim3((unsigned)grid), dim3(kBlock),
+                                              args, kGemvDynSmem, h->stream);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchCooperativeKernel failed: %s", cudaGetErrorString(e));
+    return DPGO_ECUDA;
+  }
+  h->launches++;
+  return DPGO_OK;
+}
+
 int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
                 dpgo_ropt_result *res) {
-  return solve_host(h, P, x_in, x_out, res);
+  if (!h->d_fused) {
+    if (cudaMalloc(&h->d_fused, sizeof(FusedOut)) != cudaSuccess ||
+        cudaMallocHost(&h->h_fused, sizeof(FusedOut)) != cudaSuccess) {
+      set_error("allocation of the fused result block failed");
+      return DPGO_ECUDA;
+    }
+  }
+  FusedParams fp;
+  fp.Q = BsrView{h->d_rowptr, h->d_colidx, h->d_blocks};
+  fp.G = h->d_G;
+  fp.Pinv = h->d_Pinv;
+  fp.zpart = h->d_zpart;
+  fp.ld = h->ld; fp.KT = h->KT; fp.nsplit = h->nsplit; fp.n = h->n;
+  fp.zstride = h->vpad;
+  fp.x_in = x_in; fp.x_out = x_out;
+  fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;
+  fp.grad = h->d_grad; fp.grad2 = h->d_grad2; fp.S = h->d_S; fp.S2 = h->d_S2;
+  fp.eta = h->d_eta; fp.r = h->d_r; fp.z = h->d_z; fp.delta = h->d_delta; fp.Hd = h->d_Hd;
+  fp.partials = h->d_partials;
+  fp.out = (FusedOut *)h->d_fused;
+  fp.gradnorm_tol = P->gradnorm_tol; fp.init_radius = P->RTR_initial_radius;
+  fp.theta = P->tcg_theta; fp.kappa = P->tcg_kappa; fp.accept_rho = P->accept_rho;
+  fp.shrink = P->shrink; fp.magnify = P->magnify;
+  fp.max_outer = P->RTR_iterations; fp.max_inner = P->RTR_tCG_iterations;
+  int rc = DPGO_EINVAL;
+  switch (h->d * 16 + h->r) {
+    case 2 * 16 + 2: rc = launch_fused<2, 2>(h, fp); break;
+    case 2 * 16 + 3: rc = launch_fused<3, 2>(h, fp); break;
+    case 2 * 16 + 4: rc = launch_fused<4, 2>(h, fp); break;
+    case 2 * 16 + 5: rc = launch_fused<5, 2>(h, fp); break;
+    case 3 * 16 + 3: rc = launch_fused<3, 3>(h, fp); break;
+    case 3 * 16 + 4: rc = launch_fused<4, 3>(h, fp); break;
+    case 3 * 16 + 5: rc = launch_fused<5, 3>(h, fp); break;
+    case 3 * 16 + 6: rc = launch_fused<6, 3>(h, fp); break;
+    default: set_error("unsupported (d=%d, r=%d)", h->d, h->r); return DPGO_EINVAL;
+  }
+  if (rc != DPGO_OK) return rc;
+  if (cudaMemcpyAsync(h->h_fused, h->d_fused, sizeof(FusedOut), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess) {
+    set_error("fused RTR kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DPGO_ECUDA;
+  }
+  const FusedOut &o = *(const FusedOut *)h->h_fused;
+  res->success = 1;
+  res->tcg_status = o.tcg_status;
+  res->f_init = o.f_init; res->gradnorm_init = o.gn_init;
+  res->f_opt = o.f_opt; res->gradnorm_opt = o.gn_opt;
+  res->outer_iters = o.outer; res->inner_iters = o.inner;
+  res->accepted = o.accepted; res->rejected = o.rejected;
+  res->n_qx = o.n_qx; res->n_precon = o.n_precon; res->n_pose_sweeps = o.n_sweeps;
+  if (P->verbose)
+    printf("[dpgo_b200] fused RTR: f %.10g -> %.10g, |g| %.4g -> %.4g, %d outer, %d tCG, %lld barriers\n",
+           o.f_init, o.f_opt, o.gn_init, o.gn_opt, o.outer, o.inner, o.n_barriers);
+  return DPGO_OK;
 }
+
 }  // namespace dpgo

@@ -16,7 +16,6 @@ namespace dpgo {
 constexpr int kBlock = 256;          // threads per CTA for every phase
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kGemvCols = 64;        // output columns per dense-precon tile (2 per lane)
-constexpr int kGemvUnroll = 8;       // k-loop unroll (loads in flight per lane)
 
 struct BsrView {
   const int *rowptr;     // [n+1]
@@ -331,65 +330,159 @@ __device__ __forceinline__ void phase_tangent(const Ctx &ctx, const double *X, c
   }
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kStageK = 32;                                  // inner indices per pipeline stage
+constexpr int kStages = 4;                                   // stages in flight per CTA
+constexpr int kStageDoubles = kStageK * kGemvCols;           // 2048 doubles = 16 KB
+constexpr int kGemvDynSmem = kStages * kStageDoubles * 8 + kStages * 8;
+
+struct GemvPipe {
+  double *stage;      // [kStages][kStageK][kGemvCols]
+  uint32_t bar;       // shared address of the first mbarrier
+  uint32_t count;     // chunks consumed so far by this CTA (mbarrier phase bookkeeping)
+};
+
+// one-time set-up of the pipeline barriers (all threads of the CTA must call)
+__device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
+  GemvPipe pp;
+  pp.stage = reinterpret_cast<double *>(dsm);
+  pp.bar = smem_u32(dsm + (size_t)kStages * kStageDoubles * 8);
+  pp.count = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(pp.bar + 8 * s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  return pp;
+}
+
 // Dense preconditioner, part 1: partial products of the r x N array `vec` with the dense
-// symmetric inverse Pinv (ld x ld, zero padded).  Tile = kGemvCols output columns x KT inner
-// indices; the 8 warps of the CTA split the inner range, lanes own 2 adjacent output columns
-// (one 16-byte streaming load per inner index), partial sums meet in shared memory.
+// symmetric inverse Pinv.  Tile = kGemvCols output columns x KT inner indices.  Pinv is stored
+// "stage-major": the kStageK x kGemvCols sub-block (inner chunk kc, column block cb) is one
+// contiguous 16 KB run at ((kc * ncb + cb) * kStageDoubles), element (kk, jj) at kk*64 + jj, zero
+// padded to ld rows x ldk columns -- so that one TMA bulk copy (cp.async.bulk, SASS UBLKCP)
+// moves a whole pipeline stage HBM -> shared memory; kStages stages are in flight per CTA, so
+// the bytes in flight do not cost registers; the 8 warps split the inner indices of a stage,
+// lanes own 2 adjacent output columns, partial sums meet in shared memory at the end of a tile.
 //   zpart[s][:, j] = sum_{k in split s} vec[:, k] * Pinv[j, k]
 // ref: QuadraticProblem::PreConditioner, src/QuadraticProblem.cpp:56-69 (the solve).
 template <int R>
-__device__ __forceinline__ void phase_precon_gemv(const double *Pinv, int ld, const double *vec,
-                                                  double *zpart, int KT, int nsplit) {
+__device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pinv, int ld,
+                                                  const double *vec, double *zpart, size_t zstride,
+                                                  int KT, int nsplit) {
   __shared__ double sacc[kWarpsPerBlock][R][kGemvCols];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ncb = ld / kGemvCols;
   const int ntiles = ncb * nsplit;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const int cpt = KT / kStageK;  // chunks per tile
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int G = my_tiles * cpt;
+  const uint32_t stage0 = smem_u32(pp.stage);
+
+  auto issue = [&](int g) {  // one thread: stream chunk g of this CTA into its slot (16 KB bulk copy)
+    const int t = blockIdx.x + (g / cpt) * gridDim.x;
     const int cb = t % ncb, s = t / ncb;
-    const int k0 = s * KT;
-    const int k1 = min(ld, k0 + KT);
-    const int j = cb * kGemvCols + 2 * lane;
-    double a0[R], a1[R];
+    const int kc = (s * KT) / kStageK + (g % cpt);
+    const uint32_t slot = (pp.count + g) % kStages;
+    const uint32_t bar = pp.bar + 8 * slot;
+    mbar_expect_tx(bar, kStageDoubles * 8);
+    const double *src = Pinv + ((size_t)kc * ncb + cb) * kStageDoubles;
+    bulk_g2s(stage0 + slot * kStageDoubles * 8, src, kStageDoubles * 8, bar);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < kStages && g < G; ++g) issue(g);
+  }
+  double a0[R], a1[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
-    for (int k = k0 + w * kGemvUnroll; k < k1; k += kWarpsPerBlock * kGemvUnroll) {
-      double2 p[kGemvUnroll];
+  for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
+  for (int g = 0; g < G; ++g) {
+    const int t = blockIdx.x + (g / cpt) * gridDim.x;
+    const int cb = t % ncb, s = t / ncb;
+    const int c = g % cpt;
+    const int k = s * KT + c * kStageK;
+    // the vector entries this warp needs (plain coherent loads, L1/L2 resident)
+    double rv[kStageK / kWarpsPerBlock][R];
 #pragma unroll
-      for (int u = 0; u < kGemvUnroll; ++u)
-        p[u] = __ldcs(reinterpret_cast<const double2 *>(Pinv + (size_t)(k + u) * ld + j));
+    for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
+      const double *rp = vec + (size_t)(k + w + u * kWarpsPerBlock) * R;
 #pragma unroll
-      for (int u = 0; u < kGemvUnroll; ++u) {
-        const double *rv = vec + (size_t)(k + u) * R;
+      for (int q = 0; q < R; ++q) rv[u][q] = rp[q];
+    }
+    const uint32_t seq = pp.count + g;
+    const uint32_t slot = seq % kStages;
+    mbar_wait(pp.bar + 8 * slot, (seq / kStages) & 1u);
+    const double *st = pp.stage + (size_t)slot * kStageDoubles;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          const double x = rv[q];
-          a0[q] = fma(p[u].x, x, a0[q]);
-          a1[q] = fma(p[u].y, x, a1[q]);
-        }
+    for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
+      const double2 pv = *reinterpret_cast<const double2 *>(st + (w + u * kWarpsPerBlock) * kGemvCols + 2 * lane);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        a0[q] = fma(pv.x, rv[u][q], a0[q]);
+        a1[q] = fma(pv.y, rv[u][q], a1[q]);
       }
     }
+    if (c == cpt - 1) {  // tile finished: combine the 8 warps, emit the partial result
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-      sacc[w][q][2 * lane] = a0[q];
-      sacc[w][q][2 * lane + 1] = a1[q];
+      for (int q = 0; q < R; ++q) {
+        sacc[w][q][2 * lane] = a0[q];
+        sacc[w][q][2 * lane + 1] = a1[q];
+        a0[q] = 0.0;
+        a1[q] = 0.0;
+      }
     }
-    __syncthreads();
-    for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
-      const int q = o / kGemvCols, jj = o % kGemvCols;
-      double x = 0.0;
+    __syncthreads();  // every warp is done with this stage (and sacc is complete)
+    if (threadIdx.x == 0 && g + kStages < G) issue(g + kStages);
+    if (c == cpt - 1) {
+      for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+        const int q = o / kGemvCols, jj = o % kGemvCols;
+        double x = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-      zpart[(size_t)s * ld * R + (size_t)(cb * kGemvCols + jj) * R + q] = x;
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+        zpart[(size_t)s * zstride + (size_t)(cb * kGemvCols + jj) * R + q] = x;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
+  pp.count += G;
 }
 
 // Dense preconditioner, part 2: z = Proj_Y( sum_s zpart[s] ); acc = {<z, rvec>};
 // optionally also writes delta = -z (first tCG direction).
 template <int R, int D>
-__device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double *zpart, int ld,
-                                                    int nsplit, const double *Y, const double *rvec,
+__device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double *zpart,
+                                                    size_t zstride, int nsplit, const double *Y, const double *rvec,
                                                     double *z, double *neg_out, int n,
                                                     double (&acc)[1]) {
   using Gm = Geo<R, D>;
@@ -403,7 +496,7 @@ __device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double
     for (int q = 0; q < R; ++q) w[q] = 0.0;
     if (valid) {
       for (int s = 0; s < nsplit; ++s) {
-        const double *zp = zpart + (size_t)s * ld * R + off;
+        const double *zp = zpart + (size_t)s * zstride + off;
 #pragma unroll
         for (int q = 0; q < R; ++q) w[q] += zp[q];
       }
