@@ -237,6 +237,9 @@ def bench_single(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
         "gpu_launches": int(launches),
+        "fused_phase_ms": dict(zip(["cost_grad", "precon_gemv", "precon_finish", "hessvec", "tcg_update",
+                                    "tcg_direction", "retract_copy", "unused"], res.get("phase_ms", []))),
+        "grid_barriers_per_step": res.get("n_barriers", 0),
         "roofline": roofline, "qx": qx,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                          "ms_per_step": cpu_ms,

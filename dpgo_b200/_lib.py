@@ -29,10 +29,13 @@ class RoptResult(C.Structure):
                 ("gradnorm_init", C.c_double), ("f_opt", C.c_double), ("gradnorm_opt", C.c_double),
                 ("elapsed_ms", C.c_double), ("outer_iters", C.c_int32), ("inner_iters", C.c_int32),
                 ("accepted", C.c_int32), ("rejected", C.c_int32), ("n_qx", C.c_int64),
-                ("n_precon", C.c_int64), ("n_pose_sweeps", C.c_int64), ("n_launches", C.c_int64)]
+                ("n_precon", C.c_int64), ("n_pose_sweeps", C.c_int64), ("n_launches", C.c_int64),
+                ("phase_ms", C.c_double * 8), ("n_barriers", C.c_int64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_ms"] = list(self.phase_ms)
+        return d
 
 
 _dp = C.POINTER(C.c_double)

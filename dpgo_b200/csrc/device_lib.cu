@@ -256,11 +256,12 @@ __global__ void k_flush(double *buf, size_t len, double v) {
 // launch helpers
 // ---------------------------------------------------------------------------------------------
 static inline int pose_grid(const dpgo_dev *h, int lanes_per_pose) {
-  // lanes_per_pose = D+1 for lane-group phases, 1 for thread-per-pose phases
+  // lanes_per_pose = D+1 for lane-group phases, 1 for thread-per-pose phases; one pass over
+  // the poses (no SM-count cap: the hardware scheduler balances the many small CTAs)
   const int gpw = 32 / lanes_per_pose;
   const long warps = ((long)h->n + gpw - 1) / gpw;
   long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const long cap = (long)h->num_sms * 8;
+  const long cap = (long)h->partial_blocks;   // size of the partials buffer
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -861,14 +862,24 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
   h->N = (d + 1) * n;
   h->ld = ((h->N + 63) / 64) * 64;
   h->vlen = (size_t)r * h->N;
-  // tiling of the dense preconditioner apply: at most 16 inner splits, each a multiple of 64
-  // wide; arrays are zero padded to ldk = nsplit * KT columns so that every tile is full
+  // tiling of the dense preconditioner apply: tiles of 64 output columns x KT inner indices.
+  // Pick the number of inner splits (6..24) whose tile count balances best over one wave of
+  // 2 CTAs per SM, counting the zero padding to ldk = nsplit * KT columns as waste.
   {
-    int KT = ((h->ld / 16 + 63) / 64) * 64;
-    if (KT < 512) KT = 512;
-    h->KT = KT;
-    h->nsplit = (h->ld + KT - 1) / KT;
-    h->ldk = h->nsplit * KT;
+    const int ncb = h->ld / kGemvCols;
+    const long wave = (long)h->num_sms * 2;
+    double best = -1.0;
+    for (int ns = 6; ns <= 24; ++ns) {
+      int KT = (((h->ld + ns - 1) / ns + kStageK - 1) / kStageK) * kStageK;
+      if (KT < 256) KT = 256;
+      const int nsp = (h->ld + KT - 1) / KT;
+      const long tiles = (long)ncb * nsp;
+      const long rounds = (tiles + wave - 1) / wave;
+      const double eff = ((double)tiles / (double)(rounds * wave)) * ((double)h->ld / ((double)nsp * KT));
+      const double score = (tiles < wave) ? 0.5 * eff : eff;   // small problems: prefer filling the wave
+      if (score > best + 1e-9) { best = score; h->KT = KT; h->nsplit = nsp; }
+    }
+    h->ldk = h->nsplit * h->KT;
   }
   h->vpad = (size_t)r * h->ldk;
   cudaDeviceProp prop;
@@ -886,7 +897,8 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
   for (double **p : vecs) DPGO_TRY(alloc_vec(h, p, h->vpad));
   DPGO_TRY(alloc_vec(h, &h->d_S, (size_t)n * d * d));
   DPGO_TRY(alloc_vec(h, &h->d_S2, (size_t)n * d * d));
-  DPGO_TRY(alloc_vec(h, &h->d_partials, (size_t)h->num_sms * 32 * 8));
+  h->partial_blocks = std::max(h->num_sms * 32, (n + 63) / 64 + 1);
+  DPGO_TRY(alloc_vec(h, &h->d_partials, (size_t)h->partial_blocks * 8));
   DPGO_TRY(alloc_vec(h, &h->d_scalars, 64));
   CUDA_TRY(cudaMallocHost((void **)&h->h_scalars, 64 * sizeof(double)));
   CUDA_TRY(cudaEventCreate(&h->ev0));

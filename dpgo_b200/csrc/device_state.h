@@ -56,6 +56,7 @@ struct dpgo_dev {
   double *d_Pinv = nullptr, *d_zpart = nullptr;
   int KT = 0, nsplit = 0;
   int gemv_occ = 0;
+  int partial_blocks = 0;  // CTAs the partials buffer can serve (8 doubles each)
   bool finalized = false, has_precon = false;
   cusolverDnHandle_t cusolver = nullptr;
 

@@ -26,6 +26,7 @@ struct FusedOut {
   double f_init, gn_init, f_opt, gn_opt;
   int outer, inner, accepted, rejected, tcg_status, returned_initial;
   long long n_qx, n_precon, n_sweeps, n_barriers;
+  double phase_ms[8];
 };
 
 struct FusedParams {
@@ -42,6 +43,28 @@ struct FusedParams {
   FusedOut *out;
   double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
   int max_outer, max_inner;
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// per-phase device time seen by CTA 0 (phase body + the barrier that ends it)
+struct PhaseClock {
+  unsigned long long t0;
+  unsigned long long acc[8];
+  __device__ __forceinline__ void start() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+    t0 = gtimer();
+  }
+  __device__ __forceinline__ void lap(int id) {
+    const unsigned long long t = gtimer();
+    acc[id] += t - t0;
+    t0 = t;
+  }
 };
 
 struct GridReducer {
@@ -82,13 +105,17 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
   long long n_qx = 0, n_precon = 0, n_sweeps = 0;
 
   // ---- statistics at the initial point (fInit, gradNormInit) = first f / Grad of the solver
+  PhaseClock clk;
+  clk.start();
   phase_copy(ctx, p.x_in, x1, len);
   red.barrier(grid);
+  clk.lap(6);
   double f1, gn2;
   {
     double acc[2] = {0.0, 0.0}, sc[2];
     phase_fgrad<R, D>(ctx, p.Q, x1, p.G, EG, grad, S, n, acc);
     red.reduce<2>(grid, acc, sc);
+    clk.lap(0);
     f1 = sc[0];
     gn2 = sc[1];
     n_qx++;
@@ -111,10 +138,12 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
     phase_copy(ctx, grad, p.r, len);
     phase_zero(ctx, p.eta, len);
     red.barrier(grid);
+    clk.lap(1);
     {
       double acc[1] = {0.0}, sc[1];
       phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, grad, p.z, p.delta, n, acc);
       red.reduce<1>(grid, acc, sc);
+      clk.lap(2);
       tcg_begin(s, gn2, sc[0]);
       n_precon++;
     }
@@ -125,6 +154,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
         double acc[2] = {0.0, 0.0}, sc[2];
         phase_hess<R, D>(ctx, p.Q, x1, S, p.delta, p.Hd, nullptr, n, acc);
         red.reduce<2>(grid, acc, sc);
+        clk.lap(3);
         d_Hd = sc[0];
         n_qx++;
       }
@@ -133,6 +163,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
       if (tcg_curvature(s, d_Hd, Delta, &step)) {
         phase_axpby(ctx, step, p.delta, 1.0, p.eta, len);
         red.barrier(grid);
+        clk.lap(4);
         break;
       }
       double r_r;
@@ -140,22 +171,26 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
         double acc[1] = {0.0}, sc[1];
         phase_step(ctx, step, p.delta, p.Hd, p.eta, p.r, len, acc);
         red.reduce<1>(grid, acc, sc);
+        clk.lap(4);
         r_r = sc[0];
       }
       if (tcg_converged(s, r_r, p.theta, p.kappa)) break;
       phase_precon_gemv<R>(pipe, p.Pinv, p.ld, p.r, p.zpart, p.zstride, p.KT, p.nsplit);
       red.barrier(grid);
+      clk.lap(1);
       double z_r;
       {
         double acc[1] = {0.0}, sc[1];
         phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, p.r, p.z, nullptr, n, acc);
         red.reduce<1>(grid, acc, sc);
+        clk.lap(2);
         z_r = sc[0];
         n_precon++;
       }
       const double beta = tcg_direction(s, z_r);
       phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
       red.barrier(grid);
+      clk.lap(5);
     }
     inner_total += inner;
     last_status = s.status;
@@ -164,6 +199,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
     phase_retract<R, D>(ctx, x1, p.eta, x2, n);
     n_sweeps++;
     red.barrier(grid);
+    clk.lap(6);
     double f2, gn2_2, eHe, eg;
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0}, sc[4];
@@ -172,6 +208,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
       phase_hess<R, D>(ctx, p.Q, x1, S, p.eta, p.Hd, grad, n, a23);
       acc[0] = a01[0]; acc[1] = a01[1]; acc[2] = a23[0]; acc[3] = a23[1];
       red.reduce<4>(grid, acc, sc);
+      clk.lap(0);
       f2 = sc[0]; gn2_2 = sc[1]; eHe = sc[2]; eg = sc[3];
       n_qx += 2;
     }
@@ -207,6 +244,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
     o.outer = outer; o.inner = inner_total; o.accepted = accepted_cnt; o.rejected = rejected_cnt;
     o.tcg_status = last_status; o.returned_initial = returned_initial;
     o.n_qx = n_qx; o.n_precon = n_precon; o.n_sweeps = n_sweeps; o.n_barriers = red.barriers;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.phase_ms[i] = (double)clk.acc[i] * 1e-6;
     *p.out = o;
   }
 }
@@ -231,7 +270,7 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
   const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long grid = std::max(tiles, pose_blocks);
   grid = std::max(1L, std::min(grid, cap));
-  if ((size_t)grid * 8 > (size_t)h->num_sms * 32 * 8) {
+  if (grid > h->partial_blocks) {
     set_error("partials buffer too small");
     return DPGO_EINVAL;
   }
@@ -298,6 +337,8 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
   res->outer_iters = o.outer; res->inner_iters = o.inner;
   res->accepted = o.accepted; res->rejected = o.rejected;
   res->n_qx = o.n_qx; res->n_precon = o.n_precon; res->n_pose_sweeps = o.n_sweeps;
+  res->n_barriers = o.n_barriers;
+  for (int i = 0; i < 8; ++i) res->phase_ms[i] = o.phase_ms[i];
   if (P->verbose)
     printf("[dpgo_b200] fused RTR: f %.10g -> %.10g, |g| %.4g -> %.4g, %d outer, %d tCG, %lld barriers\n",
            o.f_init, o.f_opt, o.gn_init, o.gn_opt, o.outer, o.inner, o.n_barriers);

@@ -150,13 +150,33 @@ __device__ __forceinline__ void spmm_col(const BsrView &Q, const double *X, int 
     const int j = __ldg(Q.colidx + e);
     const double *m = Q.blocks + (size_t)e * (DH * DH) + c * DH;
     const double *xj = X + (size_t)j * TILE;
-    double mk[DH];
+    double mk[DH], x[TILE];
+    if constexpr (DH % 2 == 0) {  // row c of the block is 16-byte aligned: 128-bit read-only loads
 #pragma unroll
-    for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
+      for (int k = 0; k < DH / 2; ++k) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
+        mk[2 * k] = v.x;
+        mk[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
+    }
+    if constexpr (TILE % 2 == 0) {  // pose tile is 16-byte aligned: gather it with 128-bit loads
+#pragma unroll
+      for (int k = 0; k < TILE / 2; ++k) {
+        const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) x[k] = xj[k];
+    }
 #pragma unroll
     for (int k = 0; k < DH; ++k) {
 #pragma unroll
-      for (int q = 0; q < R; ++q) acc[q] = fma(xj[k * R + q], mk[k], acc[q]);
+      for (int q = 0; q < R; ++q) acc[q] = fma(x[k * R + q], mk[k], acc[q]);
     }
   }
 }
@@ -362,14 +382,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 constexpr int kStageK = 32;                                  // inner indices per pipeline stage
-constexpr int kStages = 4;                                   // stages in flight per CTA
+constexpr int kStages = 5;                                   // stages in flight per CTA
 constexpr int kStageDoubles = kStageK * kGemvCols;           // 2048 doubles = 16 KB
-constexpr int kGemvDynSmem = kStages * kStageDoubles * 8 + kStages * 8;
+constexpr int kGemvMaxR = 6;
+constexpr int kGemvDynSmem = kStages * kStageDoubles * 8 + kStages * 8 + kStages * kStageK * kGemvMaxR * 8;
 
 struct GemvPipe {
   double *stage;      // [kStages][kStageK][kGemvCols]
+  double *svec;       // [kStages][kStageK * R] slice of the input array that goes with a stage
   uint32_t bar;       // shared address of the first mbarrier
-  uint32_t count;     // chunks consumed so far by this CTA (mbarrier phase bookkeeping)
+  uint32_t slot;      // ring slot of the next chunk to consume (persists across phases)
+  uint32_t parity;    // mbarrier phase parity of that slot
 };
 
 // one-time set-up of the pipeline barriers (all threads of the CTA must call)
@@ -377,7 +400,9 @@ __device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
   GemvPipe pp;
   pp.stage = reinterpret_cast<double *>(dsm);
   pp.bar = smem_u32(dsm + (size_t)kStages * kStageDoubles * 8);
-  pp.count = 0;
+  pp.svec = reinterpret_cast<double *>(dsm + (size_t)kStages * kStageDoubles * 8 + kStages * 8);
+  pp.slot = 0;
+  pp.parity = 0;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(pp.bar + 8 * s, 1);
@@ -386,6 +411,12 @@ __device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
   __syncthreads();
   return pp;
 }
+
+// position of a pipeline chunk: tile (column block cb, inner split s) and chunk c within it.
+// Advanced incrementally -- no integer division in the per-chunk path.
+struct GemvCursor {
+  int t, c, cb, s;
+};
 
 // Dense preconditioner, part 1: partial products of the r x N array `vec` with the dense
 // symmetric inverse Pinv.  Tile = kGemvCols output columns x KT inner indices.  Pinv is stored
@@ -408,52 +439,65 @@ __device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pi
   const int cpt = KT / kStageK;  // chunks per tile
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int G = my_tiles * cpt;
+  if (G == 0) return;
   const uint32_t stage0 = smem_u32(pp.stage);
+  const int cps = KT / kStageK;  // chunks per split (== cpt)
 
-  auto issue = [&](int g) {  // one thread: stream chunk g of this CTA into its slot (16 KB bulk copy)
-    const int t = blockIdx.x + (g / cpt) * gridDim.x;
-    const int cb = t % ncb, s = t / ncb;
-    const int kc = (s * KT) / kStageK + (g % cpt);
-    const uint32_t slot = (pp.count + g) % kStages;
-    const uint32_t bar = pp.bar + 8 * slot;
-    mbar_expect_tx(bar, kStageDoubles * 8);
-    const double *src = Pinv + ((size_t)kc * ncb + cb) * kStageDoubles;
-    bulk_g2s(stage0 + slot * kStageDoubles * 8, src, kStageDoubles * 8, bar);
+  auto cursor_next = [&](GemvCursor &cu) {
+    if (++cu.c == cpt) {
+      cu.c = 0;
+      cu.t += gridDim.x;
+      cu.cb = cu.t % ncb;
+      cu.s = cu.t / ncb;
+    }
+  };
+  // producer side: thread 0 streams the 16 KB stage, R*32 threads copy the matching slice of vec
+  auto produce = [&](const GemvCursor &cu, uint32_t slot) {
+    const int kc = cu.s * cps + cu.c;
+    if (threadIdx.x == 0) {
+      const uint32_t bar = pp.bar + 8 * slot;
+      mbar_expect_tx(bar, kStageDoubles * 8);
+      bulk_g2s(stage0 + slot * (kStageDoubles * 8), Pinv + ((size_t)kc * ncb + cu.cb) * kStageDoubles,
+               kStageDoubles * 8, bar);
+    }
+    if (threadIdx.x < kStageK * R)
+      pp.svec[slot * (kStageK * R) + threadIdx.x] = vec[(size_t)kc * (kStageK * R) + threadIdx.x];
   };
 
-  if (threadIdx.x == 0) {
-    for (int g = 0; g < kStages && g < G; ++g) issue(g);
+  GemvCursor ci, cc;  // issue / consume cursors
+  ci.t = cc.t = blockIdx.x;
+  ci.c = cc.c = 0;
+  ci.cb = cc.cb = ci.t % ncb;
+  ci.s = cc.s = ci.t / ncb;
+  uint32_t slot_i = pp.slot;
+  int issued = 0;
+  for (; issued < kStages && issued < G; ++issued) {
+    produce(ci, slot_i);
+    cursor_next(ci);
+    slot_i = (slot_i + 1 == kStages) ? 0 : slot_i + 1;
   }
+  __syncthreads();
   double a0[R], a1[R];
 #pragma unroll
   for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
   for (int g = 0; g < G; ++g) {
-    const int t = blockIdx.x + (g / cpt) * gridDim.x;
-    const int cb = t % ncb, s = t / ncb;
-    const int c = g % cpt;
-    const int k = s * KT + c * kStageK;
-    // the vector entries this warp needs (plain coherent loads, L1/L2 resident)
-    double rv[kStageK / kWarpsPerBlock][R];
-#pragma unroll
-    for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
-      const double *rp = vec + (size_t)(k + w + u * kWarpsPerBlock) * R;
-#pragma unroll
-      for (int q = 0; q < R; ++q) rv[u][q] = rp[q];
-    }
-    const uint32_t seq = pp.count + g;
-    const uint32_t slot = seq % kStages;
-    mbar_wait(pp.bar + 8 * slot, (seq / kStages) & 1u);
+    const uint32_t slot = pp.slot;
+    mbar_wait(pp.bar + 8 * slot, pp.parity);
     const double *st = pp.stage + (size_t)slot * kStageDoubles;
+    const double *sv = pp.svec + slot * (kStageK * R);
 #pragma unroll
     for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
-      const double2 pv = *reinterpret_cast<const double2 *>(st + (w + u * kWarpsPerBlock) * kGemvCols + 2 * lane);
+      const int kk = w + u * kWarpsPerBlock;
+      const double2 pv = *reinterpret_cast<const double2 *>(st + kk * kGemvCols + 2 * lane);
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        a0[q] = fma(pv.x, rv[u][q], a0[q]);
-        a1[q] = fma(pv.y, rv[u][q], a1[q]);
+        const double x = sv[kk * R + q];
+        a0[q] = fma(pv.x, x, a0[q]);
+        a1[q] = fma(pv.y, x, a1[q]);
       }
     }
-    if (c == cpt - 1) {  // tile finished: combine the 8 warps, emit the partial result
+    const bool tile_end = (cc.c == cpt - 1);
+    if (tile_end) {  // tile finished: combine the 8 warps, emit the partial result
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         sacc[w][q][2 * lane] = a0[q];
@@ -463,19 +507,24 @@ __device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pi
       }
     }
     __syncthreads();  // every warp is done with this stage (and sacc is complete)
-    if (threadIdx.x == 0 && g + kStages < G) issue(g + kStages);
-    if (c == cpt - 1) {
+    if (issued < G) {  // refill the slot just freed (its readers meet another barrier first)
+      produce(ci, slot);
+      cursor_next(ci);
+      ++issued;
+    }
+    if (tile_end) {
       for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
         const int q = o / kGemvCols, jj = o % kGemvCols;
         double x = 0.0;
 #pragma unroll
         for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-        zpart[(size_t)s * zstride + (size_t)(cb * kGemvCols + jj) * R + q] = x;
+        zpart[(size_t)cc.s * zstride + (size_t)(cc.cb * kGemvCols + jj) * R + q] = x;
       }
       __syncthreads();
     }
+    cursor_next(cc);
+    if (pp.slot + 1 == kStages) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
   }
-  pp.count += G;
 }
 
 // Dense preconditioner, part 2: z = Proj_Y( sum_s zpart[s] ); acc = {<z, rvec>};

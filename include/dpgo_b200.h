@@ -69,6 +69,11 @@ typedef struct dpgo_ropt_result {
   int64_t n_precon;    /* dense (Q+0.1I)^-1 applications                       */
   int64_t n_pose_sweeps; /* per-pose sweeps (projection / retraction / ...)    */
   int64_t n_launches;  /* kernels launched by this call                        */
+  /* fused solver only: device time (ms, CTA 0's globaltimer, barrier waits included) spent in
+   * 0 cost+gradient, 1 preconditioner GEMV, 2 preconditioner finish (sum+projection),
+   * 3 Hessian-vector, 4 tCG vector update, 5 tCG direction update, 6 retraction, 7 barriers total */
+  double phase_ms[8];
+  int64_t n_barriers;  /* grid-wide barriers executed by the fused kernel          */
 } dpgo_ropt_result;
 
 void dpgo_default_params(dpgo_ropt_params *p);
