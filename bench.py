@@ -249,6 +249,16 @@ def bench_single(args):
                    "rel_gap": gap, "e2e_result_matches": bool(abs(2 * rr.f_opt - 2 * res["f_opt"]) < 1e-9),
                    "x_finite": bool(np.isfinite(Xg).all())},
     }
+    if args.team_steps > 0:
+        # strong-scaling series (BASELINE configs[2]) measured at this N as well, so that the
+        # 1 -> 2 -> 4 -> 8 GPU rows of the multi-agent workload have a 1-GPU anchor
+        gp.close()
+        from tools import bench_team
+        t = bench_team.measure(args.team_steps, 3, 0, 1, 0)
+        line["grid3D_8agents"] = {
+            "workload": bench_team.WORKLOAD, "n_gpus": 1, "value": t["value"], "unit": UNIT,
+            "ms_per_step": t["ms_per_step"], "steps": t["steps"], "e2e_value": t.get("e2e_value"),
+            "cost2_after_timed_rounds": t["cost2"], "gradnorm": t["gradnorm"]}
     print(json.dumps(line))
 
 
@@ -260,6 +270,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--team-steps", type=int, default=10,
+                    help="colour rounds of the grid3D/8-agent series appended to the N=1 line (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

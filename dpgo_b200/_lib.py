@@ -52,6 +52,7 @@ SIGNATURES = {
     "dpgo_destroy": (C.c_int, [H]),
     "dpgo_dims": (C.c_int, [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dpgo_sync": (C.c_int, [H]),
+    "dpgo_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
     "dpgo_set_private_edges": (C.c_int, [H, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),
     "dpgo_set_shared_edges": (C.c_int, [H, C.c_int, C.c_int, _ip, _ip, _bp, _dp, _dp, _dp, _dp, _dp]),
     "dpgo_set_priors": (C.c_int, [H, C.c_int, _ip, _dp, C.c_double, C.c_double]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "dpgo_optimize_slot": (C.c_int, [H, C.POINTER(RoptParams), C.c_int, C.POINTER(RoptResult)]),
     "dpgo_set_public_indices": (C.c_int, [H, C.c_int, _ip]),
     "dpgo_pack_public_dev": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "dpgo_gather_tiles_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),

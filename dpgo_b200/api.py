@@ -236,9 +236,18 @@ class DeviceProblem:
     def pack_public_dev(self, slot, dev_ptr):
         check(lib.dpgo_pack_public_dev(self._h, int(slot), C.c_void_p(dev_ptr)))
 
+    def gather_tiles_dev(self, slot, num, idx_dev_ptr, out_dev_ptr):
+        check(lib.dpgo_gather_tiles_dev(self._h, int(slot), int(num), C.c_void_p(idx_dev_ptr),
+                                        C.c_void_p(out_dev_ptr)))
+
     def max_translation_distance(self, a, b):
         v = C.c_double()
         check(lib.dpgo_max_translation_distance(self._h, a, b, C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        v = C.c_int64()
+        check(lib.dpgo_launch_count(self._h, C.byref(v)))
         return v.value
 
     def sync(self):

@@ -937,6 +937,12 @@ int dpgo_dims(dpgo_handle h, int *n, int *d, int *r) {
   return DPGO_OK;
 }
 
+int dpgo_launch_count(dpgo_handle h, int64_t *count) {
+  CHECK_ARG(h != nullptr && count != nullptr);
+  *count = h->launches;
+  return DPGO_OK;
+}
+
 int dpgo_sync(dpgo_handle h) {
   H_CHECK(h);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1252,6 +1258,20 @@ int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev) {
   int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
   k_gather_tiles<<<grid, 256, 0, h->stream>>>(h->d_slot[slot], h->d_public_idx, h->num_public, tile,
                                               tiles_dev);
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+
+int dpgo_gather_tiles_dev(dpgo_handle h, int slot, int num, const int32_t *idx_dev,
+                          double *tiles_dev) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4 && num >= 0);
+  if (num == 0) return DPGO_OK;
+  CHECK_ARG(idx_dev != nullptr && tiles_dev != nullptr);
+  const int tile = h->r * (h->d + 1);
+  const size_t total = (size_t)num * tile;
+  int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+  k_gather_tiles<<<grid, 256, 0, h->stream>>>(h->d_slot[slot], idx_dev, num, tile, tiles_dev);
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }

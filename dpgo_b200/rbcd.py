@@ -1,0 +1,296 @@
+"""Multi-agent synchronous RBCD on device-resident agents (one dpgo_handle per agent).
+
+Host-side mirror of the reference's driver and agent loop for the hot path:
+  * partition / edge classification: examples/MultiRobotExample.cpp:71-119
+  * PGOAgent::iterate, updateX, Nesterov updates, periodic restart:
+    src/PGOAgent.cpp:376-432, 880-995
+  * public-pose exchange (getSharedPoseDict / updateNeighborPoses and the aux variants):
+    src/PGOAgent.cpp:97-146, 650-702 -- here packed device buffers moved with NCCL send/recv
+    (torch.distributed) between ranks, or device-to-device copies inside one rank.
+All per-pose arithmetic runs behind the C-ABI (CUDA); this module only sequences calls.
+
+Block schedule: the reference's synchronous driver updates ONE agent per iteration (greedy).
+To use more than one GPU the agents of one colour of the robot graph are updated concurrently
+(they share no edge, so this equals updating them one after another).
+"""
+import math
+
+import numpy as np
+
+from .api import SLOT_V, SLOT_X, SLOT_XPREV, SLOT_Y, DeviceProblem, default_params
+
+
+def partition(p1, p2, n, num_robots):
+    """Contiguous equal split, last robot takes the remainder
+    (examples/MultiRobotExample.cpp:71-88).  Returns (ranges, robot_of_pose, local_idx)."""
+    per = n // num_robots
+    if per <= 0:
+        raise ValueError("more robots than poses")
+    starts = [k * per for k in range(num_robots)]
+    ends = [(k + 1) * per for k in range(num_robots)]
+    ends[-1] = n
+    rob = np.minimum(np.arange(n) // per, num_robots - 1)
+    loc = np.arange(n) - np.asarray(starts)[rob]
+    return list(zip(starts, ends)), rob, loc
+
+
+class AgentSpec:
+    """Everything agent `a` needs, computed once on every rank (cheap, deterministic)."""
+
+    def __init__(self, a, d, ranges, rob, loc, p1, p2, R, t, kappa, tau):
+        self.id = a
+        self.n = ranges[a][1] - ranges[a][0]
+        r1, r2 = rob[p1], rob[p2]
+        l1, l2 = loc[p1], loc[p2]
+        priv = np.where((r1 == a) & (r2 == a))[0]
+        sh = np.where(((r1 == a) | (r2 == a)) & (r1 != r2))[0]
+        self.priv = dict(p1=l1[priv], p2=l2[priv], R=R[priv], t=t[priv], kappa=kappa[priv], tau=tau[priv])
+        out = r1[sh] == a                               # my pose is the tail (m.r1 == id_)
+        my = np.where(out, l1[sh], l2[sh])
+        nb_r = np.where(out, r2[sh], r1[sh])
+        nb_f = np.where(out, l2[sh], l1[sh])
+        # neighbour slots: PoseGraph::nbr_shared_pose_ids_ is a std::set ordered by (robot, frame)
+        keys = sorted(set(zip(nb_r.tolist(), nb_f.tolist())))
+        slot_of = {k: i for i, k in enumerate(keys)}
+        self.nbr_keys = keys
+        self.shared = dict(my_idx=my, nbr_slot=np.array([slot_of[(int(r_), int(f_))] for r_, f_ in zip(nb_r, nb_f)],
+                                                        dtype=np.int32),
+                           outgoing=out.astype(np.uint8), R=R[sh], t=t[sh], kappa=kappa[sh], tau=tau[sh])
+        self.neighbors = sorted(set(k[0] for k in keys))
+        # contiguous slot range [lo, hi) of each neighbour robot and the frames it must send
+        self.nbr_range, self.nbr_frames = {}, {}
+        for b in self.neighbors:
+            idx = [i for i, k in enumerate(keys) if k[0] == b]
+            self.nbr_range[b] = (idx[0], idx[-1] + 1)
+            self.nbr_frames[b] = np.array([keys[i][1] for i in idx], dtype=np.int32)
+        self.public = sorted(set(my.tolist()))
+
+
+def color_robot_graph(specs):
+    color = {}
+    for s in specs:
+        used = {color[b] for b in s.neighbors if b in color}
+        c = 0
+        while c in used:
+            c += 1
+        color[s.id] = c
+    ncol = max(color.values()) + 1 if color else 1
+    return [[s.id for s in specs if color[s.id] == c] for c in range(ncol)]
+
+
+class DeviceAgent:
+    """Device-resident PGOAgent state: X, Y, V, XPrev slots + Nesterov scalars."""
+
+    def __init__(self, spec, d, r, num_robots, device, stream, acceleration=True, restart_interval=30,
+                 params=None):
+        import torch
+        self.spec, self.d, self.r, self.id = spec, d, r, spec.id
+        self.num_robots = num_robots
+        self.acceleration = acceleration
+        self.restart_interval = restart_interval
+        self.params = params if params is not None else default_params()
+        self.prob = DeviceProblem(spec.n, d, r, device, stream)
+        p, s = spec.priv, spec.shared
+        self.prob.set_private_edges(p["p1"], p["p2"], p["R"], p["t"], p["kappa"], p["tau"])
+        self.prob.set_shared_edges(s["my_idx"], s["nbr_slot"], s["outgoing"], s["R"], s["t"], s["kappa"],
+                                   s["tau"], num_nbr_slots=len(spec.nbr_keys))
+        self.prob.finalize(True)
+        tile = r * (d + 1)
+        dev = torch.device("cuda", device)
+        nslots = max(len(spec.nbr_keys), 1)
+        self.nbr = torch.zeros(nslots * tile, dtype=torch.float64, device=dev)       # neighbours' X
+        self.nbr_aux = torch.zeros(nslots * tile, dtype=torch.float64, device=dev)   # neighbours' Y
+        self.tile = tile
+        self.iteration = 0
+        self.gamma = self.alpha = 0.0
+        self.last_result = None
+        self.updates = 0
+        # send side: for each neighbour b, which of my frames it needs (device index lists)
+        self.send_idx, self.send_buf, self.send_buf_aux = {}, {}, {}
+
+    def prepare_send(self, b, frames):
+        import torch
+        dev = self.nbr.device
+        self.send_idx[b] = torch.as_tensor(np.asarray(frames, dtype=np.int32), device=dev)
+        self.send_buf[b] = torch.empty(len(frames) * self.tile, dtype=torch.float64, device=dev)
+        self.send_buf_aux[b] = torch.empty(len(frames) * self.tile, dtype=torch.float64, device=dev)
+
+    def set_X(self, X):                                   # PGOAgent::setX + initializeAcceleration
+        self.prob.slot_set(SLOT_X, X)
+        if self.acceleration:
+            for s in (SLOT_XPREV, SLOT_V, SLOT_Y):
+                self.prob.slot_copy(s, SLOT_X)
+            self.gamma = self.alpha = 0.0
+
+    def get_X(self):
+        return self.prob.slot_get(SLOT_X)
+
+    def pack_for(self, b):
+        """Fill the send buffers for neighbour b with my X (and Y) poses it needs."""
+        idx = self.send_idx[b]
+        self.prob.gather_tiles_dev(SLOT_X, idx.numel(), idx.data_ptr(), self.send_buf[b].data_ptr())
+        if self.acceleration:
+            self.prob.gather_tiles_dev(SLOT_Y, idx.numel(), idx.data_ptr(), self.send_buf_aux[b].data_ptr())
+
+    def recv_view(self, b, aux):
+        lo, hi = self.spec.nbr_range[b]
+        buf = self.nbr_aux if aux else self.nbr
+        return buf[lo * self.tile:hi * self.tile]
+
+    def _update_X(self, do_opt, acceleration):            # PGOAgent::updateX :938-995
+        if not do_opt:
+            if acceleration:
+                self.prob.slot_copy(SLOT_X, SLOT_Y)
+            return
+        buf = self.nbr_aux if acceleration else self.nbr
+        self.prob.set_neighbor_poses_dev(buf.data_ptr())   # setNeighborPoses + constructG on device
+        self.last_result = self.prob.optimize_slot(SLOT_Y if acceleration else SLOT_X, self.params)
+        self.updates += 1
+
+    def iterate(self, do_opt):                            # PGOAgent::iterate :376-432
+        self.iteration += 1
+        self.prob.slot_copy(SLOT_XPREV, SLOT_X)
+        if not self.acceleration:
+            self._update_X(do_opt, False)
+            return
+        R = self.num_robots
+        self.gamma = (1 + math.sqrt(1 + 4 * R * R * self.gamma * self.gamma)) / (2 * R)   # :910-914
+        self.alpha = 1 / (self.gamma * R)                                                # :916-920
+        self.prob.nesterov_update_Y(self.alpha)
+        self._update_X(do_opt, True)
+        self.prob.nesterov_update_V(self.gamma)
+        if (self.iteration + 1) % self.restart_interval == 0:                            # :880-897
+            self.prob.slot_copy(SLOT_X, SLOT_XPREV)
+            self._update_X(do_opt, False)
+            self.prob.slot_copy(SLOT_V, SLOT_X)
+            self.prob.slot_copy(SLOT_Y, SLOT_X)
+            self.gamma = self.alpha = 0.0
+
+
+def exchange_poses(agents, specs, owner, rank, active, acceleration):
+    """Move the public poses every agent in `active` needs from its neighbours: X (and the
+    auxiliary Y under acceleration).  `agents` maps agent id -> object with pack_for(b),
+    send_buf[b], send_buf_aux[b], recv_view(b, aux) for the agents this rank owns.  Same-rank
+    pairs are device copies; cross-rank pairs are grouped NCCL (or gloo) send/recv.  Every rank
+    walks the (active agent, neighbour) pairs in the same order, so sends and receives match."""
+    import torch.distributed as dist
+    ops = []
+    for a in active:
+        for b in specs[a].neighbors:
+            ob, oa = owner[b], owner[a]
+            if ob == rank:
+                agents[b].pack_for(a)
+            if ob == rank and oa == rank:          # same GPU: device-to-device copy
+                agents[a].recv_view(b, False).copy_(agents[b].send_buf[a])
+                if acceleration:
+                    agents[a].recv_view(b, True).copy_(agents[b].send_buf_aux[a])
+            elif ob == rank:                        # send
+                ops.append(dist.P2POp(dist.isend, agents[b].send_buf[a], oa))
+                if acceleration:
+                    ops.append(dist.P2POp(dist.isend, agents[b].send_buf_aux[a], oa))
+            elif oa == rank:                        # receive straight into the slot range of b
+                ops.append(dist.P2POp(dist.irecv, agents[a].recv_view(b, False), ob))
+                if acceleration:
+                    ops.append(dist.P2POp(dist.irecv, agents[a].recv_view(b, True), ob))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def block_owner(num_robots, world):
+    """Block distribution of agents over ranks (keeps both colours of a chain on every rank)."""
+    per_rank = (num_robots + world - 1) // world
+    return [min(a // per_rank, world - 1) for a in range(num_robots)]
+
+
+def build_specs(p1, p2, R, t, kappa, tau, n, d, num_robots):
+    p1 = np.asarray(p1, dtype=np.int64); p2 = np.asarray(p2, dtype=np.int64)
+    R = np.asarray(R, dtype=np.float64); t = np.asarray(t, dtype=np.float64)
+    kappa = np.asarray(kappa, dtype=np.float64); tau = np.asarray(tau, dtype=np.float64)
+    ranges, rob, loc = partition(p1, p2, n, num_robots)
+    return ranges, [AgentSpec(a, d, ranges, rob, loc, p1, p2, R, t, kappa, tau) for a in range(num_robots)]
+
+
+class DeviceTeam:
+    """All agents of one pose graph, sharded over the ranks of a torch.distributed world
+    (block distribution: agent a lives on rank a // (A / world))."""
+
+    def __init__(self, p1, p2, R, t, kappa, tau, n, d, r, num_robots, device=0, stream=None,
+                 rank=0, world=1, acceleration=True, params=None, restart_interval=30):
+        self.d, self.r, self.n, self.A = d, r, n, num_robots
+        self.rank, self.world = rank, world
+        self.acceleration = acceleration
+        self.ranges, self.specs = build_specs(p1, p2, R, t, kappa, tau, n, d, num_robots)
+        self.owner = block_owner(num_robots, world)
+        self.colors = color_robot_graph(self.specs)
+        self.agents = {a: DeviceAgent(self.specs[a], d, r, num_robots, device, stream, acceleration,
+                                      restart_interval, params)
+                       for a in range(num_robots) if self.owner[a] == rank}
+        for a, ag in self.agents.items():
+            for b in ag.spec.neighbors:
+                # what b needs from a = the frames of a listed in b's neighbour slots for robot a
+                ag.prepare_send(b, self.specs[b].nbr_frames[a])
+        self.round = 0
+
+    def set_X(self, X):
+        dh = self.d + 1
+        for a, ag in self.agents.items():
+            s, e = self.ranges[a]
+            ag.set_X(X[:, s * dh:e * dh])
+
+    # -- public-pose exchange towards the agents in `active` (ref: MultiRobotExample.cpp:183-204)
+    def exchange(self, active):
+        exchange_poses(self.agents, self.specs, self.owner, self.rank, active, self.acceleration)
+
+    def step_colored(self):
+        """One round of the coloured parallel schedule: the agents of the current colour optimize,
+        everybody else performs the non-optimizing iterate (Nesterov bookkeeping)."""
+        active = self.colors[self.round % len(self.colors)]
+        for a, ag in self.agents.items():
+            if a not in active:
+                ag.iterate(False)
+        self.exchange(active)
+        for a, ag in self.agents.items():
+            if a in active:
+                ag.iterate(True)
+        self.round += 1
+        return active
+
+    def step_single(self, selected):
+        """One iteration of the reference's greedy driver: only `selected` optimizes."""
+        for a, ag in self.agents.items():
+            if a != selected:
+                ag.iterate(False)
+        self.exchange([selected])
+        if selected in self.agents:
+            self.agents[selected].iterate(True)
+        self.round += 1
+
+    def greedy_select(self, central, X=None):
+        """Next agent of the reference's greedy driver: largest block of the centralized
+        Riemannian gradient (examples/MultiRobotExample.cpp:233-247).  `central` is a
+        DeviceProblem of the whole graph."""
+        X = self.assemble() if X is None else X
+        RG = central.RieGrad(X)
+        dh = self.d + 1
+        norms = [np.linalg.norm(RG[:, s * dh:e * dh]) for (s, e) in self.ranges]
+        return int(np.argmax(norms)), float(np.linalg.norm(RG))
+
+    def assemble(self):
+        """Centralized X (host).  With world > 1 every rank gets the full matrix (all_gather)."""
+        dh = self.d + 1
+        X = np.zeros((self.r, dh * self.n))
+        for a, ag in self.agents.items():
+            s, e = self.ranges[a]
+            X[:, s * dh:e * dh] = ag.get_X()
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+            dist.all_reduce(t)
+            X = t.cpu().numpy()
+        return X
+
+    def close(self):
+        for ag in self.agents.values():
+            ag.prob.close()

@@ -88,6 +88,8 @@ const char *dpgo_version(void);
 int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out);
 int dpgo_destroy(dpgo_handle h);
 int dpgo_dims(dpgo_handle h, int *n, int *d, int *r);
+/* number of CUDA kernels this handle has launched so far (bench.py's gpu_launches) */
+int dpgo_launch_count(dpgo_handle h, int64_t *count);
 int dpgo_sync(dpgo_handle h);
 
 /* ---- data matrices (ref: PoseGraph::constructQ/G, constructConnectionLaplacianSE) -------- */
@@ -167,6 +169,11 @@ int dpgo_optimize_slot(dpgo_handle h, const dpgo_ropt_params *params, int from,
  * (ref: src/PGOAgent.cpp:97-110, :132-146). */
 int dpgo_set_public_indices(dpgo_handle h, int num_public, const int32_t *idx);
 int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev);
+/* Same with a caller-owned DEVICE index list: out[k] = tile idx_dev[k] of slot `slot` -- used to
+ * pack, per neighbour, exactly the poses that neighbour needs (getSharedPoseDictWithNeighbor,
+ * ref: src/PGOAgent.cpp:112-130) straight into the NCCL send buffer. */
+int dpgo_gather_tiles_dev(dpgo_handle h, int slot, int num, const int32_t *idx_dev,
+                          double *tiles_dev);
 /* max_i || p_i(a) - p_i(b) ||  (LiftedPoseArray::maxTranslationDistance, used for
  * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
 int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);
