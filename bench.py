@@ -34,6 +34,28 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 METRIC = "rbcd_iterations_per_sec"
 UNIT = "iterations/s"
 
+_JSON_FD = None
+
+
+def capture_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries (NCCL's version banner, cuSOLVER,
+    verbose solvers) also write to fd 1, so fd 1 is pointed at stderr for the duration of the
+    run and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
 
 def load_fixture(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -142,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_cost_2f": 2 * res.fOpt,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -152,7 +174,11 @@ def bench_single(args):
     import torch
     import dpgo_b200
     torch.cuda.set_device(0)
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for everything: the library's kernels are launched on it and
+    # torch.cuda.Event (which only sees torch's current stream) times the same stream
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     name, r = "sphere2500", 5
     z, d, n = load_fixture(name)
     X0 = np.asfortranarray(lifting_matrix(d, r) @ z["T_chordal"])
@@ -259,7 +285,7 @@ def bench_single(args):
             "workload": bench_team.WORKLOAD, "n_gpus": 1, "value": t["value"], "unit": UNIT,
             "ms_per_step": t["ms_per_step"], "steps": t["steps"], "e2e_value": t.get("e2e_value"),
             "cost2_after_timed_rounds": t["cost2"], "gradnorm": t["gradnorm"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -273,6 +299,7 @@ def main():
     ap.add_argument("--team-steps", type=int, default=10,
                     help="colour rounds of the grid3D/8-agent series appended to the N=1 line (0 = skip)")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -282,7 +309,7 @@ def main():
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return bench_single(args)
     from tools import bench_team
-    return bench_team.run(args)
+    return bench_team.run(args, emit)
 
 
 if __name__ == "__main__":

@@ -42,5 +42,43 @@ def build_device_lib(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+REFERENCE_EXAMPLES = "/root/reference/examples"
+
+
+def build_host(force=False):
+    """C++ drop-in host API (libDPGO.so), its acceptance tests, and -- when the reference tree is
+    present (build container only) -- the reference's own example drivers compiled UNMODIFIED
+    against the drop-in headers (only the built binaries travel to the GPU box)."""
+    inc = os.path.join(HOST, "include")
+    srcs = sorted(os.path.join(HOST, "src", f) for f in os.listdir(os.path.join(HOST, "src")) if f.endswith(".cpp"))
+    hdrs = []
+    for root, _, files in os.walk(inc):
+        hdrs += [os.path.join(root, f) for f in files]
+    hdrs += [os.path.join(HOST, "src", "check.h"), os.path.join(HERE, "..", "include", "dpgo_b200.h"), LIB]
+    lib = os.path.join(HOST, "libDPGO.so")
+    link = ["-L" + HERE, "-ldpgo_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath,$ORIGIN/../..", "-pthread"]
+    if force or _stale(lib, srcs + hdrs):
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-shared", "-I" + inc] + srcs + link + ["-o", lib]
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    bindir = os.path.join(HOST, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    targets = [(os.path.join(HOST, "tests", "host_tests.cpp"), "host_tests")]
+    if os.path.isdir(REFERENCE_EXAMPLES):
+        targets += [(os.path.join(REFERENCE_EXAMPLES, "MultiRobotExample.cpp"), "multi-robot-example"),
+                    (os.path.join(REFERENCE_EXAMPLES, "SingleRobotExample.cpp"), "single-robot-example"),
+                    (os.path.join(REFERENCE_EXAMPLES, "ChordalInitializationExample.cpp"),
+                     "chordal-initialization-example")]
+    for src, name in targets:
+        out = os.path.join(bindir, name)
+        if force or _stale(out, [src, lib] + hdrs):
+            cmd = ["g++", "-std=c++17", "-O2", "-I" + inc, src, "-L" + HOST, "-lDPGO"] + link + ["-o", out]
+            print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+    return lib
+
+
 if __name__ == "__main__":
     build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)

@@ -1,0 +1,569 @@
+// PGOAgent over the device hot path.  Control flow follows the reference's src/PGOAgent.cpp
+// (cited per function); all per-pose arithmetic is delegated to CUDA kernels via the C-ABI.
+#include <DPGO/DPGO_solver.h>
+#include <DPGO/PGOAgent.h>
+#include <DPGO/QuadraticOptimizer.h>
+#include <DPGO/QuadraticProblem.h>
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "check.h"
+
+using std::lock_guard;
+using std::mutex;
+
+namespace DPGO {
+
+PGOAgent::PGOAgent(unsigned ID, const PGOAgentParameters &params)
+    : mID(ID), d(params.d), r(params.r), X(params.r, params.d, 1), mParams(params),
+      mState(PGOAgentState::WAIT_FOR_DATA), mStatus(ID, PGOAgentState::WAIT_FOR_DATA, 0, 0, false, 0),
+      mRobustCost(params.robustCostParams), mPoseGraph(std::make_shared<PoseGraph>(ID, params.r, params.d)),
+      mInstanceNumber(0), mIterationNumber(0), gamma(0), alpha(0), Y(params.r, params.d, 1) {
+  if (mID == 0) setLiftingMatrix(fixedStiefelVariable(d, r));  // reference: src/PGOAgent.cpp:45
+  mTeamRobotActive.assign(mParams.numRobots, true);
+}
+
+PGOAgent::~PGOAgent() { endOptimizationLoop(); }
+
+// ---- device slot helpers ---------------------------------------------------------------------
+void PGOAgent::uploadState() {
+  dpgo_dev *h = mPoseGraph->deviceHandle();
+  DPGO_CHECK(h != nullptr);
+  const Matrix Xm = X.getData();
+  DPGO_DEVICE_CALL(dpgo_slot_set(h, DPGO_SLOT_X, Xm.data()));
+  mDeviceStateValid = true;
+}
+
+void PGOAgent::downloadX() {
+  Matrix M(r, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
+  DPGO_DEVICE_CALL(dpgo_slot_get(mPoseGraph->deviceHandle(), DPGO_SLOT_X, M.data()));
+  X.setData(M);
+}
+
+void PGOAgent::downloadY() {
+  Matrix M(r, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
+  DPGO_DEVICE_CALL(dpgo_slot_get(mPoseGraph->deviceHandle(), DPGO_SLOT_Y, M.data()));
+  Y.setData(M);
+}
+
+// ---- state -------------------------------------------------------------------------------------
+void PGOAgent::setX(const Matrix &Xin) {  // reference :52-63
+  lock_guard<mutex> lock(mPosesMutex);
+  DPGO_CHECK(mState != PGOAgentState::WAIT_FOR_DATA);
+  DPGO_CHECK(static_cast<unsigned>(Xin.rows()) == relaxation_rank());
+  DPGO_CHECK(static_cast<unsigned>(Xin.cols()) == (dimension() + 1) * num_poses());
+  mState = PGOAgentState::INITIALIZED;
+  X = LiftedPoseArray(relaxation_rank(), dimension(), num_poses());
+  X.setData(Xin);
+  uploadState();
+  if (mParams.acceleration) initializeAcceleration();
+}
+
+void PGOAgent::setXToInitialGuess() {
+  DPGO_CHECK(mState != PGOAgentState::WAIT_FOR_DATA);
+  DPGO_CHECK(XInit.has_value());
+  lock_guard<mutex> lock(mPosesMutex);
+  X = XInit.value();
+  uploadState();
+}
+
+bool PGOAgent::getX(Matrix &Mout) {
+  lock_guard<mutex> lock(mPosesMutex);
+  Mout = X.getData();
+  return true;
+}
+
+bool PGOAgent::getSharedPose(unsigned index, Matrix &Mout) {
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mPosesMutex);
+  if (index >= num_poses()) return false;
+  Mout = X.pose(index);
+  return true;
+}
+
+bool PGOAgent::getAuxSharedPose(unsigned index, Matrix &Mout) {
+  DPGO_CHECK(mParams.acceleration);
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mPosesMutex);
+  if (index >= num_poses()) return false;
+  Mout = Y.pose(index);
+  return true;
+}
+
+bool PGOAgent::getSharedPoseDict(PoseDict &map) {  // reference :97-110
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  map.clear();
+  lock_guard<mutex> lock(mPosesMutex);
+  for (const auto &pid : mPoseGraph->myPublicPoseIDs()) {
+    DPGO_CHECK(pid.robot_id == getID());
+    map.emplace(pid, LiftedPose(X.pose(pid.frame_id)));
+  }
+  return true;
+}
+
+bool PGOAgent::getSharedPoseDictWithNeighbor(PoseDict &map, unsigned neighborID) {  // :112-130
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  map.clear();
+  lock_guard<mutex> lock(mPosesMutex);
+  for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
+    const PoseID pid(getID(), static_cast<unsigned>(m.r1 == getID() ? m.p1 : m.p2));
+    map.emplace(pid, LiftedPose(X.pose(pid.frame_id)));
+  }
+  return true;
+}
+
+bool PGOAgent::getAuxSharedPoseDict(PoseDict &map) {  // :132-146
+  DPGO_CHECK(mParams.acceleration);
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  map.clear();
+  lock_guard<mutex> lock(mPosesMutex);
+  for (const auto &pid : mPoseGraph->myPublicPoseIDs()) {
+    DPGO_CHECK(pid.robot_id == getID());
+    map.emplace(pid, LiftedPose(Y.pose(pid.frame_id)));
+  }
+  return true;
+}
+
+bool PGOAgent::getAuxSharedPoseDictWithNeighbor(PoseDict &map, unsigned neighborID) {
+  DPGO_CHECK(mParams.acceleration);
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  map.clear();
+  lock_guard<mutex> lock(mPosesMutex);
+  for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
+    const PoseID pid(getID(), static_cast<unsigned>(m.r1 == getID() ? m.p1 : m.p2));
+    map.emplace(pid, LiftedPose(Y.pose(pid.frame_id)));
+  }
+  return true;
+}
+
+void PGOAgent::setLiftingMatrix(const Matrix &M) {
+  DPGO_CHECK(static_cast<unsigned>(M.rows()) == r && static_cast<unsigned>(M.cols()) == d);
+  YLift.emplace(M);
+}
+
+bool PGOAgent::getLiftingMatrix(Matrix &M) const {
+  if (!YLift.has_value()) return false;
+  M = YLift.value();
+  return true;
+}
+
+void PGOAgent::setGlobalAnchor(const Matrix &M) {
+  DPGO_CHECK(static_cast<unsigned>(M.rows()) == relaxation_rank());
+  DPGO_CHECK(static_cast<unsigned>(M.cols()) == dimension() + 1);
+  LiftedPose Xa(r, d);
+  Xa.pose() = M;
+  globalAnchor.emplace(Xa);
+}
+
+// ---- measurements / initialisation ---------------------------------------------------------------
+void PGOAgent::addMeasurement(const RelativeSEMeasurement &factor) {
+  if (mState != PGOAgentState::WAIT_FOR_DATA) {
+    std::fprintf(stderr, "[PGOAgent] Robot state is not WAIT_FOR_DATA. Ignore new measurements!\n");
+    return;
+  }
+  lock_guard<mutex> lock(mMeasurementsMutex);
+  mPoseGraph->addMeasurement(factor);
+}
+
+void PGOAgent::setMeasurements(const std::vector<RelativeSEMeasurement> &inputOdometry,
+                               const std::vector<RelativeSEMeasurement> &inputPrivateLoopClosures,
+                               const std::vector<RelativeSEMeasurement> &inputSharedLoopClosures) {  // :185-197
+  DPGO_CHECK(!isOptimizationRunning());
+  DPGO_CHECK(mState == PGOAgentState::WAIT_FOR_DATA);
+  if (inputOdometry.empty()) return;
+  mPoseGraph = std::make_shared<PoseGraph>(mID, r, d);
+  mDeviceStateValid = false;
+  std::vector<RelativeSEMeasurement> all = inputOdometry;
+  all.insert(all.end(), inputPrivateLoopClosures.begin(), inputPrivateLoopClosures.end());
+  all.insert(all.end(), inputSharedLoopClosures.begin(), inputSharedLoopClosures.end());
+  mPoseGraph->setMeasurements(all);
+}
+
+void PGOAgent::initialize(const PoseArray *TInitPtr) {  // reference :199-306
+  if (mState != PGOAgentState::WAIT_FOR_DATA) return;
+  endOptimizationLoop();
+  if (mPoseGraph->n() == 0) return;
+
+  if (TInitPtr && TInitPtr->d() == dimension() && TInitPtr->n() == num_poses()) {
+    TLocalInit.emplace(*TInitPtr);
+  } else {
+    PoseArray T(dimension(), num_poses());
+    switch (mParams.localInitializationMethod) {
+      case InitializationMethod::Odometry: T = odometryInitialization(mPoseGraph->odometry()); break;
+      case InitializationMethod::Chordal: T = chordalInitialization(mPoseGraph->localMeasurements()); break;
+      case InitializationMethod::GNC_TLS:
+        // robust single-robot initialisation is outside this build: fall back to the chordal one
+        T = chordalInitialization(mPoseGraph->localMeasurements());
+        break;
+    }
+    DPGO_CHECK(T.d() == dimension());
+    TLocalInit.emplace(T);
+  }
+
+  // express the local trajectory in the frame of its first pose
+  PoseArray Tt(dimension(), num_poses());
+  const Pose Tw0(TLocalInit.value().pose(0));
+  const Pose T0w = Tw0.inverse();
+  for (unsigned i = 0; i < num_poses(); ++i) Tt.pose(i) = (T0w * Pose(TLocalInit.value().pose(i))).pose();
+  TLocalInit.emplace(Tt);
+
+  X = LiftedPoseArray(relaxation_rank(), dimension(), num_poses());
+  Y = X;
+  mState = PGOAgentState::WAIT_FOR_INITIALIZATION;
+  if (mID == 0 || !mParams.multirobotInitialization) initializeInGlobalFrame(Pose(d));
+  if (mParams.asynchronous) startOptimizationLoop();
+}
+
+void PGOAgent::initializeInGlobalFrame(const Pose &T_world_robot) {  // reference :308-374
+  DPGO_CHECK(YLift.has_value());
+  DPGO_CHECK(T_world_robot.d() == dimension());
+  checkRotationMatrix(T_world_robot.rotation());
+  bool halted = false;
+  if (isOptimizationRunning()) {
+    halted = true;
+    endOptimizationLoop();
+  }
+  {
+    lock_guard<mutex> lock(mPosesMutex);
+    clearNeighborPoses();
+    PoseArray T = TLocalInit.value();
+    for (unsigned i = 0; i < num_poses(); ++i) T.pose(i) = (T_world_robot * Pose(T.pose(i))).pose();
+    X.setData(YLift.value() * T.getData());
+    XInit.emplace(X);
+    mState = PGOAgentState::INITIALIZED;
+    uploadState();
+    if (mParams.acceleration) initializeAcceleration();
+  }
+  if (halted) startOptimizationLoop();
+}
+
+// ---- the RBCD iteration --------------------------------------------------------------------------
+bool PGOAgent::iterate(bool doOptimization) {  // reference :376-432
+  mIterationNumber++;
+  if (mState != PGOAgentState::INITIALIZED) return true;
+  dpgo_dev *h = mPoseGraph->deviceHandle();
+  if (!mDeviceStateValid) {
+    lock_guard<mutex> lock(mPosesMutex);
+    uploadState();
+    if (mParams.acceleration) initializeAcceleration();
+  }
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_XPREV, DPGO_SLOT_X));  // XPrev = X
+  bool success;
+  if (mParams.acceleration) {
+    updateGamma();
+    updateAlpha();
+    updateY();
+    success = updateX(doOptimization, true);
+    updateV();
+    if (shouldRestart()) restartNesterovAcceleration(doOptimization);
+  } else {
+    success = updateX(doOptimization, false);
+  }
+  {
+    lock_guard<mutex> lock(mPosesMutex);
+    downloadX();
+    if (mParams.acceleration) downloadY();
+  }
+  if (doOptimization) {
+    mStatus.agentID = getID();
+    mStatus.state = mState;
+    mStatus.instanceNumber = instance_number();
+    mStatus.iterationNumber = iteration_number();
+    double change = 0;
+    DPGO_DEVICE_CALL(dpgo_max_translation_distance(h, DPGO_SLOT_X, DPGO_SLOT_XPREV, &change));
+    mStatus.relativeChange = change;
+    bool ready = success && !(change > mParams.relChangeTol);
+    const auto stat = mPoseGraph->statistics();
+    if (stat.total_loop_closures > 0) {
+      const double ratio = (stat.accept_loop_closures + stat.reject_loop_closures) / stat.total_loop_closures;
+      if (ratio < mParams.robustOptMinConvergenceRatio) ready = false;
+    }
+    mStatus.readyToTerminate = ready;
+  }
+  if (doOptimization || mParams.acceleration) mPublishPublicPosesRequested = true;
+  mPublishAsynchronousRequested = true;
+  return success;
+}
+
+bool PGOAgent::updateX(bool doOptimization, bool acceleration) {  // reference :938-995
+  std::unique_lock<mutex> tLock(mPosesMutex), mLock(mMeasurementsMutex), nLock(mNeighborPosesMutex);
+  dpgo_dev *h = mPoseGraph->deviceHandle();
+  if (!doOptimization) {
+    if (acceleration) DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_X, DPGO_SLOT_Y));  // X = Y
+    return true;
+  }
+  if (acceleration) DPGO_CHECK(mParams.acceleration);
+  DPGO_CHECK(mState == PGOAgentState::INITIALIZED);
+  mPoseGraph->setNeighborPoses(acceleration ? neighborAuxPoseDict : neighborPoseDict);
+  const ROptParameters &lp = mParams.localOptimizationParams;
+  const bool rtr = lp.method == ROptParameters::ROptMethod::RTR;
+  const bool want_precon = rtr || lp.RGD_use_preconditioner;
+  if ((want_precon && !mPoseGraph->hasPreconditioner()) || !mPoseGraph->constructDataMatrices()) {
+    std::fprintf(stderr, "[PGOAgent] Robot %u cannot construct data matrices... Skip optimization.\n", getID());
+    mLocalOptResult = ROPTResult(false);
+    return false;
+  }
+  dpgo_ropt_params prm;
+  dpgo_default_params(&prm);
+  prm.method = rtr ? 0 : 1;
+  prm.verbose = mParams.verbose ? 1 : 0;
+  prm.gradnorm_tol = lp.gradnorm_tol;
+  prm.RGD_stepsize = lp.RGD_stepsize;
+  prm.RGD_use_preconditioner = lp.RGD_use_preconditioner ? 1 : 0;
+  prm.RTR_iterations = lp.RTR_iterations;
+  prm.RTR_tCG_iterations = lp.RTR_tCG_iterations;
+  prm.RTR_initial_radius = lp.RTR_initial_radius;
+  dpgo_ropt_result res;
+  DPGO_DEVICE_CALL(dpgo_optimize_slot(h, &prm, acceleration ? DPGO_SLOT_Y : DPGO_SLOT_X, &res));
+  mLocalOptResult = ROPTResult(res.success != 0, res.f_init, res.gradnorm_init, res.f_opt, res.gradnorm_opt,
+                               res.elapsed_ms);
+  mLocalOptResult.tCGStatus = static_cast<tCGstatusSet>(res.tcg_status);
+  if (mParams.verbose)
+    std::printf("df: %f, init_gradnorm: %f, opt_gradnorm: %f. \n", res.f_init - res.f_opt, res.gradnorm_init,
+                res.gradnorm_opt);
+  return true;
+}
+
+// ---- Nesterov acceleration (reference :880-936) --------------------------------------------------
+bool PGOAgent::shouldRestart() const {
+  return mParams.acceleration && ((mIterationNumber + 1) % mParams.restartInterval == 0);
+}
+
+void PGOAgent::restartNesterovAcceleration(bool doOptimization) {
+  if (!(mParams.acceleration && mState == PGOAgentState::INITIALIZED)) return;
+  dpgo_dev *h = mPoseGraph->deviceHandle();
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_X, DPGO_SLOT_XPREV));  // X = XPrev
+  updateX(doOptimization, false);
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_V, DPGO_SLOT_X));
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_Y, DPGO_SLOT_X));
+  gamma = 0;
+  alpha = 0;
+}
+
+void PGOAgent::initializeAcceleration() {
+  DPGO_CHECK(mParams.acceleration);
+  if (mState != PGOAgentState::INITIALIZED) return;
+  dpgo_dev *h = mPoseGraph->deviceHandle();
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_XPREV, DPGO_SLOT_X));
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_V, DPGO_SLOT_X));
+  DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_Y, DPGO_SLOT_X));
+  Y = X;
+  gamma = 0;
+  alpha = 0;
+}
+
+void PGOAgent::updateGamma() {
+  const double R = static_cast<double>(mParams.numRobots);
+  gamma = (1 + std::sqrt(1 + 4 * R * R * gamma * gamma)) / (2 * R);
+}
+void PGOAgent::updateAlpha() { alpha = 1 / (gamma * static_cast<double>(mParams.numRobots)); }
+void PGOAgent::updateY() { DPGO_DEVICE_CALL(dpgo_nesterov_update_Y(mPoseGraph->deviceHandle(), alpha)); }
+void PGOAgent::updateV() { DPGO_DEVICE_CALL(dpgo_nesterov_update_V(mPoseGraph->deviceHandle(), gamma)); }
+
+// ---- neighbours ----------------------------------------------------------------------------------
+Pose PGOAgent::computeNeighborTransform(const RelativeSEMeasurement &m, const LiftedPose &nbr) {  // :515-560
+  DPGO_CHECK(YLift.has_value());
+  // T_world_robot = T_world_nbr * T_nbr_me (edge) * inverse(T_robot_me (local init))
+  Pose dT(d);
+  dT.rotation() = m.R;
+  dT.translation() = m.t;
+  Pose T_world_nbr(d);
+  T_world_nbr.rotation() = projectToRotationGroup(YLift.value().transpose() * nbr.rotation());
+  T_world_nbr.translation() = YLift.value().transpose() * nbr.translation();
+  const bool outgoing = (m.r1 == getID());
+  const Pose T_local(TLocalInit.value().pose(static_cast<unsigned>(outgoing ? m.p1 : m.p2)));
+  const Pose T_world_me = outgoing ? T_world_nbr * dT.inverse() : T_world_nbr * dT;
+  return T_world_me * T_local.inverse();
+}
+
+void PGOAgent::updateNeighborPoses(unsigned neighborID, const PoseDict &poseDict) {  // :650-678
+  DPGO_CHECK(neighborID != mID);
+  if (!YLift) return;
+  if (!hasNeighborStatus(neighborID)) return;
+  if (getNeighborStatus(neighborID).state != PGOAgentState::INITIALIZED) return;
+  if (mState == PGOAgentState::WAIT_FOR_INITIALIZATION) {
+    // single-measurement alignment (the reference runs a two-stage robust averaging here)
+    for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
+      const bool outgoing = (m.r1 == getID());
+      const PoseID nID(neighborID, static_cast<unsigned>(outgoing ? m.p2 : m.p1));
+      auto it = poseDict.find(nID);
+      if (it == poseDict.end()) continue;
+      initializeInGlobalFrame(computeNeighborTransform(m, it->second));
+      break;
+    }
+  }
+  if (mState != PGOAgentState::INITIALIZED) return;
+  lock_guard<mutex> lock(mNeighborPosesMutex);
+  for (const auto &kv : poseDict) {
+    DPGO_CHECK(kv.first.robot_id == neighborID);
+    DPGO_CHECK(kv.second.r() == r && kv.second.d() == d);
+    if (!mPoseGraph->requireNeighborPose(kv.first)) continue;
+    neighborPoseDict[kv.first] = kv.second;
+  }
+}
+
+void PGOAgent::updateAuxNeighborPoses(unsigned neighborID, const PoseDict &poseDict) {  // :680-702
+  DPGO_CHECK(mParams.acceleration);
+  DPGO_CHECK(neighborID != mID);
+  if (!YLift) return;
+  if (!hasNeighborStatus(neighborID)) return;
+  if (getNeighborStatus(neighborID).state != PGOAgentState::INITIALIZED) return;
+  if (mState != PGOAgentState::INITIALIZED) return;
+  lock_guard<mutex> lock(mNeighborPosesMutex);
+  for (const auto &kv : poseDict) {
+    DPGO_CHECK(kv.first.robot_id == neighborID);
+    DPGO_CHECK(kv.second.r() == r && kv.second.d() == d);
+    if (!mPoseGraph->requireNeighborPose(kv.first)) continue;
+    neighborAuxPoseDict[kv.first] = kv.second;
+  }
+}
+
+void PGOAgent::clearNeighborPoses() {
+  lock_guard<mutex> lock(mNeighborPosesMutex);
+  neighborPoseDict.clear();
+  neighborAuxPoseDict.clear();
+}
+
+void PGOAgent::clearActiveNeighborPoses() {
+  lock_guard<mutex> lock(mNeighborPosesMutex);
+  for (const auto &pid : mPoseGraph->activeNeighborPublicPoseIDs()) {
+    neighborPoseDict.erase(pid);
+    neighborAuxPoseDict.erase(pid);
+  }
+}
+
+bool PGOAgent::hasNeighbor(unsigned neighborID) const { return mPoseGraph->hasNeighbor(neighborID); }
+
+std::vector<unsigned> PGOAgent::getNeighbors() const {
+  const auto ids = mPoseGraph->neighborIDs();
+  return std::vector<unsigned>(ids.begin(), ids.end());
+}
+
+bool PGOAgent::isRobotActive(unsigned robot_id) const {
+  return robot_id < mTeamRobotActive.size() && mTeamRobotActive[robot_id];
+}
+
+// ---- rounding (reference :718-767) ------------------------------------------------------------------
+bool PGOAgent::getTrajectoryInLocalFrame(Matrix &Trajectory) {
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mPosesMutex);
+  PoseArray T(d, num_poses());
+  T.setData(X.rotation(0).transpose() * X.getData());
+  const Matrix t0 = T.translation(0);
+  for (unsigned i = 0; i < num_poses(); ++i) {
+    T.rotation(i) = projectToRotationGroup(T.rotation(i));
+    T.translation(i) = T.translation(i) - t0;
+  }
+  Trajectory = T.getData();
+  return true;
+}
+
+bool PGOAgent::getTrajectoryInGlobalFrame(PoseArray &Trajectory) {
+  if (!globalAnchor) return false;
+  const LiftedPose Xa = globalAnchor.value();
+  DPGO_CHECK(Xa.r() == relaxation_rank() && Xa.d() == dimension());
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mPosesMutex);
+  PoseArray T(d, num_poses());
+  T.setData(Xa.rotation().transpose() * X.getData());
+  const Matrix t0 = Xa.rotation().transpose() * Xa.translation();
+  for (unsigned i = 0; i < num_poses(); ++i) {
+    T.rotation(i) = projectToRotationGroup(T.rotation(i));
+    T.translation(i) = T.translation(i) - t0;
+  }
+  Trajectory = T;
+  return true;
+}
+
+bool PGOAgent::getTrajectoryInGlobalFrame(Matrix &Trajectory) {
+  PoseArray T(d, num_poses());
+  if (!getTrajectoryInGlobalFrame(T)) return false;
+  Trajectory = T.getData();
+  return true;
+}
+
+bool PGOAgent::getPoseInGlobalFrame(unsigned poseID, Matrix &T) {
+  if (!globalAnchor) return false;
+  const LiftedPose Xa = globalAnchor.value();
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mPosesMutex);
+  if (poseID >= num_poses()) return false;
+  const Matrix Ya = Xa.rotation();
+  const Matrix t0 = Ya.transpose() * Xa.translation();
+  Matrix Ti = Ya.transpose() * X.pose(poseID);
+  Ti.block(0, d, d, 1) -= t0;
+  T = Ti;
+  return true;
+}
+
+Matrix PGOAgent::localPoseGraphOptimization() {  // reference :823-828
+  ROptParameters pgo_params;
+  pgo_params.verbose = true;
+  return solvePGO(mPoseGraph->localMeasurements(), pgo_params).getData();
+}
+
+// ---- termination / reset -----------------------------------------------------------------------------
+bool PGOAgent::shouldTerminate() {  // reference :844-878
+  if (iteration_number() >= mParams.maxNumIters) return true;
+  for (unsigned robot_id = 0; robot_id < mParams.numRobots; ++robot_id) {
+    if (!isRobotActive(robot_id)) continue;
+    const auto it = mTeamStatus.find(robot_id);
+    if (it == mTeamStatus.end()) return false;
+    if (it->second.state != PGOAgentState::INITIALIZED) return false;
+    if (!it->second.readyToTerminate) return false;
+  }
+  return true;
+}
+
+void PGOAgent::reset() {  // reference :434-473
+  endOptimizationLoop();
+  mInstanceNumber++;
+  mIterationNumber = 0;
+  mState = PGOAgentState::WAIT_FOR_DATA;
+  mStatus = PGOAgentStatus(getID(), mState, mInstanceNumber, mIterationNumber, false, 0);
+  mTeamStatus.clear();
+  mTeamRobotActive.assign(mParams.numRobots, false);
+  globalAnchor.reset();
+  TLocalInit.reset();
+  XInit.reset();
+  mPublishPublicPosesRequested = false;
+  mPublishAsynchronousRequested = false;
+  mPoseGraph->reset();
+  clearNeighborPoses();
+  mDeviceStateValid = false;
+}
+
+// ---- asynchronous mode (reference :475-513) ------------------------------------------------------------
+void PGOAgent::startOptimizationLoop() {
+  DPGO_CHECK(!mParams.acceleration);  // "Asynchronous mode does not support acceleration!"
+  if (isOptimizationRunning()) return;
+  mOptimizationThread = std::make_unique<std::thread>(&PGOAgent::runOptimizationLoop, this);
+}
+
+void PGOAgent::runOptimizationLoop() {
+  std::random_device rd;
+  std::mt19937 rng(rd());
+  std::exponential_distribution<double> wait(mParams.asynchronousOptimizationRate);
+  while (true) {
+    iterate(true);
+    usleep(static_cast<useconds_t>(1e6 * wait(rng)));
+    if (mEndLoopRequested) break;
+  }
+}
+
+void PGOAgent::endOptimizationLoop() {
+  if (!isOptimizationRunning()) return;
+  mEndLoopRequested = true;
+  mOptimizationThread->join();
+  mOptimizationThread.reset(nullptr);
+  mEndLoopRequested = false;
+}
+
+bool PGOAgent::isOptimizationRunning() { return mOptimizationThread != nullptr; }
+
+}  // namespace DPGO

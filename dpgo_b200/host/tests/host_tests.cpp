@@ -1,0 +1,204 @@
+// Acceptance tests of the C++ drop-in API on a GPU box.  They restate the reference's gtest
+// cases (tests/testTriangleGraph.cpp, testPGO.cpp:testPrior, testLineGraph.cpp,
+// testConstruction.cpp, testPoses.cpp, testUtils.cpp, testOptimizationThread.cpp) against this
+// implementation, without gtest.  Exit code 0 = all passed.
+#include <DPGO/DPGO_solver.h>
+#include <DPGO/PGOAgent.h>
+#include <DPGO/QuadraticOptimizer.h>
+#include <DPGO/QuadraticProblem.h>
+
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+using namespace DPGO;
+
+static int g_failed = 0;
+#define EXPECT(cond)                                                          \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      std::printf("  FAILED: %s (%s:%d)\n", #cond, __FILE__, __LINE__);       \
+      g_failed++;                                                             \
+    }                                                                         \
+  } while (0)
+
+static Matrix mat(std::initializer_list<std::initializer_list<double>> rows) {
+  const std::ptrdiff_t r = static_cast<std::ptrdiff_t>(rows.size());
+  const std::ptrdiff_t c = static_cast<std::ptrdiff_t>(rows.begin()->size());
+  Matrix m(r, c);
+  std::ptrdiff_t i = 0;
+  for (const auto &row : rows) {
+    std::ptrdiff_t j = 0;
+    for (double v : row) m(i, j++) = v;
+    ++i;
+  }
+  return m;
+}
+
+static Matrix inv4(const Matrix &T) {  // inverse of a homogeneous transform [R t; 0 1]
+  const Matrix R = T.block(0, 0, 3, 3), t = T.block(0, 3, 3, 1);
+  Matrix out = Matrix::Identity(4, 4);
+  out.block(0, 0, 3, 3) = R.transpose();
+  out.block(0, 3, 3, 1) = -(R.transpose() * t);
+  return out;
+}
+
+struct Triangle {
+  Matrix Ttrue;
+  std::vector<RelativeSEMeasurement> odometry, private_lcs, shared;
+};
+
+static Triangle makeTriangle(unsigned id) {  // tests/testTriangleGraph.cpp:15-47
+  const unsigned d = 3;
+  const Matrix Tw0 = Matrix::Identity(4, 4);
+  const Matrix Tw1 = mat({{0.1436, 0.7406, 0.6564, 1}, {-0.8179, -0.2845, 0.5000, 1}, {0.5571, -0.6087, 0.5649, 1}, {0, 0, 0, 1}});
+  const Matrix Tw2 = mat({{-0.4069, -0.4150, -0.8138, 2}, {0.4049, 0.7166, -0.5679, 2}, {0.8188, -0.5606, -0.1236, 2}, {0, 0, 0, 1}});
+  Triangle tr;
+  tr.Ttrue = Matrix(d, 3 * (d + 1));
+  tr.Ttrue.block(0, 0, 3, 4) = Tw0.block(0, 0, 3, 4);
+  tr.Ttrue.block(0, 4, 3, 4) = Tw1.block(0, 0, 3, 4);
+  tr.Ttrue.block(0, 8, 3, 4) = Tw2.block(0, 0, 3, 4);
+  auto edge = [&](const Matrix &A, const Matrix &B, size_t i, size_t j) {
+    const Matrix dT = inv4(A) * B;
+    return RelativeSEMeasurement(id, id, i, j, dT.block(0, 0, d, d), dT.block(0, d, d, 1), 1.0, 1.0);
+  };
+  tr.odometry.push_back(edge(Tw0, Tw1, 0, 1));
+  tr.odometry.push_back(edge(Tw1, Tw2, 1, 2));
+  tr.private_lcs.push_back(edge(Tw0, Tw2, 0, 2));
+  return tr;
+}
+
+static void testTriangleGraph() {
+  std::printf("[TriangleGraph]\n");
+  const unsigned id = 0, d = 3, r = 3;
+  PGOAgentParameters options(d, r, 1);
+  PGOAgent agent(id, options);
+  Triangle tr = makeTriangle(id);
+  agent.setMeasurements(tr.odometry, tr.private_lcs, tr.shared);
+  agent.initialize();
+  const Matrix TLocal = agent.localPoseGraphOptimization();
+  EXPECT((tr.Ttrue - TLocal).norm() <= 1e-4);
+  Matrix T;
+  EXPECT(agent.getTrajectoryInLocalFrame(T));
+  EXPECT((tr.Ttrue - T).norm() <= 1e-4);
+  agent.iterate();
+  EXPECT(agent.getID() == id && agent.num_poses() == 3 && agent.dimension() == d && agent.relaxation_rank() == r);
+  agent.getTrajectoryInLocalFrame(T);
+  EXPECT((tr.Ttrue - T).norm() <= 1e-4);
+}
+
+static void testPrior() {  // tests/testPGO.cpp:131-190
+  std::printf("[testPrior]\n");
+  RelativeSEMeasurement m(0, 0, 0, 1, Matrix::Identity(3, 3), Matrix::Zero(3, 1), 10000, 100);
+  m.fixedWeight = true;
+  std::vector<RelativeSEMeasurement> measurements{m};
+  PoseArray T = odometryInitialization(measurements);
+  auto pose_graph = std::make_shared<PoseGraph>(0, 3, 3);
+  pose_graph->setMeasurements(measurements);
+  Matrix prior_rotation = projectToRotationGroup(
+      mat({{0.7236, 0.1817, 0.6658}, {-0.6100, 0.6198, 0.4938}, {-0.3230, -0.7634, 0.5594}}));
+  Pose prior(3);
+  prior.rotation() = prior_rotation;
+  pose_graph->setPrior(1, prior);
+  QuadraticProblem problem(pose_graph);
+  EXPECT((T.pose(0) - prior.pose()).norm() > 1e-6);
+  EXPECT((T.pose(1) - prior.pose()).norm() > 1e-6);
+  ROptParameters params;
+  params.RTR_iterations = 50;
+  params.RTR_tCG_iterations = 500;
+  params.gradnorm_tol = 1e-5;
+  QuadraticOptimizer optimizer(&problem, params);
+  T.setData(optimizer.optimize(T.getData()));
+  EXPECT((T.pose(0) - prior.pose()).norm() < 1e-6);
+  EXPECT((T.pose(1) - prior.pose()).norm() < 1e-6);
+  EXPECT(optimizer.getOptResult().success);
+}
+
+static void testLineGraphAndConstruction() {  // testLineGraph.cpp, testConstruction.cpp
+  std::printf("[LineGraph / Construction]\n");
+  const unsigned d = 3, r = 3;
+  PGOAgentParameters options(d, r, 1);
+  PGOAgent agent(1, options);
+  EXPECT(agent.getID() == 1 && agent.dimension() == d && agent.relaxation_rank() == r && agent.num_poses() == 0);
+  PGOAgent a0(0, options);
+  std::vector<RelativeSEMeasurement> odom, none;
+  for (size_t i = 0; i < 4; ++i) {
+    Matrix t(3, 1);
+    t(0, 0) = 1.0;
+    odom.emplace_back(0, 0, i, i + 1, Matrix::Identity(3, 3), t, 1.0, 1.0);
+  }
+  a0.setMeasurements(odom, none, none);
+  a0.initialize();
+  a0.iterate();
+  EXPECT(a0.num_poses() == 5 && a0.dimension() == d && a0.relaxation_rank() == r);
+}
+
+static void testPosesAndUtils() {  // testPoses.cpp, testUtils.cpp
+  std::printf("[Poses / Utils]\n");
+  std::mt19937 rng(7);
+  std::normal_distribution<double> N(0, 1);
+  for (unsigned d = 2; d <= 3; ++d) {
+    Pose T(d);
+    Matrix M(d, d);
+    for (unsigned i = 0; i < d; ++i)
+      for (unsigned j = 0; j < d; ++j) M(i, j) = N(rng);
+    T.rotation() = projectToRotationGroup(M);
+    for (unsigned i = 0; i < d; ++i) T.translation()(i, 0) = N(rng);
+    EXPECT(std::fabs(T.rotation().determinant() - 1.0) < 1e-9);
+    const Pose I1 = T * T.inverse(), I2 = T.inverse() * T;
+    EXPECT((I1.matrix() - Matrix::Identity(d + 1, d + 1)).norm() < 1e-9);
+    EXPECT((I2.matrix() - Matrix::Identity(d + 1, d + 1)).norm() < 1e-9);
+    EXPECT((T.identity().matrix() - Matrix::Identity(d + 1, d + 1)).norm() < 1e-12);
+  }
+  const Matrix L = fixedStiefelVariable(3, 5);
+  EXPECT((L.transpose() * L - Matrix::Identity(3, 3)).norm() < 1e-9);
+  EXPECT((L - fixedStiefelVariable(3, 5)).norm() == 0);
+  for (int k = 0; k < 20; ++k) {
+    Matrix M(5, 3);
+    for (int i = 0; i < 5; ++i)
+      for (int j = 0; j < 3; ++j) M(i, j) = N(rng);
+    const Matrix Y = projectToStiefelManifold(M);
+    EXPECT((Y.transpose() * Y - Matrix::Identity(3, 3)).norm() < 1e-9);
+  }
+  EXPECT(std::fabs(chi2inv(0.9, 6) - 10.6446) < 1e-3);   // testUtils.cpp: chi2inv values
+  EXPECT(std::fabs(chi2inv(0.5, 3) - 2.36597) < 1e-4);
+}
+
+static void testOptimizationThread() {  // testOptimizationThread.cpp:29-92
+  std::printf("[OptimizationThread]\n");
+  const unsigned id = 0, d = 3, r = 3;
+  PGOAgentParameters options(d, r, 1);
+  options.asynchronous = false;
+  PGOAgent agent(id, options);
+  Triangle tr = makeTriangle(id);
+  agent.setMeasurements(tr.odometry, tr.private_lcs, tr.shared);
+  agent.initialize();
+  agent.setX(agent.localPoseGraphOptimization());
+  for (int k = 0; k < 3; ++k) {
+    EXPECT(!agent.isOptimizationRunning());
+    agent.startOptimizationLoop();
+    EXPECT(agent.isOptimizationRunning());
+    usleep(200000);
+    agent.endOptimizationLoop();
+    EXPECT(!agent.isOptimizationRunning());
+  }
+  Matrix T;
+  agent.getTrajectoryInLocalFrame(T);
+  EXPECT((tr.Ttrue - T).norm() <= 1e-4);
+}
+
+int main() {
+  testPosesAndUtils();
+  testTriangleGraph();
+  testPrior();
+  testLineGraphAndConstruction();
+  testOptimizationThread();
+  if (g_failed) {
+    std::printf("%d check(s) FAILED\n", g_failed);
+    return 1;
+  }
+  std::printf("all host tests passed\n");
+  return 0;
+}

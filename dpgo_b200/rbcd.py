@@ -223,6 +223,12 @@ class DeviceTeam:
         self.ranges, self.specs = build_specs(p1, p2, R, t, kappa, tau, n, d, num_robots)
         self.owner = block_owner(num_robots, world)
         self.colors = color_robot_graph(self.specs)
+        if stream is None:
+            # all agents, the torch copies and the NCCL ops must be ordered on ONE stream: use
+            # torch's current stream (the legacy default stream has the CUDA handle 0x1)
+            import torch
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream().cuda_stream or 1
         self.agents = {a: DeviceAgent(self.specs[a], d, r, num_robots, device, stream, acceleration,
                                       restart_interval, params)
                        for a in range(num_robots) if self.owner[a] == rank}

@@ -29,7 +29,11 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     from dpgo_b200 import rbcd
     from bench import lifting_matrix
     torch.cuda.set_device(local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream per rank: library kernels, torch device copies, NCCL stream
+    # dependencies and the timing events are all ordered on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     z, d, n = _fixture(dataset)
     X0 = np.asfortranarray(lifting_matrix(d, r) @ z["T_chordal"])
     t0 = time.time()
@@ -132,7 +136,7 @@ def cpu_team_baseline(rounds=2, dataset="grid3D", agents=8, r=5):
     return dict(value=upd / dt, ms_per_step=dt / rounds * 1e3, rounds=rounds, cost2=s["cost"])
 
 
-def run(args):
+def run(args, emit=None):
     import torch
     import torch.distributed as dist
     from bench import METRIC, UNIT, ClockSampler
@@ -141,6 +145,9 @@ def run(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -175,7 +182,7 @@ def run(args):
                                        "sequential on one core as the reference runs them"},
             "parity": {"cost2_after_timed_rounds": res["cost2"], "gradnorm": res["gradnorm"]},
         }
-        print(json.dumps(line))
+        (emit or (lambda l: print(json.dumps(l), flush=True)))(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
