@@ -234,13 +234,26 @@ def bench_single(args):
     pre_us = gp.time_precon(20, False)
     pre_bytes = gp.bytes_precon()
     qx_us_warm, qx_us_cold, qx_bytes = gp.time_qx(50, False), gp.time_qx(20, True), gp.bytes_qx()
-    step_bytes = (npc * pre_bytes + nq * qx_bytes) / K
-    roofline = {"bound": "hbm", "kernel": "k_precon_gemv (dense (Q+0.1I)^-1 apply, 800 MB > L2)",
-                "achieved": pre_bytes / pre_us / 1e3, "peak": peak, "unit": "GB/s",
-                "frac": pre_bytes / pre_us / 1e3 / peak, "peak_source": peak_src, "traffic": None,
-                "share_of_step": (npc / K) * pre_us / (ms / K * 1e3),
-                "step_algorithmic_bytes": step_bytes,
-                "step_achieved_gbs": step_bytes / (ms / K * 1e-3) / 1e9}
+    # algorithmic bytes of one step = one launch of the fused kernel ("bytes per unit"):
+    # every preconditioner application streams the dense inverse once (N^2*8 + 2 r N 8), every
+    # Q*X pass reads the block-CSR once (SURVEY 8(d) formula), every per-pose sweep reads 2 and
+    # writes 1 lifted array
+    sweep_bytes = 3.0 * X0.size * 8
+    step_bytes = (npc * pre_bytes + nq * qx_bytes + nsw * sweep_bytes) / K
+    step_s = ms / K * 1e-3
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
+    if os.path.exists(tpath):     # dram__bytes_read+write of k_rtr_fused from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm",
+                "kernel": "k_rtr_fused<5,3> (whole optimize() = 1 launch; dominated by the dense (Q+0.1I)^-1 apply)",
+                "achieved": step_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": step_bytes / step_s / 1e9 / peak, "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_launch": step_bytes, "launch_ms": ms / K,
+                "precon_apply_alone": {"kernel": "k_precon_gemv<5>", "bytes": pre_bytes, "us": pre_us,
+                                       "achieved": pre_bytes / pre_us / 1e3,
+                                       "frac": pre_bytes / pre_us / 1e3 / peak,
+                                       "share_of_step": (npc / K) * pre_us / (ms / K * 1e3)}}
     qx = {"bytes": qx_bytes, "warm_us": qx_us_warm, "warm_gbs": qx_bytes / qx_us_warm / 1e3,
           "cold_l2_us": qx_us_cold, "cold_l2_gbs": qx_bytes / qx_us_cold / 1e3,
           "cold_l2_frac_of_peak": qx_bytes / qx_us_cold / 1e3 / peak,

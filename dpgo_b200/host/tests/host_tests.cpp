@@ -37,12 +37,33 @@ static Matrix mat(std::initializer_list<std::initializer_list<double>> rows) {
   return m;
 }
 
-static Matrix inv4(const Matrix &T) {  // inverse of a homogeneous transform [R t; 0 1]
-  const Matrix R = T.block(0, 0, 3, 3), t = T.block(0, 3, 3, 1);
-  Matrix out = Matrix::Identity(4, 4);
-  out.block(0, 0, 3, 3) = R.transpose();
-  out.block(0, 3, 3, 1) = -(R.transpose() * t);
-  return out;
+static Matrix inv4(const Matrix &T) {  // true matrix inverse (Gauss-Jordan, partial pivoting): the
+  // hard-coded poses of the reference test are rounded to 4 digits, so R^T is NOT the inverse
+  const int n = 4;
+  Matrix A = T, B = Matrix::Identity(n, n);
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int i = c + 1; i < n; ++i)
+      if (std::fabs(A(i, c)) > std::fabs(A(piv, c))) piv = i;
+    for (int j = 0; j < n; ++j) {
+      std::swap(A(c, j), A(piv, j));
+      std::swap(B(c, j), B(piv, j));
+    }
+    const double p = A(c, c);
+    for (int j = 0; j < n; ++j) {
+      A(c, j) /= p;
+      B(c, j) /= p;
+    }
+    for (int i = 0; i < n; ++i) {
+      if (i == c) continue;
+      const double f = A(i, c);
+      for (int j = 0; j < n; ++j) {
+        A(i, j) -= f * A(c, j);
+        B(i, j) -= f * B(c, j);
+      }
+    }
+  }
+  return B;
 }
 
 struct Triangle {
