@@ -86,6 +86,18 @@ class Agent:
                 self.X = self.Y.copy()
             return True
         G = pgo.construct_G(self.graph, self.nbr_aux if acceleration else self.nbr)
+        X0 = self.Y if acceleration else self.X
+        if getattr(self, "use_cpu_port", False):
+            # compiled single-thread restatement (oracle/cpu_port): same algorithm, C++ speed
+            from .cpu_port import CpuProblem
+            if getattr(self, "_cpu", None) is None:
+                self._cpu = CpuProblem(self.Q, G, self.d)
+            self._cpu.set_G(G)
+            p = self.params
+            self.X, res = self._cpu.optimize(X0, p.gradnorm_tol, p.RTR_iterations, p.RTR_tCG_iterations,
+                                             p.RTR_initial_radius)
+            self.last_result = res
+            return True
         prob = pgo.QuadraticProblem(self.Q, G, self.d)
         if self._prob is not None:
             prob._lu = self._prob._lu           # Q unchanged => preconditioner unchanged

@@ -119,6 +119,8 @@ def cpu_team_baseline(rounds=2, dataset="grid3D", agents=8, r=5):
     z, d, n = _fixture(dataset)
     meas = pgo.make_measurements(d, z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"])
     team = orbcd.Team(meas, n, agents, r, acceleration=True)
+    for a in team.agents:
+        a.use_cpu_port = True         # compiled local solves (oracle/cpu_port)
     team.set_X(pgo.lifting_matrix(d, r) @ z["T_chordal"])
     colors = orbcd.robot_graph_coloring(team.agents)
     team.step_colored(colors, 0)      # warm-up round: factorizes every agent's preconditioner
@@ -178,7 +180,7 @@ def run(args, emit=None):
                          "note": "see the N=1 line: the dominant kernel and its roofline are measured there"},
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",
                              "ms_per_step": cpu["ms_per_step"],
-                             "sample": f"{cpu['rounds']} colour rounds of the oracle's 8 agents (numpy/SuperLU), "
+                             "sample": f"{cpu['rounds']} colour rounds of the oracle's 8 agents (compiled C++ local solves, oracle/cpu_port), "
                                        "sequential on one core as the reference runs them"},
             "parity": {"cost2_after_timed_rounds": res["cost2"], "gradnorm": res["gradnorm"]},
         }
