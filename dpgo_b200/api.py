@@ -92,6 +92,10 @@ class DeviceProblem:
             if len(idx) else np.zeros((0, self.r * (self.d + 1))))
         check(lib.dpgo_set_priors(self._h, len(idx), _i(idx), _d(tiles), prior_kappa, prior_tau))
 
+    def set_precon_mode(self, mode):
+        """0 = full dense inverse (default), 1 = symmetric half storage."""
+        check(lib.dpgo_set_precon_mode(self._h, int(mode)))
+
     def finalize(self, build_precon=True):
         check(lib.dpgo_finalize(self._h, 1 if build_precon else 0))
 
@@ -276,10 +280,12 @@ class DeviceProblem:
 
 
 def problem_from_measurements(p1, p2, R, t, kappa, tau, n, d, r, device=0, stream=None,
-                              build_precon=True, weight=None):
+                              build_precon=True, weight=None, precon_mode=None):
     """Single-robot problem (all edges private), as examples/MultiRobotExample.cpp:61-63 builds
     `problemCentral`."""
     prob = DeviceProblem(n, d, r, device, stream)
     prob.set_private_edges(p1, p2, R, t, kappa, tau, weight)
+    if precon_mode is not None:
+        prob.set_precon_mode(precon_mode)
     prob.finalize(build_precon)
     return prob

@@ -55,7 +55,14 @@ struct dpgo_dev {
   // dense preconditioner
   double *d_Pinv = nullptr, *d_zpart = nullptr;
   int KT = 0, nsplit = 0;
+  // symmetric half-storage variant (precon_mode == 1): T blocks of 128, NG groups of kSymS
+  // blocks, work items (ig >= kg), partial buffers zD (in d_zpart) and zT
+  int precon_mode = 0;   // measured on B200 (round 1): the full variant is faster inside the fused solver
+  int symT = 0, symNG = 0, sym_nitems = 0;
+  void *d_sym_items = nullptr;
+  double *d_zT = nullptr;
   int gemv_occ = 0;
+  int symv_occ = 0;
   int partial_blocks = 0;  // CTAs the partials buffer can serve (8 doubles each)
   bool finalized = false, has_precon = false;
   cusolverDnHandle_t cusolver = nullptr;

@@ -36,6 +36,9 @@ struct FusedParams {
   double *zpart;
   int ld, KT, nsplit, n;
   size_t zstride;
+  int precon_mode, symT, symNG, nitems;   // symmetric half-storage variant
+  const SymItem *items;
+  double *zT;
   const double *x_in;
   double *x_out;
   double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
@@ -51,26 +54,31 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-// per-phase device time seen by CTA 0 (phase body + the barrier that ends it)
+// per-phase device time seen by CTA 0 (phase body + the barrier that ends it); the accumulators
+// live in shared memory so that they do not occupy registers across the phases
 struct PhaseClock {
-  unsigned long long t0;
-  unsigned long long acc[8];
-  __device__ __forceinline__ void start() {
+  unsigned long long *acc;  // [9] in shared memory: 8 phase sums + last timestamp
+  __device__ __forceinline__ void start(unsigned long long *smem) {
+    acc = smem;
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0;
-    t0 = gtimer();
+      for (int i = 0; i < 8; ++i) acc[i] = 0;
+      acc[8] = gtimer();
+    }
   }
   __device__ __forceinline__ void lap(int id) {
-    const unsigned long long t = gtimer();
-    acc[id] += t - t0;
-    t0 = t;
+    if (threadIdx.x == 0) {
+      const unsigned long long t = gtimer();
+      acc[id] += t - acc[8];
+      acc[8] = t;
+    }
   }
 };
 
 struct GridReducer {
   double *buf[2];
   int flip;
-  long long barriers;
+  int barriers;
   // block partials -> grid barrier -> every CTA sums all partials in the same order
   template <int K>
   __device__ __forceinline__ void reduce(cg::grid_group &grid, double (&acc)[K], double (&out)[K]) {
@@ -86,7 +94,7 @@ struct GridReducer {
   }
 };
 
-template <int R, int D>
+template <int R, int D, bool SYM>
 __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::grid_group grid = cg::this_grid();
@@ -102,11 +110,27 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
 
   double *x1 = p.xa, *x2 = p.xb, *EG = p.EG, *EG2 = p.EG2, *grad = p.grad, *grad2 = p.grad2;
   double *S = p.S, *S2 = p.S2;
-  long long n_qx = 0, n_precon = 0, n_sweeps = 0;
+  int n_qx = 0, n_precon = 0, n_sweeps = 0;
+
+  // the two storage variants of the dense inverse (uniform branch)
+  auto precon_stream = [&](const double *v) {
+    if constexpr (SYM)
+      phase_precon_symv<R>(pipe, p.Pinv, p.symT, p.items, p.nitems, v, p.zpart, p.zT, p.zstride);
+    else
+      phase_precon_gemv<R>(pipe, p.Pinv, p.ld, v, p.zpart, p.zstride, p.KT, p.nsplit);
+  };
+  auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
+    if constexpr (SYM)
+      phase_precon_finish_sym<R, D>(pipe.scratch, p.zpart, p.zT, p.zstride, p.symNG, Ycur, rvec, p.z,
+                                    neg_out, n, a1);
+    else
+      phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, Ycur, rvec, p.z, neg_out, n, a1);
+  };
 
   // ---- statistics at the initial point (fInit, gradNormInit) = first f / Grad of the solver
+  __shared__ unsigned long long s_clk[9];
   PhaseClock clk;
-  clk.start();
+  clk.start(s_clk);
   phase_copy(ctx, p.x_in, x1, len);
   red.barrier(grid);
   clk.lap(6);
@@ -133,22 +157,37 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
 
   while (run) {
     // ------------------------------------------------------------------ truncated CG
+    // One call site per phase: the loop starts with the preconditioner (on grad the first time,
+    // on the residual r afterwards), then the direction update, then the Hessian product.
     TcgState s;
-    phase_precon_gemv<R>(pipe, p.Pinv, p.ld, grad, p.zpart, p.zstride, p.KT, p.nsplit);
-    phase_copy(ctx, grad, p.r, len);
-    phase_zero(ctx, p.eta, len);
-    red.barrier(grid);
-    clk.lap(1);
-    {
-      double acc[1] = {0.0}, sc[1];
-      phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, grad, p.z, p.delta, n, acc);
-      red.reduce<1>(grid, acc, sc);
-      clk.lap(2);
-      tcg_begin(s, gn2, sc[0]);
-      n_precon++;
-    }
     int inner = 0;
-    for (int j = 0; j < p.max_inner; ++j) {
+    bool first = true;
+    for (int j = 0;; ++j) {
+      const double *pvec = first ? grad : p.r;
+      precon_stream(pvec);
+      if (first) {
+        phase_copy(ctx, grad, p.r, len);
+        phase_zero(ctx, p.eta, len);
+      }
+      red.barrier(grid);
+      clk.lap(1);
+      {
+        double acc[1] = {0.0}, sc[1];
+        precon_finish(x1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
+        red.reduce<1>(grid, acc, sc);
+        clk.lap(2);
+        n_precon++;
+        if (first) {
+          tcg_begin(s, gn2, sc[0]);
+        } else {
+          const double beta = tcg_direction(s, sc[0]);
+          phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
+          red.barrier(grid);
+          clk.lap(5);
+        }
+      }
+      first = false;
+      if (j >= p.max_inner) break;
       double d_Hd;
       {
         double acc[2] = {0.0, 0.0}, sc[2];
@@ -175,22 +214,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
         r_r = sc[0];
       }
       if (tcg_converged(s, r_r, p.theta, p.kappa)) break;
-      phase_precon_gemv<R>(pipe, p.Pinv, p.ld, p.r, p.zpart, p.zstride, p.KT, p.nsplit);
-      red.barrier(grid);
-      clk.lap(1);
-      double z_r;
-      {
-        double acc[1] = {0.0}, sc[1];
-        phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, x1, p.r, p.z, nullptr, n, acc);
-        red.reduce<1>(grid, acc, sc);
-        clk.lap(2);
-        z_r = sc[0];
-        n_precon++;
-      }
-      const double beta = tcg_direction(s, z_r);
-      phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
-      red.barrier(grid);
-      clk.lap(5);
+      if (j + 1 >= p.max_inner) break;   // the reference's loop ends without a further direction
     }
     inner_total += inner;
     last_status = s.status;
@@ -250,13 +274,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
   }
 }
 
-template <int R, int D>
-static int launch_fused(dpgo_dev *h, FusedParams &fp) {
+template <int R, int D, bool SYM>
+static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
   static int occ_cache = -1;
   if (occ_cache < 0) {
     int occ = 0;
-    if (cudaFuncSetAttribute(k_rtr_fused<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvDynSmem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D>, kBlock, kGemvDynSmem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_rtr_fused<R, D, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvDynSmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D, SYM>, kBlock, kGemvDynSmem) != cudaSuccess ||
         occ < 1) {
       set_error("fused kernel does not fit on the device");
       return DPGO_ECUDA;
@@ -265,7 +289,7 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
   }
   const long cap = (long)h->num_sms * occ_cache;
   // enough CTAs for the widest phase, never more than can be co-resident
-  const long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
+  const long tiles = (h->precon_mode == 1) ? (long)h->sym_nitems : (long)(h->ld / kGemvCols) * h->nsplit;
   const int gpw = 32 / (h->d + 1);
   const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long grid = std::max(tiles, pose_blocks);
@@ -275,7 +299,7 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
     return DPGO_EINVAL;
   }
   void *args[] = {&fp};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_rtr_fused<R, D>, dim3((unsigned)grid), dim3(kBlock),
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_rtr_fused<R, D, SYM>, dim3((unsigned)grid), dim3(kBlock),
                                               args, kGemvDynSmem, h->stream);
   if (e != cudaSuccess) {
     set_error("cudaLaunchCooperativeKernel failed: %s", cudaGetErrorString(e));
@@ -283,6 +307,11 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
   }
   h->launches++;
   return DPGO_OK;
+}
+
+template <int R, int D>
+static int launch_fused(dpgo_dev *h, FusedParams &fp) {
+  return (h->precon_mode == 1) ? launch_fused_v<R, D, true>(h, fp) : launch_fused_v<R, D, false>(h, fp);
 }
 
 int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
@@ -301,6 +330,8 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
   fp.zpart = h->d_zpart;
   fp.ld = h->ld; fp.KT = h->KT; fp.nsplit = h->nsplit; fp.n = h->n;
   fp.zstride = h->vpad;
+  fp.precon_mode = h->precon_mode; fp.symT = h->symT; fp.symNG = h->symNG; fp.nitems = h->sym_nitems;
+  fp.items = (const SymItem *)h->d_sym_items; fp.zT = h->d_zT;
   fp.x_in = x_in; fp.x_out = x_out;
   fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;
   fp.grad = h->d_grad; fp.grad2 = h->d_grad2; fp.S = h->d_S; fp.S2 = h->d_S2;

@@ -382,14 +382,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 constexpr int kStageK = 32;                                  // inner indices per pipeline stage
-constexpr int kStages = 5;                                   // stages in flight per CTA
+constexpr int kStages = 4;                                   // stages in flight per CTA
 constexpr int kStageDoubles = kStageK * kGemvCols;           // 2048 doubles = 16 KB
 constexpr int kGemvMaxR = 6;
-constexpr int kGemvDynSmem = kStages * kStageDoubles * 8 + kStages * 8 + kStages * kStageK * kGemvMaxR * 8;
+// symmetric (half-storage) variant: 128 x 128 blocks, 16 inner indices x 128 columns per stage
+constexpr int kSymB = 128;
+constexpr int kSymStageK = 16;
+constexpr int kSymStagesPerTile = kSymB / kSymStageK;        // 8 stages = one 128 KB block
+constexpr int kSymS = 2;                                     // blocks per side of a work item
+static_assert(kSymStageK * kSymB == kStageDoubles, "both variants stream 16 KB stages");
+// scratch shared by the two variants: cross-warp reduction buffers (+ transposed accumulators)
+constexpr int kGemvScratch = (4 * kGemvMaxR * kSymB + kSymS * kSymB * kGemvMaxR) * 8;
+static_assert(kGemvScratch >= kWarpsPerBlock * kGemvMaxR * kGemvCols * 8, "scratch too small");
+constexpr int kGemvDynSmem =
+    kStages * kStageDoubles * 8 + kStages * 8 + kStages * kStageK * kGemvMaxR * 8 + kGemvScratch;
 
 struct GemvPipe {
   double *stage;      // [kStages][kStageK][kGemvCols]
   double *svec;       // [kStages][kStageK * R] slice of the input array that goes with a stage
+  double *scratch;    // kGemvScratch bytes
   uint32_t bar;       // shared address of the first mbarrier
   uint32_t slot;      // ring slot of the next chunk to consume (persists across phases)
   uint32_t parity;    // mbarrier phase parity of that slot
@@ -401,6 +412,7 @@ __device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
   pp.stage = reinterpret_cast<double *>(dsm);
   pp.bar = smem_u32(dsm + (size_t)kStages * kStageDoubles * 8);
   pp.svec = reinterpret_cast<double *>(dsm + (size_t)kStages * kStageDoubles * 8 + kStages * 8);
+  pp.scratch = pp.svec + kStages * kStageK * kGemvMaxR;
   pp.slot = 0;
   pp.parity = 0;
   if (threadIdx.x == 0) {
@@ -432,7 +444,7 @@ template <int R>
 __device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pinv, int ld,
                                                   const double *vec, double *zpart, size_t zstride,
                                                   int KT, int nsplit) {
-  __shared__ double sacc[kWarpsPerBlock][R][kGemvCols];
+  double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ncb = ld / kGemvCols;
   const int ntiles = ncb * nsplit;
@@ -524,6 +536,247 @@ __device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pi
     }
     cursor_next(cc);
     if (pp.slot + 1 == kStages) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
+  }
+}
+
+// ---- symmetric (half-storage) variant ---------------------------------------------------------
+// Only the blocks (I, K), I >= K, of the symmetric inverse are stored (128 x 128 doubles each,
+// lower-triangular packed, 8 stages of 16 inner indices x 128 columns per block), so one apply
+// streams ~N^2/2 * 8 bytes.  Each streamed stage st[kk][jj] = P[I*128+jj, K*128+16h+kk] is used twice:
+//   direct      z[I-block][jj] += st[kk][jj] * vec[K-block][kk]     (lane-local, like the full variant)
+//   transposed  z[K-block][kk] += st[kk][jj] * vec[I-block][jj]     (off-diagonal blocks; the sum
+//               over jj crosses lanes: 8-slot halving butterfly of warp shuffles per kk)
+// A work item is a kSymS x kSymS group of blocks (ig, kg), ig >= kg: direct sums of a block row
+// live in registers across the item's columns and go to zD[kg]; transposed sums accumulate in
+// shared memory over the item's rows and go to zT[ig].  Every (partial buffer, column) pair is
+// written by exactly one CTA and summed in a fixed order by phase_precon_finish_sym.
+struct SymItem {
+  int ig, kg, ntiles, pad;
+};
+
+struct SymCursor {
+  int item, ig, kg, I, K, h;
+};
+
+template <int R>
+__device__ __forceinline__ void phase_precon_symv(GemvPipe &pp, const double *Psym, int T,
+                                                  const SymItem *items, int nitems, const double *vec,
+                                                  double *zD, double *zT, size_t zstride) {
+  static_assert(R <= kGemvMaxR, "scratch sized for R <= kGemvMaxR");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double(*sacc)[R][kSymB] = reinterpret_cast<double(*)[R][kSymB]>(pp.scratch);          // [4][R][128]
+  double *accT = pp.scratch + 4 * kGemvMaxR * kSymB;                                     // [kSymS][128][R]
+  int G = 0;
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) G += items[it].ntiles * kSymStagesPerTile;
+  if (G == 0) return;
+  const uint32_t stage0 = smem_u32(pp.stage);
+
+  auto cur_init = [&](SymCursor &c, int item) {
+    c.item = item;
+    if (item < nitems) {
+      const SymItem d = items[item];
+      c.ig = d.ig; c.kg = d.kg;
+      c.I = d.ig * kSymS; c.K = d.kg * kSymS; c.h = 0;
+    }
+  };
+  auto last_K = [&](const SymCursor &c) { return min(c.kg * kSymS + kSymS - 1, c.I); };
+  auto last_I = [&](const SymCursor &c) { return min(c.ig * kSymS + kSymS - 1, T - 1); };
+  auto cur_next = [&](SymCursor &c) {
+    if (++c.h < kSymStagesPerTile) return;
+    c.h = 0;
+    if (c.K < last_K(c)) { c.K++; return; }
+    c.K = c.kg * kSymS;
+    if (c.I < last_I(c)) { c.I++; return; }
+    cur_init(c, c.item + gridDim.x);
+  };
+  auto produce = [&](const SymCursor &c, uint32_t slot) {
+    if (threadIdx.x == 0) {
+      const uint32_t bar = pp.bar + 8 * slot;
+      mbar_expect_tx(bar, kStageDoubles * 8);
+      const size_t tile = (size_t)c.I * (c.I + 1) / 2 + c.K;
+      bulk_g2s(stage0 + slot * (kStageDoubles * 8),
+               Psym + (tile * kSymStagesPerTile + c.h) * kStageDoubles, kStageDoubles * 8, bar);
+    }
+    if (threadIdx.x < kSymStageK * R)
+      pp.svec[slot * (kStageK * R) + threadIdx.x] =
+          vec[((size_t)c.K * kSymB + c.h * kSymStageK) * R + threadIdx.x];
+  };
+
+  SymCursor ci, cc;
+  cur_init(ci, blockIdx.x);
+  cur_init(cc, blockIdx.x);
+  uint32_t slot_i = pp.slot;
+  int issued = 0;
+  for (; issued < kStages && issued < G; ++issued) {
+    produce(ci, slot_i);
+    cur_next(ci);
+    slot_i = (slot_i + 1 == kStages) ? 0 : slot_i + 1;
+  }
+  __syncthreads();
+
+  const int jj[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 64 + 2 * lane + 1};
+  double a[4][R], rI[4][R];
+  for (int g = 0; g < G; ++g) {
+    const bool row_start = (cc.K == cc.kg * kSymS && cc.h == 0);
+    const bool item_start = row_start && (cc.I == cc.ig * kSymS);
+    if (item_start) {
+      for (int o = threadIdx.x; o < kSymS * kSymB * R; o += kBlock) accT[o] = 0.0;
+      __syncthreads();
+    }
+    if (row_start) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double *rp = vec + ((size_t)cc.I * kSymB + jj[c]) * R;
+#pragma unroll
+        for (int q = 0; q < R; ++q) { rI[c][q] = rp[q]; a[c][q] = 0.0; }
+      }
+    }
+    const bool offdiag = (cc.I != cc.K);
+    const uint32_t slot = pp.slot;
+    mbar_wait(pp.bar + 8 * slot, pp.parity);
+    const double *st = pp.stage + (size_t)slot * kStageDoubles;
+    const double *sv = pp.svec + slot * (kStageK * R);
+    double *aT = accT + ((size_t)(cc.K - cc.kg * kSymS) * kSymB + cc.h * kSymStageK) * R;
+#pragma unroll
+    for (int u = 0; u < kSymStageK / kWarpsPerBlock; ++u) {
+      const int kk = w + u * kWarpsPerBlock;
+      const double2 p0 = *reinterpret_cast<const double2 *>(st + kk * kSymB + 2 * lane);
+      const double2 p1 = *reinterpret_cast<const double2 *>(st + kk * kSymB + 64 + 2 * lane);
+      const double pv[4] = {p0.x, p0.y, p1.x, p1.y};
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double x = sv[kk * R + q];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          a[c][q] = fma(pv[c], x, a[c][q]);
+          v[q] = fma(pv[c], rI[c][q], v[q]);
+        }
+      }
+      if (offdiag) {  // warp-uniform
+        // 8 slots over 32 lanes: halve the slot set on lane bits 4, 3, 2, then all-reduce bits 1, 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool up = (lane & 16) != 0;
+          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 4], 16);
+          v[i] = (up ? v[i + 4] : v[i]) + recv;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool up = (lane & 8) != 0;
+          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 2], 8);
+          v[i] = (up ? v[i + 2] : v[i]) + recv;
+        }
+        {
+          const bool up = (lane & 4) != 0;
+          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[0] : v[1], 4);
+          v[0] = (up ? v[1] : v[0]) + recv;
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        const int slot_q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0 && slot_q < R) aT[kk * R + slot_q] += v[0];
+      }
+    }
+    const bool row_end = (cc.h == kSymStagesPerTile - 1) && (cc.K == last_K(cc));
+    const bool item_end = row_end && (cc.I == last_I(cc));
+    __syncthreads();  // every warp is done with this stage
+    if (issued < G) {
+      produce(ci, slot);
+      cur_next(ci);
+      ++issued;
+    }
+    if (row_end) {  // combine the 8 warps' direct sums for block row I -> zD[kg]
+      if (w >= 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int q = 0; q < R; ++q) sacc[w - 4][q][jj[c]] = a[c][q];
+      }
+      __syncthreads();
+      if (w < 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int q = 0; q < R; ++q) sacc[w][q][jj[c]] += a[c][q];
+      }
+      __syncthreads();
+      for (int o = threadIdx.x; o < R * kSymB; o += kBlock) {
+        const int q = o / kSymB, j = o % kSymB;
+        const double x = (sacc[0][q][j] + sacc[1][q][j]) + (sacc[2][q][j] + sacc[3][q][j]);
+        zD[(size_t)cc.kg * zstride + ((size_t)cc.I * kSymB + j) * R + q] = x;
+      }
+      __syncthreads();
+    }
+    if (item_end) {  // transposed sums of this item's block columns -> zT[ig]
+      const int kb0 = cc.kg * kSymS;
+      const int nkb = min(kSymS, T - kb0);
+      for (int o = threadIdx.x; o < nkb * kSymB * R; o += kBlock)
+        zT[(size_t)cc.ig * zstride + (size_t)kb0 * kSymB * R + o] = accT[o];
+      __syncthreads();
+    }
+    cur_next(cc);
+    if (pp.slot + 1 == kStages) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
+  }
+}
+
+// z = Proj_Y( sum of the NG+1 partials that exist for a column ); acc = {<z, rvec>}.  A CTA takes
+// one warp-row of poses at a time and its 8 warps split the partial buffers, so the ~40 dependent
+// L2/HBM reads per column become 5 per warp.
+template <int R, int D>
+__device__ __forceinline__ void phase_precon_finish_sym(double *scratch, const double *zD, const double *zT,
+                                                        size_t zstride, int NG, const double *Y,
+                                                        const double *rvec, double *z, double *neg_out,
+                                                        int n, double (&acc)[1]) {
+  using Gm = Geo<R, D>;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const LanePos lp = lane_pos<D>(lane);
+  double(*sfin)[32][R] = reinterpret_cast<double(*)[32][R]>(scratch);  // [8][32][R]
+  const int nchunks = (n + Gm::GPW - 1) / Gm::GPW;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int i = chunk * Gm::GPW + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double part[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) part[q] = 0.0;
+    if (valid) {
+      const int col = i * Gm::DH + lp.c;
+      const int gi = (col / kSymB) / kSymS;
+      for (int s = w; s <= NG; s += kWarpsPerBlock) {
+        const double *zp = (s <= gi) ? zD + (size_t)s * zstride + off : zT + (size_t)(s - 1) * zstride + off;
+#pragma unroll
+        for (int q = 0; q < R; ++q) part[q] += zp[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) sfin[w][lane][q] = part[q];
+    __syncthreads();
+    if (w == 0) {
+      double wv[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        double x = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sfin[ww][lane][q];
+        wv[q] = x;
+      }
+      double sym[D];
+      group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), wv, lp, valid, sym);
+      if (valid) {
+        store_col<R>(z + off, wv);
+        double rr[R];
+        load_col<R>(rvec + off, rr);
+        acc[0] += dot_col<R>(wv, rr);
+        if (neg_out) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) neg_out[off + q] = -wv[q];
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -115,6 +115,13 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
  * CHOLMOD factorization, src/PoseGraph.cpp:598-613 -- both are exact solves).
  * build_precon = 0 skips the preconditioner (then only unpreconditioned ops are available). */
 int dpgo_finalize(dpgo_handle h, int build_precon);
+/* Storage of the dense inverse: 0 (default) = full matrix (N^2*8 bytes streamed per application),
+ * 1 = symmetric half storage (blocks I >= K only, every streamed block is used for both
+ * z_I += P_IK r_K and z_K += P_IK^T r_I: ~N^2/2*8 bytes per application, half the memory).  Same
+ * result up to summation order.  On B200 the half-storage apply is FP64-issue/latency bound at
+ * the same wall time as the full one, so the full variant is the default; the half variant is
+ * kept for memory-limited problems.  Takes effect at the next dpgo_finalize(h, 1). */
+int dpgo_set_precon_mode(dpgo_handle h, int mode);
 /* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
 int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,

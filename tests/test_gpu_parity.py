@@ -211,3 +211,33 @@ def test_linearity_and_symmetry_at_scale(datasets):
     assert abs(2 * gp.f(pgo.lifting_matrix(d, r) @ z["T_chordal"]) - float(z["cost2_chordal"])) \
         <= 1e-10 * float(z["cost2_chordal"])
     gp.close()
+
+
+@pytest.mark.parametrize("name,r", [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 5)])
+def test_precon_storage_variants(datasets, name, r):
+    """The dense inverse in full and in symmetric half storage (dpgo_set_precon_mode 0 / 1): the same
+    operator (1e-8 vs the oracle's exact solve, 1e-10 against each other) and the same solve."""
+    import dpgo_b200
+    meas, n, z = datasets(name)
+    d = meas.d
+    X, V, rng = random_state(n, d, r, 11)
+    Vt = pgo.tangent_project(X, V, d)
+    op = oracle_problem(meas, n, r)
+    ref = op.precondition(X, Vt)
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    outs, sols = [], []
+    for mode in (0, 1):
+        gp = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau,
+                                                 n, d, r, precon_mode=mode)
+        outs.append(gp.precon(X, Vt))
+        assert rel(outs[-1], ref) < 1e-8
+        for fused in (0, 1):
+            Xg, res = gp.optimize(X0, dpgo_b200.default_params(fused=fused))
+            sols.append((Xg, res))
+        gp.close()
+    assert rel(outs[0], outs[1]) < 1e-10
+    Xo, ro = pgo.optimize(op, X0)
+    for Xg, res in sols:
+        assert (res["outer_iters"], res["inner_iters"]) == (ro.outer, ro.inner_total)
+        assert abs(res["f_opt"] - ro.fOpt) <= 1e-9 * abs(ro.fOpt)
+        assert rel(Xg, Xo) < 1e-6
