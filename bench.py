@@ -214,29 +214,40 @@ def bench_single(args):
     z, d, n = load_fixture(name)
     X0 = np.asfortranarray(lifting_matrix(d, r) @ z["T_chordal"])
     gp = dpgo_b200.problem_from_measurements(z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"],
-                                             n, d, r, device=0, stream=stream)
+                                             n, d, r, device=0, stream=stream,
+                                             precon_mode=args.precon_mode)
     prm = dpgo_b200.default_params(fused=1 if args.fused else 0)
-    gp.slot_set(dpgo_b200.SLOT_Y, X0)
     K, W = args.steps, max(args.warmup, 3)
+    # L2 is flushed between timed steps (a 256 MB write, outside the per-step event pairs): the
+    # two-level preconditioner (58 MB) would otherwise stay L2-resident from one step to the next.
+    # Inside a step the solver re-reads it ~36 times; that reuse is part of the step.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed_device_steps(prob):
+        prob.slot_set(dpgo_b200.SLOT_Y, X0)
+        for _ in range(W):
+            r_ = prob.optimize_slot(dpgo_b200.SLOT_Y, prm)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        tot = {"n_launches": 0, "n_qx": 0, "n_precon": 0, "n_pose_sweeps": 0}
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            r_ = prob.optimize_slot(dpgo_b200.SLOT_Y, prm)
+            e1.record()
+            for k in tot:
+                tot[k] += r_[k]
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in evs), tot, r_
 
     # ---- device-resident timing: X0 lives in HBM (slot Y), result stays in HBM (slot X)
-    for _ in range(W):
-        res = gp.optimize_slot(dpgo_b200.SLOT_Y, prm)
-    torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    nq = npc = nsw = 0
-    ev0.record()
-    for _ in range(K):
-        res = gp.optimize_slot(dpgo_b200.SLOT_Y, prm)
-        launches += res["n_launches"]; nq += res["n_qx"]; npc += res["n_precon"]; nsw += res["n_pose_sweeps"]
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ms, tot, res = timed_device_steps(gp)
     clocks = sampler.stop()
+    launches, nq, npc, nsw = tot["n_launches"], tot["n_qx"], tot["n_precon"], tot["n_pose_sweeps"]
     value = K / (ms / 1e3)
+    mode = gp.precon_mode()
 
     # ---- end to end through the public call with HOST buffers (pinned): H2D of X0 and D2H of X
     xin = torch.from_numpy(np.ascontiguousarray(X0.T)).pin_memory()     # same bytes as col-major r x N
@@ -249,42 +260,67 @@ def bench_single(args):
     for _ in range(W):
         check(lib.dpgo_optimize(gp._h, C.byref(prm), pin, pout, C.byref(rr)))
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ev0.record()
+    e2e_ms = 0.0
     for _ in range(K):
-        check(lib.dpgo_optimize(gp._h, C.byref(prm), pin, pout, C.byref(rr)))
-    ev1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(lib.dpgo_optimize(gp._h, C.byref(prm), pin, pout, C.byref(rr)))   # returns after the D2H copy
+        e2e_ms += (time.perf_counter() - t0) * 1e3
     e2e_value = K / (e2e_ms / 1e3)
     nbytes = X0.size * 8
     Xg = xout.numpy().T.copy()
 
-    # ---- roofline of the dominant kernel (dense preconditioner apply), CUDA events on the same stream
+    # ---- roofline of the dominant kernel, CUDA events on the same stream
     peak, peak_src = measured_peaks()
     pre_us = gp.time_precon(20, False)
+    pre_us_cold = gp.time_precon(10, True)
     pre_bytes = gp.bytes_precon()
     qx_us_warm, qx_us_cold, qx_bytes = gp.time_qx(50, False), gp.time_qx(20, True), gp.bytes_qx()
     # algorithmic bytes of one step = one launch of the fused kernel ("bytes per unit"):
-    # every preconditioner application streams the dense inverse once (N^2*8 + 2 r N 8), every
-    # Q*X pass reads the block-CSR once (SURVEY 8(d) formula), every per-pose sweep reads 2 and
-    # writes 1 lifted array
+    # every preconditioner application streams its dense blocks once, every Q*X pass reads the
+    # block-CSR once (SURVEY 8(d) formula), every per-pose sweep reads 2 and writes 1 lifted array
     sweep_bytes = 3.0 * X0.size * 8
-    step_bytes = (npc * pre_bytes + nq * qx_bytes + nsw * sweep_bytes) / K
-    step_s = ms / K * 1e-3
+
+    def step_roofline(ms_, npc_, nq_, nsw_, pre_bytes_):
+        sb = (npc_ * pre_bytes_ + nq_ * qx_bytes + nsw_ * sweep_bytes) / K
+        return sb, sb / (ms_ / K * 1e-3) / 1e9
+
+    step_bytes, step_gbs = step_roofline(ms, npc, nq, nsw, pre_bytes)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_fused_traffic.json")
     if os.path.exists(tpath):     # dram__bytes_read+write of k_rtr_fused from the committed ncu --set full capture
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch_mode%d" % mode, tj.get("dram_bytes_per_launch") if mode == 0 else None)
+    pre_kernel = {0: "k_precon_gemv<5> (full dense inverse, 800 MB)",
+                  1: "k_precon_symv<5> (symmetric half storage)",
+                  2: "k_strip_gemv<5> x3 + k_dd_sep_rhs + k_dd_back_rhs (two-level, 58 MB, L2 resident)"}[mode]
     roofline = {"bound": "hbm",
-                "kernel": "k_rtr_fused<5,3> (whole optimize() = 1 launch; dominated by the dense (Q+0.1I)^-1 apply)",
-                "achieved": step_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": step_bytes / step_s / 1e9 / peak, "peak_source": peak_src, "traffic": traffic,
+                "kernel": "k_rtr_fused<5,3,%d> (whole optimize() = 1 launch; dominated by the (Q+0.1I)^-1 apply)" % mode,
+                "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                "frac": step_gbs / peak, "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": step_bytes, "launch_ms": ms / K,
-                "precon_apply_alone": {"kernel": "k_precon_gemv<5>", "bytes": pre_bytes, "us": pre_us,
+                "precon_apply_alone": {"kernel": pre_kernel, "bytes": pre_bytes, "us": pre_us,
+                                       "us_cold_l2": pre_us_cold,
                                        "achieved": pre_bytes / pre_us / 1e3,
                                        "frac": pre_bytes / pre_us / 1e3 / peak,
                                        "share_of_step": (npc / K) * pre_us / (ms / K * 1e3)}}
+    if mode == 2:
+        roofline["note"] = ("two-level exact preconditioner: 14x fewer algorithmic bytes than the dense inverse and "
+                            "L2 resident within a step, so the step is grid-barrier / latency bound, not HBM bound; "
+                            "the HBM-bound formulation of the same solve is timed below (dense_inverse_variant)")
+        gp0 = dpgo_b200.problem_from_measurements(z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"],
+                                                  n, d, r, device=0, stream=stream, precon_mode=0)
+        ms0, tot0, res0 = timed_device_steps(gp0)
+        b0 = gp0.bytes_precon()
+        sb0, gbs0 = step_roofline(ms0, tot0["n_precon"], tot0["n_qx"], tot0["n_pose_sweeps"], b0)
+        us0 = gp0.time_precon(20, False)
+        roofline["dense_inverse_variant"] = {
+            "kernel": "k_rtr_fused<5,3,0>", "ms_per_step": ms0 / K, "value": K / (ms0 / 1e3),
+            "algorithmic_bytes_per_launch": sb0, "achieved": gbs0, "frac": gbs0 / peak,
+            "precon_apply_alone": {"bytes": b0, "us": us0, "achieved": b0 / us0 / 1e3, "frac": b0 / us0 / 1e3 / peak},
+            "final_cost_2f": 2 * res0["f_opt"], "tcg_iters": res0["inner_iters"]}
+        gp0.close()
     qx = {"bytes": qx_bytes, "warm_us": qx_us_warm, "warm_gbs": qx_bytes / qx_us_warm / 1e3,
           "cold_l2_us": qx_us_cold, "cold_l2_gbs": qx_bytes / qx_us_cold / 1e3,
           "cold_l2_frac_of_peak": qx_bytes / qx_us_cold / 1e3 / peak,
@@ -300,15 +336,18 @@ def bench_single(args):
         "dtype": "f64", "data": "sphere2500.g2o (fixture parsed from the reference's data file)",
         "config": {"workload": "sphere2500 1 agent r=5 RTR(3 outer, <=50 tCG) from lifted chordal init",
                    "n": n, "d": d, "r": r, "solver": "fused persistent kernel" if args.fused else "one launch per op",
-                   "l2": "inputs larger than L2 (dense preconditioner 800 MB streamed every apply)",
+                   "l2": "flushed between timed steps (256 MB device write outside the per-step CUDA-event pairs)",
+                   "preconditioner": {0: "full dense inverse", 1: "symmetric half storage",
+                                      2: "two-level (nested dissection + Schur complement)"}[mode],
                    "outer_iters": res["outer_iters"], "tcg_iters": res["inner_iters"],
                    "qx_per_step": nq / K, "precon_per_step": npc / K},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
         "gpu_launches": int(launches),
-        "fused_phase_ms": dict(zip(["cost_grad", "precon_gemv", "precon_finish", "hessvec", "tcg_update",
-                                    "tcg_direction", "retract_copy", "unused"], res.get("phase_ms", []))),
+        "fused_phase_ms": dict(zip(["cost_grad", "precon_stream", "precon_finish", "hessvec", "tcg_update",
+                                    "tcg_direction", "retract_copy", "unused", "dd_interior_y", "dd_sep_rhs",
+                                    "dd_schur", "dd_back_rhs", "dd_interior_w"], res.get("phase_ms", []))),
         "grid_barriers_per_step": res.get("n_barriers", 0),
         "roofline": roofline, "qx": qx,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
@@ -339,6 +378,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--precon-mode", type=int, default=None,
+                    help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level "
+                         "(default: the library's choice by size)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--team-steps", type=int, default=10,
                     help="colour rounds of the grid3D/8-agent series appended to the N=1 line (0 = skip)")

@@ -30,7 +30,7 @@ class RoptResult(C.Structure):
                 ("elapsed_ms", C.c_double), ("outer_iters", C.c_int32), ("inner_iters", C.c_int32),
                 ("accepted", C.c_int32), ("rejected", C.c_int32), ("n_qx", C.c_int64),
                 ("n_precon", C.c_int64), ("n_pose_sweeps", C.c_int64), ("n_launches", C.c_int64),
-                ("phase_ms", C.c_double * 8), ("n_barriers", C.c_int64)]
+                ("phase_ms", C.c_double * 16), ("n_barriers", C.c_int64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,6 +58,8 @@ SIGNATURES = {
     "dpgo_set_priors": (C.c_int, [H, C.c_int, _ip, _dp, C.c_double, C.c_double]),
     "dpgo_finalize": (C.c_int, [H, C.c_int]),
     "dpgo_set_precon_mode": (C.c_int, [H, C.c_int]),
+    "dpgo_get_precon_mode": (C.c_int, [H, C.POINTER(C.c_int)]),
+    "dpgo_set_precon_tuning": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
     "dpgo_update_weights": (C.c_int, [H, _dp, _dp, C.c_int]),
     "dpgo_get_Q_bsr": (C.c_int, [H, C.POINTER(C.c_int), _ip, _ip, _dp]),
     "dpgo_set_G": (C.c_int, [H, _dp]),

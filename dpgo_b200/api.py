@@ -93,8 +93,17 @@ class DeviceProblem:
         check(lib.dpgo_set_priors(self._h, len(idx), _i(idx), _d(tiles), prior_kappa, prior_tau))
 
     def set_precon_mode(self, mode):
-        """0 = full dense inverse (default), 1 = symmetric half storage."""
+        """-1 = by size (default), 0 = full dense inverse, 1 = symmetric half storage,
+        2 = two-level (nested-dissection domains + separator Schur complement)."""
         check(lib.dpgo_set_precon_mode(self._h, int(mode)))
+
+    def precon_mode(self):
+        v = C.c_int()
+        check(lib.dpgo_get_precon_mode(self._h, C.byref(v)))
+        return v.value
+
+    def set_precon_tuning(self, split_interior=0, split_schur=0, prefetch=-1):
+        check(lib.dpgo_set_precon_tuning(self._h, int(split_interior), int(split_schur), int(prefetch)))
 
     def finalize(self, build_precon=True):
         check(lib.dpgo_finalize(self._h, 1 if build_precon else 0))
@@ -280,12 +289,14 @@ class DeviceProblem:
 
 
 def problem_from_measurements(p1, p2, R, t, kappa, tau, n, d, r, device=0, stream=None,
-                              build_precon=True, weight=None, precon_mode=None):
+                              build_precon=True, weight=None, precon_mode=None, precon_tuning=None):
     """Single-robot problem (all edges private), as examples/MultiRobotExample.cpp:61-63 builds
     `problemCentral`."""
     prob = DeviceProblem(n, d, r, device, stream)
     prob.set_private_edges(p1, p2, R, t, kappa, tau, weight)
     if precon_mode is not None:
         prob.set_precon_mode(precon_mode)
+    if precon_tuning is not None:
+        prob.set_precon_tuning(*precon_tuning)
     prob.finalize(build_precon)
     return prob

@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libdpgo_b200.so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
-CU_SOURCES = ["device_lib.cu", "fused_rtr.cu"]
+CU_SOURCES = ["device_lib.cu", "fused_rtr.cu", "precon_dd.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-cudart", "shared", "-diag-suppress", "177"]
 

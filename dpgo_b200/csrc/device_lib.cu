@@ -404,6 +404,8 @@ static int read_scalars(dpgo_dev *h, int nblocks, int K, double *out) {
   return DPGO_OK;
 }
 
+int read_partials(dpgo_dev *h, int nblocks, int K, double *out) { return read_scalars(h, nblocks, K, out); }
+
 // --- op launchers (device pointers) ---
 int op_qx(dpgo_dev *h, const BsrView &Q, const double *X, const double *G, double *out) {
   const int grid = pose_grid(h, h->d + 1);
@@ -449,6 +451,7 @@ int op_precon(dpgo_dev *h, const double *Y, const double *rvec, double *z, doubl
     set_error("preconditioner not built (dpgo_finalize(h, 1))");
     return DPGO_ESTATE;
   }
+  if (h->precon_mode == 2) return op_precon_dd(h, Y, rvec, z, neg_out, z_r);
   int g2;
   if (h->precon_mode == 1) {
     DPGO_TRY(launch_symv(h, rvec));
@@ -812,7 +815,18 @@ static int build_cross_host(dpgo_dev *h) {
   return DPGO_OK;
 }
 
+// Measured on B200 (profiles/r01_summary.md): one two-level apply costs ~45 us of fixed phase /
+// barrier overhead plus ~19 MB of traffic, one full dense apply costs N^2*8 bytes at L2/HBM speed;
+// the two meet near N = 6000 scalars.
+static const int kAutoTwoLevelMinN = 6000;
+
 static int build_precon(dpgo_dev *h) {
+  h->precon_mode = (h->precon_request >= 0) ? h->precon_request : (h->N >= kAutoTwoLevelMinN ? 2 : 0);
+  if (h->precon_mode == 2) {   // two-level exact preconditioner (precon_dd.cu)
+    DPGO_TRY(dd_build(h));
+    h->has_precon = true;
+    return DPGO_OK;
+  }
   const int N = h->N, ld = h->ld;
   // scratch: dense P = Q + 0.1 I, column-major N x N (leading dimension ld)
   double *A = nullptr;
@@ -1032,6 +1046,7 @@ int dpgo_destroy(dpgo_handle h) {
   if (!h) return DPGO_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  dd_free(h);
   void *ptrs[] = {h->d_rowptr, h->d_colidx, h->d_browidx, h->d_blocks, h->d_crowptr, h->d_ccolidx,
                   h->d_cblocks, h->d_Gconst, h->d_G, h->d_nbr, h->d_Pinv, h->d_zpart, h->d_slot[0],
                   h->d_slot[1], h->d_slot[2], h->d_slot[3], h->d_xa, h->d_xb, h->d_EG, h->d_EG2,
@@ -1119,11 +1134,28 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
 
 int dpgo_set_precon_mode(dpgo_handle h, int mode) {
   CHECK_ARG(h != nullptr);
-  CHECK_ARG(mode == 0 || mode == 1);
-  if (mode != h->precon_mode) {
-    h->precon_mode = mode;
+  CHECK_ARG(mode >= -1 && mode <= 2);
+  if (mode != h->precon_request) {
+    h->precon_request = mode;
     h->has_precon = false;
   }
+  return DPGO_OK;
+}
+
+int dpgo_get_precon_mode(dpgo_handle h, int *mode) {
+  CHECK_ARG(h != nullptr && mode != nullptr);
+  if (!h->has_precon) { set_error("preconditioner not built"); return DPGO_ESTATE; }
+  *mode = h->precon_mode;
+  return DPGO_OK;
+}
+
+int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, int prefetch) {
+  CHECK_ARG(h != nullptr);
+  CHECK_ARG(split_interior <= 16 && split_schur <= 64);
+  h->dd_split1 = split_interior > 0 ? split_interior : 0;
+  h->dd_split3 = split_schur > 0 ? split_schur : 0;
+  h->dd_prefetch = (prefetch < 0) ? 1 : (prefetch ? 1 : 0);
+  h->has_precon = false;
   return DPGO_OK;
 }
 
@@ -1480,6 +1512,8 @@ int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec) {
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
   H_CHECK(h); NEED_FINAL(h);
   if (!h->has_precon) { set_error("preconditioner not built"); return DPGO_ESTATE; }
+  if (h->precon_mode == 2)
+    return time_launches(h, reps, flush_l2, [&]() { return dd_time_apply(h, h->d_slot[0]); }, usec);
   if (h->precon_mode == 1)
     return time_launches(h, reps, flush_l2, [&]() { return launch_symv(h, h->d_slot[0]); }, usec);
   return time_launches(h, reps, flush_l2, [&]() {
@@ -1504,6 +1538,10 @@ int dpgo_bytes_precon(dpgo_handle h, double *bytes) {
   CHECK_ARG(h && bytes);
   // dense inverse read once (all of it, or its lower triangle incl. diagonal when the symmetric
   // half-storage variant is active) + vector read + result written
+  if (h->precon_mode == 2) {
+    *bytes = dd_bytes(h);
+    return DPGO_OK;
+  }
   const double N = (double)h->N;
   const double mat = (h->precon_mode == 1) ? N * (N + 1) / 2 * 8 : N * N * 8;
   *bytes = mat + 2.0 * h->r * N * 8;

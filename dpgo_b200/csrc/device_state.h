@@ -22,6 +22,18 @@ void set_error(const char *fmt, ...);
 
 }  // namespace dpgo
 
+struct dpgo_dev;
+namespace dpgo {
+// device_lib.cu
+int read_partials(dpgo_dev *h, int nblocks, int K, double *out);
+// precon_dd.cu: two-level (domain decomposition) exact preconditioner, precon_mode == 2
+int dd_build(dpgo_dev *h);
+void dd_free(dpgo_dev *h);
+int op_precon_dd(dpgo_dev *h, const double *Y, const double *rvec, double *z, double *neg_out, double *z_r);
+int dd_time_apply(dpgo_dev *h, const double *vec);   // the streaming phases only (no finish)
+double dd_bytes(const dpgo_dev *h);
+}  // namespace dpgo
+
 struct dpgo_dev {
   int device = 0, n = 0, d = 0, r = 0;
   int N = 0;       // (d+1) n
@@ -57,7 +69,10 @@ struct dpgo_dev {
   int KT = 0, nsplit = 0;
   // symmetric half-storage variant (precon_mode == 1): T blocks of 128, NG groups of kSymS
   // blocks, work items (ig >= kg), partial buffers zD (in d_zpart) and zT
-  int precon_mode = 0;   // measured on B200 (round 1): the full variant is faster inside the fused solver
+  // precon_mode is the RESOLVED storage variant (0 full dense inverse, 1 symmetric half, 2 two-level);
+  // precon_request is what the caller asked for (-1 = choose by size at build time)
+  int precon_mode = 0;
+  int precon_request = -1;
   int symT = 0, symNG = 0, sym_nitems = 0;
   void *d_sym_items = nullptr;
   double *d_zT = nullptr;
@@ -78,6 +93,9 @@ struct dpgo_dev {
   double *h_scalars = nullptr;  // pinned
   void *d_fused = nullptr;      // fused-kernel parameter / result block
   void *h_fused = nullptr;      // pinned mirror
+  void *dd = nullptr;           // dpgo::DdState (precon_mode == 2)
+  int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
+  int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
   int *d_public_idx = nullptr;
   int num_public = 0;
   double *d_flush = nullptr;

@@ -22,11 +22,13 @@ namespace cg = cooperative_groups;
 
 namespace dpgo {
 
+DdView dd_view(const dpgo_dev *h);  // precon_dd.cu
+
 struct FusedOut {
   double f_init, gn_init, f_opt, gn_opt;
   int outer, inner, accepted, rejected, tcg_status, returned_initial;
   long long n_qx, n_precon, n_sweeps, n_barriers;
-  double phase_ms[8];
+  double phase_ms[16];
 };
 
 struct FusedParams {
@@ -39,6 +41,7 @@ struct FusedParams {
   int precon_mode, symT, symNG, nitems;   // symmetric half-storage variant
   const SymItem *items;
   double *zT;
+  DdView dd;                              // two-level variant (precon_mode == 2)
   const double *x_in;
   double *x_out;
   double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
@@ -57,20 +60,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // per-phase device time seen by CTA 0 (phase body + the barrier that ends it); the accumulators
 // live in shared memory so that they do not occupy registers across the phases
 struct PhaseClock {
-  unsigned long long *acc;  // [9] in shared memory: 8 phase sums + last timestamp
+  unsigned long long *acc;  // [17] in shared memory: 16 phase sums + last timestamp
   __device__ __forceinline__ void start(unsigned long long *smem) {
     acc = smem;
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0;
-      acc[8] = gtimer();
+      for (int i = 0; i < 16; ++i) acc[i] = 0;
+      acc[16] = gtimer();
     }
   }
   __device__ __forceinline__ void lap(int id) {
     if (threadIdx.x == 0) {
       const unsigned long long t = gtimer();
-      acc[id] += t - acc[8];
-      acc[8] = t;
+      acc[id] += t - acc[16];
+      acc[16] = t;
     }
   }
 };
@@ -94,13 +97,13 @@ struct GridReducer {
   }
 };
 
-template <int R, int D, bool SYM>
-__global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
+template <int R, int D, int MODE>
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::grid_group grid = cg::this_grid();
   const Ctx ctx = make_ctx();
   const int n = p.n;
-  GemvPipe pipe = gemv_pipe_init(dsm);
+  GemvPipe pipe = gemv_pipe_init<MODE == 2 ? kDdStages : kStages>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
   GridReducer red;
   red.buf[0] = p.partials;
@@ -112,15 +115,43 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
   double *S = p.S, *S2 = p.S2;
   int n_qx = 0, n_precon = 0, n_sweeps = 0;
 
-  // the two storage variants of the dense inverse (uniform branch)
+  __shared__ unsigned long long s_clk[17];
+  PhaseClock clk;
+  // the three variants of the exact preconditioner (compile-time: one per kernel instantiation)
   auto precon_stream = [&](const double *v) {
-    if constexpr (SYM)
+    if constexpr (MODE == 2) {
+      const DdView &dd = p.dd;
+      const size_t zs = (size_t)dd.pcols * R;
+      const bool pf = dd.prefetch != 0;
+      constexpr int ST = kDdStages;
+      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, v, dd.icol, dd.y, zs);
+      if (dd.nS > 0) {
+        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V);
+        red.barrier(grid);
+        clk.lap(8);
+        phase_dd_sep_rhs<R, D>(ctx, dd, v);
+        red.barrier(grid);
+        clk.lap(9);
+        phase_strip_gemv<R, ST>(pipe, dd.P3, dd.V, dd.t, nullptr, dd.zs, zs, pf);
+        if (pf) strip_prefetch<ST>(pipe, dd.P1, dd.V);
+        red.barrier(grid);
+        clk.lap(10);
+        phase_dd_back_rhs<R, D>(ctx, dd);
+        red.barrier(grid);
+        clk.lap(11);
+        phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, dd.u, nullptr, dd.w, zs, pf);
+      }
+      // no separator (a single domain): z = y, w stays zero
+    } else if constexpr (MODE == 1) {
       phase_precon_symv<R>(pipe, p.Pinv, p.symT, p.items, p.nitems, v, p.zpart, p.zT, p.zstride);
-    else
+    } else {
       phase_precon_gemv<R>(pipe, p.Pinv, p.ld, v, p.zpart, p.zstride, p.KT, p.nsplit);
+    }
   };
   auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
-    if constexpr (SYM)
+    if constexpr (MODE == 2)
+      phase_dd_finish<R, D>(ctx, p.dd, Ycur, rvec, p.z, neg_out, n, a1);
+    else if constexpr (MODE == 1)
       phase_precon_finish_sym<R, D>(pipe.scratch, p.zpart, p.zT, p.zstride, p.symNG, Ycur, rvec, p.z,
                                     neg_out, n, a1);
     else
@@ -128,8 +159,6 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
   };
 
   // ---- statistics at the initial point (fInit, gradNormInit) = first f / Grad of the solver
-  __shared__ unsigned long long s_clk[9];
-  PhaseClock clk;
   clk.start(s_clk);
   phase_copy(ctx, p.x_in, x1, len);
   red.barrier(grid);
@@ -170,7 +199,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
         phase_zero(ctx, p.eta, len);
       }
       red.barrier(grid);
-      clk.lap(1);
+      clk.lap(MODE == 2 ? 12 : 1);
       {
         double acc[1] = {0.0}, sc[1];
         precon_finish(x1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
@@ -269,18 +298,23 @@ __global__ void __launch_bounds__(kBlock, 2) k_rtr_fused(FusedParams p) {
     o.tcg_status = last_status; o.returned_initial = returned_initial;
     o.n_qx = n_qx; o.n_precon = n_precon; o.n_sweeps = n_sweeps; o.n_barriers = red.barriers;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o.phase_ms[i] = (double)clk.acc[i] * 1e-6;
+    for (int i = 0; i < 16; ++i) o.phase_ms[i] = (double)clk.acc[i] * 1e-6;
+    if (MODE == 2) {
+#pragma unroll
+      for (int i = 8; i <= 12; ++i) o.phase_ms[1] += o.phase_ms[i];
+    }
     *p.out = o;
   }
 }
 
-template <int R, int D, bool SYM>
+template <int R, int D, int MODE>
 static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
+  constexpr int smem = (MODE == 2) ? kDdDynSmem : kGemvDynSmem;
   static int occ_cache = -1;
   if (occ_cache < 0) {
     int occ = 0;
-    if (cudaFuncSetAttribute(k_rtr_fused<R, D, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvDynSmem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D, SYM>, kBlock, kGemvDynSmem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_rtr_fused<R, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D, MODE>, kBlock, smem) != cudaSuccess ||
         occ < 1) {
       set_error("fused kernel does not fit on the device");
       return DPGO_ECUDA;
@@ -289,7 +323,9 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
   }
   const long cap = (long)h->num_sms * occ_cache;
   // enough CTAs for the widest phase, never more than can be co-resident
-  const long tiles = (h->precon_mode == 1) ? (long)h->sym_nitems : (long)(h->ld / kGemvCols) * h->nsplit;
+  long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
+  if (h->precon_mode == 1) tiles = h->sym_nitems;
+  if (h->precon_mode == 2) tiles = fp.dd.V;
   const int gpw = 32 / (h->d + 1);
   const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long grid = std::max(tiles, pose_blocks);
@@ -299,8 +335,8 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
     return DPGO_EINVAL;
   }
   void *args[] = {&fp};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_rtr_fused<R, D, SYM>, dim3((unsigned)grid), dim3(kBlock),
-                                              args, kGemvDynSmem, h->stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_rtr_fused<R, D, MODE>, dim3((unsigned)grid), dim3(kBlock),
+                                              args, smem, h->stream);
   if (e != cudaSuccess) {
     set_error("cudaLaunchCooperativeKernel failed: %s", cudaGetErrorString(e));
     return DPGO_ECUDA;
@@ -311,7 +347,9 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
 
 template <int R, int D>
 static int launch_fused(dpgo_dev *h, FusedParams &fp) {
-  return (h->precon_mode == 1) ? launch_fused_v<R, D, true>(h, fp) : launch_fused_v<R, D, false>(h, fp);
+  if (h->precon_mode == 2) return launch_fused_v<R, D, 2>(h, fp);
+  if (h->precon_mode == 1) return launch_fused_v<R, D, 1>(h, fp);
+  return launch_fused_v<R, D, 0>(h, fp);
 }
 
 int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
@@ -332,6 +370,7 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
   fp.zstride = h->vpad;
   fp.precon_mode = h->precon_mode; fp.symT = h->symT; fp.symNG = h->symNG; fp.nitems = h->sym_nitems;
   fp.items = (const SymItem *)h->d_sym_items; fp.zT = h->d_zT;
+  if (h->precon_mode == 2) fp.dd = dd_view(h); else memset(&fp.dd, 0, sizeof(fp.dd));
   fp.x_in = x_in; fp.x_out = x_out;
   fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;
   fp.grad = h->d_grad; fp.grad2 = h->d_grad2; fp.S = h->d_S; fp.S2 = h->d_S2;
@@ -369,7 +408,7 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
   res->accepted = o.accepted; res->rejected = o.rejected;
   res->n_qx = o.n_qx; res->n_precon = o.n_precon; res->n_pose_sweeps = o.n_sweeps;
   res->n_barriers = o.n_barriers;
-  for (int i = 0; i < 8; ++i) res->phase_ms[i] = o.phase_ms[i];
+  for (int i = 0; i < 16; ++i) res->phase_ms[i] = o.phase_ms[i];
   if (P->verbose)
     printf("[dpgo_b200] fused RTR: f %.10g -> %.10g, |g| %.4g -> %.4g, %d outer, %d tCG, %lld barriers\n",
            o.f_init, o.f_opt, o.gn_init, o.gn_opt, o.outer, o.inner, o.n_barriers);

@@ -398,26 +398,28 @@ constexpr int kGemvDynSmem =
     kStages * kStageDoubles * 8 + kStages * 8 + kStages * kStageK * kGemvMaxR * 8 + kGemvScratch;
 
 struct GemvPipe {
-  double *stage;      // [kStages][kStageK][kGemvCols]
-  double *svec;       // [kStages][kStageK * R] slice of the input array that goes with a stage
+  double *stage;      // [STAGES][kStageK][kGemvCols]
+  double *svec;       // [STAGES][kStageK * R] slice of the input array that goes with a stage
   double *scratch;    // kGemvScratch bytes
   uint32_t bar;       // shared address of the first mbarrier
   uint32_t slot;      // ring slot of the next chunk to consume (persists across phases)
   uint32_t parity;    // mbarrier phase parity of that slot
 };
 
-// one-time set-up of the pipeline barriers (all threads of the CTA must call)
+// one-time set-up of the pipeline barriers (all threads of the CTA must call); STAGES = ring depth
+// (kStages for the HBM-bound dense variants, kDdStages for the L2-resident two-level variant)
+template <int STAGES = kStages>
 __device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
   GemvPipe pp;
   pp.stage = reinterpret_cast<double *>(dsm);
-  pp.bar = smem_u32(dsm + (size_t)kStages * kStageDoubles * 8);
-  pp.svec = reinterpret_cast<double *>(dsm + (size_t)kStages * kStageDoubles * 8 + kStages * 8);
-  pp.scratch = pp.svec + kStages * kStageK * kGemvMaxR;
+  pp.bar = smem_u32(dsm + (size_t)STAGES * kStageDoubles * 8);
+  pp.svec = reinterpret_cast<double *>(dsm + (size_t)STAGES * kStageDoubles * 8 + STAGES * 8);
+  pp.scratch = pp.svec + STAGES * kStageK * kGemvMaxR;
   pp.slot = 0;
   pp.parity = 0;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(pp.bar + 8 * s, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(pp.bar + 8 * s, 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -777,6 +779,327 @@ __device__ __forceinline__ void phase_precon_finish_sym(double *scratch, const d
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- two-level (domain decomposition) exact preconditioner ---------------------------------------
+// Nested dissection of the pose graph gives interior domains D_1..D_K (no edges between them) and a
+// separator S.  With A = Q + 0.1 I permuted to [D_1 .. D_K | S]:
+//     A^-1 r :   y_I = A_II^-1 r_I ;  t = r_S - A_SI y_I ;  z_S = Sigma^-1 t ;  z_I = y_I - A_II^-1 (A_IS z_S)
+// where A_II^-1 = blockdiag(A_k^-1) and Sigma = A_SS - A_SI A_II^-1 A_IS are stored as dense inverses
+// (exact block elimination: same operator as the full dense inverse up to rounding, ~14x fewer
+// bytes on sphere2500 and L2-resident).  All work arrays live in the permuted, 64-padded scalar
+// column space; a dense block is streamed as "strips" (64 output columns x a range of 32-index
+// chunks, stage-major like the full variant).
+// The two-level kernels run ONE CTA per SM with a deep ring: the dense blocks are L2 resident, so a
+// strip phase is bound by the latency of a bulk copy, not by bandwidth -- a whole strip (<= 12
+// stages) is put in flight at once.
+constexpr int kDdStages = 10;
+constexpr int kDdScratch = kWarpsPerBlock * kGemvMaxR * kGemvCols * 8;
+constexpr int kDdDynSmem =
+    kDdStages * kStageDoubles * 8 + kDdStages * 8 + kDdStages * kStageK * kGemvMaxR * 8 + kDdScratch;
+static_assert(kDdDynSmem <= 227 * 1024, "two-level pipeline does not fit in shared memory");
+
+struct DdStrip {
+  int cb, kc0, nchunks, slot;   // output column block, first inner chunk, #chunks, partial slot
+  long long data_off;           // first stage of the strip in the matrix buffer (units of stages)
+};
+
+// strips of one phase, grouped by "virtual CTA" (balanced on the host, longest strip first):
+// virtual CTA v owns strips[cta[v] .. cta[v+1]) = chunks[v] pipeline stages
+struct DdStripSet {
+  const double *M;
+  const DdStrip *strips;
+  const int *cta;      // [V + 1]
+  const int *chunks;   // [V]
+};
+
+struct DdView {
+  DdStripSet P1;                // blockdiag(A_k^-1)  (nsplit1 partial slots)
+  DdStripSet P3;                // Sigma^-1           (nsplit3 partial slots)
+  int V;                        // virtual CTAs (= SMs of the device the plan was built for)
+  int nsplit1, nsplit3;
+  BsrView A_SI;                 // rows: separator poses; colidx: permuted scalar column of the interior pose
+  BsrView A_BS;                 // rows: interior poses WITH a separator neighbour; colidx: permuted column of it
+  int nS, nB;
+  const int *pcol;              // [n]  permuted scalar column of pose i (tile start)
+  const int *srow;              // [nS] original pose id of separator row s (its permuted column is sep_col0 + s*(d+1))
+  const int *bcol;              // [nB] permuted scalar column of boundary row b
+  const int *icol;              // [pcols] original scalar column of a permuted column (-1: padding)
+  int sep_col0, pcols;          // first separator column; padded column count
+  double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
+                                // nsplit3 partial slots; u is zero outside the boundary rows)
+  int prefetch;                 // issue the first matrix stages of P3 / P5 before the preceding barrier
+};
+
+struct StripCursor {
+  int v, si, end, c;
+  DdStrip d;
+};
+
+// position the cursor on the first strip of virtual CTA v0 or of the next non-empty one this CTA owns
+__device__ __forceinline__ void strip_cursor_seek(StripCursor &cu, const DdStripSet &S, int V) {
+  while (cu.v < V && cu.si >= cu.end) {
+    cu.v += gridDim.x;
+    if (cu.v < V) {
+      cu.si = __ldg(S.cta + cu.v);
+      cu.end = __ldg(S.cta + cu.v + 1);
+    }
+  }
+  cu.c = 0;
+  if (cu.v < V) cu.d = S.strips[cu.si];
+}
+__device__ __forceinline__ void strip_cursor_init(StripCursor &cu, const DdStripSet &S, int V) {
+  cu.v = blockIdx.x;
+  cu.si = cu.end = 0;
+  if (cu.v < V) {
+    cu.si = __ldg(S.cta + cu.v);
+    cu.end = __ldg(S.cta + cu.v + 1);
+  }
+  strip_cursor_seek(cu, S, V);
+}
+__device__ __forceinline__ void strip_cursor_next(StripCursor &cu, const DdStripSet &S, int V) {
+  if (++cu.c == cu.d.nchunks) {
+    ++cu.si;
+    strip_cursor_seek(cu, S, V);
+  }
+}
+
+// Issue the TMA copies of this CTA's first min(STAGES, G) matrix stages of a strip phase.  The
+// matrix does not depend on the phases before it, so this is called BEFORE the grid barrier that
+// makes the input array visible; phase_strip_gemv(..., prefetched = true) then only stages the
+// matching slices of the input.  Precondition: every stage of the ring has been consumed.
+template <int STAGES>
+__device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStripSet &S, int V) {
+  if (threadIdx.x != 0) return;
+  const uint32_t stage0 = smem_u32(pp.stage);
+  StripCursor cu;
+  strip_cursor_init(cu, S, V);
+  uint32_t slot = pp.slot;
+  for (int issued = 0; issued < STAGES && cu.v < V; ++issued) {
+    const uint32_t bar = pp.bar + 8 * slot;
+    mbar_expect_tx(bar, kStageDoubles * 8);
+    bulk_g2s(stage0 + slot * (kStageDoubles * 8), S.M + (size_t)(cu.d.data_off + cu.c) * kStageDoubles,
+             kStageDoubles * 8, bar);
+    strip_cursor_next(cu, S, V);
+    slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+  }
+}
+
+// out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
+template <int R, int STAGES>
+__device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const double *vec,
+                                                 const int *icol, double *out, size_t outstride,
+                                                 bool prefetched = false) {
+  // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while the
+  // slice that goes with a stage is staged (saves a separate permutation pass + grid barrier)
+  double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int G = 0;
+  for (int v = blockIdx.x; v < V; v += gridDim.x) G += __ldg(S.chunks + v);
+  if (G == 0) return;
+  const uint32_t stage0 = smem_u32(pp.stage);
+  auto produce = [&](const StripCursor &cu, uint32_t slot, bool matrix) {
+    if (matrix && threadIdx.x == 0) {
+      const uint32_t bar = pp.bar + 8 * slot;
+      mbar_expect_tx(bar, kStageDoubles * 8);
+      bulk_g2s(stage0 + slot * (kStageDoubles * 8), S.M + (size_t)(cu.d.data_off + cu.c) * kStageDoubles,
+               kStageDoubles * 8, bar);
+    }
+    if (threadIdx.x < kStageK * R) {
+      double val;
+      if (icol) {
+        const int oc = __ldg(icol + (cu.d.kc0 + cu.c) * kStageK + threadIdx.x / R);
+        val = (oc >= 0) ? vec[(size_t)oc * R + threadIdx.x % R] : 0.0;
+      } else {
+        val = vec[(size_t)(cu.d.kc0 + cu.c) * (kStageK * R) + threadIdx.x];
+      }
+      pp.svec[slot * (kStageK * R) + threadIdx.x] = val;
+    }
+  };
+  StripCursor ci, cc;
+  strip_cursor_init(ci, S, V);
+  cc = ci;
+  uint32_t slot_i = pp.slot;
+  int issued = 0;
+  for (; issued < STAGES && issued < G; ++issued) {
+    produce(ci, slot_i, !prefetched);
+    strip_cursor_next(ci, S, V);
+    slot_i = (slot_i + 1 == STAGES) ? 0 : slot_i + 1;
+  }
+  __syncthreads();
+  double a0[R], a1[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
+  for (int g = 0; g < G; ++g) {
+    const uint32_t slot = pp.slot;
+    mbar_wait(pp.bar + 8 * slot, pp.parity);
+    const double *st = pp.stage + (size_t)slot * kStageDoubles;
+    const double *sv = pp.svec + slot * (kStageK * R);
+#pragma unroll
+    for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
+      const int kk = w + u * kWarpsPerBlock;
+      const double2 pv = *reinterpret_cast<const double2 *>(st + kk * kGemvCols + 2 * lane);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double x = sv[kk * R + q];
+        a0[q] = fma(pv.x, x, a0[q]);
+        a1[q] = fma(pv.y, x, a1[q]);
+      }
+    }
+    const bool strip_end = (cc.c == cc.d.nchunks - 1);
+    if (strip_end) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        sacc[w][q][2 * lane] = a0[q];
+        sacc[w][q][2 * lane + 1] = a1[q];
+        a0[q] = 0.0;
+        a1[q] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (issued < G) {
+      produce(ci, slot, true);
+      strip_cursor_next(ci, S, V);
+      ++issued;
+    }
+    if (strip_end) {
+      for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+        const int q = o / kGemvCols, jj = o % kGemvCols;
+        double x = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+        out[(size_t)cc.d.slot * outstride + ((size_t)cc.d.cb * kGemvCols + jj) * R + q] = x;
+      }
+      __syncthreads();
+    }
+    strip_cursor_next(cc, S, V);
+    if (pp.slot + 1 == STAGES) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
+  }
+}
+
+// One warp per block row of a sparse coupling matrix: lane = (el, c) handles the blocks
+// e0 + el, e0 + el + 8, ... of the row and column c of the pose tile, so the dependent loads
+// (colidx -> tile of X) of up to 8 blocks are in flight together; the 8 partial sums are combined
+// by a fixed shuffle tree.  Returns (lanes c < d+1) column c of sum_e X[col_e] * B_e^T, where the
+// tile of block e starts at scalar column colidx[e] of the permuted array X = sum of `nsum` arrays
+// `xstride` apart.
+template <int R, int D>
+__device__ __forceinline__ void dd_row_product(const BsrView &B, const double *X, int nsum, size_t xstride,
+                                               int row, int lane, double (&acc)[R]) {
+  constexpr int DH = D + 1, TILE = R * DH, EL = 8;
+  static_assert(EL * DH <= 32, "lane layout");
+  const int el = lane / DH, c = lane - el * DH;
+  const bool active = lane < EL * DH;
+  const int e0 = __ldg(B.rowptr + row), e1 = __ldg(B.rowptr + row + 1);
+#pragma unroll
+  for (int q = 0; q < R; ++q) acc[q] = 0.0;
+  for (int eb = e0; eb < e1; eb += EL) {
+    const int e = eb + el;
+    if (active && e < e1) {
+      const double *xj = X + (size_t)__ldg(B.colidx + e) * R;
+      const double *m = B.blocks + (size_t)e * (DH * DH) + c * DH;
+      double x[TILE];
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) x[k] = xj[k];
+#pragma unroll 2
+      for (int s = 1; s < nsum; ++s) {
+        const double *xs = xj + (size_t)s * xstride;
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) x[k] += xs[k];
+      }
+#pragma unroll
+      for (int k = 0; k < DH; ++k) {
+        const double mk = __ldg(m + k);
+#pragma unroll
+        for (int q = 0; q < R; ++q) acc[q] = fma(x[k * R + q], mk, acc[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int delta = 4 * DH; delta >= DH; delta >>= 1) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], delta);
+  }
+}
+
+// P2:  t_S = r_S - A_SI y_I   (r in the original column order, y = sum of its partial slots)
+template <int R, int D>
+__device__ __forceinline__ void phase_dd_sep_rhs(const Ctx &ctx, const DdView &dd, const double *rvec) {
+  constexpr int DH = D + 1;
+  const size_t zstride = (size_t)dd.pcols * R;
+  for (int s = ctx.warp; s < dd.nS; s += ctx.nwarps) {
+    double acc[R];
+    dd_row_product<R, D>(dd.A_SI, dd.y, dd.nsplit1, zstride, s, ctx.lane, acc);
+    if (ctx.lane < DH) {
+      const size_t off = ((size_t)dd.sep_col0 + (size_t)s * DH + ctx.lane) * R;
+      const size_t ooff = ((size_t)__ldg(dd.srow + s) * DH + ctx.lane) * R;
+#pragma unroll
+      for (int q = 0; q < R; ++q) dd.t[off + q] = rvec[ooff + q] - acc[q];
+    }
+  }
+}
+
+// P4:  u_B = A_BS z_S  with z_S = sum of the nsplit3 partial results of the Schur GEMV (u stays
+// zero at interior poses without a separator neighbour)
+template <int R, int D>
+__device__ __forceinline__ void phase_dd_back_rhs(const Ctx &ctx, const DdView &dd) {
+  constexpr int DH = D + 1;
+  const size_t zstride = (size_t)dd.pcols * R;
+  for (int b = ctx.warp; b < dd.nB; b += ctx.nwarps) {
+    double acc[R];
+    dd_row_product<R, D>(dd.A_BS, dd.zs, dd.nsplit3, zstride, b, ctx.lane, acc);
+    if (ctx.lane < DH) {
+      const size_t off = ((size_t)__ldg(dd.bcol + b) + ctx.lane) * R;
+#pragma unroll
+      for (int q = 0; q < R; ++q) dd.u[off + q] = acc[q];
+    }
+  }
+}
+
+// finish:  z = Proj_Y( unpermute( interior: y - w ; separator: sum of zs partials ) ); acc = {<z, rvec>}
+template <int R, int D>
+__device__ __forceinline__ void phase_dd_finish(const Ctx &ctx, const DdView &dd, const double *Y,
+                                                const double *rvec, double *z, double *neg_out, int n,
+                                                double (&acc)[1]) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  const size_t zstride = (size_t)dd.pcols * R;
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double wv[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) wv[q] = 0.0;
+    if (valid) {
+      const int pc0 = dd.pcol[i];
+      const size_t poff = ((size_t)pc0 + lp.c) * R;
+      if (pc0 >= dd.sep_col0) {
+        for (int s = 0; s < dd.nsplit3; ++s) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) wv[q] += dd.zs[(size_t)s * zstride + poff + q];
+        }
+      } else {
+        for (int s = 0; s < dd.nsplit1; ++s) {
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+            wv[q] += dd.y[(size_t)s * zstride + poff + q] - dd.w[(size_t)s * zstride + poff + q];
+        }
+      }
+    }
+    double sym[D];
+    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), wv, lp, valid, sym);
+    if (valid) {
+      store_col<R>(z + off, wv);
+      double rr[R];
+      load_col<R>(rvec + off, rr);
+      acc[0] += dot_col<R>(wv, rr);
+      if (neg_out) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) neg_out[off + q] = -wv[q];
+      }
+    }
   }
 }
 

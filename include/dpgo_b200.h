@@ -71,8 +71,10 @@ typedef struct dpgo_ropt_result {
   int64_t n_launches;  /* kernels launched by this call                        */
   /* fused solver only: device time (ms, CTA 0's globaltimer, barrier waits included) spent in
    * 0 cost+gradient, 1 preconditioner GEMV, 2 preconditioner finish (sum+projection),
-   * 3 Hessian-vector, 4 tCG vector update, 5 tCG direction update, 6 retraction, 7 barriers total */
-  double phase_ms[8];
+   * 3 Hessian-vector, 4 tCG vector update, 5 tCG direction update, 6 retraction / copies, 7 unused;
+   * two-level preconditioner (mode 2) only, the parts of slot 1: 8 interior strips (y), 9 separator
+   * right-hand side, 10 Schur strips, 11 back-substitution right-hand side, 12 interior strips (w) */
+  double phase_ms[16];
   int64_t n_barriers;  /* grid-wide barriers executed by the fused kernel          */
 } dpgo_ropt_result;
 
@@ -115,13 +117,27 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
  * CHOLMOD factorization, src/PoseGraph.cpp:598-613 -- both are exact solves).
  * build_precon = 0 skips the preconditioner (then only unpreconditioned ops are available). */
 int dpgo_finalize(dpgo_handle h, int build_precon);
-/* Storage of the dense inverse: 0 (default) = full matrix (N^2*8 bytes streamed per application),
- * 1 = symmetric half storage (blocks I >= K only, every streamed block is used for both
- * z_I += P_IK r_K and z_K += P_IK^T r_I: ~N^2/2*8 bytes per application, half the memory).  Same
- * result up to summation order.  On B200 the half-storage apply is FP64-issue/latency bound at
- * the same wall time as the full one, so the full variant is the default; the half variant is
- * kept for memory-limited problems.  Takes effect at the next dpgo_finalize(h, 1). */
+/* How the exact preconditioner (Q + 0.1 I)^{-1} is stored and applied.  All variants give the same
+ * operator (up to summation order); they differ in bytes streamed per application:
+ *  -1 (default) choose by size when the preconditioner is built: 2 when N = (d+1)n >= 6000, else 0;
+ *   0 full dense inverse, N^2*8 bytes per application (one streaming pass, 2 grid phases);
+ *   1 symmetric half storage (blocks I >= K only, each streamed block used for both z_I += P_IK r_K
+ *     and z_K += P_IK^T r_I): ~N^2/2*8 bytes, half the memory.  On B200 it is FP64-issue/latency
+ *     bound at the wall time of the full one, so it is kept only for memory-limited problems;
+ *   2 two-level: nested-dissection domains with dense interior inverses A_II^{-1} and a dense
+ *     inverse of the separator Schur complement S = A_SS - A_SI A_II^{-1} A_IS; one application is
+ *     z_S = S^{-1}(r_S - A_SI A_II^{-1} r_I), z_I = A_II^{-1}(r_I - A_IS z_S): 3 strip GEMVs and 2
+ *     sparse couplings, ~N^2*8/5 bytes on sphere2500 (L2 resident), 5 grid phases.
+ * Takes effect at the next dpgo_finalize(h, 1) / dpgo_update_weights(..., 1). */
 int dpgo_set_precon_mode(dpgo_handle h, int mode);
+/* The variant in use (0 / 1 / 2) once the preconditioner is built. */
+int dpgo_get_precon_mode(dpgo_handle h, int *mode);
+/* Tuning of the two-level variant (measurement knobs; 0 / negative = library default): how many
+ * partial slots the inner dimension of the interior strips and of the Schur strips is split into
+ * (more splits = more CTAs busy per phase, more partial sums to add), and whether the first
+ * pipeline stages of a strip phase are issued before the grid barrier that precedes it
+ * (prefetch: 1 on, 0 off, negative = default on).  Takes effect at the next preconditioner build. */
+int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, int prefetch);
 /* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
 int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,

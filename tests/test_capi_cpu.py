@@ -34,7 +34,7 @@ def test_struct_layout_matches_header():
     assert (p.RTR_iterations, p.RTR_tCG_iterations, p.RTR_initial_radius) == (3, 50, 100.0)
     assert (p.tcg_theta, p.tcg_kappa, p.accept_rho, p.shrink, p.magnify) == (1.0, 0.1, 0.1, 0.25, 2.0)
     assert C.sizeof(_lib.RoptParams) == 88
-    assert C.sizeof(_lib.RoptResult) == 168
+    assert C.sizeof(_lib.RoptResult) == 232
 
 
 def test_contract_violations_return_einval():

@@ -215,8 +215,9 @@ def test_linearity_and_symmetry_at_scale(datasets):
 
 @pytest.mark.parametrize("name,r", [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 5)])
 def test_precon_storage_variants(datasets, name, r):
-    """The dense inverse in full and in symmetric half storage (dpgo_set_precon_mode 0 / 1): the same
-    operator (1e-8 vs the oracle's exact solve, 1e-10 against each other) and the same solve."""
+    """The exact preconditioner in its three forms (dpgo_set_precon_mode 0 / 1 / 2): full dense
+    inverse, symmetric half storage, two-level block elimination over a nested dissection -- the
+    same operator (1e-8 vs the oracle's exact solve, 1e-9 against each other) and the same solve."""
     import dpgo_b200
     meas, n, z = datasets(name)
     d = meas.d
@@ -226,7 +227,7 @@ def test_precon_storage_variants(datasets, name, r):
     ref = op.precondition(X, Vt)
     X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
     outs, sols = [], []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         gp = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau,
                                                  n, d, r, precon_mode=mode)
         outs.append(gp.precon(X, Vt))
@@ -236,8 +237,40 @@ def test_precon_storage_variants(datasets, name, r):
             sols.append((Xg, res))
         gp.close()
     assert rel(outs[0], outs[1]) < 1e-10
+    assert rel(outs[0], outs[2]) < 1e-9      # two-level block elimination: same operator
     Xo, ro = pgo.optimize(op, X0)
     for Xg, res in sols:
         assert (res["outer_iters"], res["inner_iters"]) == (ro.outer, ro.inner_total)
         assert abs(res["f_opt"] - ro.fOpt) <= 1e-9 * abs(ro.fOpt)
         assert rel(Xg, Xo) < 1e-6
+
+
+@pytest.mark.parametrize("name,r", [("sphere2500", 5), ("city10000", 3)])
+def test_two_level_precon_tuning(datasets, name, r):
+    """Inner splits of the strips and the pre-barrier prefetch change neither the operator nor the
+    solve (partial sums are added in a fixed order).  sphere2500 and a 2D graph (city10000: many
+    small separators, domains of different sizes)."""
+    import dpgo_b200
+    meas, n, z = datasets(name)
+    d = meas.d
+    X, V, rng = random_state(n, d, r, 13)
+    Vt = pgo.tangent_project(X, V, d)
+    ref = oracle_problem(meas, n, r).precondition(X, Vt)
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    sols = []
+    for tuning in [(1, 1, 0), (1, 4, 1), (3, 12, 1), (4, 7, 0), (0, 0, -1)]:
+        gp = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau,
+                                                 n, d, r, precon_mode=2, precon_tuning=tuning)
+        assert rel(gp.precon(X, Vt), ref) < 1e-8, tuning
+        for fused in (1, 0):
+            prm = dpgo_b200.default_params(fused=fused)
+            prm.RTR_iterations = 1
+            prm.RTR_tCG_iterations = 15
+            sols.append(gp.optimize(X0, prm))
+        gp.close()
+    Xa, ra = sols[0]
+    assert ra["inner_iters"] > 0
+    for Xb, rb in sols[1:]:
+        assert ra["inner_iters"] == rb["inner_iters"]
+        assert abs(ra["f_opt"] - rb["f_opt"]) <= 1e-10 * abs(rb["f_opt"])
+        assert rel(Xa, Xb) < 1e-8
