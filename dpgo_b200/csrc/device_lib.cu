@@ -815,10 +815,10 @@ static int build_cross_host(dpgo_dev *h) {
   return DPGO_OK;
 }
 
-// Measured on B200 (profiles/r01_summary.md): one two-level apply costs ~45 us of fixed phase /
-// barrier overhead plus ~19 MB of traffic, one full dense apply costs N^2*8 bytes at L2/HBM speed;
-// the two meet near N = 6000 scalars.
-static const int kAutoTwoLevelMinN = 6000;
+// Measured on B200 (profiles/r01_summary.md, tools/dd_probe.py): the two-level apply has a fixed cost
+// of ~25-30 us (5 grid phases), the full dense apply streams N^2*8 bytes; inside the fused solver
+// the two-level variant is ahead from N = 4000 (1.03 -> 0.87 ms per solve) and behind at N = 500.
+static const int kAutoTwoLevelMinN = 3000;
 
 static int build_precon(dpgo_dev *h) {
   h->precon_mode = (h->precon_request >= 0) ? h->precon_request : (h->N >= kAutoTwoLevelMinN ? 2 : 0);

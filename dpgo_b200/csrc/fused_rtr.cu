@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
   cg::grid_group grid = cg::this_grid();
   const Ctx ctx = make_ctx();
   const int n = p.n;
-  GemvPipe pipe = gemv_pipe_init<MODE == 2 ? kDdStages : kStages>(dsm);
+  GemvPipe pipe = gemv_pipe_init<(MODE == 2 ? kDdStages : kStages), (MODE == 2 ? kDdVecChunks : kStages)>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
   GridReducer red;
   red.buf[0] = p.partials;
@@ -117,6 +117,11 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
 
   __shared__ unsigned long long s_clk[17];
   PhaseClock clk;
+  __shared__ StripPlanStore s_plan[MODE == 2 ? 2 : 1];   // two-level variant: this CTA's strips of P1 / P3
+  if constexpr (MODE == 2) {
+    strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
+    strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
+  }
   // the three variants of the exact preconditioner (compile-time: one per kernel instantiation)
   auto precon_stream = [&](const double *v) {
     if constexpr (MODE == 2) {
@@ -124,22 +129,22 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
       constexpr int ST = kDdStages;
-      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, v, dd.icol, dd.y, zs);
+      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs);
       if (dd.nS > 0) {
-        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V);
+        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
         red.barrier(grid);
         clk.lap(8);
         phase_dd_sep_rhs<R, D>(ctx, dd, v);
         red.barrier(grid);
         clk.lap(9);
-        phase_strip_gemv<R, ST>(pipe, dd.P3, dd.V, dd.t, nullptr, dd.zs, zs, pf);
-        if (pf) strip_prefetch<ST>(pipe, dd.P1, dd.V);
+        phase_strip_gemv<R, ST>(pipe, dd.P3, dd.V, &s_plan[1], dd.t, nullptr, dd.zs, zs, pf);
+        if (pf) strip_prefetch<ST>(pipe, dd.P1, dd.V, &s_plan[0]);
         red.barrier(grid);
         clk.lap(10);
         phase_dd_back_rhs<R, D>(ctx, dd);
         red.barrier(grid);
         clk.lap(11);
-        phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, dd.u, nullptr, dd.w, zs, pf);
+        phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.u, nullptr, dd.w, zs, pf);
       }
       // no separator (a single domain): z = y, w stays zero
     } else if constexpr (MODE == 1) {

@@ -408,13 +408,13 @@ struct GemvPipe {
 
 // one-time set-up of the pipeline barriers (all threads of the CTA must call); STAGES = ring depth
 // (kStages for the HBM-bound dense variants, kDdStages for the L2-resident two-level variant)
-template <int STAGES = kStages>
+template <int STAGES = kStages, int VCH = STAGES>
 __device__ __forceinline__ GemvPipe gemv_pipe_init(unsigned char *dsm) {
   GemvPipe pp;
   pp.stage = reinterpret_cast<double *>(dsm);
   pp.bar = smem_u32(dsm + (size_t)STAGES * kStageDoubles * 8);
   pp.svec = reinterpret_cast<double *>(dsm + (size_t)STAGES * kStageDoubles * 8 + STAGES * 8);
-  pp.scratch = pp.svec + STAGES * kStageK * kGemvMaxR;
+  pp.scratch = pp.svec + VCH * kStageK * kGemvMaxR;   // svec holds VCH chunks' worth of the input
   pp.slot = 0;
   pp.parity = 0;
   if (threadIdx.x == 0) {
@@ -795,9 +795,10 @@ __device__ __forceinline__ void phase_precon_finish_sym(double *scratch, const d
 // strip phase is bound by the latency of a bulk copy, not by bandwidth -- a whole strip (<= 12
 // stages) is put in flight at once.
 constexpr int kDdStages = 10;
+constexpr int kDdVecChunks = kDdStages;   // chunks of the input array staged with a wave
 constexpr int kDdScratch = kWarpsPerBlock * kGemvMaxR * kGemvCols * 8;
 constexpr int kDdDynSmem =
-    kDdStages * kStageDoubles * 8 + kDdStages * 8 + kDdStages * kStageK * kGemvMaxR * 8 + kDdScratch;
+    kDdStages * kStageDoubles * 8 + kDdStages * 8 + kDdVecChunks * kStageK * kGemvMaxR * 8 + kDdScratch;
 static_assert(kDdDynSmem <= 227 * 1024, "two-level pipeline does not fit in shared memory");
 
 struct DdStrip {
@@ -832,13 +833,66 @@ struct DdView {
   int prefetch;                 // issue the first matrix stages of P3 / P5 before the preceding barrier
 };
 
+// Per-CTA cache (shared memory, filled once per kernel) of the head of this CTA's strip list of one
+// phase: the schedule is static, and reading it from global memory would put two dependent
+// L2 round trips in front of every strip phase.
+constexpr int kDdPlanMax = 4;
+struct StripPlanStore {
+  DdStrip strip[kDdPlanMax];
+  int G, n, si0, end0;
+};
+struct StripPlan {
+  const DdStrip *cached;   // this CTA's first `ncached` strips in processing order
+  int ncached, G, si0, end0;
+};
+
+// all threads of the CTA call
+__device__ __forceinline__ void strip_plan_fill(StripPlanStore *st, const DdStripSet &S, int V) {
+  if (threadIdx.x == 0) {
+    int G = 0;
+    for (int v = blockIdx.x; v < V; v += gridDim.x) G += S.chunks[v];
+    int v = blockIdx.x, si = 0, end = 0;
+    if (v < V) {
+      si = S.cta[v];
+      end = S.cta[v + 1];
+    }
+    st->G = G;
+    st->si0 = si;
+    st->end0 = end;
+    int n = 0;
+    while (n < kDdPlanMax) {
+      while (v < V && si >= end) {
+        v += gridDim.x;
+        if (v < V) {
+          si = S.cta[v];
+          end = S.cta[v + 1];
+        }
+      }
+      if (v >= V) break;
+      st->strip[n++] = S.strips[si++];
+    }
+    st->n = n;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ StripPlan strip_plan_load(const StripPlanStore *st) {
+  StripPlan p;
+  p.cached = st->strip;
+  p.ncached = st->n;
+  p.G = st->G;
+  p.si0 = st->si0;
+  p.end0 = st->end0;
+  return p;
+}
+
 struct StripCursor {
-  int v, si, end, c;
+  int v, si, end, c, j;   // virtual CTA, strip index (global table), end of v's strips, chunk, sequence number
   DdStrip d;
 };
 
-// position the cursor on the first strip of virtual CTA v0 or of the next non-empty one this CTA owns
-__device__ __forceinline__ void strip_cursor_seek(StripCursor &cu, const DdStripSet &S, int V) {
+// position the cursor on the strip at (v, si) or on the first strip of the next non-empty virtual
+// CTA this CTA owns
+__device__ __forceinline__ void strip_cursor_seek(StripCursor &cu, const DdStripSet &S, int V, const StripPlan &pl) {
   while (cu.v < V && cu.si >= cu.end) {
     cu.v += gridDim.x;
     if (cu.v < V) {
@@ -847,134 +901,132 @@ __device__ __forceinline__ void strip_cursor_seek(StripCursor &cu, const DdStrip
     }
   }
   cu.c = 0;
-  if (cu.v < V) cu.d = S.strips[cu.si];
+  if (cu.v < V) cu.d = (cu.j < pl.ncached) ? pl.cached[cu.j] : S.strips[cu.si];
 }
-__device__ __forceinline__ void strip_cursor_init(StripCursor &cu, const DdStripSet &S, int V) {
+__device__ __forceinline__ void strip_cursor_init(StripCursor &cu, const DdStripSet &S, int V, const StripPlan &pl) {
   cu.v = blockIdx.x;
-  cu.si = cu.end = 0;
-  if (cu.v < V) {
-    cu.si = __ldg(S.cta + cu.v);
-    cu.end = __ldg(S.cta + cu.v + 1);
-  }
-  strip_cursor_seek(cu, S, V);
+  cu.si = pl.si0;
+  cu.end = pl.end0;
+  cu.j = 0;
+  strip_cursor_seek(cu, S, V, pl);
 }
-__device__ __forceinline__ void strip_cursor_next(StripCursor &cu, const DdStripSet &S, int V) {
-  if (++cu.c == cu.d.nchunks) {
-    ++cu.si;
-    strip_cursor_seek(cu, S, V);
+__device__ __forceinline__ void strip_cursor_next_strip(StripCursor &cu, const DdStripSet &S, int V,
+                                                        const StripPlan &pl) {
+  ++cu.si;
+  ++cu.j;
+  strip_cursor_seek(cu, S, V, pl);
+}
+
+// thread 0: put chunks [c0, c0 + nw) of strip d in flight into stage slots 0 .. nw-1
+__device__ __forceinline__ void strip_issue_wave(const GemvPipe &pp, const DdStripSet &S, const DdStrip &d, int c0,
+                                                 int nw) {
+  const uint32_t stage0 = smem_u32(pp.stage);
+  for (int i = 0; i < nw; ++i) {
+    const uint32_t bar = pp.bar + 8 * i;
+    mbar_expect_tx(bar, kStageDoubles * 8);
+    bulk_g2s(stage0 + i * (kStageDoubles * 8), S.M + (size_t)(d.data_off + c0 + i) * kStageDoubles,
+             kStageDoubles * 8, bar);
   }
 }
 
-// Issue the TMA copies of this CTA's first min(STAGES, G) matrix stages of a strip phase.  The
-// matrix does not depend on the phases before it, so this is called BEFORE the grid barrier that
-// makes the input array visible; phase_strip_gemv(..., prefetched = true) then only stages the
-// matching slices of the input.  Precondition: every stage of the ring has been consumed.
+// Issue the TMA copies of the first wave of this CTA's first strip of a strip phase.  The matrix
+// does not depend on the phases before it, so this is called BEFORE the grid barrier that makes the
+// input array visible; phase_strip_gemv(..., prefetched = true) then skips that issue.
+// Precondition: every stage has been consumed (true between strip phases).
 template <int STAGES>
-__device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStripSet &S, int V) {
+__device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStripSet &S, int V,
+                                               const StripPlanStore *st) {
   if (threadIdx.x != 0) return;
-  const uint32_t stage0 = smem_u32(pp.stage);
+  const StripPlan pl = strip_plan_load(st);
   StripCursor cu;
-  strip_cursor_init(cu, S, V);
-  uint32_t slot = pp.slot;
-  for (int issued = 0; issued < STAGES && cu.v < V; ++issued) {
-    const uint32_t bar = pp.bar + 8 * slot;
-    mbar_expect_tx(bar, kStageDoubles * 8);
-    bulk_g2s(stage0 + slot * (kStageDoubles * 8), S.M + (size_t)(cu.d.data_off + cu.c) * kStageDoubles,
-             kStageDoubles * 8, bar);
-    strip_cursor_next(cu, S, V);
-    slot = (slot + 1 == STAGES) ? 0 : slot + 1;
-  }
+  strip_cursor_init(cu, S, V, pl);
+  if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
+// A strip is processed in waves of <= STAGES chunks: thread 0 puts the whole wave in flight (one
+// TMA bulk copy per 16 KB stage, each with its own mbarrier), all threads stage the matching slice
+// of `vec` (one round of global-load latency per wave), then the 8 warps split the wave into
+// (chunk, 8-row) units and each waits only for the stages it reads -- no CTA-wide barrier per
+// stage.  pp.parity is a bit mask here: bit i = phase parity of stage slot i.
 template <int R, int STAGES>
-__device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const double *vec,
-                                                 const int *icol, double *out, size_t outstride,
-                                                 bool prefetched = false) {
-  // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while the
-  // slice that goes with a stage is staged (saves a separate permutation pass + grid barrier)
+__device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
+                                                 const double *vec, const int *icol, double *out,
+                                                 size_t outstride, bool prefetched = false) {
+  // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
+  // is staged (saves a separate permutation pass + grid barrier)
+  static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int G = 0;
-  for (int v = blockIdx.x; v < V; v += gridDim.x) G += __ldg(S.chunks + v);
-  if (G == 0) return;
-  const uint32_t stage0 = smem_u32(pp.stage);
-  auto produce = [&](const StripCursor &cu, uint32_t slot, bool matrix) {
-    if (matrix && threadIdx.x == 0) {
-      const uint32_t bar = pp.bar + 8 * slot;
-      mbar_expect_tx(bar, kStageDoubles * 8);
-      bulk_g2s(stage0 + slot * (kStageDoubles * 8), S.M + (size_t)(cu.d.data_off + cu.c) * kStageDoubles,
-               kStageDoubles * 8, bar);
-    }
-    if (threadIdx.x < kStageK * R) {
-      double val;
-      if (icol) {
-        const int oc = __ldg(icol + (cu.d.kc0 + cu.c) * kStageK + threadIdx.x / R);
-        val = (oc >= 0) ? vec[(size_t)oc * R + threadIdx.x % R] : 0.0;
-      } else {
-        val = vec[(size_t)(cu.d.kc0 + cu.c) * (kStageK * R) + threadIdx.x];
-      }
-      pp.svec[slot * (kStageK * R) + threadIdx.x] = val;
-    }
-  };
-  StripCursor ci, cc;
-  strip_cursor_init(ci, S, V);
-  cc = ci;
-  uint32_t slot_i = pp.slot;
-  int issued = 0;
-  for (; issued < STAGES && issued < G; ++issued) {
-    produce(ci, slot_i, !prefetched);
-    strip_cursor_next(ci, S, V);
-    slot_i = (slot_i + 1 == STAGES) ? 0 : slot_i + 1;
-  }
-  __syncthreads();
-  double a0[R], a1[R];
+  const StripPlan pl = strip_plan_load(st);
+  if (pl.G == 0) return;
+  StripCursor cu;
+  strip_cursor_init(cu, S, V, pl);
+  bool in_flight = prefetched;   // first wave of the current strip already issued
+  while (cu.v < V) {
+    const DdStrip d = cu.d;
+    double a0[R], a1[R];
 #pragma unroll
-  for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
-  for (int g = 0; g < G; ++g) {
-    const uint32_t slot = pp.slot;
-    mbar_wait(pp.bar + 8 * slot, pp.parity);
-    const double *st = pp.stage + (size_t)slot * kStageDoubles;
-    const double *sv = pp.svec + slot * (kStageK * R);
-#pragma unroll
-    for (int u = 0; u < kStageK / kWarpsPerBlock; ++u) {
-      const int kk = w + u * kWarpsPerBlock;
-      const double2 pv = *reinterpret_cast<const double2 *>(st + kk * kGemvCols + 2 * lane);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double x = sv[kk * R + q];
-        a0[q] = fma(pv.x, x, a0[q]);
-        a1[q] = fma(pv.y, x, a1[q]);
-      }
-    }
-    const bool strip_end = (cc.c == cc.d.nchunks - 1);
-    if (strip_end) {
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        sacc[w][q][2 * lane] = a0[q];
-        sacc[w][q][2 * lane + 1] = a1[q];
-        a0[q] = 0.0;
-        a1[q] = 0.0;
-      }
-    }
-    __syncthreads();
-    if (issued < G) {
-      produce(ci, slot, true);
-      strip_cursor_next(ci, S, V);
-      ++issued;
-    }
-    if (strip_end) {
-      for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
-        const int q = o / kGemvCols, jj = o % kGemvCols;
-        double x = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-        out[(size_t)cc.d.slot * outstride + ((size_t)cc.d.cb * kGemvCols + jj) * R + q] = x;
+    for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
+    for (int c0 = 0; c0 < d.nchunks; c0 += STAGES) {
+      const int nw = min(STAGES, d.nchunks - c0);
+      if (!in_flight && threadIdx.x == 0) strip_issue_wave(pp, S, d, c0, nw);
+      in_flight = false;
+      {  // the slice of vec that goes with the wave
+        const int k0 = (d.kc0 + c0) * kStageK;
+        const int cnt = nw * kStageK * R;
+        for (int o = threadIdx.x; o < cnt; o += kBlock) {
+          double val;
+          if (icol) {
+            const int k = o / R, q = o - k * R;
+            const int oc = __ldg(icol + k0 + k);
+            val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
+          } else {
+            val = vec[(size_t)k0 * R + o];
+          }
+          pp.svec[o] = val;
+        }
       }
       __syncthreads();
+      for (int u = w; u < 4 * nw; u += kWarpsPerBlock) {
+        const int ch = u >> 2, r0 = (u & 3) * 8;
+        mbar_wait(pp.bar + 8 * ch, (pp.parity >> ch) & 1u);
+        const double *stp = pp.stage + (size_t)ch * kStageDoubles + r0 * kGemvCols + 2 * lane;
+        const double *sv = pp.svec + (ch * kStageK + r0) * R;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const double2 pv = *reinterpret_cast<const double2 *>(stp + kk * kGemvCols);
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const double x = sv[kk * R + q];
+            a0[q] = fma(pv.x, x, a0[q]);
+            a1[q] = fma(pv.y, x, a1[q]);
+          }
+        }
+      }
+      pp.parity ^= (1u << nw) - 1u;
+      __syncthreads();   // the wave is consumed: stage slots and svec may be reused
     }
-    strip_cursor_next(cc, S, V);
-    if (pp.slot + 1 == STAGES) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
+    // put the first wave of the next strip in flight, then finish this one
+    strip_cursor_next_strip(cu, S, V, pl);
+    if (cu.v < V) {
+      if (threadIdx.x == 0) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
+      in_flight = true;
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      sacc[w][q][2 * lane] = a0[q];
+      sacc[w][q][2 * lane + 1] = a1[q];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+      const int q = o / kGemvCols, jj = o % kGemvCols;
+      double x = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+      out[(size_t)d.slot * outstride + ((size_t)d.cb * kGemvCols + jj) * R + q] = x;
+    }
+    __syncthreads();
   }
 }
 
@@ -1029,13 +1081,16 @@ __device__ __forceinline__ void phase_dd_sep_rhs(const Ctx &ctx, const DdView &d
   constexpr int DH = D + 1;
   const size_t zstride = (size_t)dd.pcols * R;
   for (int s = ctx.warp; s < dd.nS; s += ctx.nwarps) {
-    double acc[R];
+    double acc[R], rr[R];
+    const int cl = (ctx.lane < DH) ? ctx.lane : 0;
+    const size_t ooff = ((size_t)__ldg(dd.srow + s) * DH + cl) * R;   // issued before the product: independent
+#pragma unroll
+    for (int q = 0; q < R; ++q) rr[q] = rvec[ooff + q];
     dd_row_product<R, D>(dd.A_SI, dd.y, dd.nsplit1, zstride, s, ctx.lane, acc);
     if (ctx.lane < DH) {
       const size_t off = ((size_t)dd.sep_col0 + (size_t)s * DH + ctx.lane) * R;
-      const size_t ooff = ((size_t)__ldg(dd.srow + s) * DH + ctx.lane) * R;
 #pragma unroll
-      for (int q = 0; q < R; ++q) dd.t[off + q] = rvec[ooff + q] - acc[q];
+      for (int q = 0; q < R; ++q) dd.t[off + q] = rr[q] - acc[q];
     }
   }
 }
@@ -1048,9 +1103,10 @@ __device__ __forceinline__ void phase_dd_back_rhs(const Ctx &ctx, const DdView &
   const size_t zstride = (size_t)dd.pcols * R;
   for (int b = ctx.warp; b < dd.nB; b += ctx.nwarps) {
     double acc[R];
+    const int col0 = __ldg(dd.bcol + b);
     dd_row_product<R, D>(dd.A_BS, dd.zs, dd.nsplit3, zstride, b, ctx.lane, acc);
     if (ctx.lane < DH) {
-      const size_t off = ((size_t)__ldg(dd.bcol + b) + ctx.lane) * R;
+      const size_t off = ((size_t)col0 + ctx.lane) * R;
 #pragma unroll
       for (int q = 0; q < R; ++q) dd.u[off + q] = acc[q];
     }

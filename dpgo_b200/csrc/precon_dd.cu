@@ -202,8 +202,10 @@ template <int R>
 __global__ void __launch_bounds__(kBlock, 1) k_strip_gemv(DdStripSet S, int V, const double *vec, const int *icol,
                                                           double *out, size_t outstride) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  GemvPipe pp = gemv_pipe_init<kDdStages>(dsm);
-  phase_strip_gemv<R, kDdStages>(pp, S, V, vec, icol, out, outstride);
+  GemvPipe pp = gemv_pipe_init<kDdStages, kDdVecChunks>(dsm);
+  __shared__ StripPlanStore plan;
+  strip_plan_fill(&plan, S, V);
+  phase_strip_gemv<R, kDdStages>(pp, S, V, &plan, vec, icol, out, outstride);
 }
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_dd_sep_rhs(DdView dd, const double *rvec) {
@@ -276,7 +278,8 @@ int dd_build(dpgo_dev *h) {
   for (int i = 0; i < n; ++i)
     for (int e = h->rowptr[i]; e < h->rowptr[i + 1]; ++e)
       if (h->colidx[e] != i) adj[i].push_back(h->colidx[e]);
-  const int thr = std::max(8, 384 / dh);   // interior blocks of <= 384 scalars (6 column blocks of 64)
+  // interior blocks of <= 320 scalars (5 column blocks of 64): a strip is one wave of kDdStages chunks
+  const int thr = std::max(8, kDdStages * kStageK / dh);
   Dissector ds(adj, thr);
   {
     std::vector<int> all(n);
@@ -413,14 +416,15 @@ int dd_build(dpgo_dev *h) {
   const int nchS = padS / kStageK, ncbS = padS / kGemvCols;
   int nsplit3 = h->dd_split3;
   if (nsplit3 <= 0) {
-    // waves of V CTAs x (fill latency ~ 3 chunk times + chunks per strip), plus the cost of one
-    // more partial array for the consumers
+    // waves of V CTAs x time of a strip, plus the cost of one more partial array for the consumers
     nsplit3 = 1;
     double best_cost = 1e300;
-    for (int ns = 1; ns <= std::min(std::max(nchS, 1), 16); ++ns) {
+    for (int ns = 1; ns <= std::min(std::max(nchS, 1), 32); ++ns) {
       const int cps = (nchS + ns - 1) / ns;
       const long strips = (long)ncbS * ((nchS + cps - 1) / std::max(cps, 1));
-      const double cost = (double)((strips + V - 1) / V) * (cps + 3.0) + 0.25 * ns;
+      // per strip: fixed latency + rounds of 8 warps over (chunk, 8-row) units + extra waves
+      const double per_strip = 4.0 + 2.0 * ((cps + 1) / 2) / 4.0 + 3.0 * ((cps + kDdStages - 1) / kDdStages - 1);
+      const double cost = (double)((strips + V - 1) / V) * per_strip + 0.3 * ns;
       if (cost < best_cost - 1e-9) { best_cost = cost; nsplit3 = ns; }
     }
   }

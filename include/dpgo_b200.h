@@ -119,7 +119,7 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
 int dpgo_finalize(dpgo_handle h, int build_precon);
 /* How the exact preconditioner (Q + 0.1 I)^{-1} is stored and applied.  All variants give the same
  * operator (up to summation order); they differ in bytes streamed per application:
- *  -1 (default) choose by size when the preconditioner is built: 2 when N = (d+1)n >= 6000, else 0;
+ *  -1 (default) choose by size when the preconditioner is built: 2 when N = (d+1)n >= 3000, else 0;
  *   0 full dense inverse, N^2*8 bytes per application (one streaming pass, 2 grid phases);
  *   1 symmetric half storage (blocks I >= K only, each streamed block used for both z_I += P_IK r_K
  *     and z_K += P_IK^T r_I): ~N^2/2*8 bytes, half the memory.  On B200 it is FP64-issue/latency

@@ -51,7 +51,7 @@ def main():
     quick = "--quick" in sys.argv
     z, d, n, T0 = fixture("sphere2500")
     run("sphere2500", z, d, n, T0, 5, 0)
-    for tuning in [(0, 0, 0), (0, 0, 1), (1, 4, 1), (1, 5, 1), (1, 8, 1), (2, 6, 1)]:
+    for tuning in [(0, 0, 0), (0, 0, 1), (1, 4, 1), (1, 8, 1)]:
         run("sphere2500", z, d, n, T0, 5, 2, tuning)
     z, d, n, T0 = fixture("smallGrid3D")
     for mode in (0, 2):
