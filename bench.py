@@ -223,21 +223,25 @@ def bench_single(args):
     # Inside a step the solver re-reads it ~36 times; that reuse is part of the step.
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def timed_device_steps(prob):
+    def timed_device_steps(prob, flush_l2=True):
         prob.slot_set(dpgo_b200.SLOT_Y, X0)
         for _ in range(W):
             r_ = prob.optimize_slot(dpgo_b200.SLOT_Y, prm)
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        tot = {"n_launches": 0, "n_qx": 0, "n_precon": 0, "n_pose_sweeps": 0}
+        tot = {"n_launches": 0, "n_qx": 0, "n_precon": 0, "n_pose_sweeps": 0, "elapsed_ms": 0.0}
+        per_step = []
         for e0, e1 in evs:
-            flush.zero_()
+            if flush_l2:
+                flush.zero_()
             e0.record()
             r_ = prob.optimize_slot(dpgo_b200.SLOT_Y, prm)
             e1.record()
             for k in tot:
                 tot[k] += r_[k]
+            per_step.append(round(r_["elapsed_ms"], 4))
         torch.cuda.synchronize()
+        tot["per_step_ms"] = per_step
         return sum(e0.elapsed_time(e1) for e0, e1 in evs), tot, r_
 
     # ---- device-resident timing: X0 lives in HBM (slot Y), result stays in HBM (slot X)
@@ -245,6 +249,7 @@ def bench_single(args):
     sampler.start()
     ms, tot, res = timed_device_steps(gp)
     clocks = sampler.stop()
+    ms_warm, tot_warm, _ = timed_device_steps(gp, flush_l2=False)
     launches, nq, npc, nsw = tot["n_launches"], tot["n_qx"], tot["n_precon"], tot["n_pose_sweeps"]
     value = K / (ms / 1e3)
     mode = gp.precon_mode()
@@ -345,6 +350,12 @@ def bench_single(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
         "gpu_launches": int(launches),
+        # the same K steps again without the L2 flush, and the part of a step spent inside the solver
+        # kernel (CUDA events around the launch inside the library; the rest is the call's launch +
+        # result read-back)
+        "ms_per_step_warm_l2": ms_warm / K,
+        "solver_kernel_ms_per_step": {"l2_flushed": tot["elapsed_ms"] / K, "l2_warm": tot_warm["elapsed_ms"] / K,
+                                      "l2_flushed_steps": tot["per_step_ms"]},
         "fused_phase_ms": dict(zip(["cost_grad", "precon_stream", "precon_finish", "hessvec", "tcg_update",
                                     "tcg_direction", "retract_copy", "unused", "dd_interior_y", "dd_sep_rhs",
                                     "dd_schur", "dd_back_rhs", "dd_interior_w"], res.get("phase_ms", []))),

@@ -101,7 +101,7 @@ template <int R, int D, int MODE>
 __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::grid_group grid = cg::this_grid();
-  const Ctx ctx = make_ctx();
+  const Ctx ctx = make_ctx_spread();
   const int n = p.n;
   GemvPipe pipe = gemv_pipe_init<(MODE == 2 ? kDdStages : kStages), (MODE == 2 ? kDdVecChunks : kStages)>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;

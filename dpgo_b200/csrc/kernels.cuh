@@ -48,6 +48,19 @@ __device__ __forceinline__ Ctx make_ctx() {
   return c;
 }
 
+// Warp numbering for the persistent fused solver: warp w of CTA b is global warp b + grid * w, so
+// that a phase with fewer warps of work than the grid holds (2500 poses = 313 warps) is dealt over
+// every SM instead of filling the first CTAs (latency-bound phases: more LSUs / L1s in parallel).
+__device__ __forceinline__ Ctx make_ctx_spread() {
+  Ctx c;
+  c.nthreads = gridDim.x * blockDim.x;
+  c.nwarps = c.nthreads >> 5;
+  c.lane = threadIdx.x & 31;
+  c.warp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
+  c.tid = c.warp * 32 + c.lane;
+  return c;
+}
+
 struct LanePos {
   int grp;        // pose group within the warp
   int c;          // column of the tile owned by this lane
@@ -1054,11 +1067,21 @@ __device__ __forceinline__ void dd_row_product(const BsrView &B, const double *X
       double x[TILE];
 #pragma unroll
       for (int k = 0; k < TILE; ++k) x[k] = xj[k];
-#pragma unroll 2
-      for (int s = 1; s < nsum; ++s) {
-        const double *xs = xj + (size_t)s * xstride;
+      // partial slots: 3 at a time, so that their loads are in flight together (fixed order)
+      for (int s = 1; s < nsum; s += 3) {
+        const double *xa = xj + (size_t)s * xstride;
+        const bool hb = s + 1 < nsum, hc = s + 2 < nsum;
+        const double *xb = hb ? xa + xstride : xa;
+        const double *xc = hc ? xb + xstride : xa;
+        double ta[TILE], tb[TILE], tc[TILE];
 #pragma unroll
-        for (int k = 0; k < TILE; ++k) x[k] += xs[k];
+        for (int k = 0; k < TILE; ++k) { ta[k] = xa[k]; tb[k] = xb[k]; tc[k] = xc[k]; }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+          x[k] += ta[k];
+          if (hb) x[k] += tb[k];
+          if (hc) x[k] += tc[k];
+        }
       }
 #pragma unroll
       for (int k = 0; k < DH; ++k) {
@@ -1080,7 +1103,9 @@ template <int R, int D>
 __device__ __forceinline__ void phase_dd_sep_rhs(const Ctx &ctx, const DdView &dd, const double *rvec) {
   constexpr int DH = D + 1;
   const size_t zstride = (size_t)dd.pcols * R;
-  for (int s = ctx.warp; s < dd.nS; s += ctx.nwarps) {
+  // rows are dealt round-robin over the CTAs (row -> CTA row % grid), so that a short phase uses
+  // every SM instead of filling the first CTAs' warps
+  for (int s = blockIdx.x + gridDim.x * (threadIdx.x >> 5); s < dd.nS; s += gridDim.x * kWarpsPerBlock) {
     double acc[R], rr[R];
     const int cl = (ctx.lane < DH) ? ctx.lane : 0;
     const size_t ooff = ((size_t)__ldg(dd.srow + s) * DH + cl) * R;   // issued before the product: independent
@@ -1101,7 +1126,7 @@ template <int R, int D>
 __device__ __forceinline__ void phase_dd_back_rhs(const Ctx &ctx, const DdView &dd) {
   constexpr int DH = D + 1;
   const size_t zstride = (size_t)dd.pcols * R;
-  for (int b = ctx.warp; b < dd.nB; b += ctx.nwarps) {
+  for (int b = blockIdx.x + gridDim.x * (threadIdx.x >> 5); b < dd.nB; b += gridDim.x * kWarpsPerBlock) {
     double acc[R];
     const int col0 = __ldg(dd.bcol + b);
     dd_row_product<R, D>(dd.A_BS, dd.zs, dd.nsplit3, zstride, b, ctx.lane, acc);
@@ -1132,9 +1157,22 @@ __device__ __forceinline__ void phase_dd_finish(const Ctx &ctx, const DdView &dd
       const int pc0 = dd.pcol[i];
       const size_t poff = ((size_t)pc0 + lp.c) * R;
       if (pc0 >= dd.sep_col0) {
-        for (int s = 0; s < dd.nsplit3; ++s) {
+        // partial slots of the Schur product, 4 at a time (loads in flight together, fixed order)
+        for (int s = 0; s < dd.nsplit3; s += 4) {
+          double tq[4][R];
 #pragma unroll
-          for (int q = 0; q < R; ++q) wv[q] += dd.zs[(size_t)s * zstride + poff + q];
+          for (int j = 0; j < 4; ++j) {
+            const size_t so = (size_t)min(s + j, dd.nsplit3 - 1) * zstride + poff;
+#pragma unroll
+            for (int q = 0; q < R; ++q) tq[j][q] = dd.zs[so + q];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (s + j < dd.nsplit3) {
+#pragma unroll
+              for (int q = 0; q < R; ++q) wv[q] += tq[j][q];
+            }
+          }
         }
       } else {
         for (int s = 0; s < dd.nsplit1; ++s) {
