@@ -101,7 +101,10 @@ template <int R, int D, int MODE>
 __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::grid_group grid = cg::this_grid();
-  const Ctx ctx = make_ctx_spread();
+  // per-pose phases: deal the warps over every CTA once there is at least one warp of poses per CTA
+  // (measured: sphere2500 -3 %), keep them packed in the first CTAs for small problems (1000
+  // poses: packed is 8 % faster)
+  const Ctx ctx = ((p.n + Geo<R, D>::GPW - 1) / Geo<R, D>::GPW >= (int)gridDim.x) ? make_ctx_spread() : make_ctx();
   const int n = p.n;
   GemvPipe pipe = gemv_pipe_init<(MODE == 2 ? kDdStages : kStages), (MODE == 2 ? kDdVecChunks : kStages)>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
