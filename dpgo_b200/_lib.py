@@ -85,6 +85,7 @@ SIGNATURES = {
     "dpgo_set_public_indices": (C.c_int, [H, C.c_int, _ip]),
     "dpgo_pack_public_dev": (C.c_int, [H, C.c_int, C.c_void_p]),
     "dpgo_gather_tiles_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dpgo_measurement_errors": (C.c_int, [H, C.c_int, C.c_void_p, _dp, _dp]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),

@@ -45,6 +45,7 @@ class DeviceProblem:
         check(lib.dpgo_create(int(device), self.n, self.d, self.r,
                               C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.last_result = None
+        self.num_private_edges = self.num_shared_edges = 0
 
     def close(self):
         if self._h:
@@ -74,6 +75,7 @@ class DeviceProblem:
         R, t, kappa, tau, weight = self._edge_arrays(self.d, R, t, kappa, tau, weight, m)
         check(lib.dpgo_set_private_edges(self._h, m, _i(p1), _i(p2), _d(R), _d(t), _d(kappa), _d(tau),
                                          _d(weight)))
+        self.num_private_edges = m
 
     def set_shared_edges(self, my_idx, nbr_slot, outgoing, R, t, kappa, tau, num_nbr_slots, weight=None):
         m = len(my_idx)
@@ -84,6 +86,7 @@ class DeviceProblem:
         check(lib.dpgo_set_shared_edges(self._h, m, int(num_nbr_slots), _i(my_idx), _i(nbr_slot),
                                         outgoing.ctypes.data_as(_bp), _d(R), _d(t), _d(kappa),
                                         _d(tau), _d(weight)))
+        self.num_shared_edges = m
 
     def set_priors(self, idx, poses, prior_kappa=10000.0, prior_tau=100.0):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -252,6 +255,14 @@ class DeviceProblem:
     def gather_tiles_dev(self, slot, num, idx_dev_ptr, out_dev_ptr):
         check(lib.dpgo_gather_tiles_dev(self._h, int(slot), int(num), C.c_void_p(idx_dev_ptr),
                                         C.c_void_p(out_dev_ptr)))
+
+    def measurement_errors(self, slot, nbr_dev_ptr=None):
+        """Squared residual of every private / shared edge at the poses in `slot`
+        (computeMeasurementError, src/DPGO_utils.cpp:501-507), computed on the device."""
+        ep = np.zeros(max(self.num_private_edges, 1))
+        es = np.zeros(max(self.num_shared_edges, 1))
+        check(lib.dpgo_measurement_errors(self._h, int(slot), C.c_void_p(nbr_dev_ptr or 0), _d(ep), _d(es)))
+        return ep[:self.num_private_edges], es[:self.num_shared_edges]
 
     def max_translation_distance(self, a, b):
         v = C.c_double()

@@ -927,6 +927,42 @@ static int alloc_vec(dpgo_dev *h, double **p, size_t elems) {
   return DPGO_OK;
 }
 
+// Squared measurement errors kappa |Y1 R~ - Y2|_F^2 + tau |p2 - p1 - Y1 t~|^2 of a set of edges
+// (ref: computeMeasurementError, src/DPGO_utils.cpp:501-507): one thread per edge.  Private
+// edges take both poses from X; a shared edge takes my pose from X and the neighbour's from the
+// slot buffer (outgoing: my pose is the tail).
+__global__ void k_edge_errors(int m, int r, int d, const int *a, const int *b, const unsigned char *outgoing,
+                              const double *Rm, const double *tm, const double *kappa, const double *tau,
+                              const double *X, const double *nbr, double *out) {
+  const int dh = d + 1, tile = r * dh;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+    const double *T1, *T2;
+    if (nbr == nullptr) {                 // private edge: a = p1, b = p2
+      T1 = X + (size_t)a[e] * tile;
+      T2 = X + (size_t)b[e] * tile;
+    } else if (outgoing[e]) {             // shared, my pose a[e] is the tail
+      T1 = X + (size_t)a[e] * tile;
+      T2 = nbr + (size_t)b[e] * tile;
+    } else {
+      T1 = nbr + (size_t)b[e] * tile;
+      T2 = X + (size_t)a[e] * tile;
+    }
+    const double *R = Rm + (size_t)e * d * d, *t = tm + (size_t)e * d;
+    double rot = 0.0, tr = 0.0;
+    for (int q = 0; q < r; ++q) {
+      double pt = T2[d * r + q] - T1[d * r + q];
+      for (int c = 0; c < d; ++c) {
+        double v = -T2[c * r + q];
+        for (int k = 0; k < d; ++k) v = fma(T1[k * r + q], R[k * d + c], v);
+        rot = fma(v, v, rot);
+        pt = fma(-T1[c * r + q], t[c], pt);
+      }
+      tr = fma(pt, pt, tr);
+    }
+    out[e] = kappa[e] * rot + tau[e] * tr;
+  }
+}
+
 static int copy_edges(EdgeSet &E, int m, int d, const int32_t *a, const int32_t *b,
                       const uint8_t *outgoing, const double *R, const double *t, const double *kappa,
                       const double *tau, const double *weight) {
@@ -1436,6 +1472,72 @@ int dpgo_gather_tiles_dev(dpgo_handle h, int slot, int num, const int32_t *idx_d
   int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
   k_gather_tiles<<<grid, 256, 0, h->stream>>>(h->d_slot[slot], idx_dev, num, tile, tiles_dev);
   LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int to_device(const std::vector<T> &v, T **out) {
+  *out = nullptr;
+  if (v.empty()) return DPGO_OK;
+  CUDA_TRY(cudaMalloc((void **)out, v.size() * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return DPGO_OK;
+}
+
+// errors of one edge set: uploads the (small) edge arrays, runs k_edge_errors, copies the result back
+int edge_errors(dpgo_dev *h, const EdgeSet &E, const double *X, const double *nbr, double *out_host) {
+  if (E.m == 0) return DPGO_OK;
+  int *a = nullptr, *b = nullptr;
+  unsigned char *og = nullptr;
+  double *R = nullptr, *t = nullptr, *ka = nullptr, *ta = nullptr, *out = nullptr;
+  int rc = DPGO_OK;
+  auto cleanup = [&]() {
+    cudaFree(a); cudaFree(b); cudaFree(og); cudaFree(R); cudaFree(t); cudaFree(ka); cudaFree(ta); cudaFree(out);
+  };
+  std::vector<int> av(E.a.begin(), E.a.end()), bv(E.b.begin(), E.b.end());
+  std::vector<unsigned char> ogv(E.outgoing.begin(), E.outgoing.end());
+  if ((rc = to_device(av, &a)) || (rc = to_device(bv, &b)) || (rc = to_device(ogv, &og)) ||
+      (rc = to_device(E.R, &R)) || (rc = to_device(E.t, &t)) || (rc = to_device(E.kappa, &ka)) ||
+      (rc = to_device(E.tau, &ta))) {
+    cleanup();
+    return rc;
+  }
+  if (cudaMalloc((void **)&out, (size_t)E.m * sizeof(double)) != cudaSuccess) {
+    cleanup();
+    set_error("allocation of the edge error buffer failed");
+    return DPGO_ECUDA;
+  }
+  const int grid = std::max(1, std::min((E.m + 255) / 256, h->num_sms * 8));
+  k_edge_errors<<<grid, 256, 0, h->stream>>>(E.m, h->r, h->d, a, b, og, R, t, ka, ta, X, nbr, out);
+  h->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out, (size_t)E.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (e != cudaSuccess) {
+    set_error("edge error kernel failed: %s", cudaGetErrorString(e));
+    return DPGO_ECUDA;
+  }
+  return DPGO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dpgo_measurement_errors(dpgo_handle h, int slot, const double *nbr_poses_dev, double *err_private,
+                            double *err_shared) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4);
+  CHECK_ARG((h->priv.m == 0 || err_private) && (h->shared.m == 0 || err_shared));
+  if (h->priv.m > 0) DPGO_TRY(edge_errors(h, h->priv, h->d_slot[slot], nullptr, err_private));
+  if (h->shared.m > 0) {
+    const double *nbr = nbr_poses_dev ? nbr_poses_dev : h->d_nbr;
+    if (!nbr) { set_error("no neighbour poses"); return DPGO_ESTATE; }
+    DPGO_TRY(edge_errors(h, h->shared, h->d_slot[slot], nbr, err_shared));
+  }
   return DPGO_OK;
 }
 

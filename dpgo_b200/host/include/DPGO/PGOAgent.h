@@ -188,7 +188,22 @@ class PGOAgent {
 
   void runOptimizationLoop();
   Pose computeNeighborTransform(const RelativeSEMeasurement &measurement, const LiftedPose &neighbor_pose);
+
+  // robust optimization (GNC / M-estimators), reference: include/DPGO/PGOAgent.h:676-708,
+  // src/PGOAgent.cpp:997-1155.  Like the reference these are driven by a subclass / the ROS layer.
+  unsigned mWeightUpdateCount = 0, mTrajectoryResetCount = 0, mLatestWeightUpdateIteration = 0;
+  int mRobustOptInnerIter = 0;
+  void initializeRobustOptimization();
+  bool shouldUpdateMeasurementWeights() const;
+  void updateMeasurementWeights();
+  bool computeMeasurementResidual(const RelativeSEMeasurement &measurement, double *residual) const;
+  bool setMeasurementWeight(const PoseID &src_ID, const PoseID &dst_ID, double weight, bool fixed_weight = false);
+  bool isRobotInitialized(unsigned robot_id) const;
   bool isRobotActive(unsigned robot_id) const;
+  void setRobotActive(unsigned robot_id, bool active = true);
+  size_t numActiveRobots() const;
+  bool anchorFirstPose();
+  bool anchorFirstPose(const LiftedPose &prior);
 
  private:
   // device-slot bookkeeping

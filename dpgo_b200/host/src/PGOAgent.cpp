@@ -239,12 +239,15 @@ void PGOAgent::initializeInGlobalFrame(const Pose &T_world_robot) {  // referenc
     uploadState();
     if (mParams.acceleration) initializeAcceleration();
   }
+  // robust optimization starts from unit weights on every non-fixed loop closure (:348-352)
+  if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2) initializeRobustOptimization();
   if (halted) startOptimizationLoop();
 }
 
 // ---- the RBCD iteration --------------------------------------------------------------------------
 bool PGOAgent::iterate(bool doOptimization) {  // reference :376-432
   mIterationNumber++;
+  if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2) mRobustOptInnerIter++;
   if (mState != PGOAgentState::INITIALIZED) return true;
   dpgo_dev *h = mPoseGraph->deviceHandle();
   if (!mDeviceStateValid) {
@@ -277,7 +280,11 @@ bool PGOAgent::iterate(bool doOptimization) {  // reference :376-432
     double change = 0;
     DPGO_DEVICE_CALL(dpgo_max_translation_distance(h, DPGO_SLOT_X, DPGO_SLOT_XPREV, &change));
     mStatus.relativeChange = change;
-    bool ready = success && !(change > mParams.relChangeTol);
+    // loose threshold during the first inner iterations of robust optimization (:410-415)
+    double relative_change_tol = mParams.relChangeTol;
+    if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2 && mWeightUpdateCount == 0)
+      relative_change_tol = 5;
+    bool ready = success && !(change > relative_change_tol);
     const auto stat = mPoseGraph->statistics();
     if (stat.total_loop_closures > 0) {
       const double ratio = (stat.accept_loop_closures + stat.reject_loop_closures) / stat.total_loop_closures;
@@ -510,6 +517,10 @@ Matrix PGOAgent::localPoseGraphOptimization() {  // reference :823-828
 // ---- termination / reset -----------------------------------------------------------------------------
 bool PGOAgent::shouldTerminate() {  // reference :844-878
   if (iteration_number() >= mParams.maxNumIters) return true;
+  // not before the weights have been updated often enough (:853-857)
+  if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2 &&
+      mWeightUpdateCount < static_cast<unsigned>(mParams.robustOptNumWeightUpdates))
+    return false;
   for (unsigned robot_id = 0; robot_id < mParams.numRobots; ++robot_id) {
     if (!isRobotActive(robot_id)) continue;
     const auto it = mTeamStatus.find(robot_id);
@@ -524,6 +535,10 @@ void PGOAgent::reset() {  // reference :434-473
   endOptimizationLoop();
   mInstanceNumber++;
   mIterationNumber = 0;
+  mLatestWeightUpdateIteration = 0;
+  mRobustOptInnerIter = 0;
+  mWeightUpdateCount = 0;
+  mTrajectoryResetCount = 0;
   mState = PGOAgentState::WAIT_FOR_DATA;
   mStatus = PGOAgentStatus(getID(), mState, mInstanceNumber, mIterationNumber, false, 0);
   mTeamStatus.clear();
@@ -565,5 +580,124 @@ void PGOAgent::endOptimizationLoop() {
 }
 
 bool PGOAgent::isOptimizationRunning() { return mOptimizationThread != nullptr; }
+
+// ---- robust optimization (reference :997-1215) --------------------------------------------------------
+bool PGOAgent::shouldUpdateMeasurementWeights() const {  // :997-1046
+  if (mParams.robustCostParams.costType == RobustCostParameters::Type::L2) return false;
+  if (mWeightUpdateCount >= static_cast<unsigned>(mParams.robustOptNumWeightUpdates)) return false;
+  if (mRobustOptInnerIter >= mParams.robustOptInnerIters) return true;
+  for (unsigned robot_id = 0; robot_id < mParams.numRobots; ++robot_id) {
+    if (!isRobotActive(robot_id)) continue;
+    const auto it = mTeamStatus.find(robot_id);
+    if (it == mTeamStatus.end()) return false;
+    const PGOAgentStatus &st = it->second;
+    DPGO_CHECK(st.agentID == robot_id);
+    if (st.iterationNumber < mLatestWeightUpdateIteration) return false;  // outdated status
+    if (st.state != PGOAgentState::INITIALIZED) return false;
+    if (!st.readyToTerminate) return false;
+  }
+  return true;
+}
+
+void PGOAgent::initializeRobustOptimization() {  // :1048-1060
+  mRobustCost.reset();
+  lock_guard<mutex> lock(mMeasurementsMutex);
+  for (RelativeSEMeasurement *m : mPoseGraph->activeLoopClosures())
+    if (!m->fixedWeight) m->weight = 1.0;
+  mPoseGraph->weightsChanged();
+}
+
+bool PGOAgent::computeMeasurementResidual(const RelativeSEMeasurement &m, double *residual) const {  // :1062-1102
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  DPGO_CHECK(residual != nullptr);
+  // X is the host mirror of the device iterate (refreshed at the end of every iterate())
+  Matrix Y1, p1, Y2, p2;
+  if (m.r1 == m.r2) {
+    Y1 = X.rotation(m.p1); p1 = X.translation(m.p1);
+    Y2 = X.rotation(m.p2); p2 = X.translation(m.p2);
+  } else if (m.r1 == getID()) {
+    Y1 = X.rotation(m.p1); p1 = X.translation(m.p1);
+    const auto it = neighborPoseDict.find(PoseID(m.r2, m.p2));
+    if (it == neighborPoseDict.end()) return false;
+    Y2 = it->second.rotation(); p2 = it->second.translation();
+  } else {
+    Y2 = X.rotation(m.p2); p2 = X.translation(m.p2);
+    const auto it = neighborPoseDict.find(PoseID(m.r1, m.p1));
+    if (it == neighborPoseDict.end()) return false;
+    Y1 = it->second.rotation(); p1 = it->second.translation();
+  }
+  *residual = std::sqrt(computeMeasurementError(m, Y1, p1, Y2, p2));
+  return true;
+}
+
+void PGOAgent::updateMeasurementWeights() {  // :1104-1142
+  if (mState != PGOAgentState::INITIALIZED) return;
+  {
+    lock_guard<mutex> lock(mMeasurementsMutex);
+    double residual = 0;
+    for (RelativeSEMeasurement *m : mPoseGraph->activeLoopClosures()) {
+      if (m->fixedWeight) continue;
+      if (computeMeasurementResidual(*m, &residual)) m->weight = mRobustCost.weight(residual);
+    }
+  }
+  mWeightUpdateCount++;
+  mLatestWeightUpdateIteration = iteration_number();
+  mRobustOptInnerIter = 0;
+  mPoseGraph->clearDataMatrices();  // Q and the preconditioner are rebuilt on the device at the next solve
+  mRobustCost.update();
+  mTeamStatus.clear();
+  mStatus.readyToTerminate = false;
+  mStatus.relativeChange = 0;
+  if (mTrajectoryResetCount < static_cast<unsigned>(mParams.robustOptNumResets)) {
+    mTrajectoryResetCount++;
+    setXToInitialGuess();
+    clearNeighborPoses();
+  }
+  if (mParams.acceleration) initializeAcceleration();
+}
+
+bool PGOAgent::setMeasurementWeight(const PoseID &src_ID, const PoseID &dst_ID, double weight, bool fixed_weight) {
+  RelativeSEMeasurement *m = mPoseGraph->findMeasurement(src_ID, dst_ID);
+  if (!m) return false;
+  lock_guard<mutex> lock(mMeasurementsMutex);
+  m->weight = weight;
+  m->fixedWeight = fixed_weight;
+  mPoseGraph->weightsChanged();
+  return true;
+}
+
+bool PGOAgent::isRobotInitialized(unsigned robot_id) const {
+  if (robot_id == getID()) return mState == PGOAgentState::INITIALIZED;
+  if (!hasNeighborStatus(robot_id)) return false;
+  return getNeighborStatus(robot_id).state == PGOAgentState::INITIALIZED;
+}
+
+void PGOAgent::setRobotActive(unsigned robot_id, bool active) {
+  if (robot_id >= mParams.numRobots) return;
+  mTeamRobotActive[robot_id] = active;
+  if (mPoseGraph->hasNeighbor(robot_id)) mPoseGraph->setNeighborActive(robot_id, active);
+}
+
+size_t PGOAgent::numActiveRobots() const {
+  size_t num_active = 0;
+  for (unsigned robot_id = 0; robot_id < mParams.numRobots; ++robot_id)
+    if (isRobotActive(robot_id)) num_active++;
+  return num_active;
+}
+
+bool PGOAgent::anchorFirstPose() {
+  if (num_poses() == 0) return false;
+  LiftedPose prior(relaxation_rank(), dimension());
+  prior.setData(X.pose(0));
+  mPoseGraph->setPrior(0, prior);
+  return true;
+}
+
+bool PGOAgent::anchorFirstPose(const LiftedPose &prior) {
+  DPGO_CHECK(prior.d() == dimension());
+  DPGO_CHECK(prior.r() == relaxation_rank());
+  mPoseGraph->setPrior(0, prior);
+  return true;
+}
 
 }  // namespace DPGO

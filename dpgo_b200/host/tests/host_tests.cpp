@@ -210,12 +210,66 @@ static void testOptimizationThread() {  // testOptimizationThread.cpp:29-92
   EXPECT((tr.Ttrue - T).norm() <= 1e-4);
 }
 
+// GNC robust optimization (src/PGOAgent.cpp:997-1142): a grossly wrong loop closure is driven to
+// weight 0 by the graduated schedule and the trajectory returns to the odometry solution.
+struct RobustAgent : PGOAgent {
+  using PGOAgent::PGOAgent;
+  using PGOAgent::computeMeasurementResidual;
+  using PGOAgent::setMeasurementWeight;
+  using PGOAgent::shouldUpdateMeasurementWeights;
+  using PGOAgent::updateMeasurementWeights;
+  PoseGraph::Statistics stats() { return mPoseGraph->statistics(); }
+  unsigned weightUpdates() const { return mWeightUpdateCount; }
+};
+
+static void testRobustWeights() {
+  std::printf("[RobustWeights]\n");
+  const unsigned id = 0, d = 3, r = 3;
+  PGOAgentParameters options(d, r, 1);
+  options.robustCostParams = RobustCostParameters(RobustCostParameters::Type::GNC_TLS);
+  options.robustOptInnerIters = 2;
+  options.robustOptNumWeightUpdates = 20;
+  RobustAgent agent(id, options);
+  Triangle tr = makeTriangle(id);
+  RelativeSEMeasurement &lc = tr.private_lcs[0];
+  lc.t(0, 0) += 50.0;  // outlier
+  agent.setMeasurements(tr.odometry, tr.private_lcs, tr.shared);
+  agent.initialize();
+  double res0 = 0;
+  EXPECT(agent.computeMeasurementResidual(lc, &res0));
+  EXPECT(res0 > 5.0);
+  EXPECT(!agent.shouldTerminate());
+  for (int outer = 0; outer < 20; ++outer) {
+    EXPECT(!agent.shouldUpdateMeasurementWeights());
+    agent.iterate();
+    agent.iterate();
+    EXPECT(agent.shouldUpdateMeasurementWeights());
+    agent.updateMeasurementWeights();
+  }
+  EXPECT(agent.weightUpdates() == 20);
+  EXPECT(!agent.shouldUpdateMeasurementWeights());  // reached robustOptNumWeightUpdates
+  const auto st = agent.stats();
+  EXPECT(st.total_loop_closures == 1 && st.reject_loop_closures == 1 && st.accept_loop_closures == 0);
+  agent.iterate();
+  Matrix T;
+  EXPECT(agent.getTrajectoryInLocalFrame(T));
+  // the local solves stop at gradnorm 1e-2 (ROptParameters default) and the smallest non-zero
+  // eigenvalue of this 3-pose chain is 1, so the estimate is within ~1e-2 of the odometry solution
+  // (an accepted outlier would displace pose 2 by tens of units)
+  EXPECT((tr.Ttrue - T).norm() <= 2e-2);
+  // weights can also be pinned from outside (dpgo_ros does this for the neighbour's decision)
+  EXPECT(agent.setMeasurementWeight(PoseID(id, 0), PoseID(id, 2), 1.0, true));
+  EXPECT(!agent.setMeasurementWeight(PoseID(id, 0), PoseID(id, 1 + 5), 1.0, true));
+  EXPECT(agent.stats().accept_loop_closures == 1);
+}
+
 int main() {
   testPosesAndUtils();
   testTriangleGraph();
   testPrior();
   testLineGraphAndConstruction();
   testOptimizationThread();
+  testRobustWeights();
   if (g_failed) {
     std::printf("%d check(s) FAILED\n", g_failed);
     return 1;

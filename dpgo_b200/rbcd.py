@@ -45,6 +45,9 @@ class AgentSpec:
         priv = np.where((r1 == a) & (r2 == a))[0]
         sh = np.where(((r1 == a) | (r2 == a)) & (r1 != r2))[0]
         self.priv = dict(p1=l1[priv], p2=l2[priv], R=R[priv], t=t[priv], kappa=kappa[priv], tau=tau[priv])
+        # the reader's fixedWeight flag (consecutive GLOBAL pose ids, src/DPGO_utils.cpp:178,232)
+        self.priv_fixed = (p1[priv] + 1 == p2[priv])
+        self.shared_fixed = (p1[sh] + 1 == p2[sh])
         out = r1[sh] == a                               # my pose is the tail (m.r1 == id_)
         my = np.where(out, l1[sh], l2[sh])
         nb_r = np.where(out, r2[sh], r1[sh])
@@ -105,6 +108,8 @@ class DeviceAgent:
         self.gamma = self.alpha = 0.0
         self.last_result = None
         self.updates = 0
+        self.w_private = np.ones(len(p["p1"]))
+        self.w_shared = np.ones(len(s["my_idx"]))
         # send side: for each neighbour b, which of my frames it needs (device index lists)
         self.send_idx, self.send_buf, self.send_buf_aux = {}, {}, {}
 
@@ -146,6 +151,22 @@ class DeviceAgent:
         self.prob.set_neighbor_poses_dev(buf.data_ptr())   # setNeighborPoses + constructG on device
         self.last_result = self.prob.optimize_slot(SLOT_Y if acceleration else SLOT_X, self.params)
         self.updates += 1
+
+    def update_measurement_weights(self, robust):
+        """PGOAgent::updateMeasurementWeights (src/PGOAgent.cpp:1104-1142, robustOptNumResets = 0):
+        residual of every loop closure at X and the neighbours' X by one device pass
+        (dpgo_measurement_errors), new weights for the edges whose weight is not fixed, GNC
+        schedule step, Q and preconditioner rebuilt on the device, acceleration restarted."""
+        ep, es = self.prob.measurement_errors(SLOT_X, self.nbr.data_ptr())
+        wp = np.where(self.spec.priv_fixed, self.w_private, robust.weights(np.sqrt(ep)))
+        ws = np.where(self.spec.shared_fixed, self.w_shared, robust.weights(np.sqrt(es)))
+        self.w_private, self.w_shared = wp, ws
+        robust.update()
+        self.prob.update_weights(wp, ws, True)
+        if self.acceleration:                             # initializeAcceleration :899-908
+            for s in (SLOT_XPREV, SLOT_V, SLOT_Y):
+                self.prob.slot_copy(s, SLOT_X)
+            self.gamma = self.alpha = 0.0
 
     def iterate(self, do_opt):                            # PGOAgent::iterate :376-432
         self.iteration += 1
@@ -271,6 +292,35 @@ class DeviceTeam:
         if selected in self.agents:
             self.agents[selected].iterate(True)
         self.round += 1
+
+    def step_all(self):
+        """Every agent optimizes in the same round from the poses its neighbours published at the
+        end of the previous one: the deterministic instance of the asynchronous parallel mode
+        (src/PGOAgent.cpp:486-499; no acceleration there, :477).  All GPUs are busy every round."""
+        if self.acceleration:
+            raise ValueError("the asynchronous / all-agents schedule does not allow acceleration")
+        everyone = list(range(self.A))
+        self.exchange(everyone)
+        for ag in self.agents.values():
+            ag.iterate(True)
+        self.round += 1
+        return everyone
+
+    def update_weights(self, robust=None):
+        """All agents refresh their neighbours' X and re-weight their loop closures (one RobustCost
+        per agent, as every PGOAgent owns one).  Returns {agent: (w_private, w_shared)} for the
+        agents of this rank."""
+        from .robust import RobustCost
+        if not hasattr(self, "robust"):
+            self.robust = {a: (robust() if callable(robust) else RobustCost()) for a in self.agents}
+        acc, self.acceleration = self.acceleration, False      # X only
+        try:
+            self.exchange(list(range(self.A)))
+        finally:
+            self.acceleration = acc
+        for a, ag in self.agents.items():
+            ag.update_measurement_weights(self.robust[a])
+        return {a: (ag.w_private.copy(), ag.w_shared.copy()) for a, ag in self.agents.items()}
 
     def greedy_select(self, central, X=None):
         """Next agent of the reference's greedy driver: largest block of the centralized

@@ -197,6 +197,17 @@ int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev);
  * ref: src/PGOAgent.cpp:112-130) straight into the NCCL send buffer. */
 int dpgo_gather_tiles_dev(dpgo_handle h, int slot, int num, const int32_t *idx_dev,
                           double *tiles_dev);
+/* Squared residual of every measurement of this agent at the poses in `slot`:
+ *   err = kappa |Y1 R~ - Y2|_F^2 + tau |p2 - p1 - Y1 t~|^2
+ * (ref: computeMeasurementError, src/DPGO_utils.cpp:501-507; PGOAgent::computeMeasurementResidual,
+ * src/PGOAgent.cpp:1062-1102 takes the square root), one device thread per edge -- the input of
+ * the GNC / M-estimator weight update (PGOAgent::updateMeasurementWeights :1104-1142; follow with
+ * dpgo_update_weights).  err_private / err_shared are host arrays in the order of
+ * dpgo_set_private_edges / dpgo_set_shared_edges.  Shared edges read the neighbours' poses from
+ * `nbr_poses_dev` (num_nbr_slots tiles, device memory) or, when it is NULL, from the buffer last
+ * given to dpgo_set_neighbor_poses(_dev). */
+int dpgo_measurement_errors(dpgo_handle h, int slot, const double *nbr_poses_dev, double *err_private,
+                            double *err_shared);
 /* max_i || p_i(a) - p_i(b) ||  (LiftedPoseArray::maxTranslationDistance, used for
  * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
 int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);

@@ -542,6 +542,57 @@ def optimize(prob, Y, prm: ROptParameters | None = None):
 # --------------------------------------------------------------------------------------
 # initialization
 # --------------------------------------------------------------------------------------
+def measurement_error(R, t, kappa, tau, Y1, p1, Y2, p2):
+    """computeMeasurementError, src/DPGO_utils.cpp:501-507 (squared, weighted by kappa / tau)."""
+    rot = float(np.sum((Y1 @ R - Y2) ** 2))
+    tr = float(np.sum((p2 - p1 - Y1 @ t) ** 2))
+    return kappa * rot + tau * tr
+
+
+class RobustCost:
+    """RobustCost, src/DPGO_robust.cpp:45-134 (defaults: include/DPGO/DPGO_robust.h)."""
+
+    def __init__(self, cost_type="GNC_TLS", gnc_max_iters=20, gnc_barc=5.0, gnc_mu_step=1.4, gnc_init_mu=1e-4,
+                 huber_threshold=3.0, tls_threshold=10.0):
+        self.type = cost_type
+        self.gnc_max_iters, self.barc, self.mu_step, self.init_mu = gnc_max_iters, gnc_barc, gnc_mu_step, gnc_init_mu
+        self.huber, self.tls = huber_threshold, tls_threshold
+        self.reset()
+
+    def reset(self):                      # :98-112
+        self.mu = self.init_mu
+        self.gnc_iteration = 0
+
+    def weight(self, r):                  # :54-96
+        if self.type == "L2":
+            return 1.0
+        if self.type == "L1":
+            return 1.0 / r
+        if self.type == "Huber":
+            return 1.0 if r < self.huber else self.huber / r
+        if self.type == "TLS":
+            return 1.0 if r < self.tls else 0.0
+        if self.type == "GM":
+            a = 1 + r * r
+            return 1.0 / (a * a)
+        if self.type == "GNC_TLS":        # eq. (14) of the GNC paper
+            r2, c2, mu = r * r, self.barc * self.barc, self.mu
+            if r2 >= (mu + 1) / mu * c2:
+                return 0.0
+            if r2 <= mu / (mu + 1) * c2:
+                return 1.0
+            return float(np.sqrt(c2 * mu * (mu + 1) / r2) - mu)
+        raise ValueError(self.type)
+
+    def update(self):                     # :114-132
+        if self.type != "GNC_TLS":
+            return
+        self.gnc_iteration += 1
+        if self.gnc_iteration > self.gnc_max_iters:
+            return
+        self.mu *= self.mu_step
+
+
 def odometry_initialization(odom: Measurements, n: int):
     """odometryInitialization, src/DPGO_solver.cpp:271-303 (identity start)."""
     d = odom.d

@@ -14,7 +14,9 @@ from . import pgo
 
 def partition(meas: pgo.Measurements, n: int, num_robots: int):
     """examples/MultiRobotExample.cpp:71-119: contiguous equal split, last robot takes the
-    remainder.  Returns (ranges, list of (private, shared) Measurements per robot)."""
+    remainder.  Returns (ranges, list of (private, shared) Measurements per robot).  Every
+    returned Measurements carries `fixed` = the reader's fixedWeight flag (consecutive GLOBAL
+    pose ids, src/DPGO_utils.cpp:178,232), which the driver copies along."""
     per = n // num_robots
     assert per > 0
     starts = [k * per for k in range(num_robots)]
@@ -32,6 +34,8 @@ def partition(meas: pgo.Measurements, n: int, num_robots: int):
         P = pgo.Measurements(P.d, r1[priv], l1[priv], r2[priv], l2[priv], P.R, P.t, P.kappa, P.tau, P.weight)
         S = meas.subset(sh)
         S = pgo.Measurements(S.d, r1[sh], l1[sh], r2[sh], l2[sh], S.R, S.t, S.kappa, S.tau, S.weight)
+        P.fixed = (meas.p1[priv] + 1 == meas.p2[priv])
+        S.fixed = (meas.p1[sh] + 1 == meas.p2[sh])
         out.append((P, S))
     return list(zip(starts, ends)), out
 
@@ -78,6 +82,49 @@ class Agent:
         for k, v in poses.items():
             if k in need:
                 tgt[k] = v
+
+    # -- robust weights
+    def measurement_residuals(self):
+        """sqrt(computeMeasurementError) of every private / shared edge at X and the neighbours' X
+        (PGOAgent::computeMeasurementResidual, src/PGOAgent.cpp:1062-1102)."""
+        d = self.d
+        rot = lambda T: T[:, :d]
+        tr = lambda T: T[:, d]
+        P, S = self.graph.private, self.graph.shared
+        rp = np.zeros(len(P))
+        for k in range(len(P)):
+            T1, T2 = self._pose(self.X, int(P.p1[k])), self._pose(self.X, int(P.p2[k]))
+            rp[k] = math.sqrt(pgo.measurement_error(P.R[k], P.t[k], P.kappa[k], P.tau[k], rot(T1), tr(T1), rot(T2), tr(T2)))
+        rs = np.zeros(0 if S is None else len(S))
+        for k in range(len(rs)):
+            if S.r1[k] == self.id:
+                T1, T2 = self._pose(self.X, int(S.p1[k])), self.nbr[(int(S.r2[k]), int(S.p2[k]))]
+            else:
+                T1, T2 = self.nbr[(int(S.r1[k]), int(S.p1[k]))], self._pose(self.X, int(S.p2[k]))
+            rs[k] = math.sqrt(pgo.measurement_error(S.R[k], S.t[k], S.kappa[k], S.tau[k], rot(T1), tr(T1), rot(T2), tr(T2)))
+        return rp, rs
+
+    def update_measurement_weights(self, robust: pgo.RobustCost):
+        """PGOAgent::updateMeasurementWeights, src/PGOAgent.cpp:1104-1142 (robustOptNumResets = 0:
+        the trajectory estimate is kept): re-weight every loop closure whose weight is not
+        fixed, advance the GNC schedule, drop the data matrices, restart the acceleration."""
+        rp, rs = self.measurement_residuals()
+        P, S = self.graph.private, self.graph.shared
+        for k in range(len(P)):
+            if not P.fixed[k]:
+                P.weight[k] = robust.weight(rp[k])
+        for k in range(len(rs)):
+            if not S.fixed[k]:
+                S.weight[k] = robust.weight(rs[k])
+        robust.update()
+        self.Q = pgo.construct_Q(self.graph)            # clearDataMatrices
+        self._prob = None
+        self._cpu = None
+        if self.acceleration:                           # initializeAcceleration :899-908
+            self.XPrev = self.X.copy()
+            self.gamma = self.alpha = 0.0
+            self.V = self.X.copy()
+            self.Y = self.X.copy()
 
     # -- iterate
     def _update_X(self, do_opt, acceleration):  # updateX :938-995
@@ -204,3 +251,30 @@ class Team:
         X = self.assemble()
         return dict(robots=sorted(active), cost=2 * self.central.f(X),
                     gradnorm=self.central.rgrad_norm(X))
+
+    def step_all(self):
+        """Every agent optimizes in the same round from the poses its neighbours published at the
+        end of the previous one -- the deterministic (equal-rate, no jitter) instance of the
+        asynchronous parallel mode (src/PGOAgent.cpp:486-499; acceleration is not allowed there,
+        :477)."""
+        assert not self.acceleration
+        for a in self.agents:
+            self._exchange_to(a)
+        for a in self.agents:
+            a.iterate(True)
+        X = self.assemble()
+        return dict(cost=2 * self.central.f(X), gradnorm=self.central.rgrad_norm(X))
+
+    def update_weights(self):
+        """All agents refresh their neighbours' poses and re-weight their loop closures (each
+        agent owns a RobustCost with the same schedule, as every PGOAgent does)."""
+        if not hasattr(self, "robust"):
+            self.robust = [pgo.RobustCost() for _ in self.agents]
+        for a in self.agents:
+            for other in self.agents:
+                if other.id != a.id:
+                    a.update_neighbor_poses(other.shared_pose_dict(False), False)
+        for a, rc in zip(self.agents, self.robust):
+            a.update_measurement_weights(rc)
+        # the centralized cost the driver reports uses the current weights of the global graph
+        return [(a.graph.private.weight.copy(), a.graph.shared.weight.copy()) for a in self.agents]

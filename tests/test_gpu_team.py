@@ -77,3 +77,77 @@ def test_greedy_schedule_parity(datasets):
         assert abs(2 * central_g.f(Xg) - so["cost"]) <= 1e-8 * so["cost"]
         assert abs(gn - so["gradnorm"]) <= 1e-6 * so["gradnorm"]
     gt.close(); central_g.close()
+
+
+def test_measurement_errors_parity(datasets):
+    """computeMeasurementError (src/DPGO_utils.cpp:501-507) of every private / shared edge by the
+    device edge kernel vs the oracle's per-edge loop, at a non-trivial iterate."""
+    meas, n, d, ot, gt = _teams(datasets, "smallGrid3D", 5, 5, acceleration=False)
+    colors = orbcd.robot_graph_coloring(ot.agents)
+    for k in range(2):
+        ot.step_colored(colors, k)
+        gt.step_colored()
+    for a in ot.agents:
+        for other in ot.agents:
+            if other.id != a.id:
+                a.update_neighbor_poses(other.shared_pose_dict(False), False)
+    gt.exchange(list(range(5)))
+    for a in ot.agents:
+        rp, rs = a.measurement_residuals()
+        ga = gt.agents[a.id]
+        ep, es = ga.prob.measurement_errors(0, ga.nbr.data_ptr())
+        assert np.allclose(ep, rp ** 2, rtol=1e-9, atol=1e-12)
+        assert np.allclose(es, rs ** 2, rtol=1e-9, atol=1e-12)
+        assert np.array_equal(ga.spec.priv_fixed, a.graph.private.fixed)
+        assert np.array_equal(ga.spec.shared_fixed, a.graph.shared.fixed)
+    gt.close()
+
+
+def test_gnc_weight_update_parity(datasets):
+    """BASELINE config 5: city10000 (2D), 4 agents, r = 3, GNC_TLS loop-closure weights
+    (PGOAgent::updateMeasurementWeights, src/PGOAgent.cpp:1104-1142; RobustCost defaults): the
+    device path (edge-error kernel, Q and two-level preconditioner rebuilt on the device after
+    every weight update) follows the oracle's agents through two weight updates."""
+    meas, n, d, ot, gt = _teams(datasets, "city10000", 4, 3, acceleration=False)
+    colors = orbcd.robot_graph_coloring(ot.agents)
+    assert colors == gt.colors
+    central = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((3, 3 * n)), d)
+    k = 0
+    for stage, rounds in enumerate((4, 4, 2)):
+        for _ in range(rounds):
+            so = ot.step_colored(colors, k)
+            gt.step_colored()
+            k += 1
+            cost_g = 2 * central.f(gt.assemble())
+            assert abs(cost_g - so["cost"]) <= 1e-7 * so["cost"], (stage, k, cost_g, so["cost"])
+        if stage < 2:
+            wo = ot.update_weights()
+            wg = gt.update_weights()
+            for a in range(4):
+                assert np.allclose(wg[a][0], wo[a][0], rtol=0, atol=1e-6), (stage, a)
+                assert np.allclose(wg[a][1], wo[a][1], rtol=0, atol=1e-6), (stage, a)
+                lc = ~ot.agents[a].graph.private.fixed
+                assert np.all(wo[a][0][~lc] == 1.0) and wo[a][0][lc].min() < 0.5   # weights really moved
+            assert abs(gt.robust[0].mu - ot.robust[0].mu) < 1e-15
+    Xo, Xg = ot.assemble(), gt.assemble()
+    assert np.linalg.norm(Xg - Xo) <= 1e-6 * np.linalg.norm(Xo)
+    gt.close()
+
+
+def test_all_agents_schedule_parity(datasets):
+    """BASELINE config 4: torus3D, 8 agents, r = 5, every agent optimizes in every round with the
+    poses of the previous round (the equal-rate instance of asynchronous parallel RBCD,
+    src/PGOAgent.cpp:486-499; no acceleration)."""
+    meas, n, d, ot, gt = _teams(datasets, "torus3D", 8, 5, acceleration=False)
+    central = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((5, 4 * n)), d)
+    prev = None
+    for k in range(6):
+        so = ot.step_all()
+        gt.step_all()
+        Xg = gt.assemble()
+        cost_g = 2 * central.f(Xg)
+        assert abs(cost_g - so["cost"]) <= 1e-8 * so["cost"], (k, cost_g, so["cost"])
+        prev = so["cost"]
+    Xo = ot.assemble()
+    assert np.linalg.norm(Xg - Xo) <= 1e-6 * np.linalg.norm(Xo)
+    gt.close()
