@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "device_state.h"
+#include "dissect.h"
 #include "kernels.cuh"
 #include "rtr_logic.h"
 
@@ -1175,6 +1176,26 @@ int dpgo_set_precon_mode(dpgo_handle h, int mode) {
     h->precon_request = mode;
     h->has_precon = false;
   }
+  return DPGO_OK;
+}
+
+int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
+                             int max_domain_poses, int32_t *group, int *num_domains) {
+  CHECK_ARG(n >= 0 && rowptr && (colidx || n == 0 || rowptr[n] == 0) && group && num_domains);
+  CHECK_ARG(dh >= 2 && dh <= 4);
+  for (int i = 0; i < n; ++i) {
+    CHECK_ARG(rowptr[i] <= rowptr[i + 1]);
+    for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) CHECK_ARG(colidx[e] >= 0 && colidx[e] < n);
+  }
+  const std::vector<std::vector<int>> adj = bsr_adjacency(n, rowptr, colidx);
+  Dissector ds(adj, max_domain_poses > 0 ? max_domain_poses : two_level_max_domain_poses(dh));
+  std::vector<int> all(n);
+  for (int i = 0; i < n; ++i) all[i] = i;
+  ds.run(std::move(all));
+  for (int i = 0; i < n; ++i) group[i] = -1;
+  for (size_t k = 0; k < ds.domains.size(); ++k)
+    for (int v : ds.domains[k]) group[v] = (int32_t)k;
+  *num_domains = (int)ds.domains.size();
   return DPGO_OK;
 }
 

@@ -32,6 +32,7 @@ void dd_free(dpgo_dev *h);
 int op_precon_dd(dpgo_dev *h, const double *Y, const double *rvec, double *z, double *neg_out, double *z_r);
 int dd_time_apply(dpgo_dev *h, const double *vec);   // the streaming phases only (no finish)
 double dd_bytes(const dpgo_dev *h);
+int two_level_max_domain_poses(int dh);   // interior domains hold at most this many poses
 }  // namespace dpgo
 
 struct dpgo_dev {

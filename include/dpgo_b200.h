@@ -132,6 +132,14 @@ int dpgo_finalize(dpgo_handle h, int build_precon);
 int dpgo_set_precon_mode(dpgo_handle h, int mode);
 /* The variant in use (0 / 1 / 2) once the preconditioner is built. */
 int dpgo_get_precon_mode(dpgo_handle h, int *mode);
+/* Host-only inspection of the partition the two-level variant is built on (no device needed): the
+ * nested dissection of a pose graph given as a block-CSR pattern (n block rows, rowptr[n+1],
+ * colidx) into interior domains of at most max_domain_poses poses (<= 0: the library's value for
+ * (d+1) = dh scalars per pose) and a vertex separator.  group[i] = domain id of pose i, or -1 for
+ * a separator pose; *num_domains = number of domains.  No block of the pattern joins two
+ * different domains. */
+int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
+                             int max_domain_poses, int32_t *group, int *num_domains);
 /* Tuning of the two-level variant (measurement knobs; 0 / negative = library default): how many
  * partial slots the inner dimension of the interior strips and of the Schur strips is split into
  * (more splits = more CTAs busy per phase, more partial sums to add), and whether the first
