@@ -14,6 +14,7 @@
 #define DPGO_B200_PGOAGENT_H
 
 #include <DPGO/DPGO_robust.h>
+#include <DPGO/PGOLogger.h>
 #include <DPGO/DPGO_types.h>
 #include <DPGO/DPGO_utils.h>
 #include <DPGO/PoseGraph.h>
@@ -160,6 +161,7 @@ class PGOAgent {
   PGOAgentState mState;
   PGOAgentStatus mStatus;
   RobustCost mRobustCost;
+  PGOLogger mLogger;
   std::shared_ptr<PoseGraph> mPoseGraph;
   unsigned mInstanceNumber, mIterationNumber;
   std::optional<Matrix> YLift;
@@ -208,6 +210,7 @@ class PGOAgent {
  private:
   // device-slot bookkeeping
   bool mDeviceStateValid = false;  // slots X / Y / V / XPREV hold the agent's sequences
+  Matrix TLocalInitInGlobal_;      // initial trajectory in the global frame (logged when logData)
   void uploadState();              // host X -> device slots (after setX / re-initialisation)
   void downloadX();
   void downloadY();

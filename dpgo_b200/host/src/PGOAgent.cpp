@@ -22,7 +22,7 @@ namespace DPGO {
 PGOAgent::PGOAgent(unsigned ID, const PGOAgentParameters &params)
     : mID(ID), d(params.d), r(params.r), X(params.r, params.d, 1), mParams(params),
       mState(PGOAgentState::WAIT_FOR_DATA), mStatus(ID, PGOAgentState::WAIT_FOR_DATA, 0, 0, false, 0),
-      mRobustCost(params.robustCostParams), mPoseGraph(std::make_shared<PoseGraph>(ID, params.r, params.d)),
+      mRobustCost(params.robustCostParams), mLogger(params.logDirectory), mPoseGraph(std::make_shared<PoseGraph>(ID, params.r, params.d)),
       mInstanceNumber(0), mIterationNumber(0), gamma(0), alpha(0), Y(params.r, params.d, 1) {
   if (mID == 0) setLiftingMatrix(fixedStiefelVariable(d, r));  // reference: src/PGOAgent.cpp:45
   mTeamRobotActive.assign(mParams.numRobots, true);
@@ -233,12 +233,15 @@ void PGOAgent::initializeInGlobalFrame(const Pose &T_world_robot) {  // referenc
     clearNeighborPoses();
     PoseArray T = TLocalInit.value();
     for (unsigned i = 0; i < num_poses(); ++i) T.pose(i) = (T_world_robot * Pose(T.pose(i))).pose();
+    TLocalInitInGlobal_ = T.getData();
     X.setData(YLift.value() * T.getData());
     XInit.emplace(X);
     mState = PGOAgentState::INITIALIZED;
     uploadState();
     if (mParams.acceleration) initializeAcceleration();
   }
+  if (mParams.logData)  // reference :366-370
+    mLogger.logTrajectory(dimension(), num_poses(), TLocalInitInGlobal_, "trajectory_initial.csv");
   // robust optimization starts from unit weights on every non-fixed loop closure (:348-352)
   if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2) initializeRobustOptimization();
   if (halted) startOptimizationLoop();
@@ -533,6 +536,16 @@ bool PGOAgent::shouldTerminate() {  // reference :844-878
 
 void PGOAgent::reset() {  // reference :434-473
   endOptimizationLoop();
+  if (mParams.logData) {  // measurements with their final weights, rounded trajectory, raw X (:437-452)
+    std::vector<RelativeSEMeasurement> measurements = mPoseGraph->measurements();
+    mLogger.logMeasurements(measurements, "measurements.csv");
+    Matrix T;
+    if (getTrajectoryInGlobalFrame(T)) {
+      mLogger.logTrajectory(dimension(), num_poses(), T, "trajectory_optimized.csv");
+      std::cout << "Saved optimized trajectory to " << mParams.logDirectory << std::endl;
+    }
+    writeMatrixToFile(X.getData(), mParams.logDirectory + "X.txt");
+  }
   mInstanceNumber++;
   mIterationNumber = 0;
   mLatestWeightUpdateIteration = 0;

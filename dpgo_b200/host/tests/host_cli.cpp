@@ -1,16 +1,21 @@
 // CPU-only command line probe of the host-side (non-CUDA) parts of the drop-in API, used by the
 // "not gpu" tests:  host_cli parse <file.g2o>   |   host_cli chordal <file.g2o>
+//                   host_cli logroundtrip <file.g2o> <dir/>  (PGOLogger: write + reload CSV logs)
 #include <DPGO/DPGO_solver.h>
 #include <DPGO/DPGO_utils.h>
+#include <DPGO/PGOLogger.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <string>
 
 using namespace DPGO;
 
 int main(int argc, char **argv) {
-  if (argc != 3) {
-    std::fprintf(stderr, "usage: %s parse|chordal <file.g2o>\n", argv[0]);
+  if (argc != 3 && !(argc == 4 && !std::strcmp(argv[1], "logroundtrip"))) {
+    std::fprintf(stderr, "usage: %s parse|chordal <file.g2o> | logroundtrip <file.g2o> <dir/>\n", argv[0]);
     return 2;
   }
   size_t n = 0;
@@ -32,6 +37,31 @@ int main(int argc, char **argv) {
     std::printf("%td %td\n", T.rows(), T.cols());
     for (std::ptrdiff_t j = 0; j < T.cols(); ++j)
       for (std::ptrdiff_t i = 0; i < T.rows(); ++i) std::printf("%.17g\n", T(i, j));
+    return 0;
+  }
+  if (!std::strcmp(argv[1], "logroundtrip")) {
+    // measurements (with GNC weights / fixed flags) and the chordal trajectory through the CSV
+    // files; prints the largest deviation after reloading
+    std::vector<RelativeSEMeasurement> in = ms;
+    for (size_t k = 0; k < in.size(); ++k) in[k].weight = 1.0 / (1.0 + static_cast<double>(k % 7));
+    PGOLogger logger(argv[3]);
+    logger.logMeasurements(in, "measurements.csv");
+    const Matrix T = chordalInitialization(ms).getData();
+    logger.logTrajectory(static_cast<unsigned>(d), static_cast<unsigned>(n), T, "trajectory.csv");
+    const std::vector<RelativeSEMeasurement> out =
+        PGOLogger::loadMeasurements(std::string(argv[3]) + "measurements.csv", true);
+    const Matrix T2 = logger.loadTrajectory("trajectory.csv");
+    if (out.size() != in.size() || T2.cols() != T.cols()) return 3;
+    double devR = 0, devt = 0, devw = 0, devT = (T - T2).norm();
+    bool flags = true;
+    for (size_t k = 0; k < in.size(); ++k) {
+      devR = std::max(devR, (in[k].R - out[k].R).norm());
+      devt = std::max(devt, (in[k].t - out[k].t).norm());
+      devw = std::max(devw, std::fabs(in[k].weight - out[k].weight));
+      flags = flags && in[k].fixedWeight == out[k].fixedWeight && in[k].p1 == out[k].p1 && in[k].p2 == out[k].p2 &&
+              in[k].r1 == out[k].r1 && in[k].r2 == out[k].r2;
+    }
+    std::printf("RESULT %zu %.3e %.3e %.3e %.3e %d\n", out.size(), devR, devt, devw, devT, flags ? 1 : 0);
     return 0;
   }
   return 2;

@@ -70,3 +70,33 @@ def test_g2o_parser_and_chordal_init(host_built, datasets, tmp_path, name):
     T = np.array([float(v) for v in out[2:2 + r_ * c_]]).reshape(c_, r_).T
     To = pgo.chordal_initialization(m2, n2)
     assert np.linalg.norm(T - To) <= 1e-8 * np.linalg.norm(To)
+
+
+def test_pgologger_csv_round_trip(host_built, datasets, tmp_path):
+    """PGOLogger (reference: src/PGOLogger.cpp): measurements.csv / trajectory.csv written by the
+    drop-in have the reference's header rows and columns and reload to the same data (streams use
+    the default 6 significant digits, like the reference, so the round trip is exact to ~1e-5)."""
+    meas, n, z = datasets("smallGrid3D")
+    path = str(tmp_path / "g.g2o")
+    write_g2o(path, meas.d, meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau)
+    logdir = str(tmp_path) + "/"
+    out = subprocess.check_output([host_built, "logroundtrip", path, logdir], text=True)
+    res = [ln for ln in out.split("\n") if ln.startswith("RESULT")][0].split()
+    assert int(res[1]) == len(meas) and int(res[6]) == 1
+    devR, devt, devw, devT = (float(v) for v in res[2:6])
+    assert devR < 5e-5 and devt < 1e-4 and devw < 1e-5 and devT < 1e-3
+    head = open(logdir + "measurements.csv").readline().strip()
+    assert head == "robot_src,pose_src,robot_dst,pose_dst,qx,qy,qz,qw,tx,ty,tz,kappa,tau,is_known_inlier,weight"
+    rows = np.loadtxt(logdir + "measurements.csv", delimiter=",", skiprows=1)
+    assert rows.shape == (len(meas), 15)
+    assert np.array_equal(rows[:, 1].astype(int), meas.p1) and np.array_equal(rows[:, 3].astype(int), meas.p2)
+    assert np.array_equal(rows[:, 13].astype(bool), meas.p1 + 1 == meas.p2)      # is_known_inlier = fixedWeight
+    q = rows[:, 4:8]
+    assert np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
+    # quaternion (x, y, z, w) -> R equals the measurement's rotation
+    x, y, zq, w = q.T
+    R00 = 1 - 2 * (y * y + zq * zq)
+    assert np.allclose(R00, meas.R[:, 0, 0], atol=2e-5)
+    assert open(logdir + "trajectory.csv").readline().strip() == "pose_index,qx,qy,qz,qw,tx,ty,tz"
+    traj = np.loadtxt(logdir + "trajectory.csv", delimiter=",", skiprows=1)
+    assert traj.shape == (n, 8) and np.array_equal(traj[:, 0].astype(int), np.arange(n))
