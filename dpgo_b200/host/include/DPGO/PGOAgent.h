@@ -7,9 +7,9 @@
 // In scope: everything examples/MultiRobotExample.cpp and the reference's agent tests call
 // (construction, measurements, initialize, setX/getX, iterate with and without acceleration,
 // periodic restart, shared / auxiliary pose dictionaries, neighbour poses, status, anchors,
-// rounding, reset, the asynchronous optimization thread).  Out of scope for this build (see
-// DESIGN.md): GNC weight updates, robust inter-robot frame alignment (a single-measurement
-// alignment is used when an agent is not initialised through setX), CSV logging.
+// rounding, reset, the asynchronous optimization thread), the robust-optimization methods (GNC weight
+// updates), the robust inter-robot frame alignment used when an agent is initialised from a
+// neighbour, and CSV logging (PGOLogger).
 #ifndef DPGO_B200_PGOAGENT_H
 #define DPGO_B200_PGOAGENT_H
 
@@ -190,6 +190,11 @@ class PGOAgent {
 
   void runOptimizationLoop();
   Pose computeNeighborTransform(const RelativeSEMeasurement &measurement, const LiftedPose &neighbor_pose);
+  /// robust alignment of my local frame to the world frame from all loop closures with one neighbour:
+  /// GNC rotation averaging, then translation averaging on the inliers (reference :551-604) ...
+  bool computeRobustNeighborTransformTwoStage(unsigned neighborID, const PoseDict &poseDict, Pose *T_world_robot);
+  /// ... or joint GNC pose averaging (reference :606-648)
+  bool computeRobustNeighborTransform(unsigned neighborID, const PoseDict &poseDict, Pose *T_world_robot);
 
   // robust optimization (GNC / M-estimators), reference: include/DPGO/PGOAgent.h:676-708,
   // src/PGOAgent.cpp:997-1155.  Like the reference these are driven by a subclass / the ROS layer.

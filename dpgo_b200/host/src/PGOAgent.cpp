@@ -391,21 +391,84 @@ Pose PGOAgent::computeNeighborTransform(const RelativeSEMeasurement &m, const Li
   return T_world_me * T_local.inverse();
 }
 
+namespace {
+// one candidate alignment per inter-robot loop closure whose neighbour pose is available
+template <typename Transform>
+void candidateAlignments(const std::vector<RelativeSEMeasurement> &edges, unsigned neighborID, const PoseDict &poseDict,
+                         Transform transform, std::vector<Matrix> &RVec, std::vector<Vector> &tVec) {
+  for (const RelativeSEMeasurement &m : edges) {
+    const PoseID nbr(neighborID, static_cast<unsigned>(m.r1 == neighborID ? m.p1 : m.p2));
+    const auto it = poseDict.find(nbr);
+    if (it == poseDict.end()) continue;
+    const Pose T = transform(m, it->second);
+    RVec.emplace_back(T.rotation());
+    tVec.emplace_back(T.translation());
+  }
+}
+}  // namespace
+
+bool PGOAgent::computeRobustNeighborTransformTwoStage(unsigned neighborID, const PoseDict &poseDict,
+                                                      Pose *T_world_robot) {  // reference :551-604
+  std::vector<Matrix> RVec;
+  std::vector<Vector> tVec;
+  candidateAlignments(mPoseGraph->sharedLoopClosuresWithRobot(neighborID), neighborID, poseDict,
+                      [this](const RelativeSEMeasurement &m, const LiftedPose &p) { return computeNeighborTransform(m, p); },
+                      RVec, tVec);
+  if (RVec.empty()) return false;
+  Matrix ROpt;
+  Vector tOpt;
+  std::vector<size_t> inliers;
+  const double maxRotationError = angular2ChordalSO3(0.5);  // about 30 degrees
+  robustSingleRotationAveraging(ROpt, inliers, RVec, Vector(), maxRotationError);
+  std::printf("Robot %u attempts initialization from neighbor %u: finds %zu/%zu inliers.\n", getID(), neighborID,
+              inliers.size(), RVec.size());
+  if (inliers.size() < mParams.robustInitMinInliers) return false;
+  std::vector<Vector> tIn;
+  for (size_t i : inliers) tIn.push_back(tVec[i]);
+  singleTranslationAveraging(tOpt, tIn);
+  DPGO_CHECK(T_world_robot != nullptr && T_world_robot->d() == dimension());
+  T_world_robot->rotation() = ROpt;
+  T_world_robot->translation() = tOpt;
+  return true;
+}
+
+bool PGOAgent::computeRobustNeighborTransform(unsigned neighborID, const PoseDict &poseDict,
+                                              Pose *T_world_robot) {  // reference :606-648
+  std::vector<Matrix> RVec;
+  std::vector<Vector> tVec;
+  candidateAlignments(mPoseGraph->sharedLoopClosuresWithRobot(neighborID), neighborID, poseDict,
+                      [this](const RelativeSEMeasurement &m, const LiftedPose &p) { return computeNeighborTransform(m, p); },
+                      RVec, tVec);
+  if (RVec.empty()) return false;
+  const std::ptrdiff_t m = static_cast<std::ptrdiff_t>(RVec.size());
+  Vector kappa(m, 1), tau(m, 1);
+  for (std::ptrdiff_t i = 0; i < m; ++i) {
+    kappa(i) = 1.82;  // rotation stddev of about 30 degrees
+    tau(i) = 0.01;    // translation stddev of 10 m
+  }
+  const double cbar = RobustCost::computeErrorThresholdAtQuantile(0.9, 3);
+  Matrix ROpt;
+  Vector tOpt;
+  std::vector<size_t> inliers;
+  robustSinglePoseAveraging(ROpt, tOpt, inliers, RVec, tVec, kappa, tau, cbar);
+  std::printf("Robot %u attempts initialization from neighbor %u: finds %zu/%zu inliers.\n", getID(), neighborID,
+              inliers.size(), RVec.size());
+  if (inliers.size() < mParams.robustInitMinInliers) return false;
+  DPGO_CHECK(T_world_robot != nullptr && T_world_robot->d() == dimension());
+  T_world_robot->rotation() = ROpt;
+  T_world_robot->translation() = tOpt;
+  return true;
+}
+
 void PGOAgent::updateNeighborPoses(unsigned neighborID, const PoseDict &poseDict) {  // :650-678
   DPGO_CHECK(neighborID != mID);
   if (!YLift) return;
   if (!hasNeighborStatus(neighborID)) return;
   if (getNeighborStatus(neighborID).state != PGOAgentState::INITIALIZED) return;
   if (mState == PGOAgentState::WAIT_FOR_INITIALIZATION) {
-    // single-measurement alignment (the reference runs a two-stage robust averaging here)
-    for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
-      const bool outgoing = (m.r1 == getID());
-      const PoseID nID(neighborID, static_cast<unsigned>(outgoing ? m.p2 : m.p1));
-      auto it = poseDict.find(nID);
-      if (it == poseDict.end()) continue;
-      initializeInGlobalFrame(computeNeighborTransform(m, it->second));
-      break;
-    }
+    Pose T_world_robot(dimension());
+    if (computeRobustNeighborTransformTwoStage(neighborID, poseDict, &T_world_robot))
+      initializeInGlobalFrame(T_world_robot);
   }
   if (mState != PGOAgentState::INITIALIZED) return;
   lock_guard<mutex> lock(mNeighborPosesMutex);

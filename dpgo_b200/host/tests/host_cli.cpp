@@ -1,8 +1,11 @@
 // CPU-only command line probe of the host-side (non-CUDA) parts of the drop-in API, used by the
 // "not gpu" tests:  host_cli parse <file.g2o>   |   host_cli chordal <file.g2o>
 //                   host_cli logroundtrip <file.g2o> <dir/>  (PGOLogger: write + reload CSV logs)
+//                   host_cli averaging <file>  (robust single rotation / pose averaging of the
+//                                               candidate alignments listed in <file>)
 #include <DPGO/DPGO_solver.h>
 #include <DPGO/DPGO_utils.h>
+#include <DPGO/DPGO_robust.h>
 #include <DPGO/PGOLogger.h>
 
 #include <algorithm>
@@ -17,6 +20,51 @@ int main(int argc, char **argv) {
   if (argc != 3 && !(argc == 4 && !std::strcmp(argv[1], "logroundtrip"))) {
     std::fprintf(stderr, "usage: %s parse|chordal <file.g2o> | logroundtrip <file.g2o> <dir/>\n", argv[0]);
     return 2;
+  }
+  if (!std::strcmp(argv[1], "averaging")) {
+    std::FILE *f = std::fopen(argv[2], "r");
+    if (!f) return 3;
+    int cnt = 0, dim = 0;
+    if (std::fscanf(f, "%d %d", &cnt, &dim) != 2) return 3;
+    std::vector<Matrix> RVec;
+    std::vector<Vector> tVec;
+    for (int k = 0; k < cnt; ++k) {
+      Matrix R(dim, dim);
+      Vector t(dim, 1);
+      for (int a = 0; a < dim; ++a)
+        for (int b = 0; b < dim; ++b)
+          if (std::fscanf(f, "%lf", &R(a, b)) != 1) return 3;
+      for (int a = 0; a < dim; ++a)
+        if (std::fscanf(f, "%lf", &t(a, 0)) != 1) return 3;
+      RVec.push_back(R);
+      tVec.push_back(t);
+    }
+    std::fclose(f);
+    auto dump = [&](const char *tag, const Matrix &R, const Vector &t, const std::vector<size_t> &inl) {
+      std::printf("%s", tag);
+      for (std::ptrdiff_t a = 0; a < R.rows(); ++a)
+        for (std::ptrdiff_t b = 0; b < R.cols(); ++b) std::printf(" %.17g", R(a, b));
+      for (std::ptrdiff_t a = 0; a < t.rows(); ++a) std::printf(" %.17g", t(a, 0));
+      std::printf(" |");
+      for (size_t i : inl) std::printf(" %zu", i);
+      std::printf("\n");
+    };
+    Matrix ROpt;
+    Vector tOpt;
+    std::vector<size_t> inl;
+    // the two-stage alignment of PGOAgent::computeRobustNeighborTransformTwoStage
+    robustSingleRotationAveraging(ROpt, inl, RVec, Vector(), angular2ChordalSO3(0.5));
+    std::vector<Vector> tin;
+    for (size_t i : inl) tin.push_back(tVec[i]);
+    if (tin.empty()) tin = tVec;
+    singleTranslationAveraging(tOpt, tin);
+    dump("TWOSTAGE", ROpt, tOpt, inl);
+    // the joint alignment of PGOAgent::computeRobustNeighborTransform
+    Vector kappa(cnt, 1), tau(cnt, 1);
+    for (int k = 0; k < cnt; ++k) { kappa(k) = 1.82; tau(k) = 0.01; }
+    robustSinglePoseAveraging(ROpt, tOpt, inl, RVec, tVec, kappa, tau, RobustCost::computeErrorThresholdAtQuantile(0.9, 3));
+    dump("JOINT", ROpt, tOpt, inl);
+    return 0;
   }
   size_t n = 0;
   const std::vector<RelativeSEMeasurement> ms = read_g2o_file(argv[2], n);

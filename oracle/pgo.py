@@ -593,6 +593,52 @@ class RobustCost:
         self.mu *= self.mu_step
 
 
+def single_rotation_averaging(Rs, kappa):
+    """singleRotationAveraging, src/DPGO_solver.cpp:42-57."""
+    return project_rotation(np.einsum("i,ijk->jk", kappa, Rs))
+
+
+def _gnc_averaging(n, threshold, max_iters, solve, residual_sq):
+    """The GNC-TLS loop of robustSingleRotationAveraging / robustSinglePoseAveraging
+    (src/DPGO_solver.cpp:72-134, 136-218)."""
+    w_tol = 1e-8
+    w = np.ones(n)
+    est = solve(w)
+    rsq = np.array([residual_sq(est, i) for i in range(n)])
+    mu_init = min(threshold ** 2 / (2 * rsq.max() - threshold ** 2), 1e-5)
+    if mu_init > 0:
+        cost = RobustCost("GNC_TLS", gnc_max_iters=max_iters, gnc_barc=threshold, gnc_init_mu=mu_init)
+        for _ in range(max_iters):
+            est = solve(w)
+            w = np.array([cost.weight(math.sqrt(residual_sq(est, i))) for i in range(n)])
+            if np.all((w < w_tol) | (w > 1 - w_tol)):
+                break
+            cost.update()
+    return est, [i for i in range(n) if w[i] > 1 - w_tol]
+
+
+def robust_single_rotation_averaging(Rs, kappa=None, threshold=0.1):
+    Rs = np.asarray(Rs)
+    kappa = np.ones(len(Rs)) if kappa is None else np.asarray(kappa, dtype=float)
+    return _gnc_averaging(len(Rs), threshold, 1000, lambda w: single_rotation_averaging(Rs, kappa * w),
+                          lambda R, i: kappa[i] * np.sum((R - Rs[i]) ** 2))
+
+
+def robust_single_pose_averaging(Rs, ts, kappa=None, tau=None, threshold=0.1):
+    Rs, ts = np.asarray(Rs), np.asarray(ts)
+    n = len(Rs)
+    kappa = 10000 * np.ones(n) if kappa is None else np.asarray(kappa, dtype=float)
+    tau = 100 * np.ones(n) if tau is None else np.asarray(tau, dtype=float)
+
+    def solve(w):                        # singlePoseAveraging :59-70
+        return single_rotation_averaging(Rs, kappa * w), (tau * w) @ ts / np.sum(tau * w)
+
+    def res(est, i):
+        return kappa[i] * np.sum((est[0] - Rs[i]) ** 2) + tau[i] * np.sum((est[1] - ts[i]) ** 2)
+    (R, t), inl = _gnc_averaging(n, threshold, 10000, solve, res)
+    return R, t, inl
+
+
 def odometry_initialization(odom: Measurements, n: int):
     """odometryInitialization, src/DPGO_solver.cpp:271-303 (identity start)."""
     d = odom.d

@@ -100,3 +100,59 @@ def test_pgologger_csv_round_trip(host_built, datasets, tmp_path):
     assert open(logdir + "trajectory.csv").readline().strip() == "pose_index,qx,qy,qz,qw,tx,ty,tz"
     traj = np.loadtxt(logdir + "trajectory.csv", delimiter=",", skiprows=1)
     assert traj.shape == (n, 8) and np.array_equal(traj[:, 0].astype(int), np.arange(n))
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    if th < 1e-15:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+@pytest.mark.parametrize("n_out", [0, 3, 7])
+def test_robust_frame_alignment_averaging(host_built, tmp_path, n_out):
+    """robustSingleRotationAveraging / robustSinglePoseAveraging (src/DPGO_solver.cpp:72-218), the
+    solvers behind PGOAgent::computeRobustNeighborTransform(TwoStage): the C++ drop-in agrees with
+    the oracle's restatement on the same candidate alignments, finds exactly the inliers, and
+    recovers the true alignment."""
+    from scipy.stats import chi2
+    rng = np.random.default_rng(10 + n_out)
+    n_in = 12
+    R_true = _rodrigues(np.array([0.3, -0.8, 0.5]))
+    t_true = np.array([4.0, -2.0, 1.0])
+    Rs = [R_true @ _rodrigues(0.03 * rng.standard_normal(3)) for _ in range(n_in)]
+    ts = [t_true + 0.05 * rng.standard_normal(3) for _ in range(n_in)]
+    for _ in range(n_out):                         # gross outliers: random rotation, far translation
+        Rs.append(_rodrigues(rng.uniform(1.5, 3.0) * np.array([1.0, 0, 0]) + rng.standard_normal(3)))
+        ts.append(t_true + rng.uniform(30, 60, 3))
+    order = rng.permutation(len(Rs))
+    Rs, ts = np.array(Rs)[order], np.array(ts)[order]
+    truth = sorted(int(i) for i in np.where(order < n_in)[0])
+    path = tmp_path / "cands.txt"
+    with open(path, "w") as f:
+        f.write(f"{len(Rs)} 3\n")
+        for R, t in zip(Rs, ts):
+            f.write(" ".join(repr(float(v)) for v in list(R.ravel()) + list(t)) + "\n")
+    out = subprocess.check_output([host_built, "averaging", str(path)], text=True).strip().split("\n")
+
+    def parse(line):
+        head, inl = line.split("|")
+        v = [float(x) for x in head.split()[1:]]
+        return np.array(v[:9]).reshape(3, 3), np.array(v[9:12]), [int(i) for i in inl.split()]
+    R2, t2, inl2 = parse([ln for ln in out if ln.startswith("TWOSTAGE")][0])
+    Rj, tj, inlj = parse([ln for ln in out if ln.startswith("JOINT")][0])
+    # oracle restatement on the same input
+    Ro, inlo = pgo.robust_single_rotation_averaging(Rs, None, 2 * np.sqrt(2) * np.sin(0.25))
+    assert inl2 == inlo == truth
+    assert np.linalg.norm(R2 - Ro) < 1e-12
+    assert np.linalg.norm(t2 - ts[truth].mean(axis=0)) < 1e-12
+    Rjo, tjo, inljo = pgo.robust_single_pose_averaging(Rs, ts, 1.82 * np.ones(len(Rs)), 0.01 * np.ones(len(Rs)),
+                                                       np.sqrt(chi2.ppf(0.9, 6)))
+    assert inlj == inljo == truth
+    assert np.linalg.norm(Rj - Rjo) < 1e-12 and np.linalg.norm(tj - tjo) < 1e-12
+    # and both are close to the truth
+    for R, t in ((R2, t2), (Rj, tj)):
+        assert np.linalg.norm(R - R_true) < 0.05 and np.linalg.norm(t - t_true) < 0.1
+        assert abs(np.linalg.det(R) - 1) < 1e-12
