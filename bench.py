@@ -388,6 +388,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--schedule", default="colored", choices=["colored", "all"],
+                    help="multi-agent series (N > 1): coloured parallel schedule with Nesterov acceleration "
+                         "(BASELINE configs[2], default) or every agent in every round without acceleration "
+                         "(asynchronous-style, configs[3])")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--precon-mode", type=int, default=None,
                     help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level "

@@ -69,6 +69,18 @@ def _worker(rank, world, port, ret):
                 got = agents[a].nbr[slot * tile:(slot + 1) * tile]
                 got_aux = agents[a].nbr_aux[slot * tile:(slot + 1) * tile]
                 ok &= bool(torch.equal(got, Xs[b][f])) and bool(torch.equal(got_aux, Ys[b][f]))
+    # every agent active at once (DeviceTeam.step_all / update_weights): both directions of every
+    # robot-graph edge travel in the same batch, X only (no acceleration in that schedule)
+    for ag in agents.values():
+        ag.nbr.zero_(); ag.nbr_aux.zero_()
+    everyone = list(range(A))
+    rbcd.exchange_poses(agents, specs, owner, rank, everyone, False)
+    for a in everyone:
+        if owner[a] != rank:
+            continue
+        for slot, (b, f) in enumerate(specs[a].nbr_keys):
+            ok &= bool(torch.equal(agents[a].nbr[slot * tile:(slot + 1) * tile], Xs[b][f]))
+        ok &= bool(torch.count_nonzero(agents[a].nbr_aux) == 0)
     ret[rank] = (ok, owner, colors)
     dist.barrier()
     dist.destroy_process_group()

@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "grid3D 8 agents r=5 sync RBCD + Nesterov, coloured parallel schedule, RTR(3 outer, <=50 tCG)"
+# --schedule all: every agent optimizes every round from the previous round's poses, no acceleration
+# (the equal-rate instance of the reference's asynchronous mode, BASELINE configs[3]); all GPUs busy
+WORKLOAD_ALL = "grid3D 8 agents r=5 all-agents-per-round RBCD (asynchronous-style, no acceleration), RTR(3 outer, <=50 tCG)"
 
 
 def _fixture(name):
@@ -21,7 +24,8 @@ def _fixture(name):
     return z, int(z["d"]), int(z["n"])
 
 
-def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agents=8, r=5, e2e=True):
+def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agents=8, r=5, e2e=True,
+            schedule="colored"):
     """Returns a dict with the timed results (identical on every rank)."""
     import torch
     import torch.distributed as dist
@@ -38,8 +42,10 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     X0 = np.asfortranarray(lifting_matrix(d, r) @ z["T_chordal"])
     t0 = time.time()
     team = rbcd.DeviceTeam(z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"], n, d, r, agents,
-                           device=local_rank, stream=stream, rank=rank, world=world, acceleration=True)
+                           device=local_rank, stream=stream, rank=rank, world=world,
+                           acceleration=(schedule != "all"))
     setup_s = time.time() - t0
+    step = team.step_all if schedule == "all" else team.step_colored
 
     def reset():
         team.set_X(X0)
@@ -62,7 +68,7 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
         upd = 0
         cost = None
         for _ in range(nsteps):
-            active = team.step_colored()
+            active = step()
             upd += len(active)
             if with_host_eval:   # the driver's per-iteration evaluation: getX of every agent + f
                 X = team.assemble()
@@ -81,7 +87,7 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     W = max(warmup, 3)
     reset()
     for _ in range(W):
-        team.step_colored()
+        step()
     reset()
     l0 = sum(ag.prob.launch_count() for ag in team.agents.values())
     ms, wall_ms, upd, _ = timed(steps, False)
@@ -112,19 +118,23 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     return out
 
 
-def cpu_team_baseline(rounds=2, dataset="grid3D", agents=8, r=5):
+def cpu_team_baseline(rounds=2, dataset="grid3D", agents=8, r=5, schedule="colored"):
     """The oracle's agents with the same coloured schedule, one host core (the reference runs
     its agents sequentially on one thread)."""
     from oracle import pgo, rbcd as orbcd
     z, d, n = _fixture(dataset)
     meas = pgo.make_measurements(d, z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"])
-    team = orbcd.Team(meas, n, agents, r, acceleration=True)
+    team = orbcd.Team(meas, n, agents, r, acceleration=(schedule != "all"))
     for a in team.agents:
         a.use_cpu_port = True         # compiled local solves (oracle/cpu_port)
     team.set_X(pgo.lifting_matrix(d, r) @ z["T_chordal"])
     colors = orbcd.robot_graph_coloring(team.agents)
-    team.step_colored(colors, 0)      # warm-up round: factorizes every agent's preconditioner
-    team.step_colored(colors, 1)
+    if schedule == "all":
+        one = lambda k: dict(team.step_all(), robots=list(range(agents)))
+    else:
+        one = lambda k: team.step_colored(colors, k)
+    one(0)                            # warm-up rounds: factorize every agent's preconditioner
+    one(1)
     team.set_X(pgo.lifting_matrix(d, r) @ z["T_chordal"])
     for a in team.agents:
         a.iteration = 0
@@ -132,7 +142,7 @@ def cpu_team_baseline(rounds=2, dataset="grid3D", agents=8, r=5):
     upd = 0
     s = None
     for k in range(rounds):
-        s = team.step_colored(colors, k)
+        s = one(k)
         upd += len(s["robots"])
     dt = time.perf_counter() - t0
     return dict(value=upd / dt, ms_per_step=dt / rounds * 1e3, rounds=rounds, cost2=s["cost"])
@@ -154,19 +164,21 @@ def run(args, emit=None):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    res = measure(args.steps, args.warmup, rank, world, local_rank)
+    schedule = getattr(args, "schedule", "colored")
+    res = measure(args.steps, args.warmup, rank, world, local_rank, schedule=schedule)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        cpu = cpu_team_baseline(args.cpu_steps if args.cpu_steps < 4 else 2)
+        cpu = cpu_team_baseline(args.cpu_steps if args.cpu_steps < 4 else 2, schedule=schedule)
         line = {
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"],
             "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "grid3D.g2o (fixture parsed from the reference's data file)",
-            "config": {"workload": WORKLOAD, "n": res["n"], "agents": res["agents"],
+            "config": {"workload": WORKLOAD_ALL if schedule == "all" else WORKLOAD, "n": res["n"], "agents": res["agents"],
                        "agents_per_gpu": res["agents"] / world, "colors": res["colors"], "owner": res["owner"],
-                       "step": "one colour round = 4 agent updates (iterate(true)) + 4 non-optimizing iterates",
-                       "l2": "per-agent dense preconditioner 128 MB ~ L2 size; 8/N agents per GPU alternate",
+                       "step": ("one round = 8 agent updates (iterate(true))" if schedule == "all" else
+                                "one colour round = 4 agent updates (iterate(true)) + 4 non-optimizing iterates"),
+                       "l2": "per-agent two-level preconditioner 21.5 MB streamed per apply; 8/N agents per GPU alternate",
                        "exchange": "NCCL send/recv of packed public poses (X and aux Y)" if world > 1 else
                                    "device-to-device copies (single GPU)"},
             "clocks": clocks,
@@ -180,7 +192,7 @@ def run(args, emit=None):
                          "note": "see the N=1 line: the dominant kernel and its roofline are measured there"},
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",
                              "ms_per_step": cpu["ms_per_step"],
-                             "sample": f"{cpu['rounds']} colour rounds of the oracle's 8 agents (compiled C++ local solves, oracle/cpu_port), "
+                             "sample": f"{cpu['rounds']} rounds ({schedule} schedule) of the oracle's 8 agents (compiled C++ local solves, oracle/cpu_port), "
                                        "sequential on one core as the reference runs them"},
             "parity": {"cost2_after_timed_rounds": res["cost2"], "gradnorm": res["gradnorm"]},
         }
