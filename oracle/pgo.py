@@ -271,11 +271,10 @@ def retract_qf(X, Eta, d):
     diagonal of R forced positive; p+ = p + eta_p.  SURVEY 8(a) C4."""
     Zt = _tiles(X + Eta, d)
     out = Zt.copy()
-    for i in range(Zt.shape[0]):
-        Qm, Rm = np.linalg.qr(Zt[i, :, :d])
-        sg = np.sign(np.diag(Rm))
-        sg[sg == 0] = 1.0
-        out[i, :, :d] = Qm * sg
+    Qm, Rm = np.linalg.qr(Zt[:, :, :d])                     # stacked thin QR, one per pose
+    sg = np.sign(np.diagonal(Rm, axis1=1, axis2=2))
+    sg[sg == 0] = 1.0
+    out[:, :, :d] = Qm * sg[:, None, :]
     return _untile(out)
 
 
@@ -298,8 +297,9 @@ def project_rotation(M):
 def manifold_project(X, d):
     """LiftedSEManifold::project, src/manifold/LiftedSEManifold.cpp:34-45."""
     Xt = _tiles(X, d).copy()
-    for i in range(Xt.shape[0]):
-        Xt[i, :, :d] = project_stiefel(Xt[i, :, :d])
+    # project_stiefel of every pose at once (numpy's svd works on stacked matrices)
+    U, _, Vt = np.linalg.svd(Xt[:, :, :d], full_matrices=False)
+    Xt[:, :, :d] = U @ Vt
     return _untile(Xt)
 
 
