@@ -16,18 +16,21 @@ namespace DPGO {
 
 class PGOLogger {
  public:
-  /// logDir is prepended verbatim to every file name (reference: "logDirectory + filename")
-  explicit PGOLogger(std::string logDir);
+  /// `directory` is prepended verbatim to every file name passed to the non-static members
+  explicit PGOLogger(std::string directory);
   ~PGOLogger();
 
-  /// pose_index,qx,qy,qz,qw,tx,ty,tz -- T is d x (d+1)n; nothing is written for d == 2
-  void logTrajectory(unsigned d, unsigned n, const Matrix &T, const std::string &filename);
-  /// robot_src,pose_src,robot_dst,pose_dst,qx,qy,qz,qw,tx,ty,tz,kappa,tau,is_known_inlier,weight
-  void logMeasurements(std::vector<RelativeSEMeasurement> &measurements, const std::string &filename);
-  /// 3 x 4n matrix (empty when the file cannot be opened); quaternions are normalised on load
-  Matrix loadTrajectory(const std::string &filename);
-  /// `filename` is used as given (not prefixed), as in the reference
-  static std::vector<RelativeSEMeasurement> loadMeasurements(const std::string &filename, bool load_weight = false);
+  // ---- writers (3-D only: nothing is written for d == 2)
+  /// columns: pose_index,qx,qy,qz,qw,tx,ty,tz ; `trajectory` is d x (d+1)n
+  void logTrajectory(unsigned d, unsigned n, const Matrix &trajectory, const std::string &file);
+  /// columns: robot_src,pose_src,robot_dst,pose_dst,qx,qy,qz,qw,tx,ty,tz,kappa,tau,is_known_inlier,weight
+  void logMeasurements(std::vector<RelativeSEMeasurement> &edges, const std::string &file);
+
+  // ---- readers (quaternions are normalised on load)
+  /// 3 x 4n matrix, empty when the file cannot be opened
+  Matrix loadTrajectory(const std::string &file);
+  /// `path` is used as given (NOT prefixed with the log directory), as in the reference
+  static std::vector<RelativeSEMeasurement> loadMeasurements(const std::string &path, bool with_weights = false);
 
  private:
   std::string logDirectory;

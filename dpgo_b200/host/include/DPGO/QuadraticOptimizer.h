@@ -16,21 +16,24 @@ class QuadraticOptimizer {
 
   /// optimize from Y; returns the new iterate (reference: src/QuadraticOptimizer.cpp:26-48)
   Matrix optimize(const Matrix &Y);
+  /// result of the last optimize() call
+  ROPTResult getOptResult() const { return mLastResult; }
 
-  void setVerbose(bool v) { params_.verbose = v; }
-  void setAlgorithm(ROptParameters::ROptMethod alg) { params_.method = alg; }
-  void setRGDStepsize(double s) { params_.RGD_stepsize = s; }
-  void setRTRIterations(int iter) { params_.RTR_iterations = iter; }
-  void setGradientNormTolerance(double tol) { params_.gradnorm_tol = tol; }
-  void setRTRInitialRadius(double radius) { params_.RTR_initial_radius = radius; }
-  void setRTRtCGIterations(int iter) { params_.RTR_tCG_iterations = iter; }
-
-  ROPTResult getOptResult() const { return result_; }
+  // configuration (same setters as the reference; they only edit the parameter block that
+  // optimize() hands to the device solver)
+  void setProblem(QuadraticProblem *problem);
+  void setVerbose(bool on);
+  void setAlgorithm(ROptParameters::ROptMethod method);
+  void setRGDStepsize(double stepsize);
+  void setGradientNormTolerance(double tolerance);
+  void setRTRIterations(int outer_iterations);
+  void setRTRtCGIterations(int inner_iterations);
+  void setRTRInitialRadius(double initial_radius);
 
  private:
-  QuadraticProblem *problem_;  // not owned (reference: QuadraticOptimizer.h:85)
-  ROptParameters params_;
-  ROPTResult result_;
+  QuadraticProblem *mProblem;  // not owned
+  ROptParameters mOptions;
+  ROPTResult mLastResult;
 };
 
 }  // namespace DPGO
