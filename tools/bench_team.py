@@ -194,6 +194,12 @@ def run(args, emit=None):
     schedule = getattr(args, "schedule", "colored")
     res = measure(args.steps, args.warmup, rank, world, local_rank, schedule=schedule)
     clocks = sampler.stop() if rank == 0 else None
+    # second series for the record: the other parallel schedule of SURVEY 8(e) on the same graph
+    other = "colored" if schedule == "all" else "all"
+    try:
+        res2 = measure(args.steps, args.warmup, rank, world, local_rank, schedule=other, e2e=False)
+    except Exception as exc:  # the headline series above must survive a failure here
+        res2 = {"error": repr(exc)}
     if rank == 0:
         par = 8 if schedule == "all" else 4            # agents that optimize in the same round
         cpus = cpu_team_baseline(args.cpu_steps if args.cpu_steps < 4 else 2, schedule=schedule,
@@ -228,6 +234,11 @@ def run(args, emit=None):
                                                     "ms_per_step": cpu_par["ms_per_step"],
                                                     "note": "the agents that optimize in the same round on one host core each"}},
             "parity": {"cost2_after_timed_rounds": res["cost2"], "gradnorm": res["gradnorm"]},
+            "other_schedule": ({"error": res2["error"]} if "error" in res2 else {
+                "workload": WORKLOAD if other == "colored" else WORKLOAD_ALL, "value": res2["value"], "unit": UNIT,
+                "ms_per_step": res2["ms_per_step"], "steps": res2["steps"], "updates": res2["updates"],
+                "cost2_after_timed_rounds": res2["cost2"], "gradnorm": res2["gradnorm"],
+                "note": "not the headline series: same graph and agents, the other parallel block schedule"}),
         }
         (emit or (lambda l: print(json.dumps(l), flush=True)))(line)
     if world > 1:
