@@ -123,6 +123,8 @@ class PGOAgent {
   bool getTrajectoryInGlobalFrame(Matrix &Trajectory);
   bool getTrajectoryInGlobalFrame(PoseArray &Trajectory);
   bool getPoseInGlobalFrame(unsigned poseID, Matrix &T);
+  /// a cached neighbour pose expressed in the global frame fixed by the anchor (reference :789-810)
+  bool getNeighborPoseInGlobalFrame(unsigned neighborID, unsigned poseID, Matrix &T);
   bool getSharedPose(unsigned index, Matrix &Mout);
   bool getAuxSharedPose(unsigned index, Matrix &Mout);
   bool getSharedPoseDict(PoseDict &map);

@@ -574,6 +574,21 @@ bool PGOAgent::getPoseInGlobalFrame(unsigned poseID, Matrix &T) {
   return true;
 }
 
+bool PGOAgent::getNeighborPoseInGlobalFrame(unsigned neighborID, unsigned poseID, Matrix &T) {
+  if (!globalAnchor) return false;
+  const LiftedPose Xa = globalAnchor.value();
+  if (mState != PGOAgentState::INITIALIZED) return false;
+  lock_guard<mutex> lock(mNeighborPosesMutex);
+  const auto it = neighborPoseDict.find(PoseID(neighborID, poseID));
+  if (it == neighborPoseDict.end()) return false;
+  const Matrix Ya = Xa.rotation();
+  const Matrix t0 = Ya.transpose() * Xa.translation();
+  Matrix Ti = Ya.transpose() * it->second.pose();   // d x (d+1): rotation | translation
+  Ti.block(0, d, d, 1) -= t0;
+  T = Ti;
+  return true;
+}
+
 Matrix PGOAgent::localPoseGraphOptimization() {  // reference :823-828
   ROptParameters pgo_params;
   pgo_params.verbose = true;
