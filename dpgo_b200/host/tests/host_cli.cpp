@@ -11,13 +11,19 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 using namespace DPGO;
 
 int main(int argc, char **argv) {
-  if (argc != 3 && !(argc == 4 && !std::strcmp(argv[1], "logroundtrip"))) {
+  if (argc >= 2 && !std::strcmp(argv[1], "chi2") && argc == 4) {  // chi2inv(quantile, dof), testUtils.cpp:56-70
+    std::printf("%.15g\n", chi2inv(std::atof(argv[2]), static_cast<size_t>(std::atoi(argv[3]))));
+    return 0;
+  }
+  const bool averaging_with_params = (argc == 6 && !std::strcmp(argv[1], "averaging"));
+  if (argc != 3 && !(argc == 4 && !std::strcmp(argv[1], "logroundtrip")) && !averaging_with_params) {
     std::fprintf(stderr, "usage: %s parse|chordal <file.g2o> | logroundtrip <file.g2o> <dir/>\n", argv[0]);
     return 2;
   }
@@ -53,7 +59,11 @@ int main(int argc, char **argv) {
     Vector tOpt;
     std::vector<size_t> inl;
     // the two-stage alignment of PGOAgent::computeRobustNeighborTransformTwoStage
-    robustSingleRotationAveraging(ROpt, inl, RVec, Vector(), angular2ChordalSO3(0.5));
+    // optional: <rotation threshold in rad> <kappa> <tau> (defaults = PGOAgent's alignment settings)
+    const double rot_thr = averaging_with_params ? std::atof(argv[3]) : 0.5;
+    const double kap = averaging_with_params ? std::atof(argv[4]) : 1.82;
+    const double ta = averaging_with_params ? std::atof(argv[5]) : 0.01;
+    robustSingleRotationAveraging(ROpt, inl, RVec, Vector(), angular2ChordalSO3(rot_thr));
     std::vector<Vector> tin;
     for (size_t i : inl) tin.push_back(tVec[i]);
     if (tin.empty()) tin = tVec;
@@ -61,7 +71,7 @@ int main(int argc, char **argv) {
     dump("TWOSTAGE", ROpt, tOpt, inl);
     // the joint alignment of PGOAgent::computeRobustNeighborTransform
     Vector kappa(cnt, 1), tau(cnt, 1);
-    for (int k = 0; k < cnt; ++k) { kappa(k) = 1.82; tau(k) = 0.01; }
+    for (int k = 0; k < cnt; ++k) { kappa(k) = kap; tau(k) = ta; }
     robustSinglePoseAveraging(ROpt, tOpt, inl, RVec, tVec, kappa, tau, RobustCost::computeErrorThresholdAtQuantile(0.9, 3));
     dump("JOINT", ROpt, tOpt, inl);
     return 0;

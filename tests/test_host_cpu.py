@@ -156,3 +156,80 @@ def test_robust_frame_alignment_averaging(host_built, tmp_path, n_out):
     for R, t in ((R2, t2), (Rj, tj)):
         assert np.linalg.norm(R - R_true) < 0.05 and np.linalg.norm(t - t_true) < 0.1
         assert abs(np.linalg.det(R) - 1) < 1e-12
+
+
+def _random_rotation(rng):
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _averaging_cli(host_built, tmp_path, Rs, ts, rot_thr, kappa, tau):
+    path = tmp_path / "c.txt"
+    with open(path, "w") as f:
+        f.write(f"{len(Rs)} 3\n")
+        for R, t in zip(Rs, ts):
+            f.write(" ".join(repr(float(v)) for v in list(np.asarray(R).ravel()) + list(t)) + "\n")
+    out = subprocess.check_output([host_built, "averaging", str(path), repr(rot_thr), repr(kappa), repr(tau)],
+                                  text=True).strip().split("\n")
+
+    def parse(line):
+        head, inl = line.split("|")
+        v = [float(x) for x in head.split()[1:]]
+        return np.array(v[:9]).reshape(3, 3), np.array(v[9:12]), [int(i) for i in inl.split()]
+    return (parse([ln for ln in out if ln.startswith("TWOSTAGE")][0]),
+            parse([ln for ln in out if ln.startswith("JOINT")][0]))
+
+
+def test_reference_known_answers_robust_averaging(host_built, tmp_path):
+    """The reference's own tests of these solvers, restated (tests/testPGO.cpp:14-129): a single
+    measurement is returned as is; 10 identical inliers among 40 random outliers at least 1.2 x the
+    threshold away are found exactly (indices 0..9) and the estimate is within 0.02 rad / 1e-2 of
+    the truth.  Checked for the C++ drop-in and for the oracle's restatement."""
+    from scipy.stats import chi2
+    rng = np.random.default_rng(7)
+    chord = lambda rad: 2 * np.sqrt(2) * np.sin(rad / 2)
+    barc = np.sqrt(chi2.ppf(0.9, 6))
+    for trial in range(6):
+        R_true, t_true = _random_rotation(rng), np.zeros(3)
+        # trivial cases (:14-30, :62-84)
+        (R2, _, inl2), (Rj, tj, inlj) = _averaging_cli(host_built, tmp_path, [R_true], [t_true], 0.5, 10000, 100)
+        assert np.linalg.norm(R2 - R_true) <= 1e-8 and inl2 == [0]
+        assert np.linalg.norm(Rj - R_true) <= 1e-8 and np.linalg.norm(tj) <= 1e-8 and inlj == [0]
+        # rotation averaging with outliers (:32-60)
+        cbar = chord(0.3)
+        Rs = [R_true] * 10
+        while len(Rs) < 50:
+            Rr = _random_rotation(rng)
+            if np.linalg.norm(Rr - R_true) > 1.2 * cbar:
+                Rs.append(Rr)
+        (R2, _, inl2), _ = _averaging_cli(host_built, tmp_path, Rs, [t_true] * 50, 0.3, 10000, 100)
+        Ro, inlo = pgo.robust_single_rotation_averaging(np.array(Rs), np.ones(50), cbar)
+        for R, inl in ((R2, inl2), (Ro, inlo)):
+            assert inl == list(range(10))
+            assert np.linalg.norm(R - R_true) <= chord(0.02)
+            assert abs(np.linalg.det(R) - 1) < 1e-9
+        # pose averaging with outliers (:86-129)
+        Rs, ts = [R_true] * 10, [t_true] * 10
+        while len(Rs) < 50:
+            Rr, tr = _random_rotation(rng), rng.uniform(-1, 1, 3)
+            if np.sqrt(10000 * np.sum((R_true - Rr) ** 2) + 100 * np.sum((t_true - tr) ** 2)) > 1.2 * barc:
+                Rs.append(Rr); ts.append(tr)
+        _, (Rj, tj, inlj) = _averaging_cli(host_built, tmp_path, Rs, ts, 0.3, 10000, 100)
+        Rjo, tjo, inljo = pgo.robust_single_pose_averaging(np.array(Rs), np.array(ts), 10000 * np.ones(50),
+                                                           100 * np.ones(50), barc)
+        for R, t, inl in ((Rj, tj, inlj), (Rjo, tjo, inljo)):
+            assert inl == list(range(10))
+            assert np.linalg.norm(R - R_true) <= chord(0.02) and np.linalg.norm(t - t_true) <= 1e-2
+
+
+def test_chi2inv_matches_distribution(host_built):
+    """chi2inv (reference: boost quantile, src/DPGO_utils.cpp:509-512; its test samples the
+    distribution, tests/testUtils.cpp:56-70): the drop-in's own implementation vs scipy."""
+    from scipy.stats import chi2
+    for q, dof in ((0.95, 4), (0.9, 6), (0.5, 3), (0.99, 6)):
+        v = float(subprocess.check_output([host_built, "chi2", repr(q), str(dof)], text=True))
+        assert abs(v - chi2.ppf(q, dof)) < 1e-6 * chi2.ppf(q, dof)
