@@ -64,7 +64,8 @@ def build_host(force=False):
         subprocess.check_call(cmd)
     bindir = os.path.join(HOST, "bin")
     os.makedirs(bindir, exist_ok=True)
-    targets = [(os.path.join(HOST, "tests", "host_tests.cpp"), "host_tests")]
+    targets = [(os.path.join(HOST, "tests", "host_tests.cpp"), "host_tests"),
+               (os.path.join(HOST, "tests", "robust_pgo_test.cpp"), "robust_pgo_test")]
     if os.path.isdir(REFERENCE_EXAMPLES):
         targets += [(os.path.join(REFERENCE_EXAMPLES, "MultiRobotExample.cpp"), "multi-robot-example"),
                     (os.path.join(REFERENCE_EXAMPLES, "SingleRobotExample.cpp"), "single-robot-example"),
