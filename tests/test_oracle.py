@@ -160,3 +160,35 @@ def test_multi_agent_rbcd_decreases_cost(datasets):
     assert len(colors) == 2
     c2 = [team2.step_colored(colors, k)["cost"] for k in range(40)]
     assert 0 <= (c2[-1] - 2 * res.fOpt) / (2 * res.fOpt) < 1e-5
+
+
+def test_synthetic_grid_generator_matches_the_measurement_spec():
+    """dpgo_b200/synthetic.py builds the roofline-scale input of SURVEY 8(d): an L^3 lattice visited
+    along a snake path (odometry chain), every other lattice edge a loop closure, kappa = 200,
+    tau = 100.  Without noise the ground truth has zero cost under the oracle's Q."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_syn", os.path.join(root, "dpgo_b200", "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    L = 6
+    g = syn.grid3d(L, seed=3, noise_rot=0.0, noise_t=0.0)
+    n = L ** 3
+    assert g["n"] == n and g["d"] == 3
+    m = 3 * L * L * (L - 1)                                   # lattice edges
+    assert len(g["p1"]) == m and np.all(g["p1"] < g["p2"])
+    odo = g["p2"] == g["p1"] + 1
+    assert odo.sum() == n - 1 and np.all(odo[:n - 1]) and not odo[n - 1:].any()   # chain first, as in the datasets
+    assert np.all(g["kappa"] == 200.0) and np.all(g["tau"] == 100.0)
+    assert np.allclose(np.einsum("mab,mcb->mac", g["R"], g["R"]), np.eye(3), atol=1e-12)
+    meas = pgo.make_measurements(3, g["p1"], g["p2"], g["R"], g["t"], g["kappa"], g["tau"])
+    Q = pgo.connection_laplacian(meas, n)
+    T = g["T_true"]
+    assert abs(np.sum((T @ Q) * T)) < 1e-9                    # consistent measurements: zero cost at the truth
+    deg = np.bincount(np.concatenate([g["p1"], g["p2"]]), minlength=n)
+    assert deg.max() == 6 and deg.min() == 3                  # 6-neighbour lattice
+    gn = syn.grid3d(L, seed=3)                                # with the default noise the cost is small but not zero
+    measn = pgo.make_measurements(3, gn["p1"], gn["p2"], gn["R"], gn["t"], gn["kappa"], gn["tau"])
+    c = np.sum((gn["T_true"] @ pgo.connection_laplacian(measn, n)) * gn["T_true"])
+    assert 0.0 < c < 0.2 * m
