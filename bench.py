@@ -386,13 +386,15 @@ def bench_single(args):
         line["grid3D_8agents"] = {
             "workload": bench_team.WORKLOAD, "n_gpus": 1, "value": t["value"], "unit": UNIT,
             "ms_per_step": t["ms_per_step"], "steps": t["steps"], "e2e_value": t.get("e2e_value"),
-            "cost2_after_timed_rounds": t["cost2"], "gradnorm": t["gradnorm"]}
+            "cost2_after_timed_rounds": t["cost2"], "gradnorm": t["gradnorm"],
+            "host": t["host_mode"], "host_note": t["host_mode_note"], "blocking_updateX": t["blocking"]}
         try:      # 1-GPU anchor of the other parallel schedule (every agent in every round)
             t2 = bench_team.measure(args.team_steps, 3, 0, 1, 0, schedule="all", e2e=False)
             line["grid3D_8agents_all_schedule"] = {
                 "workload": bench_team.WORKLOAD_ALL, "n_gpus": 1, "value": t2["value"], "unit": UNIT,
                 "ms_per_step": t2["ms_per_step"], "steps": t2["steps"],
-                "cost2_after_timed_rounds": t2["cost2"], "gradnorm": t2["gradnorm"]}
+                "cost2_after_timed_rounds": t2["cost2"], "gradnorm": t2["gradnorm"],
+                "host": t2["host_mode"], "blocking_updateX": t2["blocking"]}
         except Exception as exc:
             line["grid3D_8agents_all_schedule"] = {"error": repr(exc)}
     emit(line)

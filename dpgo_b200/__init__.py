@@ -6,3 +6,4 @@ only bind the C-ABI for tests and bench.py.  There is no CPU fallback anywhere i
 """
 from .api import (DeviceProblem, default_params, problem_from_measurements,  # noqa: F401
                   SLOT_X, SLOT_Y, SLOT_V, SLOT_XPREV)
+from ._lib import DpgoError  # noqa: F401

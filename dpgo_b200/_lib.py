@@ -83,6 +83,8 @@ SIGNATURES = {
     "dpgo_nesterov_update_Y": (C.c_int, [H, C.c_double]),
     "dpgo_nesterov_update_V": (C.c_int, [H, C.c_double]),
     "dpgo_optimize_slot": (C.c_int, [H, C.POINTER(RoptParams), C.c_int, C.POINTER(RoptResult)]),
+    "dpgo_optimize_slot_async": (C.c_int, [H, C.POINTER(RoptParams), C.c_int]),
+    "dpgo_optimize_result": (C.c_int, [H, C.POINTER(RoptResult)]),
     "dpgo_set_public_indices": (C.c_int, [H, C.c_int, _ip]),
     "dpgo_pack_public_dev": (C.c_int, [H, C.c_int, C.c_void_p]),
     "dpgo_gather_tiles_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -245,6 +245,18 @@ class DeviceProblem:
         self.last_result = res.as_dict()
         return self.last_result
 
+    def optimize_slot_async(self, src_slot, params=None):
+        """Queue the fused solve on the handle's stream and return without waiting."""
+        check(lib.dpgo_optimize_slot_async(self._h, C.byref(params) if params is not None else None,
+                                           int(src_slot)))
+
+    def optimize_result(self):
+        """Wait for the stream; result block of the most recent optimize_slot_async."""
+        res = RoptResult()
+        check(lib.dpgo_optimize_result(self._h, C.byref(res)))
+        self.last_result = res.as_dict()
+        return self.last_result
+
     def set_public_indices(self, idx):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         check(lib.dpgo_set_public_indices(self._h, len(idx), _i(idx)))

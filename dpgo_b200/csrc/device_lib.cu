@@ -653,8 +653,11 @@ int solve_host(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doubl
   return DPGO_OK;
 }
 
+// fused_rtr.cu
 int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
-                dpgo_ropt_result *res);  // fused_rtr.cu
+                dpgo_ropt_result *res);
+int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out);
+int solve_fused_collect(dpgo_dev *h, int verbose, dpgo_ropt_result *res);
 
 // ---------------------------------------------------------------------------------------------
 // host-side graph -> block-CSR
@@ -1428,6 +1431,51 @@ int dpgo_optimize_slot(dpgo_handle h, const dpgo_ropt_params *params, int from,
   H_CHECK(h); NEED_FINAL(h);
   CHECK_ARG(from >= 0 && from < 4);
   return run_solver(h, params, h->d_slot[from], h->d_slot[DPGO_SLOT_X], result);
+}
+
+// Stream-ordered form of dpgo_optimize_slot: the fused solve and the copy of its result block are
+// queued on the handle's stream and the call returns without waiting, so that a driver can queue a
+// whole RBCD round (pack, exchange, G, solve, Nesterov updates) ahead of the device.
+int dpgo_optimize_slot_async(dpgo_handle h, const dpgo_ropt_params *params, int from) {
+  H_CHECK(h); NEED_FINAL(h);
+  CHECK_ARG(from >= 0 && from < 4);
+  dpgo_ropt_params P;
+  if (params) P = *params; else dpgo_default_params(&P);
+  CHECK_ARG(P.method == 0 && P.fused != 0);   // only the single-launch RTR solver has no host round trips
+  CHECK_ARG(P.RTR_iterations >= 0 && P.RTR_tCG_iterations >= 0);
+  if (!h->has_precon) {
+    set_error("preconditioner not built (dpgo_finalize(h, 1))");
+    return DPGO_ESTATE;
+  }
+  h->pending_l0 = h->launches;
+  h->pending_verbose = P.verbose;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  DPGO_TRY(solve_fused_launch(h, &P, h->d_slot[from], h->d_slot[DPGO_SLOT_X]));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  h->pending_launches = h->launches - h->pending_l0;
+  h->pending = true;
+  return DPGO_OK;
+}
+
+// Waits for the most recent dpgo_optimize_slot_async of this handle and returns its result block.
+int dpgo_optimize_result(dpgo_handle h, dpgo_ropt_result *result) {
+  H_CHECK(h);
+  CHECK_ARG(result != nullptr);
+  if (!h->pending) {
+    set_error("no asynchronous solve is pending on this handle");
+    return DPGO_ESTATE;
+  }
+  dpgo_ropt_result res;
+  memset(&res, 0, sizeof(res));
+  DPGO_TRY(solve_fused_collect(h, h->pending_verbose, &res));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  res.elapsed_ms = ms;
+  res.n_launches = h->pending_launches;
+  h->pending = false;
+  *result = res;
+  return DPGO_OK;
 }
 
 int dpgo_slot_set(dpgo_handle h, int slot, const double *host) {

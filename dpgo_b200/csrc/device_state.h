@@ -104,4 +104,8 @@ struct dpgo_dev {
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
+  // dpgo_optimize_slot_async / dpgo_optimize_result
+  bool pending = false;
+  int pending_verbose = 0;
+  int64_t pending_l0 = 0, pending_launches = 0;
 };

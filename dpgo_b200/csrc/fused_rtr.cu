@@ -360,8 +360,9 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
   return launch_fused_v<R, D, 0>(h, fp);
 }
 
-int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
-                dpgo_ropt_result *res) {
+// Launch half of the fused solve: the kernel and the copy of its result block to pinned host memory
+// are queued on the handle's stream; nothing waits.  solve_fused_collect() is the other half.
+int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out) {
   if (!h->d_fused) {
     if (cudaMalloc(&h->d_fused, sizeof(FusedOut)) != cudaSuccess ||
         cudaMallocHost(&h->h_fused, sizeof(FusedOut)) != cudaSuccess) {
@@ -402,8 +403,20 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
     default: set_error("unsupported (d=%d, r=%d)", h->d, h->r); return DPGO_EINVAL;
   }
   if (rc != DPGO_OK) return rc;
-  if (cudaMemcpyAsync(h->h_fused, h->d_fused, sizeof(FusedOut), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-      cudaStreamSynchronize(h->stream) != cudaSuccess) {
+  if (cudaMemcpyAsync(h->h_fused, h->d_fused, sizeof(FusedOut), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) {
+    set_error("copy of the fused result block failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DPGO_ECUDA;
+  }
+  return DPGO_OK;
+}
+
+// Collect half: wait for the stream, decode the result block of the most recent launch.
+int solve_fused_collect(dpgo_dev *h, int verbose, dpgo_ropt_result *res) {
+  if (!h->h_fused) {
+    set_error("no fused solve has been launched on this handle");
+    return DPGO_ESTATE;
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
     set_error("fused RTR kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     return DPGO_ECUDA;
   }
@@ -417,10 +430,17 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
   res->n_qx = o.n_qx; res->n_precon = o.n_precon; res->n_pose_sweeps = o.n_sweeps;
   res->n_barriers = o.n_barriers;
   for (int i = 0; i < 16; ++i) res->phase_ms[i] = o.phase_ms[i];
-  if (P->verbose)
+  if (verbose)
     printf("[dpgo_b200] fused RTR: f %.10g -> %.10g, |g| %.4g -> %.4g, %d outer, %d tCG, %lld barriers\n",
            o.f_init, o.f_opt, o.gn_init, o.gn_opt, o.outer, o.inner, o.n_barriers);
   return DPGO_OK;
+}
+
+int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,
+                dpgo_ropt_result *res) {
+  const int rc = solve_fused_launch(h, P, x_in, x_out);
+  if (rc != DPGO_OK) return rc;
+  return solve_fused_collect(h, P->verbose, res);
 }
 
 }  // namespace dpgo

@@ -107,6 +107,9 @@ class DeviceAgent:
         self.iteration = 0
         self.gamma = self.alpha = 0.0
         self.last_result = None
+        # True: updateX queues the fused solve on the stream and returns (dpgo_optimize_slot_async);
+        # the result block is fetched on demand by result().  The reference's updateX blocks.
+        self.async_solve = False
         self.updates = 0
         self.w_private = np.ones(len(p["p1"]))
         self.w_shared = np.ones(len(s["my_idx"]))
@@ -149,8 +152,19 @@ class DeviceAgent:
             return
         buf = self.nbr_aux if acceleration else self.nbr
         self.prob.set_neighbor_poses_dev(buf.data_ptr())   # setNeighborPoses + constructG on device
-        self.last_result = self.prob.optimize_slot(SLOT_Y if acceleration else SLOT_X, self.params)
+        src = SLOT_Y if acceleration else SLOT_X
+        if self.async_solve:
+            self.prob.optimize_slot_async(src, self.params)
+            self.last_result = None
+        else:
+            self.last_result = self.prob.optimize_slot(src, self.params)
         self.updates += 1
+
+    def result(self):
+        """ROPTResult of the last local solve (waits for the stream in asynchronous mode)."""
+        if self.last_result is None and self.async_solve and self.updates > 0:
+            self.last_result = self.prob.optimize_result()
+        return self.last_result
 
     def update_measurement_weights(self, robust):
         """PGOAgent::updateMeasurementWeights (src/PGOAgent.cpp:1104-1142, robustOptNumResets = 0):
@@ -258,6 +272,11 @@ class DeviceTeam:
                 # what b needs from a = the frames of a listed in b's neighbour slots for robot a
                 ag.prepare_send(b, self.specs[b].nbr_frames[a])
         self.round = 0
+
+    def set_async(self, on):
+        """Stream-ordered rounds: no host wait inside a round (see DeviceAgent.async_solve)."""
+        for ag in self.agents.values():
+            ag.async_solve = bool(on)
 
     def set_X(self, X):
         dh = self.d + 1

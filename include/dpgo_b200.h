@@ -195,6 +195,14 @@ int dpgo_nesterov_update_V(dpgo_handle h, double gamma);
 /* X <- optimize(starting from slot `from`), result left in slot X.  ref: updateX :938-995 */
 int dpgo_optimize_slot(dpgo_handle h, const dpgo_ropt_params *params, int from,
                        dpgo_ropt_result *result);
+/* Stream-ordered form of the same call for drivers that queue whole RBCD rounds ahead of the device
+ * (the reference's updateX blocks its caller; a one-process-per-GPU driver does not have to):
+ * dpgo_optimize_slot_async queues the single-launch RTR solve (params->method == 0 and
+ * params->fused != 0, else DPGO_EINVAL) and the copy of its result block on the handle's stream and
+ * returns without waiting; dpgo_optimize_result waits for the stream and returns the result of the
+ * most recent asynchronous solve (DPGO_ESTATE if there is none). */
+int dpgo_optimize_slot_async(dpgo_handle h, const dpgo_ropt_params *params, int from);
+int dpgo_optimize_result(dpgo_handle h, dpgo_ropt_result *result);
 /* Pack the public poses (indices given once) of slot `slot` into a device buffer of
  * num_public tiles -- the payload of getSharedPoseDict / getAuxSharedPoseDict
  * (ref: src/PGOAgent.cpp:97-110, :132-146). */

@@ -1,0 +1,64 @@
+"""GPU test of the stream-ordered local solve (dpgo_optimize_slot_async / dpgo_optimize_result):
+the same fused kernel as dpgo_optimize_slot, queued without a host wait.  Results must be
+identical to the blocking call, on one handle and over rounds of the multi-agent schedule.
+Kept in its own file, last in collection order."""
+import numpy as np
+import pytest
+
+from oracle import pgo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_async_solve_equals_blocking_solve(datasets):
+    import dpgo_b200
+    meas, n, z = datasets("smallGrid3D")
+    d, r = meas.d, 5
+    X0 = np.asfortranarray(pgo.lifting_matrix(d, r) @ z["T_chordal"])
+    gp = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r)
+    prm = dpgo_b200.default_params()
+    gp.slot_set(dpgo_b200.SLOT_Y, X0)
+    ref = gp.optimize_slot(dpgo_b200.SLOT_Y, prm)
+    X_ref = gp.slot_get(dpgo_b200.SLOT_X)
+    # nothing pending yet: the result call must refuse, not return stale data
+    with pytest.raises(dpgo_b200.DpgoError):
+        gp.optimize_result()
+    gp.slot_set(dpgo_b200.SLOT_Y, X0)
+    gp.optimize_slot_async(dpgo_b200.SLOT_Y, prm)
+    gp.optimize_slot_async(dpgo_b200.SLOT_Y, prm)      # queued twice: the result is the last one's
+    res = gp.optimize_result()
+    X_async = gp.slot_get(dpgo_b200.SLOT_X)
+    assert np.array_equal(X_async, X_ref)
+    for k in ("f_init", "f_opt", "gradnorm_init", "gradnorm_opt", "outer_iters", "inner_iters", "accepted",
+              "rejected", "tcg_status", "n_qx", "n_precon"):
+        assert res[k] == ref[k], k
+    assert res["n_launches"] == 1 and res["elapsed_ms"] > 0
+    with pytest.raises(dpgo_b200.DpgoError):
+        gp.optimize_result()
+    # the host-driven solver has host round trips by construction: refused, not silently blocking
+    with pytest.raises(dpgo_b200.DpgoError):
+        gp.optimize_slot_async(dpgo_b200.SLOT_Y, dpgo_b200.default_params(fused=0))
+    gp.close()
+
+
+@pytest.mark.parametrize("acceleration", [True, False])
+def test_stream_ordered_rounds_equal_blocking_rounds(datasets, acceleration):
+    from dpgo_b200 import rbcd
+    meas, n, z = datasets("smallGrid3D")
+    d, r, A = meas.d, 5, 5
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    out = {}
+    for mode in (False, True):
+        team = rbcd.DeviceTeam(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r, A,
+                               acceleration=acceleration)
+        team.set_async(mode)
+        team.set_X(X0)
+        for _ in range(8):
+            team.step_colored()
+        res = {a: ag.result() for a, ag in team.agents.items()}
+        out[mode] = (team.assemble(), res)
+        team.close()
+    assert np.array_equal(out[True][0], out[False][0])
+    for a in out[False][1]:
+        assert out[True][1][a]["f_opt"] == out[False][1][a]["f_opt"]
+        assert out[True][1][a]["inner_iters"] == out[False][1][a]["inner_iters"]
