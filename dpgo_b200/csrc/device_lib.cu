@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "dd_plan.h"
 #include "device_state.h"
 #include "dissect.h"
 #include "kernels.cuh"
@@ -452,7 +453,7 @@ int op_precon(dpgo_dev *h, const double *Y, const double *rvec, double *z, doubl
     set_error("preconditioner not built (dpgo_finalize(h, 1))");
     return DPGO_ESTATE;
   }
-  if (h->precon_mode == 2) return op_precon_dd(h, Y, rvec, z, neg_out, z_r);
+  if (h->precon_mode >= 2) return op_precon_dd(h, Y, rvec, z, neg_out, z_r);
   int g2;
   if (h->precon_mode == 1) {
     DPGO_TRY(launch_symv(h, rvec));
@@ -826,8 +827,8 @@ static const int kAutoTwoLevelMinN = 3000;
 
 static int build_precon(dpgo_dev *h) {
   h->precon_mode = (h->precon_request >= 0) ? h->precon_request : (h->N >= kAutoTwoLevelMinN ? 2 : 0);
-  if (h->precon_mode == 2) {   // two-level exact preconditioner (precon_dd.cu)
-    DPGO_TRY(dd_build(h));
+  if (h->precon_mode >= 2) {   // two-level exact preconditioner (precon_dd.cu), five- or three-phase form
+    DPGO_TRY(h->precon_mode == 3 ? dd3_build(h) : dd_build(h));
     h->has_precon = true;
     return DPGO_OK;
   }
@@ -1174,7 +1175,7 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
 
 int dpgo_set_precon_mode(dpgo_handle h, int mode) {
   CHECK_ARG(h != nullptr);
-  CHECK_ARG(mode >= -1 && mode <= 2);
+  CHECK_ARG(mode >= -1 && mode <= 3);
   if (mode != h->precon_request) {
     h->precon_request = mode;
     h->has_precon = false;
@@ -1199,6 +1200,25 @@ int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx
   for (size_t k = 0; k < ds.domains.size(); ++k)
     for (int v : ds.domains[k]) group[v] = (int32_t)k;
   *num_domains = (int)ds.domains.size();
+  return DPGO_OK;
+}
+
+int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, int dh, int max_domain_poses,
+                          int num_ctas, int split_schur, int64_t *out, int64_t out_capacity, int64_t *out_len) {
+  CHECK_ARG(n >= 1 && rowptr && colidx && out_len);
+  CHECK_ARG(dh >= 2 && dh <= 4);
+  CHECK_ARG(num_ctas >= 1 && num_ctas <= 4096 && split_schur <= 64);
+  CHECK_ARG(out != nullptr || out_capacity == 0);
+  for (int i = 0; i < n; ++i) {
+    CHECK_ARG(rowptr[i] <= rowptr[i + 1]);
+    for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) CHECK_ARG(colidx[e] >= 0 && colidx[e] < n);
+  }
+  const ThreePhasePlan plan =
+      build_three_phase_plan(n, rowptr, colidx, dh, max_domain_poses > 0 ? max_domain_poses : two_level_max_domain_poses(dh),
+                             num_ctas, split_schur, kDdStages);
+  const std::vector<int64_t> img = serialize_three_phase_plan(plan);
+  *out_len = (int64_t)img.size();
+  if (out_capacity >= (int64_t)img.size()) memcpy(out, img.data(), img.size() * sizeof(int64_t));
   return DPGO_OK;
 }
 
@@ -1683,7 +1703,7 @@ int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec) {
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
   H_CHECK(h); NEED_FINAL(h);
   if (!h->has_precon) { set_error("preconditioner not built"); return DPGO_ESTATE; }
-  if (h->precon_mode == 2)
+  if (h->precon_mode >= 2)
     return time_launches(h, reps, flush_l2, [&]() { return dd_time_apply(h, h->d_slot[0]); }, usec);
   if (h->precon_mode == 1)
     return time_launches(h, reps, flush_l2, [&]() { return launch_symv(h, h->d_slot[0]); }, usec);
@@ -1709,7 +1729,7 @@ int dpgo_bytes_precon(dpgo_handle h, double *bytes) {
   CHECK_ARG(h && bytes);
   // dense inverse read once (all of it, or its lower triangle incl. diagonal when the symmetric
   // half-storage variant is active) + vector read + result written
-  if (h->precon_mode == 2) {
+  if (h->precon_mode >= 2) {
     *bytes = dd_bytes(h);
     return DPGO_OK;
   }

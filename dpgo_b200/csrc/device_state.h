@@ -28,6 +28,7 @@ namespace dpgo {
 int read_partials(dpgo_dev *h, int nblocks, int K, double *out);
 // precon_dd.cu: two-level (domain decomposition) exact preconditioner, precon_mode == 2
 int dd_build(dpgo_dev *h);
+int dd3_build(dpgo_dev *h);               // three-phase form of the same preconditioner, precon_mode == 3
 void dd_free(dpgo_dev *h);
 int op_precon_dd(dpgo_dev *h, const double *Y, const double *rvec, double *z, double *neg_out, double *z_r);
 int dd_time_apply(dpgo_dev *h, const double *vec);   // the streaming phases only (no finish)

@@ -98,7 +98,7 @@ struct GridReducer {
 };
 
 template <int R, int D, int MODE>
-__global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
+__global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::grid_group grid = cg::this_grid();
   // per-pose phases: deal the warps over every CTA once there is at least one warp of poses per CTA
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
   // poses: packed is 8 % faster)
   const Ctx ctx = ((p.n + Geo<R, D>::GPW - 1) / Geo<R, D>::GPW >= (int)gridDim.x) ? make_ctx_spread() : make_ctx();
   const int n = p.n;
-  GemvPipe pipe = gemv_pipe_init<(MODE == 2 ? kDdStages : kStages), (MODE == 2 ? kDdVecChunks : kStages)>(dsm);
+  GemvPipe pipe = gemv_pipe_init<(MODE >= 2 ? kDdStages : kStages), (MODE >= 2 ? kDdVecChunks : kStages)>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
   GridReducer red;
   red.buf[0] = p.partials;
@@ -120,14 +120,34 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
 
   __shared__ unsigned long long s_clk[17];
   PhaseClock clk;
-  __shared__ StripPlanStore s_plan[MODE == 2 ? 2 : 1];   // two-level variant: this CTA's strips of P1 / P3
-  if constexpr (MODE == 2) {
+  __shared__ StripPlanStore s_plan[MODE == 3 ? 3 : (MODE == 2 ? 2 : 1)];   // two-level variants: this CTA's strips
+  if constexpr (MODE >= 2) {
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
+  if constexpr (MODE == 3) strip_plan_fill(&s_plan[2], p.dd.P5, p.dd.V);
   // the three variants of the exact preconditioner (compile-time: one per kernel instantiation)
   auto precon_stream = [&](const double *v) {
-    if constexpr (MODE == 2) {
+    if constexpr (MODE == 3) {
+      // three-phase form: [M_k | C_k] strips -> Sigma^-1 strips (t_S formed while staged) -> C_k^T strips
+      const DdView &dd = p.dd;
+      const size_t zs = (size_t)dd.pcols * R;
+      const bool pf = dd.prefetch != 0;
+      constexpr int ST = kDdStages;
+      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
+      if (dd.nS > 0) {
+        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
+        red.barrier(grid);
+        clk.lap(8);
+        const StageAux a3{dd.y, dd.tptr, dd.tcol, dd.sep_col0, 0, 0};
+        phase_strip_gemv<R, ST, 2>(pipe, dd.P3, dd.V, &s_plan[1], v, dd.icol, dd.zs, zs, pf, &a3);
+        if (pf) strip_prefetch<ST>(pipe, dd.P5, dd.V, &s_plan[2]);
+        red.barrier(grid);
+        clk.lap(10);
+        const StageAux a5{nullptr, nullptr, nullptr, 0, dd.nsplit3, zs};
+        phase_strip_gemv<R, ST, 3>(pipe, dd.P5, dd.V, &s_plan[2], dd.zs, nullptr, dd.w, 0, pf, &a5);
+      }
+    } else if constexpr (MODE == 2) {
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
@@ -157,7 +177,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     }
   };
   auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
-    if constexpr (MODE == 2)
+    if constexpr (MODE >= 2)
       phase_dd_finish<R, D>(ctx, p.dd, Ycur, rvec, p.z, neg_out, n, a1);
     else if constexpr (MODE == 1)
       phase_precon_finish_sym<R, D>(pipe.scratch, p.zpart, p.zT, p.zstride, p.symNG, Ycur, rvec, p.z,
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
         phase_zero(ctx, p.eta, len);
       }
       red.barrier(grid);
-      clk.lap(MODE == 2 ? 12 : 1);
+      clk.lap(MODE >= 2 ? 12 : 1);
       {
         double acc[1] = {0.0}, sc[1];
         precon_finish(x1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
@@ -307,7 +327,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     o.n_qx = n_qx; o.n_precon = n_precon; o.n_sweeps = n_sweeps; o.n_barriers = red.barriers;
 #pragma unroll
     for (int i = 0; i < 16; ++i) o.phase_ms[i] = (double)clk.acc[i] * 1e-6;
-    if (MODE == 2) {
+    if (MODE >= 2) {
 #pragma unroll
       for (int i = 8; i <= 12; ++i) o.phase_ms[1] += o.phase_ms[i];
     }
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
 
 template <int R, int D, int MODE>
 static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
-  constexpr int smem = (MODE == 2) ? kDdDynSmem : kGemvDynSmem;
+  constexpr int smem = (MODE >= 2) ? kDdDynSmem : kGemvDynSmem;
   static int occ_cache = -1;
   if (occ_cache < 0) {
     int occ = 0;
@@ -333,7 +353,7 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
   // enough CTAs for the widest phase, never more than can be co-resident
   long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
   if (h->precon_mode == 1) tiles = h->sym_nitems;
-  if (h->precon_mode == 2) tiles = fp.dd.V;
+  if (h->precon_mode >= 2) tiles = fp.dd.V;
   const int gpw = 32 / (h->d + 1);
   const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long grid = std::max(tiles, pose_blocks);
@@ -355,6 +375,7 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
 
 template <int R, int D>
 static int launch_fused(dpgo_dev *h, FusedParams &fp) {
+  if (h->precon_mode == 3) return launch_fused_v<R, D, 3>(h, fp);
   if (h->precon_mode == 2) return launch_fused_v<R, D, 2>(h, fp);
   if (h->precon_mode == 1) return launch_fused_v<R, D, 1>(h, fp);
   return launch_fused_v<R, D, 0>(h, fp);
@@ -379,7 +400,7 @@ int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_i
   fp.zstride = h->vpad;
   fp.precon_mode = h->precon_mode; fp.symT = h->symT; fp.symNG = h->symNG; fp.nitems = h->sym_nitems;
   fp.items = (const SymItem *)h->d_sym_items; fp.zT = h->d_zT;
-  if (h->precon_mode == 2) fp.dd = dd_view(h); else memset(&fp.dd, 0, sizeof(fp.dd));
+  if (h->precon_mode >= 2) fp.dd = dd_view(h); else memset(&fp.dd, 0, sizeof(fp.dd));
   fp.x_in = x_in; fp.x_out = x_out;
   fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;
   fp.grad = h->d_grad; fp.grad2 = h->d_grad2; fp.S = h->d_S; fp.S2 = h->d_S2;

@@ -826,6 +826,20 @@ struct DdStripSet {
   const DdStrip *strips;
   const int *cta;      // [V + 1]
   const int *chunks;   // [V]
+  const int *gidx;     // three-phase form, phase 5: inner index -> scalar column of the input (-1: padding);
+                       // a strip's kc0 then counts chunks of this list.  nullptr: inner indices are columns
+};
+
+// Extra inputs of the staging step of a strip phase in the three-phase form (dd_plan.h):
+//   SRC 2: vec is r in the original order; the value of scalar column c of the S segment is
+//          r[icol[c]] - sum_e sub[tcol[e]],  e in [tptr[c - col0], tptr[c - col0 + 1])
+//   SRC 3: vec is an array of `nslots` partial results `slotstride` apart, read through S.gidx
+struct StageAux {
+  const double *sub;
+  const int *tptr, *tcol;
+  int col0;
+  int nslots;
+  size_t slotstride;
 };
 
 struct DdView {
@@ -844,6 +858,10 @@ struct DdView {
   double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
                                 // nsplit3 partial slots; u is zero outside the boundary rows)
   int prefetch;                 // issue the first matrix stages of P3 / P5 before the preceding barrier
+  // three-phase form (precon_mode 3): P1 = [M_k | C_k] strips (y holds y_I and, in its T segments, the
+  // g_k), P3 as above with t_S formed while it is staged, P5 = C_k^T strips (result in w)
+  DdStripSet P5;
+  const int *tptr, *tcol;       // scalar column of the S segment -> columns of y to subtract (CSR)
 };
 
 // Per-CTA cache (shared memory, filled once per kernel) of the head of this CTA's strip list of one
@@ -962,12 +980,13 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
 // of `vec` (one round of global-load latency per wave), then the 8 warps split the wave into
 // (chunk, 8-row) units and each waits only for the stages it reads -- no CTA-wide barrier per
 // stage.  pp.parity is a bit mask here: bit i = phase parity of stage slot i.
-template <int R, int STAGES>
+template <int R, int STAGES, int SRC = 0>
 __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
                                                  const double *vec, const int *icol, double *out,
-                                                 size_t outstride, bool prefetched = false) {
+                                                 size_t outstride, bool prefetched = false,
+                                                 const StageAux *ax = nullptr) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
-  // is staged (saves a separate permutation pass + grid barrier)
+  // is staged (saves a separate permutation pass + grid barrier).  SRC 2 / 3: see StageAux.
   static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -990,7 +1009,22 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
         const int cnt = nw * kStageK * R;
         for (int o = threadIdx.x; o < cnt; o += kBlock) {
           double val;
-          if (icol) {
+          if constexpr (SRC == 2) {
+            const int k = o / R, q = o - k * R;
+            const int oc = __ldg(icol + k0 + k);
+            const int j = k0 + k - ax->col0;
+            const int e0 = __ldg(ax->tptr + j), e1 = __ldg(ax->tptr + j + 1);
+            val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
+            for (int e = e0; e < e1; ++e) val -= ax->sub[(size_t)__ldg(ax->tcol + e) * R + q];
+          } else if constexpr (SRC == 3) {
+            const int k = o / R, q = o - k * R;
+            const int col = __ldg(S.gidx + k0 + k);
+            val = 0.0;
+            if (col >= 0) {
+              const double *zp = vec + (size_t)col * R + q;
+              for (int sl = 0; sl < ax->nslots; ++sl) val += zp[(size_t)sl * ax->slotstride];
+            }
+          } else if (icol) {
             const int k = o / R, q = o - k * R;
             const int oc = __ldg(icol + k0 + k);
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;

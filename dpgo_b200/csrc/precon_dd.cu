@@ -18,6 +18,7 @@
 #include <deque>
 #include <vector>
 
+#include "dd_plan.h"
 #include "device_state.h"
 #include "dissect.h"
 #include "kernels.cuh"
@@ -58,7 +59,14 @@ struct DdState {
   int *si_rowptr = nullptr, *si_colidx = nullptr, *bs_rowptr = nullptr, *bs_colidx = nullptr;
   double *si_blocks = nullptr, *bs_blocks = nullptr;
   double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr;
+  // three-phase form (precon_mode 3, plan in dd_plan.h): M1 holds the [M_k | C_k] strips, M5 the C_k^T strips
+  bool three = false;
+  int nstrips5 = 0, ycols = 0;
+  double *M5 = nullptr;
+  DdStrip *strips5 = nullptr;
+  int *cta5 = nullptr, *chunks5 = nullptr, *tptr = nullptr, *tcol = nullptr, *gidx = nullptr;
   bool configured = false;
+  unsigned configured3 = 0;        // bit SRC: k_strip_gemv3<R, SRC> has its shared-memory attribute set
   cublasHandle_t cublas = nullptr;
 };
 
@@ -112,6 +120,29 @@ __global__ void k_dd_layout(const double *A, int m, int lda, int pad, double *ds
   }
 }
 
+// stage-major strips of a coupling block C = A_k^-1 A_kS (m x mS col-major, leading dimension ldc) restricted to
+// the columns colmap[0 .. ncomp) (the scalars of S_k, in that order), zero padded:
+//   form 0 (phase 1, output = compact column):  stage (ob, c)(kk, jj) = C(32 c + kk, colmap[64 ob + jj])
+//   form 1 (phase 5, output = domain row):      stage (ob, c)(kk, jj) = C(64 ob + jj, colmap[32 c + kk])
+// stage (ob, c) is the (ob * nch + c)-th 16 KB run of dst.
+__global__ void k_dd_layout_rect(const double *C, int m, int ldc, const int *colmap, int ncomp, int form, int nob,
+                                 int nch, double *dst) {
+  const size_t total = (size_t)nob * nch * kStageDoubles;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int jj = (int)(t % kGemvCols);
+    const size_t u = t / kGemvCols;
+    const int kk = (int)(u % kStageK);
+    const size_t v = u / kStageK;
+    const int c = (int)(v % nch);
+    const int ob = (int)(v / nch);
+    const int row = form == 0 ? c * kStageK + kk : ob * kGemvCols + jj;
+    const int comp = form == 0 ? ob * kGemvCols + jj : c * kStageK + kk;
+    double val = 0.0;
+    if (row < m && comp < ncomp) val = C[(size_t)row + (size_t)colmap[comp] * ldc];
+    dst[t] = val;
+  }
+}
+
 // ---- application kernels -----------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kBlock, 1) k_strip_gemv(DdStripSet S, int V, const double *vec, const int *icol,
@@ -121,6 +152,16 @@ __global__ void __launch_bounds__(kBlock, 1) k_strip_gemv(DdStripSet S, int V, c
   __shared__ StripPlanStore plan;
   strip_plan_fill(&plan, S, V);
   phase_strip_gemv<R, kDdStages>(pp, S, V, &plan, vec, icol, out, outstride);
+}
+// strip phases of the three-phase form (SRC: how the input slice of a wave is produced, see StageAux)
+template <int R, int SRC>
+__global__ void __launch_bounds__(kBlock, 1) k_strip_gemv3(DdStripSet S, int V, const double *vec, const int *icol,
+                                                           double *out, size_t outstride, StageAux ax) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  GemvPipe pp = gemv_pipe_init<kDdStages, kDdVecChunks>(dsm);
+  __shared__ StripPlanStore plan;
+  strip_plan_fill(&plan, S, V);
+  phase_strip_gemv<R, kDdStages, SRC>(pp, S, V, &plan, vec, icol, out, outstride, false, &ax);
 }
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_dd_sep_rhs(DdView dd, const double *rvec) {
@@ -165,6 +206,8 @@ DdView dd_view(const dpgo_dev *h) {
   v.sep_col0 = s->sep_col0; v.pcols = s->pcols;
   v.y = s->y; v.t = s->t; v.zs = s->zs; v.u = s->u; v.w = s->w;
   v.prefetch = h->dd_prefetch;
+  v.P5 = DdStripSet{s->M5, s->strips5, s->cta5, s->chunks5, s->gidx};
+  v.tptr = s->tptr; v.tcol = s->tcol;
   return v;
 }
 
@@ -173,7 +216,7 @@ void dd_free(dpgo_dev *h) {
   if (!s) return;
   void *ptrs[] = {s->M1, s->M3, s->strips1, s->strips3, s->cta1, s->cta3, s->chunks1, s->chunks3, s->pcol, s->srow,
                   s->bcol, s->icol, s->si_rowptr, s->si_colidx, s->bs_rowptr, s->bs_colidx, s->si_blocks, s->bs_blocks,
-                  s->y, s->t, s->zs, s->u, s->w};
+                  s->y, s->t, s->zs, s->u, s->w, s->M5, s->strips5, s->cta5, s->chunks5, s->tptr, s->tcol, s->gidx};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (s->cublas) cublasDestroy(s->cublas);
@@ -462,6 +505,167 @@ int dd_build(dpgo_dev *h) {
   return DPGO_OK;
 }
 
+// ---- three-phase form (precon_mode 3) ------------------------------------------------------------------
+// Same dissection, same dense inverses and Schur complement as dd_build; the index plan (column
+// spaces, strips, gather lists) comes from dd_plan.h, where the algebra is stated.  The couplings
+// C_k = A_k^-1 A_kS, which dd_build only uses to form Sigma, are kept and laid out as strips.
+static_assert(sizeof(PlanStrip) == sizeof(DdStrip) && kPlanCols == kGemvCols && kPlanStageK == kStageK,
+              "dd_plan.h mirrors the strip format of kernels.cuh");
+
+int dd3_build(dpgo_dev *h) {
+  dd_free(h);
+  DdState *s = new DdState();
+  h->dd = s;
+  s->three = true;
+  const int n = h->n, dh = h->d + 1, R = h->r;
+  const int V = std::max(1, h->num_sms);
+  const ThreePhasePlan pl = build_three_phase_plan(n, h->rowptr.data(), h->colidx.data(), dh,
+                                                   two_level_max_domain_poses(dh), V, h->dd_split3, kDdStages);
+  const int K = pl.K;
+  s->K = K; s->nS = pl.nS; s->V = V;
+  s->nI = n - pl.nS;
+  s->sep_col0 = pl.sep_col0; s->pcols = pl.pcols; s->ycols = pl.ycols;
+  s->nsplit1 = 1; s->nsplit3 = pl.nsplit3;
+  s->nstrips1 = (int)pl.strips1.size(); s->nstrips3 = (int)pl.strips3.size(); s->nstrips5 = (int)pl.strips5.size();
+  s->bytes_per_apply = pl.bytes_per_apply + 6.0 * R * h->N * 8;
+  auto to_dd = [](const std::vector<PlanStrip> &v) {
+    std::vector<DdStrip> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = DdStrip{v[i].cb, v[i].kc0, v[i].nchunks, v[i].slot, v[i].data_off};
+    return o;
+  };
+  DPGO_TRY(upload_vec(&s->strips1, to_dd(pl.strips1)));
+  DPGO_TRY(upload_vec(&s->strips3, to_dd(pl.strips3)));
+  DPGO_TRY(upload_vec(&s->strips5, to_dd(pl.strips5)));
+  DPGO_TRY(upload_vec(&s->cta1, pl.cta1)); DPGO_TRY(upload_vec(&s->chunks1, pl.chunks1));
+  DPGO_TRY(upload_vec(&s->cta3, pl.cta3)); DPGO_TRY(upload_vec(&s->chunks3, pl.chunks3));
+  DPGO_TRY(upload_vec(&s->cta5, pl.cta5)); DPGO_TRY(upload_vec(&s->chunks5, pl.chunks5));
+  DPGO_TRY(upload_vec(&s->pcol, pl.pcol));
+  DPGO_TRY(upload_vec(&s->srow, pl.srow));
+  DPGO_TRY(upload_vec(&s->icol, pl.icol));
+  DPGO_TRY(upload_vec(&s->tptr, pl.tptr));
+  DPGO_TRY(upload_vec(&s->tcol, pl.tcol));
+  DPGO_TRY(upload_vec(&s->gidx, pl.gidx));
+  // first stage of every domain's M_k / C_k / C_k^T strips, and its compact column map into C
+  std::vector<long long> baseM(K, -1), baseG(K, -1), baseW(K, -1);
+  for (size_t i = 0; i < pl.strips1.size(); ++i)
+    if (pl.tiles1[i].blk == 0) (pl.tiles1[i].kind == 0 ? baseM : baseG)[pl.tiles1[i].k] = pl.strips1[i].data_off;
+  for (size_t i = 0; i < pl.strips5.size(); ++i)
+    if (pl.tiles5[i].blk == 0) baseW[pl.tiles5[i].k] = pl.strips5[i].data_off;
+  std::vector<int> cmap, cmap_off(K + 1, 0);
+  for (int k = 0; k < K; ++k) {
+    for (int a = pl.sk_ptr[k]; a < pl.sk_ptr[k + 1]; ++a)
+      for (int c = 0; c < dh; ++c) cmap.push_back(pl.sk[a] * dh + c);
+    cmap_off[k + 1] = (int)cmap.size();
+  }
+  // ---- work arrays: y over the y space (interior results + the g_k segments), z_S partial slots, w
+  const size_t wlen = (size_t)R * s->pcols;
+  CUDA_TRY(cudaMalloc((void **)&s->y, (size_t)R * s->ycols * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->y, 0, (size_t)R * s->ycols * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s->w, wlen * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->w, 0, wlen * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s->zs, wlen * s->nsplit3 * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->zs, 0, wlen * s->nsplit3 * sizeof(double)));
+  // ---- dense blocks on the device
+  int *d_group = nullptr, *d_lpos = nullptr, *d_cmap = nullptr;
+  DPGO_TRY(upload_vec(&d_group, pl.group));
+  DPGO_TRY(upload_vec(&d_lpos, pl.lpos));
+  DPGO_TRY(upload_vec(&d_cmap, cmap));
+  const int mS = pl.nS * dh, padS = s->pcols - s->sep_col0;
+  CUDA_TRY(cudaMalloc((void **)&s->M1, std::max<size_t>((size_t)pl.stages1 * kStageDoubles, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s->M3, std::max<size_t>((size_t)pl.stages3 * kStageDoubles, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&s->M5, std::max<size_t>((size_t)pl.stages5 * kStageDoubles, 1) * sizeof(double)));
+  if (!h->cusolver) {
+    LIB_TRY(cusolverDnCreate(&h->cusolver));
+    LIB_TRY(cusolverDnSetStream(h->cusolver, h->stream));
+  }
+  LIB_TRY(cublasCreate(&s->cublas));
+  LIB_TRY(cublasSetStream(s->cublas, h->stream));
+  int maxdom = 1;
+  for (int k = 0; k < K; ++k) maxdom = std::max(maxdom, pl.dom_m[k]);
+  const int maxm = std::max(std::max(mS, 1), maxdom);
+  double *A = nullptr, *Sg = nullptr, *B = nullptr, *C = nullptr, *work = nullptr;
+  int *info = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&A, (size_t)maxdom * maxdom * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&B, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&C, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
+  int lwork = 0;
+  {
+    int l1 = 0, l2 = 0;
+    LIB_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l1));
+    LIB_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l2));
+    lwork = std::max(std::max(l1, l2), 1);
+  }
+  CUDA_TRY(cudaMalloc((void **)&work, (size_t)lwork * sizeof(double)));
+  const int bs = dh * dh;
+  const int sgrid = (int)std::min<size_t>(((size_t)h->nnzb * bs + 255) / 256, (size_t)h->num_sms * 8);
+  auto invert = [&](double *Mx, int m) -> int {
+    int hinfo = 0;
+    LIB_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
+    LIB_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
+    CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (hinfo != 0) {
+      set_error("dense block of Q + 0.1 I is not positive definite (info %d)", hinfo);
+      return DPGO_ENUMERIC;
+    }
+    return DPGO_OK;
+  };
+  auto lgrid = [&](size_t total) { return std::max(1, (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8)); };
+  if (mS > 0) {
+    CUDA_TRY(cudaMemsetAsync(Sg, 0, (size_t)mS * mS * sizeof(double), h->stream));
+    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
+                                                          d_group, d_lpos, -1, -1, 0.1, Sg, mS);
+  }
+  for (int k = 0; k < K; ++k) {
+    const int m = pl.dom_m[k];
+    CUDA_TRY(cudaMemsetAsync(A, 0, (size_t)m * m * sizeof(double), h->stream));
+    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
+                                                          d_group, d_lpos, k, k, 0.1, A, m);
+    DPGO_TRY(invert(A, m));
+    if (baseM[k] < 0) {
+      set_error("three-phase plan has no interior strips for domain %d", k);
+      return DPGO_EINVAL;
+    }
+    k_dd_layout<<<lgrid((size_t)pl.dom_pad[k] * pl.dom_pad[k]), 256, 0, h->stream>>>(
+        A, m, m, pl.dom_pad[k], s->M1 + (size_t)baseM[k] * kStageDoubles);
+    CUDA_TRY(cudaPeekAtLastError());
+    if (mS > 0) {
+      // C = A_k^-1 A_kS;  Sigma -= A_kS^T C
+      CUDA_TRY(cudaMemsetAsync(B, 0, (size_t)m * mS * sizeof(double), h->stream));
+      k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
+                                                            d_group, d_lpos, k, -1, 0.0, B, m);
+      const double one = 1.0, zero = 0.0, mone = -1.0;
+      LIB_TRY(cublasDsymm(s->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, m, mS, &one, A, m, B, m, &zero, C, m));
+      LIB_TRY(cublasDgemm(s->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mS, mS, m, &mone, B, m, C, m, &one, Sg, mS));
+      const int tm = pl.t_m[k];
+      if (tm > 0) {
+        if (baseG[k] < 0 || baseW[k] < 0) {
+          set_error("three-phase plan has no coupling strips for domain %d", k);
+          return DPGO_EINVAL;
+        }
+        const int nobG = pl.t_pad[k] / kGemvCols, nchG = pl.dom_pad[k] / kStageK;
+        k_dd_layout_rect<<<lgrid((size_t)nobG * nchG * kStageDoubles), 256, 0, h->stream>>>(
+            C, m, m, d_cmap + cmap_off[k], tm, 0, nobG, nchG, s->M1 + (size_t)baseG[k] * kStageDoubles);
+        const int nobW = pl.dom_pad[k] / kGemvCols, nchW = (tm + kStageK - 1) / kStageK;
+        k_dd_layout_rect<<<lgrid((size_t)nobW * nchW * kStageDoubles), 256, 0, h->stream>>>(
+            C, m, m, d_cmap + cmap_off[k], tm, 1, nobW, nchW, s->M5 + (size_t)baseW[k] * kStageDoubles);
+        CUDA_TRY(cudaPeekAtLastError());
+      }
+    }
+  }
+  if (mS > 0) {
+    DPGO_TRY(invert(Sg, mS));
+    k_dd_layout<<<lgrid((size_t)padS * padS), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
+    CUDA_TRY(cudaPeekAtLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(A); cudaFree(Sg); cudaFree(B); cudaFree(C); cudaFree(work); cudaFree(info);
+  cudaFree(d_group); cudaFree(d_lpos); cudaFree(d_cmap);
+  return DPGO_OK;
+}
+
 template <int R>
 static int strip_setup() {
   return cudaFuncSetAttribute(k_strip_gemv<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdDynSmem) == cudaSuccess
@@ -501,6 +705,55 @@ static int launch_strips(dpgo_dev *h, const DdStripSet &S, int nstrips, const do
   return DPGO_OK;
 }
 
+template <int R, int SRC>
+static int strip3_launch(dpgo_dev *h, const DdStripSet &S, const double *vec, const int *icol, double *out,
+                         size_t outstride, const StageAux &ax) {
+  DdState *s = (DdState *)h->dd;
+  if (!(s->configured3 & (1u << SRC))) {
+    if (cudaFuncSetAttribute(k_strip_gemv3<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdDynSmem) !=
+        cudaSuccess) {
+      set_error("three-phase strip kernel does not fit on the device");
+      return DPGO_ECUDA;
+    }
+    s->configured3 |= 1u << SRC;
+  }
+  k_strip_gemv3<R, SRC><<<s->V, kBlock, kDdDynSmem, h->stream>>>(S, s->V, vec, icol, out, outstride, ax);
+  h->launches++;
+  CUDA_TRY(cudaPeekAtLastError());
+  return DPGO_OK;
+}
+
+template <int SRC>
+static int launch_strips3(dpgo_dev *h, const DdStripSet &S, int nstrips, const double *vec, const int *icol,
+                          double *out, size_t outstride, const StageAux &ax) {
+  if (nstrips <= 0) return DPGO_OK;
+  switch (h->r) {
+    case 2: return strip3_launch<2, SRC>(h, S, vec, icol, out, outstride, ax);
+    case 3: return strip3_launch<3, SRC>(h, S, vec, icol, out, outstride, ax);
+    case 4: return strip3_launch<4, SRC>(h, S, vec, icol, out, outstride, ax);
+    case 5: return strip3_launch<5, SRC>(h, S, vec, icol, out, outstride, ax);
+    case 6: return strip3_launch<6, SRC>(h, S, vec, icol, out, outstride, ax);
+  }
+  set_error("unsupported r=%d", h->r);
+  return DPGO_EINVAL;
+}
+
+// the three strip phases of the three-phase form (everything but the final projection)
+static int dd3_apply(dpgo_dev *h, const double *vec) {
+  DdState *s = (DdState *)h->dd;
+  const DdView dd = dd_view(h);
+  const size_t zstride = (size_t)h->r * s->pcols;
+  const StageAux a1{nullptr, nullptr, nullptr, 0, 0, 0};
+  DPGO_TRY(launch_strips3<0>(h, dd.P1, s->nstrips1, vec, s->icol, s->y, 0, a1));
+  if (s->nS > 0) {
+    const StageAux a3{s->y, s->tptr, s->tcol, s->sep_col0, 0, 0};
+    DPGO_TRY(launch_strips3<2>(h, dd.P3, s->nstrips3, vec, s->icol, s->zs, zstride, a3));
+    const StageAux a5{nullptr, nullptr, nullptr, 0, s->nsplit3, zstride};
+    DPGO_TRY(launch_strips3<3>(h, dd.P5, s->nstrips5, s->zs, nullptr, s->w, 0, a5));
+  }
+  return DPGO_OK;
+}
+
 // grid for the warp-per-row sparse phases
 static inline int warp_rows_grid(const dpgo_dev *h, int rows) {
   long blocks = ((long)rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -519,6 +772,7 @@ static inline int rows_grid(const dpgo_dev *h, int rows) {
 // the five streaming / sparse phases (everything but the final projection)
 int dd_time_apply(dpgo_dev *h, const double *vec) {
   DdState *s = (DdState *)h->dd;
+  if (s->three) return dd3_apply(h, vec);
   const DdView dd = dd_view(h);
   const size_t zstride = (size_t)h->r * s->pcols;
   DPGO_TRY(launch_strips(h, dd.P1, s->nstrips1, vec, s->icol, s->y, zstride));   // gathers vec on the fly

@@ -128,9 +128,12 @@ int dpgo_finalize(dpgo_handle h, int build_precon);
  *     inverse of the separator Schur complement S = A_SS - A_SI A_II^{-1} A_IS; one application is
  *     z_S = S^{-1}(r_S - A_SI A_II^{-1} r_I), z_I = A_II^{-1}(r_I - A_IS z_S): 3 strip GEMVs and 2
  *     sparse couplings, ~N^2*8/5 bytes on sphere2500 (L2 resident), 5 grid phases.
+ *   3 (opt-in, never chosen automatically) the same two-level elimination in three grid phases: the
+ *     dense couplings C_k = A_k^{-1} A_kS are kept as strips, so that r_S - A_SI A_II^{-1} r_I comes out
+ *     of the first strip phase and z_I = y_I - C z_S out of the last; no sparse coupling phases.
  * Takes effect at the next dpgo_finalize(h, 1) / dpgo_update_weights(..., 1). */
 int dpgo_set_precon_mode(dpgo_handle h, int mode);
-/* The variant in use (0 / 1 / 2) once the preconditioner is built. */
+/* The variant in use (0 / 1 / 2 / 3) once the preconditioner is built. */
 int dpgo_get_precon_mode(dpgo_handle h, int *mode);
 /* Host-only inspection of the partition the two-level variant is built on (no device needed): the
  * nested dissection of a pose graph given as a block-CSR pattern (n block rows, rowptr[n+1],
@@ -140,6 +143,21 @@ int dpgo_get_precon_mode(dpgo_handle h, int *mode);
  * different domains. */
 int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
                              int max_domain_poses, int32_t *group, int *num_domains);
+/* Host-only inspection of the index plan of the three-phase form of the two-level variant
+ * (precon_mode 3; no device needed): same nested dissection, separator poses ordered by the set of
+ * domains they touch, the dense couplings C_k = A_k^{-1} A_kS folded into the strip phases
+ * (dpgo_b200/csrc/dd_plan.h states the algebra).  num_ctas = CTAs the strips are balanced over,
+ * split_schur <= 0 = library choice.  The plan is written to `out` as a flat int64 image:
+ * out[0] = S sections, then S pairs (offset, length), then the sections, in this order:
+ *   0 scalars {n, dh, K, nS, V, sep_col0, pcols, ycols, nsplit3, stages1, stages3, stages5, bytes_per_apply}
+ *   1 group[n]  2 pcol[n]  3 srow[nS]  4 icol[ycols]  5-7 dom_off / dom_m / dom_pad [K]
+ *   8-10 t_off / t_m / t_pad [K]  11 sk_ptr[K+1]  12 sk  13 tptr  14 tcol  15 gchunk[K]  16 gidx
+ *   17-19 strips of phase 1 / 3 / 5, 8 values each {cb, kc0, nchunks, slot, data_off, kind, k, blk}
+ *   20-22 cta1 / cta3 / cta5 [V+1] (strip ranges of the virtual CTAs).
+ * *out_len = values needed; nothing is written when out_capacity is smaller (call twice). */
+int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
+                          int max_domain_poses, int num_ctas, int split_schur, int64_t *out,
+                          int64_t out_capacity, int64_t *out_len);
 /* Tuning of the two-level variant (measurement knobs; 0 / negative = library default): how many
  * partial slots the inner dimension of the interior strips and of the Schur strips is split into
  * (more splits = more CTAs busy per phase, more partial sums to add), and whether the first

@@ -1,0 +1,101 @@
+"""CPU tests of the three-phase form of the two-level preconditioner (precon_mode 3): the index plan
+the library builds on the host (dpgo_b200/csrc/dd_plan.h through dpgo_three_phase_plan) is replayed
+in numpy (tests/three_phase_emu.py: stage buffers filled as the device set-up lays them out, the
+three strip phases with the kernels' staging rules, the finish) and must reproduce the exact
+(Q + 0.1 I)^-1 -- the reference's preconditioner (src/QuadraticProblem.cpp:56-69).  What this does
+not cover is the CUDA code itself; that is tests/test_gpu_zzz_three_phase.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+import three_phase_emu as emu
+from oracle import pgo
+
+
+def _fn():
+    from dpgo_b200 import _lib
+    return _lib.lib.dpgo_three_phase_plan
+
+
+def _pose_graph(p1, p2, n):
+    A = sp.coo_matrix((np.ones(len(p1)), (p1, p2)), shape=(n, n))
+    A = (A + A.T + sp.identity(n)).tocsr()
+    A.sort_indices()
+    return A
+
+
+def _replay(meas, n, max_poses, V, split=0, r=3, seed=0):
+    dh = meas.d + 1
+    G = _pose_graph(meas.p1, meas.p2, n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split)
+    emu.check_tables(plan)
+    A = (pgo.connection_laplacian(meas, n) + 0.1 * sp.identity(dh * n)).tocsc()
+    M, Cc, SigInv = emu.dense_blocks(A, plan)
+    bufs = emu.fill_stage_buffers(plan, M, Cc, SigInv)
+    rv = np.random.default_rng(seed).standard_normal((r, dh * n))
+    z = emu.apply(plan, bufs, rv)
+    ref = spl.splu(A).solve(rv.T).T
+    return plan, np.linalg.norm(z - ref) / np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("name,max_poses,V,split", [
+    ("tinyGrid3D", 3, 4, 0),          # a handful of poses per domain
+    ("smallGrid3D", 20, 7, 0),        # several strips per virtual CTA
+    ("smallGrid3D", 0, 148, 0),       # the library's domain size, one B200 worth of CTAs
+    ("smallGrid3D", 10, 16, 3),       # forced inner split of the Schur strips
+])
+def test_three_phase_replay_is_exact(datasets, name, max_poses, V, split):
+    meas, n, _ = datasets(name)
+    plan, err = _replay(meas, n, max_poses, V, split)
+    assert err <= 1e-11, err
+    if split:
+        assert plan["nsplit3"] == min(split, (plan["pcols"] - plan["sep_col0"]) // emu.STAGE_K)
+
+
+def test_three_phase_replay_sphere2500(datasets):
+    """BASELINE configs[1]: 41 domains, 430 separator poses; also the sizing DESIGN.md quotes."""
+    meas, n, _ = datasets("sphere2500")
+    plan, err = _replay(meas, n, 0, 148, r=2)
+    assert err <= 1e-11, err
+    assert plan["K"] >= 30 and plan["nS"] <= 0.25 * n
+    per_cta = [np.diff(plan["cta" + ph]).max() for ph in ("1", "3", "5")]
+    assert max(per_cta) <= 3                               # about one pipeline fill of strips per CTA
+    mb = [plan["stages" + ph] * emu.STAGE_K * emu.COLS * 8 / 1e6 for ph in ("1", "3", "5")]
+    assert sum(mb) < 80                                    # L2 resident on B200 (126 MB)
+
+
+def test_three_phase_plan_2d(datasets):
+    """d = 2 (three scalars per pose: tiles straddle the 32- and 64-wide blocks)."""
+    meas, n, _ = datasets("city10000")
+    keep = (meas.p1 < 400) & (meas.p2 < 400)
+    sub = pgo.make_measurements(meas.d, meas.p1[keep], meas.p2[keep], meas.R[keep], meas.t[keep],
+                                meas.kappa[keep], meas.tau[keep])
+    plan, err = _replay(sub, 400, 30, 12)
+    assert plan["dh"] == 3 and err <= 1e-11, err
+
+
+def test_three_phase_plan_without_separator():
+    """A graph below the domain threshold: one domain, no separator, phases 3 and 5 are empty."""
+    n, dh = 12, 4
+    G = _pose_graph(np.arange(n - 1), np.arange(1, n), n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 0, 8)
+    emu.check_tables(plan)
+    assert plan["K"] == 1 and plan["nS"] == 0
+    assert len(plan["strips3"]) == 0 and len(plan["strips5"]) == 0 and plan["stages5"] == 0
+    assert plan["ycols"] == plan["pcols"] == 64
+
+
+def test_three_phase_plan_rejects_bad_input():
+    fn = _fn()
+    ip, lp = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    rowptr = np.array([0, 1, 2], dtype=np.int32)
+    colidx = np.array([0, 7], dtype=np.int32)                # column out of range
+    need = C.c_int64()
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, None, 0, C.byref(need)) == -1
+    colidx[1] = 1
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 7, 0, 8, 0, None, 0, C.byref(need)) == -1
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, None, 0, C.byref(need)) == 0
+    assert need.value > 0
