@@ -21,15 +21,25 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_device_lib(force=False, verbose=False):
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def build_device_lib(force=False, verbose=False, trace=False):
+    """trace=True: measurement build (-DDPGO_TRACE: per-CTA phase times in the fused solver, read with
+    dpgo_phase_trace); always rebuilt, and the next normal build replaces it."""
+    flags = FLAGS + (["-DDPGO_TRACE"] if trace else [])
+    marker = os.path.join(CSRC, ".trace_build")
+    if trace or os.path.exists(marker):
+        force = True
+    if trace:
+        open(marker, "w").close()
+    elif os.path.exists(marker):
+        os.remove(marker)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith(".")]
     deps.append(os.path.join(HERE, "..", "include", "dpgo_b200.h"))
     objs = []
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         if force or _stale(o, deps):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
         objs.append(o)
@@ -81,5 +91,5 @@ def build_host(force=False):
 
 
 if __name__ == "__main__":
-    build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
     build_host(force="--force" in sys.argv)

@@ -659,6 +659,7 @@ int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doub
                 dpgo_ropt_result *res);
 int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out);
 int solve_fused_collect(dpgo_dev *h, int verbose, dpgo_ropt_result *res);
+int fused_phase_trace(dpgo_dev *h, double *busy_ms, int cap_ctas, int *num_ctas);
 
 // ---------------------------------------------------------------------------------------------
 // host-side graph -> block-CSR
@@ -1093,7 +1094,7 @@ int dpgo_destroy(dpgo_handle h) {
                   h->d_slot[1], h->d_slot[2], h->d_slot[3], h->d_xa, h->d_xb, h->d_EG, h->d_EG2,
                   h->d_grad, h->d_grad2, h->d_S, h->d_S2, h->d_eta, h->d_r, h->d_z, h->d_delta,
                   h->d_Hd, h->d_t0, h->d_t1, h->d_t2, h->d_partials, h->d_scalars, h->d_fused,
-                  h->d_public_idx, h->d_flush, h->d_zT, h->d_sym_items};
+                  h->d_public_idx, h->d_flush, h->d_zT, h->d_sym_items, h->d_trace};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -1714,6 +1715,12 @@ int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }, usec);
+}
+
+int dpgo_phase_trace(dpgo_handle h, double *busy_ms, int cap_ctas, int *num_ctas) {
+  H_CHECK(h);
+  CHECK_ARG(num_ctas != nullptr && cap_ctas >= 0 && (busy_ms != nullptr || cap_ctas == 0));
+  return fused_phase_trace(h, busy_ms, cap_ctas, num_ctas);
 }
 
 int dpgo_bytes_qx(dpgo_handle h, double *bytes) {

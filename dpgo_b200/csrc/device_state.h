@@ -95,7 +95,9 @@ struct dpgo_dev {
   double *h_scalars = nullptr;  // pinned
   void *d_fused = nullptr;      // fused-kernel parameter / result block
   void *h_fused = nullptr;      // pinned mirror
-  void *dd = nullptr;           // dpgo::DdState (precon_mode == 2)
+  void *d_trace = nullptr;      // -DDPGO_TRACE builds: per-CTA phase times of the last fused solve
+  int last_grid = 0;            // CTAs of the last fused launch
+  void *dd = nullptr;           // dpgo::DdState (precon_mode >= 2)
   int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
   int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
   int *d_public_idx = nullptr;

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "device_state.h"
 #include "kernels.cuh"
@@ -47,6 +48,7 @@ struct FusedParams {
   double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
   double *partials;  // [2][gridDim.x][4]
   FusedOut *out;
+  unsigned long long *trace;   // -DDPGO_TRACE builds: [gridDim.x][16] ns each CTA worked in a phase before its barrier
   double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
   int max_outer, max_inner;
 };
@@ -61,6 +63,12 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // live in shared memory so that they do not occupy registers across the phases
 struct PhaseClock {
   unsigned long long *acc;  // [17] in shared memory: 16 phase sums + last timestamp
+#ifdef DPGO_TRACE
+  // measurement builds: per-CTA time from the release of one barrier to the arrival at the next (the
+  // CTA's own work in the phase), accumulated per phase id; `pending` is filled by GridReducer
+  unsigned long long *busy;            // [16] in shared memory
+  const unsigned long long *pending;
+#endif
   __device__ __forceinline__ void start(unsigned long long *smem) {
     acc = smem;
     if (threadIdx.x == 0) {
@@ -74,6 +82,9 @@ struct PhaseClock {
       const unsigned long long t = gtimer();
       acc[id] += t - acc[16];
       acc[16] = t;
+#ifdef DPGO_TRACE
+      busy[id] += *pending;
+#endif
     }
   }
 };
@@ -82,17 +93,34 @@ struct GridReducer {
   double *buf[2];
   int flip;
   int barriers;
+#ifdef DPGO_TRACE
+  unsigned long long t_rel, pending;   // thread 0: release time of the last barrier, own work before this one
+  __device__ __forceinline__ void arrive() {
+    __syncthreads();                   // the whole CTA has finished the phase
+    if (threadIdx.x == 0) pending = gtimer() - t_rel;
+  }
+  __device__ __forceinline__ void release() {
+    if (threadIdx.x == 0) t_rel = gtimer();
+  }
+#else
+  __device__ __forceinline__ void arrive() {}
+  __device__ __forceinline__ void release() {}
+#endif
   // block partials -> grid barrier -> every CTA sums all partials in the same order
   template <int K>
   __device__ __forceinline__ void reduce(cg::grid_group &grid, double (&acc)[K], double (&out)[K]) {
     block_reduce_store<K>(acc, buf[flip] + (size_t)blockIdx.x * K);
+    arrive();
     grid.sync();
+    release();
     sum_partials<K>(buf[flip], gridDim.x, out);
     flip ^= 1;
     barriers++;
   }
   __device__ __forceinline__ void barrier(cg::grid_group &grid) {
+    arrive();
     grid.sync();
+    release();
     barriers++;
   }
 };
@@ -120,6 +148,17 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
 
   __shared__ unsigned long long s_clk[17];
   PhaseClock clk;
+#ifdef DPGO_TRACE
+  __shared__ unsigned long long s_busy[16];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s_busy[i] = 0;
+  }
+  red.pending = 0;
+  red.t_rel = gtimer();
+  clk.busy = s_busy;
+  clk.pending = &red.pending;
+#endif
   __shared__ StripPlanStore s_plan[MODE == 3 ? 3 : (MODE == 2 ? 2 : 1)];   // two-level variants: this CTA's strips
   if constexpr (MODE >= 2) {
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
@@ -319,6 +358,12 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   }
 
   phase_copy(ctx, x1, p.x_out, len);
+#ifdef DPGO_TRACE
+  if (threadIdx.x == 0 && p.trace) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p.trace[(size_t)blockIdx.x * 16 + i] = s_busy[i];
+  }
+#endif
   if (ctx.tid == 0) {
     FusedOut o;
     o.f_init = f_init; o.gn_init = gn_init; o.f_opt = f1; o.gn_opt = sqrt(gn2);
@@ -370,6 +415,7 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
     return DPGO_ECUDA;
   }
   h->launches++;
+  h->last_grid = (int)grid;
   return DPGO_OK;
 }
 
@@ -407,6 +453,17 @@ int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_i
   fp.eta = h->d_eta; fp.r = h->d_r; fp.z = h->d_z; fp.delta = h->d_delta; fp.Hd = h->d_Hd;
   fp.partials = h->d_partials;
   fp.out = (FusedOut *)h->d_fused;
+  fp.trace = nullptr;
+#ifdef DPGO_TRACE
+  if (!h->d_trace) {
+    if (cudaMalloc(&h->d_trace, (size_t)h->partial_blocks * 16 * sizeof(unsigned long long)) != cudaSuccess) {
+      set_error("allocation of the phase trace failed");
+      return DPGO_ECUDA;
+    }
+  }
+  cudaMemsetAsync(h->d_trace, 0, (size_t)h->partial_blocks * 16 * sizeof(unsigned long long), h->stream);
+  fp.trace = (unsigned long long *)h->d_trace;
+#endif
   fp.gradnorm_tol = P->gradnorm_tol; fp.init_radius = P->RTR_initial_radius;
   fp.theta = P->tcg_theta; fp.kappa = P->tcg_kappa; fp.accept_rho = P->accept_rho;
   fp.shrink = P->shrink; fp.magnify = P->magnify;
@@ -455,6 +512,30 @@ int solve_fused_collect(dpgo_dev *h, int verbose, dpgo_ropt_result *res) {
     printf("[dpgo_b200] fused RTR: f %.10g -> %.10g, |g| %.4g -> %.4g, %d outer, %d tCG, %lld barriers\n",
            o.f_init, o.f_opt, o.gn_init, o.gn_opt, o.outer, o.inner, o.n_barriers);
   return DPGO_OK;
+}
+
+// Per-CTA busy time (ms) per phase id of the last fused solve; only in -DDPGO_TRACE builds.
+int fused_phase_trace(dpgo_dev *h, double *busy_ms, int cap_ctas, int *num_ctas) {
+#ifdef DPGO_TRACE
+  if (!h->d_trace || h->last_grid <= 0) {
+    set_error("no fused solve has run on this handle");
+    return DPGO_ESTATE;
+  }
+  *num_ctas = h->last_grid;
+  if (cap_ctas < h->last_grid) return DPGO_OK;
+  std::vector<unsigned long long> tmp((size_t)h->last_grid * 16);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess ||
+      cudaMemcpy(tmp.data(), h->d_trace, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("reading the phase trace failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DPGO_ECUDA;
+  }
+  for (size_t i = 0; i < tmp.size(); ++i) busy_ms[i] = (double)tmp[i] * 1e-6;
+  return DPGO_OK;
+#else
+  (void)h; (void)busy_ms; (void)cap_ctas; (void)num_ctas;
+  set_error("the library was built without -DDPGO_TRACE");
+  return DPGO_ESTATE;
+#endif
 }
 
 int solve_fused(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out,

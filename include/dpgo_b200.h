@@ -252,6 +252,12 @@ int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double 
  * (outside the timed intervals).  Returns mean microseconds per launch. */
 int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec);
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
+/* Measurement builds only (library compiled with -DDPGO_TRACE, `python dpgo_b200/build.py --trace`;
+ * otherwise DPGO_ESTATE): how long every CTA of the last fused solve worked in each phase before
+ * reaching the phase's grid barrier, busy_ms[cta * 16 + phase] with the phase ids of
+ * dpgo_ropt_result.phase_ms.  *num_ctas = CTAs of that launch; nothing is written when cap_ctas is
+ * smaller. */
+int dpgo_phase_trace(dpgo_handle h, double *busy_ms, int cap_ctas, int *num_ctas);
 /* algorithmic bytes of one Q*X / one preconditioner application (SURVEY 8(d) formula) */
 int dpgo_bytes_qx(dpgo_handle h, double *bytes);
 int dpgo_bytes_precon(dpgo_handle h, double *bytes);
