@@ -121,15 +121,21 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     reset()
     ms, wall_ms, upd, launches, X = series(False)
     blocking = dict(value=upd / (ms / 1e3), ms_per_step=ms / steps)
-    mode, mode_note = "blocking", None
+    mode, mode_note, stream_ordered = "blocking", None, None
     if async_rounds:
         ok, why = preflight_async()
         if ok:
             ms_a, wall_a, upd_a, launches_a, Xa = series(True)
             dev = float(np.max(np.abs(Xa - X))) if Xa.shape == X.shape else float("inf")
             if upd_a == upd and dev <= 1e-12 * max(1.0, float(np.max(np.abs(X)))):
-                ms, wall_ms, launches, X = ms_a, wall_a, launches_a, Xa
-                mode, mode_note = "stream-ordered", f"max |X - X_blocking| = {dev:.3g}"
+                stream_ordered = dict(value=upd_a / (ms_a / 1e3), ms_per_step=ms_a / steps)
+                if ms_a <= ms:
+                    ms, wall_ms, launches, X = ms_a, wall_a, launches_a, Xa
+                    mode, mode_note = "stream-ordered", f"max |X - X_blocking| = {dev:.3g}"
+                else:
+                    team.set_async(False)
+                    mode_note = (f"stream-ordered series identical (max |X - X_blocking| = {dev:.3g}) but not faster: "
+                                 f"{stream_ordered['ms_per_step']:.4f} ms/step")
             else:
                 team.set_async(False)
                 mode_note = f"stream-ordered series rejected: max |X - X_blocking| = {dev:.3g}"
@@ -146,7 +152,8 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     out = dict(ms=ms, wall_ms=wall_ms, updates=upd, steps=steps, warmup=W, setup_s=setup_s,
                value=upd / (ms / 1e3), ms_per_step=ms / steps, cost2=cost, gradnorm=gradnorm,
                n=n, d=d, r=r, agents=agents, colors=team.colors, owner=team.owner,
-               fused_launches=launches, host_mode=mode, host_mode_note=mode_note, blocking=blocking)
+               fused_launches=launches, host_mode=mode, host_mode_note=mode_note, blocking=blocking,
+               stream_ordered=stream_ordered)
     if e2e:
         reset()
         e_ms, e_wall, e_upd, e_cost = timed(steps, True, central)
@@ -265,6 +272,7 @@ def run(args, emit=None):
                        "host_note": res["host_mode_note"]},
             "blocking_updateX": dict(res["blocking"], unit=UNIT,
                                      note="same rounds with the host waiting for every local solve"),
+            "stream_ordered_rounds": res["stream_ordered"],
             "clocks": clocks,
             "e2e": {"value": res.get("e2e_value"), "unit": UNIT, "ms_per_step": res.get("e2e_ms_per_step"),
                     "h2d_bytes_per_step": res.get("e2e_bytes"), "d2h_bytes_per_step": res.get("e2e_bytes"),
