@@ -59,7 +59,7 @@ SIGNATURES = {
     "dpgo_finalize": (C.c_int, [H, C.c_int]),
     "dpgo_set_precon_mode": (C.c_int, [H, C.c_int]),
     "dpgo_two_level_partition": (C.c_int, [C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, C.POINTER(C.c_int)]),
-    "dpgo_three_phase_plan": (C.c_int, [C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int,
+    "dpgo_three_phase_plan": (C.c_int, [C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
     "dpgo_get_precon_mode": (C.c_int, [H, C.POINTER(C.c_int)]),
     "dpgo_set_precon_tuning": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),

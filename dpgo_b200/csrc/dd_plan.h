@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "dissect.h"
@@ -89,12 +90,83 @@ inline void plan_balance(int V, std::vector<PlanStrip> &strips, std::vector<Plan
   tiles.swap(t2);
 }
 
+// Balancing that keeps strips with the same input slice (same kc0 / nchunks: the strips of one domain in
+// phases 1 and 5) on the same virtual CTAs, so that a CTA stages the slice once (phase_strip_gemv skips
+// the staging of a strip whose slice is already in shared memory).  Every group gets at least one CTA,
+// the remaining CTAs go one at a time to the group with the largest load per CTA (never more CTAs than
+// strips); inside a group the strips are dealt longest-first.  Falls back to plan_balance when there
+// are more groups than CTAs.
+inline void plan_balance_affine(int V, std::vector<PlanStrip> &strips, std::vector<PlanTile> &tiles,
+                                std::vector<int> &cta, std::vector<int> &chunks) {
+  std::vector<std::pair<std::pair<int, int>, std::vector<int>>> groups;
+  for (size_t i = 0; i < strips.size(); ++i) {
+    const std::pair<int, int> key(strips[i].kc0, strips[i].nchunks);
+    size_t g = 0;
+    while (g < groups.size() && groups[g].first != key) ++g;
+    if (g == groups.size()) groups.push_back({key, {}});
+    groups[g].second.push_back((int)i);
+  }
+  const int G = (int)groups.size();
+  if (G == 0 || G > V) {
+    plan_balance(V, strips, tiles, cta, chunks);
+    return;
+  }
+  // all strips of a group have the same length, so the busiest CTA of group g works
+  // ceil(strips_g / nct_g) * nchunks_g chunks: give the spare CTAs to the group where that is largest
+  std::vector<int> nct(G, 1);
+  auto worst = [&](int g) {
+    const int ns = (int)groups[g].second.size();
+    return (long)((ns + nct[g] - 1) / nct[g]) * groups[g].first.second;
+  };
+  for (int left = V - G; left > 0; --left) {
+    int best = -1;
+    for (int g = 0; g < G; ++g) {
+      if (nct[g] >= (int)groups[g].second.size()) continue;
+      if (best < 0 || worst(g) > worst(best)) best = g;
+    }
+    if (best < 0) break;
+    nct[best]++;
+  }
+  std::vector<PlanStrip> s2;
+  std::vector<PlanTile> t2;
+  cta.assign(1, 0);
+  chunks.clear();
+  for (int g = 0; g < G; ++g) {
+    std::vector<int> order = groups[g].second;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return strips[a].nchunks > strips[b].nchunks; });
+    std::vector<std::vector<int>> bins(nct[g]);
+    std::vector<int> bl(nct[g], 0);
+    for (int i : order) {
+      int best = 0;
+      for (int v = 1; v < nct[g]; ++v)
+        if (bl[v] < bl[best]) best = v;
+      bins[best].push_back(i);
+      bl[best] += strips[i].nchunks;
+    }
+    for (int v = 0; v < nct[g]; ++v) {
+      for (int i : bins[v]) {
+        s2.push_back(strips[i]);
+        t2.push_back(tiles[i]);
+      }
+      cta.push_back((int)s2.size());
+      chunks.push_back(bl[v]);
+    }
+  }
+  while ((int)chunks.size() < V) {   // idle virtual CTAs
+    cta.push_back((int)s2.size());
+    chunks.push_back(0);
+  }
+  strips.swap(s2);
+  tiles.swap(t2);
+}
+
 inline int plan_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // n block rows of a symmetric block pattern; dh scalars per pose; interior domains of <= max_domain_poses;
 // V virtual CTAs; split3 > 0 forces the inner split of the Schur strips; max_wave = stages of one wave.
+// affine: phases 1 and 5 use plan_balance_affine (strips of one domain share CTAs) instead of plan_balance.
 inline ThreePhasePlan build_three_phase_plan(int n, const int *rowptr, const int *colidx, int dh, int max_domain_poses,
-                                             int V, int split3, int max_wave) {
+                                             int V, int split3, int max_wave, bool affine = false) {
   ThreePhasePlan p;
   p.n = n; p.dh = dh; p.V = std::max(1, V);
   const std::vector<std::vector<int>> adj = bsr_adjacency(n, rowptr, colidx);
@@ -244,9 +316,11 @@ inline ThreePhasePlan build_three_phase_plan(int n, const int *rowptr, const int
   }
   p.stages5 = stage;
   p.bytes_per_apply = bytes;
-  plan_balance(p.V, p.strips1, p.tiles1, p.cta1, p.chunks1);
+  if (affine) plan_balance_affine(p.V, p.strips1, p.tiles1, p.cta1, p.chunks1);
+  else plan_balance(p.V, p.strips1, p.tiles1, p.cta1, p.chunks1);
   plan_balance(p.V, p.strips3, p.tiles3, p.cta3, p.chunks3);
-  plan_balance(p.V, p.strips5, p.tiles5, p.cta5, p.chunks5);
+  if (affine) plan_balance_affine(p.V, p.strips5, p.tiles5, p.cta5, p.chunks5);
+  else plan_balance(p.V, p.strips5, p.tiles5, p.cta5, p.chunks5);
   return p;
 }
 

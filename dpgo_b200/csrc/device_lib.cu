@@ -1205,7 +1205,8 @@ int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx
 }
 
 int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, int dh, int max_domain_poses,
-                          int num_ctas, int split_schur, int64_t *out, int64_t out_capacity, int64_t *out_len) {
+                          int num_ctas, int split_schur, int domain_affine, int64_t *out, int64_t out_capacity,
+                          int64_t *out_len) {
   CHECK_ARG(n >= 1 && rowptr && colidx && out_len);
   CHECK_ARG(dh >= 2 && dh <= 4);
   CHECK_ARG(num_ctas >= 1 && num_ctas <= 4096 && split_schur <= 64);
@@ -1216,7 +1217,7 @@ int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, i
   }
   const ThreePhasePlan plan =
       build_three_phase_plan(n, rowptr, colidx, dh, max_domain_poses > 0 ? max_domain_poses : two_level_max_domain_poses(dh),
-                             num_ctas, split_schur, kDdStages);
+                             num_ctas, split_schur, kDdStages, domain_affine != 0);
   const std::vector<int64_t> img = serialize_three_phase_plan(plan);
   *out_len = (int64_t)img.size();
   if (out_capacity >= (int64_t)img.size()) memcpy(out, img.data(), img.size() * sizeof(int64_t));

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
       constexpr int ST = kDdStages;
-      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
+      phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
       if (dd.nS > 0) {
         if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
         red.barrier(grid);

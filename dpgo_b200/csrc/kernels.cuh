@@ -986,7 +986,8 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
                                                  size_t outstride, bool prefetched = false,
                                                  const StageAux *ax = nullptr) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
-  // is staged (saves a separate permutation pass + grid barrier).  SRC 2 / 3: see StageAux.
+  // is staged (saves a separate permutation pass + grid barrier).  SRC 1: the same with icol required and
+  // the slice reused across consecutive strips that read the same one; SRC 2 / 3: see StageAux.
   static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -995,6 +996,7 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
   StripCursor cu;
   strip_cursor_init(cu, S, V, pl);
   bool in_flight = prefetched;   // first wave of the current strip already issued
+  int staged_kc0 = -1, staged_n = -1;   // SRC != 0: single-wave slice currently in svec (reused by the next strip)
   while (cu.v < V) {
     const DdStrip d = cu.d;
     double a0[R], a1[R];
@@ -1004,7 +1006,9 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
       const int nw = min(STAGES, d.nchunks - c0);
       if (!in_flight && threadIdx.x == 0) strip_issue_wave(pp, S, d, c0, nw);
       in_flight = false;
-      {  // the slice of vec that goes with the wave
+      bool staged = false;   // strips of one domain placed on this CTA share their input slice: stage it once
+      if constexpr (SRC != 0) staged = (d.nchunks <= STAGES && d.kc0 == staged_kc0 && d.nchunks == staged_n);
+      if (!staged) {  // the slice of vec that goes with the wave
         const int k0 = (d.kc0 + c0) * kStageK;
         const int cnt = nw * kStageK * R;
         for (int o = threadIdx.x; o < cnt; o += kBlock) {
@@ -1024,7 +1028,7 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
               const double *zp = vec + (size_t)col * R + q;
               for (int sl = 0; sl < ax->nslots; ++sl) val += zp[(size_t)sl * ax->slotstride];
             }
-          } else if (icol) {
+          } else if (SRC == 1 || icol) {
             const int k = o / R, q = o - k * R;
             const int oc = __ldg(icol + k0 + k);
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
@@ -1033,6 +1037,10 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
           }
           pp.svec[o] = val;
         }
+      }
+      if constexpr (SRC != 0) {
+        staged_kc0 = (d.nchunks <= STAGES) ? d.kc0 : -1;
+        staged_n = d.nchunks;
       }
       __syncthreads();
       for (int u = w; u < 4 * nw; u += kWarpsPerBlock) {

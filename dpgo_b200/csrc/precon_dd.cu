@@ -520,7 +520,8 @@ int dd3_build(dpgo_dev *h) {
   const int n = h->n, dh = h->d + 1, R = h->r;
   const int V = std::max(1, h->num_sms);
   const ThreePhasePlan pl = build_three_phase_plan(n, h->rowptr.data(), h->colidx.data(), dh,
-                                                   two_level_max_domain_poses(dh), V, h->dd_split3, kDdStages);
+                                                   two_level_max_domain_poses(dh), V, h->dd_split3, kDdStages,
+                                                   /*affine=*/h->dd_split1 == 2);
   const int K = pl.K;
   s->K = K; s->nS = pl.nS; s->V = V;
   s->nI = n - pl.nS;
@@ -744,7 +745,7 @@ static int dd3_apply(dpgo_dev *h, const double *vec) {
   const DdView dd = dd_view(h);
   const size_t zstride = (size_t)h->r * s->pcols;
   const StageAux a1{nullptr, nullptr, nullptr, 0, 0, 0};
-  DPGO_TRY(launch_strips3<0>(h, dd.P1, s->nstrips1, vec, s->icol, s->y, 0, a1));
+  DPGO_TRY(launch_strips3<1>(h, dd.P1, s->nstrips1, vec, s->icol, s->y, 0, a1));
   if (s->nS > 0) {
     const StageAux a3{s->y, s->tptr, s->tcol, s->sep_col0, 0, 0};
     DPGO_TRY(launch_strips3<2>(h, dd.P3, s->nstrips3, vec, s->icol, s->zs, zstride, a3));

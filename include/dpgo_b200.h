@@ -147,7 +147,9 @@ int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx
  * (precon_mode 3; no device needed): same nested dissection, separator poses ordered by the set of
  * domains they touch, the dense couplings C_k = A_k^{-1} A_kS folded into the strip phases
  * (dpgo_b200/csrc/dd_plan.h states the algebra).  num_ctas = CTAs the strips are balanced over,
- * split_schur <= 0 = library choice.  The plan is written to `out` as a flat int64 image:
+ * split_schur <= 0 = library choice, domain_affine != 0 = the strips of one domain share CTAs (they read
+ * the same input slice, which is then staged once per CTA) instead of the plain longest-first
+ * balancing.  The plan is written to `out` as a flat int64 image:
  * out[0] = S sections, then S pairs (offset, length), then the sections, in this order:
  *   0 scalars {n, dh, K, nS, V, sep_col0, pcols, ycols, nsplit3, stages1, stages3, stages5, bytes_per_apply}
  *   1 group[n]  2 pcol[n]  3 srow[nS]  4 icol[ycols]  5-7 dom_off / dom_m / dom_pad [K]
@@ -156,13 +158,15 @@ int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx
  *   20-22 cta1 / cta3 / cta5 [V+1] (strip ranges of the virtual CTAs).
  * *out_len = values needed; nothing is written when out_capacity is smaller (call twice). */
 int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
-                          int max_domain_poses, int num_ctas, int split_schur, int64_t *out,
-                          int64_t out_capacity, int64_t *out_len);
+                          int max_domain_poses, int num_ctas, int split_schur, int domain_affine,
+                          int64_t *out, int64_t out_capacity, int64_t *out_len);
 /* Tuning of the two-level variant (measurement knobs; 0 / negative = library default): how many
  * partial slots the inner dimension of the interior strips and of the Schur strips is split into
  * (more splits = more CTAs busy per phase, more partial sums to add), and whether the first
  * pipeline stages of a strip phase are issued before the grid barrier that precedes it
- * (prefetch: 1 on, 0 off, negative = default on).  Takes effect at the next preconditioner build. */
+ * (prefetch: 1 on, 0 off, negative = default on).  The three-phase form (mode 3) has whole interior
+ * strips; there split_interior == 2 selects the domain-affine balancing of dpgo_three_phase_plan.
+ * Takes effect at the next preconditioner build. */
 int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, int prefetch);
 /* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */

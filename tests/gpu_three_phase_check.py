@@ -66,6 +66,8 @@ def main(cases):
 
 
 if __name__ == "__main__":
-    quick = [("tinyGrid3D", 3, [None]), ("smallGrid3D", 5, [None, (0, 3, 0)]), ("sphere2500", 5, [None, (0, 7, 0)])]
+    # tunings (split_interior, split_schur, prefetch): split_interior == 2 = domain-affine strip placement
+    quick = [("tinyGrid3D", 3, [None]), ("smallGrid3D", 5, [None, (0, 3, 0), (2, 0, -1)]),
+             ("sphere2500", 5, [None, (0, 7, 0), (2, 0, -1)])]
     full = quick + [("city10000", 3, [None]), ("torus3D", 5, [None])]
     sys.exit(1 if main(full if "--full" in sys.argv else quick) else 0)

@@ -27,10 +27,10 @@ def _pose_graph(p1, p2, n):
     return A
 
 
-def _replay(meas, n, max_poses, V, split=0, r=3, seed=0):
+def _replay(meas, n, max_poses, V, split=0, r=3, seed=0, affine=0):
     dh = meas.d + 1
     G = _pose_graph(meas.p1, meas.p2, n)
-    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split, affine)
     emu.check_tables(plan)
     A = (pgo.connection_laplacian(meas, n) + 0.1 * sp.identity(dh * n)).tocsc()
     M, Cc, SigInv = emu.dense_blocks(A, plan)
@@ -67,6 +67,27 @@ def test_three_phase_replay_sphere2500(datasets):
     assert sum(mb) < 80                                    # L2 resident on B200 (126 MB)
 
 
+def test_domain_affine_balancing(datasets):
+    """Strips that read the same input slice share virtual CTAs (the kernel stages the slice once per
+    CTA); the replay stays exact and no CTA is worse off than two strips of the longest kind."""
+    meas, n, _ = datasets("smallGrid3D")
+    plan, err = _replay(meas, n, 12, 24, affine=1)
+    assert err <= 1e-11, err
+    for ph in ("1", "5"):
+        cta, st = plan["cta" + ph], plan["strips" + ph]
+        assert len(cta) == plan["V"] + 1
+        for v in range(plan["V"]):
+            mine = st[cta[v]:cta[v + 1]]
+            assert len({(int(s[1]), int(s[2])) for s in mine}) <= 1      # one (kc0, nchunks) per CTA
+    meas, n, _ = datasets("sphere2500")
+    G = _pose_graph(meas.p1, meas.p2, n)
+    pa = emu.fetch_plan(_fn(), n, G.indptr, G.indices, meas.d + 1, 0, 148, 0, 1)
+    emu.check_tables(pa)
+    st, cta = pa["strips1"], pa["cta1"]
+    per_cta = [int(st[cta[v]:cta[v + 1], 2].sum()) for v in range(148)]
+    assert max(per_cta) <= 2 * int(st[:, 2].max())
+
+
 def test_three_phase_plan_2d(datasets):
     """d = 2 (three scalars per pose: tiles straddle the 32- and 64-wide blocks)."""
     meas, n, _ = datasets("city10000")
@@ -83,6 +104,7 @@ def test_three_phase_plan_without_separator():
     G = _pose_graph(np.arange(n - 1), np.arange(1, n), n)
     plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 0, 8)
     emu.check_tables(plan)
+    emu.check_tables(emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 0, 8, 0, 1))
     assert plan["K"] == 1 and plan["nS"] == 0
     assert len(plan["strips3"]) == 0 and len(plan["strips5"]) == 0 and plan["stages5"] == 0
     assert plan["ycols"] == plan["pcols"] == 64
@@ -94,8 +116,8 @@ def test_three_phase_plan_rejects_bad_input():
     rowptr = np.array([0, 1, 2], dtype=np.int32)
     colidx = np.array([0, 7], dtype=np.int32)                # column out of range
     need = C.c_int64()
-    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, None, 0, C.byref(need)) == -1
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, 0, None, 0, C.byref(need)) == -1
     colidx[1] = 1
-    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 7, 0, 8, 0, None, 0, C.byref(need)) == -1
-    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, None, 0, C.byref(need)) == 0
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 7, 0, 8, 0, 0, None, 0, C.byref(need)) == -1
+    assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, 0, None, 0, C.byref(need)) == 0
     assert need.value > 0

@@ -15,17 +15,18 @@ SCALARS = ["n", "dh", "K", "nS", "V", "sep_col0", "pcols", "ycols", "nsplit3", "
            "bytes_per_apply"]
 
 
-def fetch_plan(fn, n, rowptr, colidx, dh, max_poses=0, V=148, split=0):
+def fetch_plan(fn, n, rowptr, colidx, dh, max_poses=0, V=148, split=0, affine=0):
     """fn = the C entry point (dpgo_three_phase_plan signature)."""
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
     colidx = np.ascontiguousarray(colidx, dtype=np.int32)
     ip, lp = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     need = C.c_int64()
-    rc = fn(n, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), dh, max_poses, V, split, None, 0, C.byref(need))
+    rc = fn(n, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), dh, max_poses, V, split, affine, None, 0,
+            C.byref(need))
     assert rc == 0
     img = np.zeros(need.value, dtype=np.int64)
-    rc = fn(n, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), dh, max_poses, V, split, img.ctypes.data_as(lp),
-            img.size, C.byref(need))
+    rc = fn(n, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), dh, max_poses, V, split, affine,
+            img.ctypes.data_as(lp), img.size, C.byref(need))
     assert rc == 0 and need.value == img.size
     ns = int(img[0])
     assert ns == len(SECTIONS)
