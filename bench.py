@@ -168,17 +168,17 @@ def run_reference(args):
         # latter (all the host threads the path can use), the former is reported beside it.
         from tools import bench_team
         rounds = max(1, min(args.steps, 4))
-        par = 8 if args.schedule == "all" else 4
+        ds = dict(dataset=args.team_dataset, agents=args.team_agents, r=args.team_r)
+        par = args.team_agents if args.schedule == "all" else max(1, args.team_agents // 2)
         th = max(1, min(par, os.cpu_count() or 1))
-        cpus = bench_team.cpu_team_baseline(rounds, schedule=args.schedule, threads=(1, th))
+        cpus = bench_team.cpu_team_baseline(rounds, schedule=args.schedule, threads=(1, th), **ds)
         cpu, seq = cpus[th], cpus[1]
         emit({
             "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": rounds, "warmup": 2, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "grid3D.g2o (fixture parsed from the reference's data file)",
-            "config": {"workload": bench_team.WORKLOAD_ALL if args.schedule == "all" else bench_team.WORKLOAD,
-                       "note": CPU_KIND},
+            "data": f"{args.team_dataset}.g2o (fixture parsed from the reference's data file)",
+            "config": {"workload": bench_team.workload(schedule=args.schedule, **ds), "note": CPU_KIND},
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": th, "kind": "port",
                              "sample": f"{rounds} rounds ({args.schedule} schedule), the {par} agents of a round on one core each, "
                                        f"{os.cpu_count()} host cores visible",
@@ -415,6 +415,9 @@ def main():
                     help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level "
                          "(default: the library's choice by size)")
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--team-dataset", default="grid3D", help="multi-agent series (N > 1): fixture in tests/golden")
+    ap.add_argument("--team-agents", type=int, default=8)
+    ap.add_argument("--team-r", type=int, default=5)
     ap.add_argument("--team-steps", type=int, default=10,
                     help="colour rounds of the grid3D/8-agent series appended to the N=1 line (0 = skip)")
     args = ap.parse_args()

@@ -19,6 +19,16 @@ WORKLOAD = "grid3D 8 agents r=5 sync RBCD + Nesterov, coloured parallel schedule
 WORKLOAD_ALL = "grid3D 8 agents r=5 all-agents-per-round RBCD (asynchronous-style, no acceleration), RTR(3 outer, <=50 tCG)"
 
 
+def workload(dataset="grid3D", agents=8, r=5, schedule="colored"):
+    if schedule == "all":
+        return (f"{dataset} {agents} agents r={r} all-agents-per-round RBCD (asynchronous-style, no acceleration), "
+                "RTR(3 outer, <=50 tCG)")
+    return f"{dataset} {agents} agents r={r} sync RBCD + Nesterov, coloured parallel schedule, RTR(3 outer, <=50 tCG)"
+
+
+assert workload() == WORKLOAD and workload(schedule="all") == WORKLOAD_ALL
+
+
 def _fixture(name):
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     return z, int(z["d"]), int(z["n"])
@@ -240,29 +250,36 @@ def run(args, emit=None):
     if rank == 0:
         sampler.start()
     schedule = getattr(args, "schedule", "colored")
-    res = measure(args.steps, args.warmup, rank, world, local_rank, schedule=schedule)
+    # BASELINE configs[2] unless asked otherwise (configs[3]: --team-dataset torus3D --schedule all;
+    # configs[4] without the weight updates: --team-dataset city10000 --team-agents 4 --team-r 3)
+    ds = dict(dataset=getattr(args, "team_dataset", "grid3D"), agents=getattr(args, "team_agents", 8),
+              r=getattr(args, "team_r", 5))
+    res = measure(args.steps, args.warmup, rank, world, local_rank, schedule=schedule, **ds)
     clocks = sampler.stop() if rank == 0 else None
     # second series for the record: the other parallel schedule of SURVEY 8(e) on the same graph
     other = "colored" if schedule == "all" else "all"
     try:
-        res2 = measure(args.steps, args.warmup, rank, world, local_rank, schedule=other, e2e=False)
+        res2 = measure(args.steps, args.warmup, rank, world, local_rank, schedule=other, e2e=False, **ds)
     except Exception as exc:  # the headline series above must survive a failure here
         res2 = {"error": repr(exc)}
     if rank == 0:
-        par = 8 if schedule == "all" else 4            # agents that optimize in the same round
+        # agents that optimize in the same round
+        par = res["agents"] if schedule == "all" else max(len(c) for c in res["colors"])
         cpus = cpu_team_baseline(args.cpu_steps if args.cpu_steps < 4 else 2, schedule=schedule,
-                                 threads=(1, min(par, os.cpu_count() or 1)))
+                                 threads=(1, min(par, os.cpu_count() or 1)), **ds)
         cpu, cpu_par = cpus[1], cpus[max(cpus)]
         line = {
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"],
             "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "grid3D.g2o (fixture parsed from the reference's data file)",
-            "config": {"workload": WORKLOAD_ALL if schedule == "all" else WORKLOAD, "n": res["n"], "agents": res["agents"],
+            "data": f"{ds['dataset']}.g2o (fixture parsed from the reference's data file)",
+            "config": {"workload": workload(schedule=schedule, **ds), "n": res["n"], "agents": res["agents"],
                        "agents_per_gpu": res["agents"] / world, "colors": res["colors"], "owner": res["owner"],
-                       "step": ("one round = 8 agent updates (iterate(true))" if schedule == "all" else
-                                "one colour round = 4 agent updates (iterate(true)) + 4 non-optimizing iterates"),
-                       "l2": "per-agent two-level preconditioner 21.5 MB streamed per apply; 8/N agents per GPU alternate",
+                       "step": (f"one round = {res['agents']} agent updates (iterate(true))" if schedule == "all" else
+                                f"one colour round = the agents of one colour ({par} at most) update (iterate(true)), "
+                                "the others do the non-optimizing iterate"),
+                       "l2": "per-agent preconditioner streamed per apply (grid3D/8: two-level, 21.5 MB); the agents "
+                             "of a GPU alternate",
                        "exchange": "NCCL send/recv of packed public poses (X and aux Y)" if world > 1 else
                                    "device-to-device copies (single GPU)",
                        "host": res["host_mode"] + " rounds" + (
@@ -291,7 +308,7 @@ def run(args, emit=None):
                                                     "note": "the agents that optimize in the same round on one host core each"}},
             "parity": {"cost2_after_timed_rounds": res["cost2"], "gradnorm": res["gradnorm"]},
             "other_schedule": ({"error": res2["error"]} if "error" in res2 else {
-                "workload": WORKLOAD if other == "colored" else WORKLOAD_ALL, "value": res2["value"], "unit": UNIT,
+                "workload": workload(schedule=other, **ds), "value": res2["value"], "unit": UNIT,
                 "ms_per_step": res2["ms_per_step"], "steps": res2["steps"], "updates": res2["updates"],
                 "cost2_after_timed_rounds": res2["cost2"], "gradnorm": res2["gradnorm"],
                 "host": res2["host_mode"], "blocking_updateX": res2["blocking"],
