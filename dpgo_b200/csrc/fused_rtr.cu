@@ -383,8 +383,15 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
 template <int R, int D, int MODE>
 static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
   constexpr int smem = (MODE >= 2) ? kDdDynSmem : kGemvDynSmem;
-  static int occ_cache = -1;
-  if (occ_cache < 0) {
+  // the shared-memory attribute and the occupancy belong to the device (one handle = one device; a
+  // process may hold handles on several): cached per device
+  static int occ_by_device[64];
+  if (h->device < 0 || h->device >= 64) {
+    set_error("device ordinal %d not supported by the fused solver", h->device);
+    return DPGO_EINVAL;
+  }
+  int &occ_cache = occ_by_device[h->device];
+  if (occ_cache <= 0) {
     int occ = 0;
     if (cudaFuncSetAttribute(k_rtr_fused<R, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rtr_fused<R, D, MODE>, kBlock, smem) != cudaSuccess ||
