@@ -134,6 +134,13 @@ __global__ void __launch_bounds__(kBlock) k_retract(const double *X, const doubl
   phase_retract<R, D>(make_ctx(), X, Eta, Xout, n);
 }
 
+// RGD step: Xout = Retraction_X(s * Dir) -- gradient scale and QF retraction in one pass
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_retract_scaled(const double *X, const double *Dir, double s,
+                                                           double *Xout, int n) {
+  phase_retract_impl<R, D, true>(make_ctx(), X, Dir, Xout, n, s);
+}
+
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_polar(double ca, const double *A, double cb,
                                                   const double *B, double cc, const double *C,
@@ -485,6 +492,12 @@ int op_retract(dpgo_dev *h, const double *X, const double *Eta, double *Xout) {
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }
+int op_retract_scaled(dpgo_dev *h, const double *X, const double *Dir, double s, double *Xout) {
+  const int grid = pose_grid(h, 1);
+  DPGO_DISPATCH(h, k_retract_scaled<R, D><<<grid, kBlock, 0, h->stream>>>(X, Dir, s, Xout, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
 int op_polar(dpgo_dev *h, double ca, const double *A, double cb, const double *B, double cc,
              const double *C, double *out) {
   const int grid = pose_grid(h, 1);
@@ -616,9 +629,8 @@ int solve_host(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, doubl
       res->n_precon++;
       dir = h->d_z;
     }
-    CUDA_TRY(cudaMemsetAsync(h->d_eta, 0, h->vlen * sizeof(double), h->stream));
-    DPGO_TRY(op_axpby(h, -P->RGD_stepsize, dir, 0.0, h->d_eta));
-    DPGO_TRY(op_retract(h, c.x1, h->d_eta, c.x2));
+    // eta = -stepsize * dir and the retraction in one kernel (the scale is applied inside)
+    DPGO_TRY(op_retract_scaled(h, c.x1, dir, -P->RGD_stepsize, c.x2));
     res->n_pose_sweeps++;
     std::swap(c.x1, c.x2);
     DPGO_TRY(op_fgrad(h, c.x1, c.EG, c.grad, c.S, &c.f1, &c.gn2));

@@ -1279,10 +1279,14 @@ __device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double
 
 // QF retraction, one thread per pose: Y+ = qf(Y + eta_Y) (Gram-Schmidt, positive diagonal),
 // p+ = p + eta_p.   ref: ProductManifold::Retraction (src/QuadraticOptimizer.cpp:134).
-template <int R, int D>
-__device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, const double *Eta,
-                                              double *Xout, int n) {
+// SCALED: the step is s * Eta (the gradient scale of QuadraticOptimizer::gradientDescent,
+// src/QuadraticOptimizer.cpp:133-134, applied inside the retraction: round(s * e) then the add, i.e. the
+// same bits as scaling into a separate array first).
+template <int R, int D, bool SCALED>
+__device__ __forceinline__ void phase_retract_impl(const Ctx &ctx, const double *X, const double *Eta,
+                                                   double *Xout, int n, double s) {
   constexpr int TILE = R * (D + 1);
+  auto step = [&](double xv, double ev) { return SCALED ? __dadd_rn(xv, __dmul_rn(s, ev)) : xv + ev; };
   for (int i = ctx.tid; i < n; i += ctx.nthreads) {
     const double *x = X + (size_t)i * TILE;
     const double *e = Eta + (size_t)i * TILE;
@@ -1291,7 +1295,7 @@ __device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, c
 #pragma unroll
     for (int k = 0; k < D; ++k) {
 #pragma unroll
-      for (int q = 0; q < R; ++q) a[k][q] = x[k * R + q] + e[k * R + q];
+      for (int q = 0; q < R; ++q) a[k][q] = step(x[k * R + q], e[k * R + q]);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -1325,8 +1329,13 @@ __device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, c
       for (int q = 0; q < R; ++q) o[k * R + q] = a[k][q];
     }
 #pragma unroll
-    for (int q = 0; q < R; ++q) o[D * R + q] = x[D * R + q] + e[D * R + q];
+    for (int q = 0; q < R; ++q) o[D * R + q] = step(x[D * R + q], e[D * R + q]);
   }
+}
+template <int R, int D>
+__device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, const double *Eta,
+                                              double *Xout, int n) {
+  phase_retract_impl<R, D, false>(ctx, X, Eta, Xout, n, 1.0);
 }
 
 // Polar projection of the Stiefel block (U V^T of the thin SVD) by one-sided Jacobi, one
