@@ -307,7 +307,8 @@ def bench_single(args):
         traffic = tj.get("dram_bytes_per_launch_mode%d" % mode, tj.get("dram_bytes_per_launch") if mode == 0 else None)
     pre_kernel = {0: "k_precon_gemv<5> (full dense inverse, 800 MB)",
                   1: "k_precon_symv<5> (symmetric half storage)",
-                  2: "k_strip_gemv<5> x3 + k_dd_sep_rhs + k_dd_back_rhs (two-level, 58 MB, L2 resident)"}[mode]
+                  2: "k_strip_gemv<5> x3 + k_dd_sep_rhs + k_dd_back_rhs (two-level, 58 MB, L2 resident)",
+                  3: "k_strip_gemv3<5,*> x3 (two-level, three-phase form, L2 resident)"}[mode]
     roofline = {"bound": "hbm",
                 "kernel": "k_rtr_fused<5,3,%d> (whole optimize() = 1 launch; dominated by the (Q+0.1I)^-1 apply)" % mode,
                 "achieved": step_gbs, "peak": peak, "unit": "GB/s",
@@ -318,7 +319,7 @@ def bench_single(args):
                                        "achieved": pre_bytes / pre_us / 1e3,
                                        "frac": pre_bytes / pre_us / 1e3 / peak,
                                        "share_of_step": (npc / K) * pre_us / (ms / K * 1e3)}}
-    if mode == 2:
+    if mode >= 2:
         roofline["note"] = ("two-level exact preconditioner: 14x fewer algorithmic bytes than the dense inverse and "
                             "L2 resident within a step, so the step is grid-barrier / latency bound, not HBM bound; "
                             "the HBM-bound formulation of the same solve is timed below (dense_inverse_variant)")
@@ -351,7 +352,8 @@ def bench_single(args):
                    "n": n, "d": d, "r": r, "solver": "fused persistent kernel" if args.fused else "one launch per op",
                    "l2": "flushed between timed steps (256 MB device write outside the per-step CUDA-event pairs)",
                    "preconditioner": {0: "full dense inverse", 1: "symmetric half storage",
-                                      2: "two-level (nested dissection + Schur complement)"}[mode],
+                                      2: "two-level (nested dissection + Schur complement)",
+                                      3: "two-level, three-phase form (couplings folded into the strips)"}[mode],
                    "outer_iters": res["outer_iters"], "tcg_iters": res["inner_iters"],
                    "qx_per_step": nq / K, "precon_per_step": npc / K},
         "clocks": clocks,
@@ -412,8 +414,8 @@ def main():
                          "(asynchronous-style, configs[3])")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--precon-mode", type=int, default=None,
-                    help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level "
-                         "(default: the library's choice by size)")
+                    help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level, "
+                         "3 two-level in three phases (default: the library's choice by size)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--team-dataset", default="grid3D", help="multi-agent series (N > 1): fixture in tests/golden")
     ap.add_argument("--team-agents", type=int, default=8)
