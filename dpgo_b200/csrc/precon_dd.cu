@@ -138,8 +138,26 @@ __global__ void k_dd_layout_rect(const double *C, int m, int ldc, const int *col
     const int row = form == 0 ? c * kStageK + kk : ob * kGemvCols + jj;
     const int comp = form == 0 ? ob * kGemvCols + jj : c * kStageK + kk;
     double val = 0.0;
-    if (row < m && comp < ncomp) val = C[(size_t)row + (size_t)colmap[comp] * ldc];
+    if (row < m && comp < ncomp) val = C[(size_t)row + (size_t)(colmap ? colmap[comp] : comp) * ldc];
     dst[t] = val;
+  }
+}
+
+// Bc(:, i) = B(:, colmap[i]) : the columns of A_kS that belong to S_k (all others are zero)
+__global__ void k_dd_gather_cols(const double *B, int m, int ldb, const int *colmap, int ncomp, double *Bc) {
+  const size_t total = (size_t)m * ncomp;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t % m), i = (int)(t / m);
+    Bc[t] = B[(size_t)row + (size_t)colmap[i] * ldb];
+  }
+}
+
+// Sigma(colmap[i], colmap[j]) -= W(i, j) : the Schur update of one domain touches only S_k x S_k
+__global__ void k_dd_scatter_sub(double *Sg, int ldS, const int *colmap, const double *W, int ncomp) {
+  const size_t total = (size_t)ncomp * ncomp;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % ncomp), j = (int)(t / ncomp);
+    Sg[(size_t)colmap[i] + (size_t)colmap[j] * ldS] -= W[t];
   }
 }
 
@@ -584,12 +602,18 @@ int dd3_build(dpgo_dev *h) {
   int maxdom = 1;
   for (int k = 0; k < K; ++k) maxdom = std::max(maxdom, pl.dom_m[k]);
   const int maxm = std::max(std::max(mS, 1), maxdom);
-  double *A = nullptr, *Sg = nullptr, *B = nullptr, *C = nullptr, *work = nullptr;
+  int maxt = 1;
+  for (int k = 0; k < K; ++k) maxt = std::max(maxt, pl.t_m[k]);
+  // A: one interior block; B: A_kS over all separator columns (zero outside S_k); Bc / Cc: A_kS and
+  // C_k = A_k^-1 A_kS restricted to the columns of S_k; W: the domain's Schur update on S_k x S_k
+  double *A = nullptr, *Sg = nullptr, *B = nullptr, *Bc = nullptr, *C = nullptr, *W = nullptr, *work = nullptr;
   int *info = nullptr;
   CUDA_TRY(cudaMalloc((void **)&A, (size_t)maxdom * maxdom * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&B, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&C, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&Bc, (size_t)maxdom * maxt * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&C, (size_t)maxdom * maxt * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&W, (size_t)maxt * maxt * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
   int lwork = 0;
   {
@@ -632,28 +656,31 @@ int dd3_build(dpgo_dev *h) {
     k_dd_layout<<<lgrid((size_t)pl.dom_pad[k] * pl.dom_pad[k]), 256, 0, h->stream>>>(
         A, m, m, pl.dom_pad[k], s->M1 + (size_t)baseM[k] * kStageDoubles);
     CUDA_TRY(cudaPeekAtLastError());
-    if (mS > 0) {
-      // C = A_k^-1 A_kS;  Sigma -= A_kS^T C
+    const int tm = pl.t_m[k];
+    if (tm > 0) {
+      // A_kS is non-zero only in the columns of S_k: C = A_k^-1 A_kS[:, S_k] (m x tm) and the Schur
+      // update Sigma[S_k, S_k] -= A_kS[:, S_k]^T C (tm x tm) are formed on those columns only
+      if (baseG[k] < 0 || baseW[k] < 0) {
+        set_error("three-phase plan has no coupling strips for domain %d", k);
+        return DPGO_EINVAL;
+      }
+      const int *cm = d_cmap + cmap_off[k];
       CUDA_TRY(cudaMemsetAsync(B, 0, (size_t)m * mS * sizeof(double), h->stream));
       k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
                                                             d_group, d_lpos, k, -1, 0.0, B, m);
-      const double one = 1.0, zero = 0.0, mone = -1.0;
-      LIB_TRY(cublasDsymm(s->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, m, mS, &one, A, m, B, m, &zero, C, m));
-      LIB_TRY(cublasDgemm(s->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mS, mS, m, &mone, B, m, C, m, &one, Sg, mS));
-      const int tm = pl.t_m[k];
-      if (tm > 0) {
-        if (baseG[k] < 0 || baseW[k] < 0) {
-          set_error("three-phase plan has no coupling strips for domain %d", k);
-          return DPGO_EINVAL;
-        }
-        const int nobG = pl.t_pad[k] / kGemvCols, nchG = pl.dom_pad[k] / kStageK;
-        k_dd_layout_rect<<<lgrid((size_t)nobG * nchG * kStageDoubles), 256, 0, h->stream>>>(
-            C, m, m, d_cmap + cmap_off[k], tm, 0, nobG, nchG, s->M1 + (size_t)baseG[k] * kStageDoubles);
-        const int nobW = pl.dom_pad[k] / kGemvCols, nchW = (tm + kStageK - 1) / kStageK;
-        k_dd_layout_rect<<<lgrid((size_t)nobW * nchW * kStageDoubles), 256, 0, h->stream>>>(
-            C, m, m, d_cmap + cmap_off[k], tm, 1, nobW, nchW, s->M5 + (size_t)baseW[k] * kStageDoubles);
-        CUDA_TRY(cudaPeekAtLastError());
-      }
+      k_dd_gather_cols<<<lgrid((size_t)m * tm), 256, 0, h->stream>>>(B, m, m, cm, tm, Bc);
+      CUDA_TRY(cudaPeekAtLastError());
+      const double one = 1.0, zero = 0.0;
+      LIB_TRY(cublasDsymm(s->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, m, tm, &one, A, m, Bc, m, &zero, C, m));
+      LIB_TRY(cublasDgemm(s->cublas, CUBLAS_OP_T, CUBLAS_OP_N, tm, tm, m, &one, Bc, m, C, m, &zero, W, tm));
+      k_dd_scatter_sub<<<lgrid((size_t)tm * tm), 256, 0, h->stream>>>(Sg, mS, cm, W, tm);
+      const int nobG = pl.t_pad[k] / kGemvCols, nchG = pl.dom_pad[k] / kStageK;
+      k_dd_layout_rect<<<lgrid((size_t)nobG * nchG * kStageDoubles), 256, 0, h->stream>>>(
+          C, m, m, nullptr, tm, 0, nobG, nchG, s->M1 + (size_t)baseG[k] * kStageDoubles);
+      const int nobW = pl.dom_pad[k] / kGemvCols, nchW = (tm + kStageK - 1) / kStageK;
+      k_dd_layout_rect<<<lgrid((size_t)nobW * nchW * kStageDoubles), 256, 0, h->stream>>>(
+          C, m, m, nullptr, tm, 1, nobW, nchW, s->M5 + (size_t)baseW[k] * kStageDoubles);
+      CUDA_TRY(cudaPeekAtLastError());
     }
   }
   if (mS > 0) {
@@ -662,7 +689,7 @@ int dd3_build(dpgo_dev *h) {
     CUDA_TRY(cudaPeekAtLastError());
   }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(A); cudaFree(Sg); cudaFree(B); cudaFree(C); cudaFree(work); cudaFree(info);
+  cudaFree(A); cudaFree(Sg); cudaFree(B); cudaFree(Bc); cudaFree(C); cudaFree(W); cudaFree(work); cudaFree(info);
   cudaFree(d_group); cudaFree(d_lpos); cudaFree(d_cmap);
   return DPGO_OK;
 }
