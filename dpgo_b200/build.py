@@ -32,7 +32,7 @@ def build_device_lib(force=False, verbose=False, trace=False):
         open(marker, "w").close()
     elif os.path.exists(marker):
         os.remove(marker)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith(".")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith(".") and not f.endswith(".o")]
     deps.append(os.path.join(HERE, "..", "include", "dpgo_b200.h"))
     objs = []
     for src in CU_SOURCES:
