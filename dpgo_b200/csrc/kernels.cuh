@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dd_stage.h"
+
 namespace dpgo {
 
 constexpr int kBlock = 256;          // threads per CTA for every phase
@@ -830,17 +832,6 @@ struct DdStripSet {
                        // a strip's kc0 then counts chunks of this list.  nullptr: inner indices are columns
 };
 
-// Extra inputs of the staging step of a strip phase in the three-phase form (dd_plan.h):
-//   SRC 2: vec is r in the original order; the value of scalar column c of the S segment is
-//          r[icol[c]] - sum_e sub[tcol[e]],  e in [tptr[c - col0], tptr[c - col0 + 1])
-//   SRC 3: vec is an array of `nslots` partial results `slotstride` apart, read through S.gidx
-struct StageAux {
-  const double *sub;
-  const int *tptr, *tcol;
-  int col0;
-  int nslots;
-  size_t slotstride;
-};
 
 struct DdView {
   DdStripSet P1;                // blockdiag(A_k^-1)  (nsplit1 partial slots)
@@ -1013,22 +1004,10 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
         const int cnt = nw * kStageK * R;
         for (int o = threadIdx.x; o < cnt; o += kBlock) {
           double val;
-          if constexpr (SRC == 2) {
+          if constexpr (SRC != 0) {   // three-phase form: dd_stage.h (shared with the host test)
             const int k = o / R, q = o - k * R;
-            const int oc = __ldg(icol + k0 + k);
-            const int j = k0 + k - ax->col0;
-            const int e0 = __ldg(ax->tptr + j), e1 = __ldg(ax->tptr + j + 1);
-            val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
-            for (int e = e0; e < e1; ++e) val -= ax->sub[(size_t)__ldg(ax->tcol + e) * R + q];
-          } else if constexpr (SRC == 3) {
-            const int k = o / R, q = o - k * R;
-            const int col = __ldg(S.gidx + k0 + k);
-            val = 0.0;
-            if (col >= 0) {
-              const double *zp = vec + (size_t)col * R + q;
-              for (int sl = 0; sl < ax->nslots; ++sl) val += zp[(size_t)sl * ax->slotstride];
-            }
-          } else if (SRC == 1 || icol) {
+            val = strip_stage_value<SRC>(k0 + k, q, R, vec, icol, S.gidx, ax);
+          } else if (icol) {
             const int k = o / R, q = o - k * R;
             const int oc = __ldg(icol + k0 + k);
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;

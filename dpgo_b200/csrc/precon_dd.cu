@@ -127,20 +127,10 @@ __global__ void k_dd_layout(const double *A, int m, int lda, int pad, double *ds
 // stage (ob, c) is the (ob * nch + c)-th 16 KB run of dst.
 __global__ void k_dd_layout_rect(const double *C, int m, int ldc, const int *colmap, int ncomp, int form, int nob,
                                  int nch, double *dst) {
+  static_assert(kGemvCols == 64 && kStageK == 32, "dd_stage.h states the stage shape");
   const size_t total = (size_t)nob * nch * kStageDoubles;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int jj = (int)(t % kGemvCols);
-    const size_t u = t / kGemvCols;
-    const int kk = (int)(u % kStageK);
-    const size_t v = u / kStageK;
-    const int c = (int)(v % nch);
-    const int ob = (int)(v / nch);
-    const int row = form == 0 ? c * kStageK + kk : ob * kGemvCols + jj;
-    const int comp = form == 0 ? ob * kGemvCols + jj : c * kStageK + kk;
-    double val = 0.0;
-    if (row < m && comp < ncomp) val = C[(size_t)row + (size_t)(colmap ? colmap[comp] : comp) * ldc];
-    dst[t] = val;
-  }
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    dst[t] = layout_rect_value(C, m, ldc, colmap, ncomp, form, nch, t);
 }
 
 // Bc(:, i) = B(:, colmap[i]) : the columns of A_kS that belong to S_k (all others are zero)

@@ -121,3 +121,119 @@ def test_three_phase_plan_rejects_bad_input():
     assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 7, 0, 8, 0, 0, None, 0, C.byref(need)) == -1
     assert fn(2, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), 4, 0, 8, 0, 0, None, 0, C.byref(need)) == 0
     assert need.value > 0
+
+
+# ---- the index arithmetic the CUDA kernels share with the host (dpgo_b200/csrc/dd_stage.h) --------------
+@pytest.fixture(scope="module")
+def host_arith(tmp_path_factory):
+    """tests/native/three_phase_host.cpp compiled with g++ (seconds): dd_stage.h outside nvcc."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path_factory.mktemp("native") / "libthree_phase_host.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared",
+                           os.path.join(root, "tests", "native", "three_phase_host.cpp"), "-o", so])
+    return C.CDLL(so)
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_kernel_staging_arithmetic_matches_the_replay(datasets, host_arith):
+    """strip_stage_value<1/2/3> (the staging step of phase_strip_gemv in the three-phase form) against the
+    numpy replay's src1 / src3 / src5 on every inner index the strips of the plan touch."""
+    meas, n, _ = datasets("smallGrid3D")
+    dh, R = meas.d + 1, 5
+    G = _pose_graph(meas.p1, meas.p2, n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 12, 24, 2)
+    rng = np.random.default_rng(3)
+    icol = plan["icol"].astype(np.int32); gidx = plan["gidx"].astype(np.int32)
+    tptr = plan["tptr"].astype(np.int32); tcol = plan["tcol"].astype(np.int32)
+    ycols, pcols, ns3, sep0 = plan["ycols"], plan["pcols"], plan["nsplit3"], plan["sep_col0"]
+    # arrays in the kernels' layout: column-major R x cols, i.e. [col][q]
+    r = rng.standard_normal((dh * n, R))
+    y = rng.standard_normal((ycols, R))
+    zs = rng.standard_normal((ns3, pcols, R))
+    assert ns3 >= 2 and len(tcol) > 0
+    fn = host_arith.tp_stage_values
+    fn.restype = C.c_int
+
+    def call(src, idx, vec):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.zeros((len(idx), R))
+        rc = fn(src, R, len(idx), _ip(idx), _dp(vec), _ip(icol), _ip(gidx), _dp(y), _ip(tptr), _ip(tcol), sep0,
+                ns3, C.c_int64(pcols * R), _dp(out))
+        assert rc == 0
+        return out
+
+    def touched(ph):
+        st = plan["strips" + ph]
+        return np.unique(np.concatenate([np.arange(32 * s[1], 32 * (s[1] + s[2])) for s in st]))
+
+    # phase 1: gathered through icol
+    idx = touched("1")
+    ref = np.where(icol[idx][:, None] >= 0, r[np.maximum(icol[idx], 0)], 0.0)
+    assert np.array_equal(call(1, idx, r), ref)
+    # phase 3: r_S minus the scattered coupling terms, in CSR order
+    idx = touched("3")
+    assert idx.min() >= sep0 and idx.max() < pcols
+    ref = np.where(icol[idx][:, None] >= 0, r[np.maximum(icol[idx], 0)], 0.0)
+    for a, col in enumerate(idx):
+        for e in range(tptr[col - sep0], tptr[col - sep0 + 1]):
+            ref[a] -= y[tcol[e]]
+    assert np.array_equal(call(2, idx, r), ref)
+    # phase 5: partial slots of z_S summed in slot order through the gather list
+    idx = touched("5")
+    assert idx.max() < len(gidx)
+    ref = np.zeros((len(idx), R))
+    for a, i in enumerate(idx):
+        if gidx[i] >= 0:
+            for sl in range(ns3):
+                ref[a] += zs[sl, gidx[i]]
+    assert np.array_equal(call(3, idx, zs), ref)
+
+
+def test_kernel_layout_arithmetic_matches_the_replay(datasets, host_arith):
+    """layout_rect_value (k_dd_layout_rect) against the stage buffers the numpy replay fills, for the
+    coupling strips of both phases, from C_k given with all separator columns + a column map (as the plan
+    defines it) and from C_k given on the columns of S_k only (as the device set-up calls it)."""
+    meas, n, _ = datasets("smallGrid3D")
+    dh = meas.d + 1
+    G = _pose_graph(meas.p1, meas.p2, n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 12, 24)
+    A = (pgo.connection_laplacian(meas, n) + 0.1 * sp.identity(dh * n)).tocsc()
+    M, Cc, SigInv = emu.dense_blocks(A, plan)
+    bufs = emu.fill_stage_buffers(plan, M, Cc, SigInv)
+    fn = host_arith.tp_layout_rect
+    fn.restype = C.c_int
+    mS = plan["nS"] * dh
+    checked = 0
+    for ph, kind, form in (("1", 1, 0), ("5", 3, 1)):
+        st = plan["strips" + ph]
+        for k in range(plan["K"]):
+            mine = st[(st[:, 5] == kind) & (st[:, 6] == k)]
+            if not len(mine):
+                continue
+            mine = mine[np.argsort(mine[:, 7])]                      # by output block
+            nob, nch, base = len(mine), int(mine[0, 2]), int(mine[0, 4])
+            assert np.array_equal(mine[:, 4], base + nch * np.arange(nob))   # [ob][c] runs, as the set-up assumes
+            m, tm = int(plan["dom_m"][k]), int(plan["t_m"][k])
+            sk = plan["sk"][plan["sk_ptr"][k]:plan["sk_ptr"][k + 1]]
+            cmap = (sk[:, None] * dh + np.arange(dh)).ravel().astype(np.int32)
+            want = bufs[ph][base:base + nob * nch].ravel()
+            Ck = np.asfortranarray(Cc[k])                            # m x tm, the columns of S_k only
+            got = np.zeros(nob * nch * 32 * 64)
+            assert fn(_dp(Ck), m, m, None, tm, form, nob, nch, _dp(got)) == 0
+            assert np.array_equal(got, want)
+            full = np.zeros((m, mS), order="F")                      # all separator columns + the column map
+            full[:, cmap] = Cc[k]
+            got2 = np.zeros_like(got)
+            assert fn(_dp(full), m, m, _ip(cmap), tm, form, nob, nch, _dp(got2)) == 0
+            assert np.array_equal(got2, want)
+            checked += 1
+    assert checked >= 4
