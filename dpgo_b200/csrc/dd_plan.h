@@ -304,9 +304,10 @@ inline ThreePhasePlan build_three_phase_plan(int n, const int *rowptr, const int
   p.stages3 = (long long)ncbS * nchS;
   bytes += (double)mS * mS * 8;
   stage = 0;
-  for (int k = 0; k < K; ++k) {   // phase 5: C_k[:, S_k]^T
+  for (int k = 0; k < K && p.nS > 0; ++k) {   // phase 5: C_k[:, S_k]^T
+    // a domain without separator neighbours (its own component) keeps empty strips (0 chunks): they
+    // write w = 0 and, when the finish is fused into this phase, complete its poses with z = y
     const int nch = plan_round_up(p.t_m[k], kPlanStageK) / kPlanStageK;
-    if (nch == 0) continue;
     for (int cb = 0; cb < p.dom_pad[k] / kPlanCols; ++cb) {
       p.strips5.push_back(PlanStrip{p.dom_off[k] / kPlanCols + cb, p.gchunk[k], nch, 0, stage});
       p.tiles5.push_back(PlanTile{3, k, cb});

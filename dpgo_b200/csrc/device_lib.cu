@@ -841,7 +841,8 @@ static const int kAutoTwoLevelMinN = 3000;
 static int build_precon(dpgo_dev *h) {
   h->precon_mode = (h->precon_request >= 0) ? h->precon_request : (h->N >= kAutoTwoLevelMinN ? 2 : 0);
   if (h->precon_mode >= 2) {   // two-level exact preconditioner (precon_dd.cu), five- or three-phase form
-    DPGO_TRY(h->precon_mode == 3 ? dd3_build(h) : dd_build(h));
+    if (h->precon_mode == 4 && h->d != 3) h->precon_mode = 3;   // the fused finish needs d + 1 = 4
+    DPGO_TRY(h->precon_mode >= 3 ? dd3_build(h) : dd_build(h));
     h->has_precon = true;
     return DPGO_OK;
   }
@@ -1188,7 +1189,7 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
 
 int dpgo_set_precon_mode(dpgo_handle h, int mode) {
   CHECK_ARG(h != nullptr);
-  CHECK_ARG(mode >= -1 && mode <= 3);
+  CHECK_ARG(mode >= -1 && mode <= 4);
   if (mode != h->precon_request) {
     h->precon_request = mode;
     h->has_precon = false;

@@ -159,13 +159,44 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   clk.busy = s_busy;
   clk.pending = &red.pending;
 #endif
-  __shared__ StripPlanStore s_plan[MODE == 3 ? 3 : (MODE == 2 ? 2 : 1)];   // two-level variants: this CTA's strips
+  __shared__ StripPlanStore s_plan[MODE >= 3 ? 3 : (MODE == 2 ? 2 : 1)];   // two-level variants: this CTA's strips
   if constexpr (MODE >= 2) {
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
-  if constexpr (MODE == 3) strip_plan_fill(&s_plan[2], p.dd.P5, p.dd.V);
+  if constexpr (MODE >= 3) strip_plan_fill(&s_plan[2], p.dd.P5, p.dd.V);
   // the three variants of the exact preconditioner (compile-time: one per kernel instantiation)
+  // MODE 4 = the three-phase form with the finish of the interior poses in the epilogue of the last strip
+  // phase and the separator poses right after it: one application = 3 grid phases, the third one ending in
+  // the <z, r> reduction (d = 3 only: 64-column strips hold whole poses)
+  auto precon_fused = [&](const double *v, const double *Ycur, double *neg_out, double (&a1)[1]) {
+    if constexpr (MODE == 4) {
+      const DdView &dd = p.dd;
+      const size_t zs = (size_t)dd.pcols * R;
+      const bool pf = dd.prefetch != 0;
+      constexpr int ST = kDdStages;
+      phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
+      if (dd.nS > 0) {
+        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
+        red.barrier(grid);
+        clk.lap(8);
+        const StageAux a3{dd.y, dd.tptr, dd.tcol, dd.sep_col0, 0, 0};
+        phase_strip_gemv<R, ST, 2>(pipe, dd.P3, dd.V, &s_plan[1], v, dd.icol, dd.zs, zs, pf, &a3);
+        if (pf) strip_prefetch<ST>(pipe, dd.P5, dd.V, &s_plan[2]);
+        red.barrier(grid);
+        clk.lap(10);
+        const StageAux a5{nullptr, nullptr, nullptr, 0, dd.nsplit3, zs};
+        StripFinish fin{dd.y, dd.icol, Ycur, v, p.z, neg_out, 0.0};
+        phase_strip_gemv<R, ST, 3, D>(pipe, dd.P5, dd.V, &s_plan[2], dd.zs, nullptr, dd.w, 0, pf, &a5, &fin);
+        a1[0] += fin.acc;
+        phase_dd_finish_sep<R, D>(ctx, dd, Ycur, v, p.z, neg_out, a1);
+      } else {   // a single domain: z = Proj(y)
+        red.barrier(grid);
+        clk.lap(8);
+        phase_dd_finish<R, D>(ctx, dd, Ycur, v, p.z, neg_out, n, a1);
+      }
+    }
+  };
   auto precon_stream = [&](const double *v) {
     if constexpr (MODE == 3) {
       // three-phase form: [M_k | C_k] strips -> Sigma^-1 strips (t_S formed while staged) -> C_k^T strips
@@ -216,7 +247,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
     }
   };
   auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
-    if constexpr (MODE >= 2)
+    if constexpr (MODE >= 2)   // (MODE 4 finishes inside precon_fused)
       phase_dd_finish<R, D>(ctx, p.dd, Ycur, rvec, p.z, neg_out, n, a1);
     else if constexpr (MODE == 1)
       phase_precon_finish_sym<R, D>(pipe.scratch, p.zpart, p.zT, p.zstride, p.symNG, Ycur, rvec, p.z,
@@ -260,6 +291,25 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
     bool first = true;
     for (int j = 0;; ++j) {
       const double *pvec = first ? grad : p.r;
+      if constexpr (MODE == 4) {
+        double acc[1] = {0.0}, sc[1];
+        precon_fused(pvec, x1, first ? p.delta : nullptr, acc);    // first: delta = -z
+        if (first) {
+          phase_copy(ctx, grad, p.r, len);
+          phase_zero(ctx, p.eta, len);
+        }
+        red.reduce<1>(grid, acc, sc);
+        clk.lap(12);
+        n_precon++;
+        if (first) {
+          tcg_begin(s, gn2, sc[0]);
+        } else {
+          const double beta = tcg_direction(s, sc[0]);
+          phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
+          red.barrier(grid);
+          clk.lap(5);
+        }
+      } else {
       precon_stream(pvec);
       if (first) {
         phase_copy(ctx, grad, p.r, len);
@@ -281,6 +331,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
           red.barrier(grid);
           clk.lap(5);
         }
+      }
       }
       first = false;
       if (j >= p.max_inner) break;
@@ -428,7 +479,10 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
 
 template <int R, int D>
 static int launch_fused(dpgo_dev *h, FusedParams &fp) {
-  if (h->precon_mode == 3) return launch_fused_v<R, D, 3>(h, fp);
+  if constexpr (D == 3) {
+    if (h->precon_mode == 4) return launch_fused_v<R, D, 4>(h, fp);
+  }
+  if (h->precon_mode >= 3) return launch_fused_v<R, D, 3>(h, fp);
   if (h->precon_mode == 2) return launch_fused_v<R, D, 2>(h, fp);
   if (h->precon_mode == 1) return launch_fused_v<R, D, 1>(h, fp);
   return launch_fused_v<R, D, 0>(h, fp);

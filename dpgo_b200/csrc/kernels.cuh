@@ -965,17 +965,29 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
+// FIND > 0 (three-phase form, d + 1 divides 64): the last strip phase also finishes the application for
+// the interior poses -- its epilogue holds w for 64 permuted columns = whole poses, so z = Proj_Y(y - w),
+// <z, r> and the optional -z are produced there instead of in a separate grid phase.
+struct StripFinish {
+  const double *yarr;      // phase-1 results (permuted columns)
+  const int *icol;         // permuted column -> original scalar column (-1: padding)
+  const double *Y;         // current iterate
+  const double *rvec;      // original order
+  double *z, *neg_out;
+  double acc;              // this thread's part of <z, r>
+};
+
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
 // A strip is processed in waves of <= STAGES chunks: thread 0 puts the whole wave in flight (one
 // TMA bulk copy per 16 KB stage, each with its own mbarrier), all threads stage the matching slice
 // of `vec` (one round of global-load latency per wave), then the 8 warps split the wave into
 // (chunk, 8-row) units and each waits only for the stages it reads -- no CTA-wide barrier per
 // stage.  pp.parity is a bit mask here: bit i = phase parity of stage slot i.
-template <int R, int STAGES, int SRC = 0>
+template <int R, int STAGES, int SRC = 0, int FIND = 0>
 __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
                                                  const double *vec, const int *icol, double *out,
                                                  size_t outstride, bool prefetched = false,
-                                                 const StageAux *ax = nullptr) {
+                                                 const StageAux *ax = nullptr, StripFinish *fin = nullptr) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
   // is staged (saves a separate permutation pass + grid barrier).  SRC 1: the same with icol required and
   // the slice reused across consecutive strips that read the same one; SRC 2 / 3: see StageAux.
@@ -983,7 +995,9 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const StripPlan pl = strip_plan_load(st);
-  if (pl.G == 0) return;
+  if constexpr (FIND == 0) {
+    if (pl.G == 0) return;       // (with the fused finish even empty strips have poses to complete)
+  }
   StripCursor cu;
   strip_cursor_init(cu, S, V, pl);
   bool in_flight = prefetched;   // first wave of the current strip already issued
@@ -1053,12 +1067,47 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
       sacc[w][q][2 * lane + 1] = a1[q];
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
-      const int q = o / kGemvCols, jj = o % kGemvCols;
-      double x = 0.0;
+    if constexpr (FIND > 0) {
+      // two full warps: thread jj owns permuted column 64 cb + jj, D + 1 adjacent lanes = one pose
+      constexpr int DH = FIND + 1;
+      static_assert(FIND == 0 || (kGemvCols % (FIND + 1) == 0 && 32 % (FIND + 1) == 0), "poses must not straddle strips");
+      if (threadIdx.x < kGemvCols) {
+        const int jj = threadIdx.x;
+        const int colp = d.cb * kGemvCols + jj;
+        const int oc = __ldg(fin->icol + colp);      // original scalar column = pose * DH + c
+        const bool valid = oc >= 0;
+        double wv[R];
 #pragma unroll
-      for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-      out[(size_t)d.slot * outstride + ((size_t)d.cb * kGemvCols + jj) * R + q] = x;
+        for (int q = 0; q < R; ++q) {
+          double x = 0.0;
+#pragma unroll
+          for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+          wv[q] = valid ? fin->yarr[(size_t)colp * R + q] - x : 0.0;
+        }
+        const LanePos lp = lane_pos<FIND>(lane);
+        const int pose = valid ? oc / DH : 0;
+        double sym[FIND];
+        group_tangent<R, FIND>(fin->Y + (size_t)pose * (R * DH), wv, lp, valid, sym);
+        if (valid) {
+          const size_t off = (size_t)oc * R;
+          store_col<R>(fin->z + off, wv);
+          double rr[R];
+          load_col<R>(fin->rvec + off, rr);
+          fin->acc += dot_col<R>(wv, rr);
+          if (fin->neg_out) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) fin->neg_out[off + q] = -wv[q];
+          }
+        }
+      }
+    } else {
+      for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+        const int q = o / kGemvCols, jj = o % kGemvCols;
+        double x = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+        out[(size_t)d.slot * outstride + ((size_t)d.cb * kGemvCols + jj) * R + q] = x;
+      }
     }
     __syncthreads();
   }
@@ -1200,6 +1249,57 @@ __device__ __forceinline__ void phase_dd_finish(const Ctx &ctx, const DdView &dd
 #pragma unroll
           for (int q = 0; q < R; ++q)
             wv[q] += dd.y[(size_t)s * zstride + poff + q] - dd.w[(size_t)s * zstride + poff + q];
+        }
+      }
+    }
+    double sym[D];
+    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), wv, lp, valid, sym);
+    if (valid) {
+      store_col<R>(z + off, wv);
+      double rr[R];
+      load_col<R>(rvec + off, rr);
+      acc[0] += dot_col<R>(wv, rr);
+      if (neg_out) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) neg_out[off + q] = -wv[q];
+      }
+    }
+  }
+}
+
+// finish of the separator poses only (three-phase form with the interior finished by the last strip phase):
+// z_S = Proj_Y( sum of the zs partial slots ); acc += <z_S, r_S>
+template <int R, int D>
+__device__ __forceinline__ void phase_dd_finish_sep(const Ctx &ctx, const DdView &dd, const double *Y,
+                                                    const double *rvec, double *z, double *neg_out,
+                                                    double (&acc)[1]) {
+  using Gm = Geo<R, D>;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  const size_t zstride = (size_t)dd.pcols * R;
+  for (int base = ctx.warp * Gm::GPW; base < dd.nS; base += ctx.nwarps * Gm::GPW) {
+    const int sp = base + lp.grp;
+    const bool valid = lp.ok && sp < dd.nS;
+    const int i = valid ? __ldg(dd.srow + sp) : 0;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double wv[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) wv[q] = 0.0;
+    if (valid) {
+      const size_t poff = ((size_t)dd.sep_col0 + (size_t)sp * Gm::DH + lp.c) * R;
+      for (int s = 0; s < dd.nsplit3; s += 4) {   // same order of additions as phase_dd_finish
+        double tq[4][R];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const size_t so = (size_t)min(s + j, dd.nsplit3 - 1) * zstride + poff;
+#pragma unroll
+          for (int q = 0; q < R; ++q) tq[j][q] = dd.zs[so + q];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (s + j < dd.nsplit3) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) wv[q] += tq[j][q];
+          }
         }
       }
     }

@@ -131,9 +131,12 @@ int dpgo_finalize(dpgo_handle h, int build_precon);
  *   3 (opt-in, never chosen automatically) the same two-level elimination in three grid phases: the
  *     dense couplings C_k = A_k^{-1} A_kS are kept as strips, so that r_S - A_SI A_II^{-1} r_I comes out
  *     of the first strip phase and z_I = y_I - C z_S out of the last; no sparse coupling phases.
+ *   4 (opt-in, d = 3 only; d = 2 falls back to 3) mode 3 with the final projection, <z, r> and -z
+ *     produced in the epilogue of the last strip phase inside the fused solver (3 grid phases per
+ *     application including the reduction); outside the fused solver it is applied like mode 3.
  * Takes effect at the next dpgo_finalize(h, 1) / dpgo_update_weights(..., 1). */
 int dpgo_set_precon_mode(dpgo_handle h, int mode);
-/* The variant in use (0 / 1 / 2 / 3) once the preconditioner is built. */
+/* The variant in use (0 .. 4) once the preconditioner is built. */
 int dpgo_get_precon_mode(dpgo_handle h, int *mode);
 /* Host-only inspection of the partition the two-level variant is built on (no device needed): the
  * nested dissection of a pose graph given as a block-CSR pattern (n block rows, rowptr[n+1],

@@ -40,10 +40,11 @@ def main(cases):
         line = {"dataset": name, "r": r, "mode2": {"apply_us": g2.time_precon(20, False), "solve_ms": r2["elapsed_ms"],
                                                    "bytes": g2.bytes_precon()}}
         g2.close()
-        for tuning in tunings:
+        # mode 4 = mode 3 with the finish fused into the last strip phase of the fused solver (d = 3)
+        for mode, tuning in [(3, t) for t in tunings] + [(4, None)]:
             g3 = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r,
-                                                     precon_mode=3, precon_tuning=tuning)
-            assert g3.precon_mode() == 3
+                                                     precon_mode=mode, precon_tuning=tuning)
+            assert g3.precon_mode() == (mode if d == 3 else 3)
             z3 = g3.precon(X, Vt)
             e_ref, e_2 = rel(z3, ref), rel(z3, z2)
             ok = e_ref < 1e-8 and e_2 < 1e-9
@@ -56,7 +57,7 @@ def main(cases):
                 sols["fused" if fused else "host"] = {"iters": [r3["outer_iters"], r3["inner_iters"]], "gap": gap,
                                                       "solve_ms": r3["elapsed_ms"], "barriers": r3["n_barriers"],
                                                       "phase_ms": r3["phase_ms"][:13]}
-            line["mode3_tuning_%s" % (tuning,)] = {"ok": bool(ok), "err_vs_oracle": e_ref, "err_vs_mode2": e_2,
+            line["mode%d_tuning_%s" % (mode, tuning)] = {"ok": bool(ok), "err_vs_oracle": e_ref, "err_vs_mode2": e_2,
                                                     "apply_us": g3.time_precon(20, False), "bytes": g3.bytes_precon(),
                                                     "solves": sols}
             failed += 0 if ok else 1

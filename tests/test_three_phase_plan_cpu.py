@@ -88,6 +88,29 @@ def test_domain_affine_balancing(datasets):
     assert max(per_cta) <= 2 * int(st[:, 2].max())
 
 
+def test_isolated_domain_keeps_empty_strips(datasets):
+    """A component small enough to be one domain has no separator neighbour: its phase-5 strips are empty
+    (0 chunks) but present, so that the phase still completes its poses (w = 0, i.e. z = y)."""
+    meas, n, _ = datasets("smallGrid3D")
+    ida = np.arange(0, 100)
+    idb = np.arange(105, 125)                               # second component, 20 poses
+    new = -np.ones(n, dtype=np.int64)
+    new[ida] = np.arange(100)
+    new[idb] = 100 + np.arange(20)
+    ina, inb = (meas.p1 < 100) & (meas.p2 < 100), (meas.p1 >= 105) & (meas.p2 >= 105)
+    keep = ina | inb
+    sub = pgo.make_measurements(meas.d, new[meas.p1[keep]], new[meas.p2[keep]], meas.R[keep], meas.t[keep],
+                                meas.kappa[keep], meas.tau[keep])
+    plan, err = _replay(sub, 120, 20, 6)
+    assert err <= 1e-11, err
+    grp = set(plan["group"][100:].tolist())
+    assert len(grp) == 1 and -1 not in grp                  # the small component is one interior domain
+    k = grp.pop()
+    assert plan["t_m"][k] == 0
+    mine = plan["strips5"][plan["strips5"][:, 6] == k]
+    assert len(mine) == plan["dom_pad"][k] // emu.COLS and np.all(mine[:, 2] == 0)
+
+
 def test_three_phase_plan_2d(datasets):
     """d = 2 (three scalars per pose: tiles straddle the 32- and 64-wide blocks)."""
     meas, n, _ = datasets("city10000")
