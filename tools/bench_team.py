@@ -135,8 +135,12 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     if async_rounds:
         ok, why = preflight_async()
         if ok:
-            ms_a, wall_a, upd_a, launches_a, Xa = series(True)
-            dev = float(np.max(np.abs(Xa - X))) if Xa.shape == X.shape else float("inf")
+            try:
+                ms_a, wall_a, upd_a, launches_a, Xa = series(True)
+                dev = float(np.max(np.abs(Xa - X))) if Xa.shape == X.shape else float("inf")
+            except Exception as exc:     # keep the blocking series (a sticky CUDA error would end the run anyway)
+                ms_a, wall_a, upd_a, launches_a, Xa, dev = ms, wall_ms, -1, launches, X, float("inf")
+                why = repr(exc)
             if upd_a == upd and dev <= 1e-12 * max(1.0, float(np.max(np.abs(X)))):
                 stream_ordered = dict(value=upd_a / (ms_a / 1e3), ms_per_step=ms_a / steps)
                 if ms_a <= ms:
@@ -148,7 +152,7 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
                                  f"{stream_ordered['ms_per_step']:.4f} ms/step")
             else:
                 team.set_async(False)
-                mode_note = f"stream-ordered series rejected: max |X - X_blocking| = {dev:.3g}"
+                mode_note = f"stream-ordered series rejected: max |X - X_blocking| = {dev:.3g}" + (f" ({why})" if why else "")
         else:
             mode_note = f"stream-ordered solve unavailable: {why}"
     central = None
