@@ -63,6 +63,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
     "dpgo_get_precon_mode": (C.c_int, [H, C.POINTER(C.c_int)]),
     "dpgo_set_precon_tuning": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
+    "dpgo_set_two_level_domain_size": (C.c_int, [H, C.c_int]),
     "dpgo_update_weights": (C.c_int, [H, _dp, _dp, C.c_int]),
     "dpgo_get_Q_bsr": (C.c_int, [H, C.POINTER(C.c_int), _ip, _ip, _dp]),
     "dpgo_set_G": (C.c_int, [H, _dp]),

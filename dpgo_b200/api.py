@@ -108,6 +108,9 @@ class DeviceProblem:
     def set_precon_tuning(self, split_interior=0, split_schur=0, prefetch=-1):
         check(lib.dpgo_set_precon_tuning(self._h, int(split_interior), int(split_schur), int(prefetch)))
 
+    def set_two_level_domain_size(self, max_domain_poses=0):
+        check(lib.dpgo_set_two_level_domain_size(self._h, int(max_domain_poses)))
+
     def finalize(self, build_precon=True):
         check(lib.dpgo_finalize(self._h, 1 if build_precon else 0))
 
@@ -312,7 +315,8 @@ class DeviceProblem:
 
 
 def problem_from_measurements(p1, p2, R, t, kappa, tau, n, d, r, device=0, stream=None,
-                              build_precon=True, weight=None, precon_mode=None, precon_tuning=None):
+                              build_precon=True, weight=None, precon_mode=None, precon_tuning=None,
+                              domain_size=None):
     """Single-robot problem (all edges private), as examples/MultiRobotExample.cpp:61-63 builds
     `problemCentral`."""
     prob = DeviceProblem(n, d, r, device, stream)
@@ -321,5 +325,7 @@ def problem_from_measurements(p1, p2, R, t, kappa, tau, n, d, r, device=0, strea
         prob.set_precon_mode(precon_mode)
     if precon_tuning is not None:
         prob.set_precon_tuning(*precon_tuning)
+    if domain_size is not None:
+        prob.set_two_level_domain_size(domain_size)
     prob.finalize(build_precon)
     return prob

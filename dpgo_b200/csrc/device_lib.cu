@@ -1254,6 +1254,13 @@ int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, i
   return DPGO_OK;
 }
 
+int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses) {
+  CHECK_ARG(h != nullptr && max_domain_poses >= 0);
+  h->dd_max_domain = max_domain_poses;
+  h->has_precon = false;
+  return DPGO_OK;
+}
+
 int dpgo_finalize(dpgo_handle h, int build_precon_flag) {
   H_CHECK(h);
   DPGO_TRY(build_Q_host(h));

@@ -245,7 +245,7 @@ int dd_build(dpgo_dev *h) {
   // ---- partition
   const std::vector<std::vector<int>> adj = bsr_adjacency(n, h->rowptr.data(), h->colidx.data());
   // interior blocks of <= 320 scalars (5 column blocks of 64): a strip is one wave of kDdStages chunks
-  const int thr = two_level_max_domain_poses(dh);
+  const int thr = h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh);
   Dissector ds(adj, thr);
   {
     std::vector<int> all(n);
@@ -528,7 +528,8 @@ int dd3_build(dpgo_dev *h) {
   const int n = h->n, dh = h->d + 1, R = h->r;
   const int V = std::max(1, h->num_sms);
   const ThreePhasePlan pl = build_three_phase_plan(n, h->rowptr.data(), h->colidx.data(), dh,
-                                                   two_level_max_domain_poses(dh), V, h->dd_split3, kDdStages,
+                                                   h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh),
+                                                   V, h->dd_split3, kDdStages,
                                                    /*affine=*/h->dd_split1 == 2);
   const int K = pl.K;
   s->K = K; s->nS = pl.nS; s->V = V;

@@ -171,6 +171,12 @@ int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, i
  * strips; there split_interior == 2 selects the domain-affine balancing of dpgo_three_phase_plan.
  * Takes effect at the next preconditioner build. */
 int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, int prefetch);
+/* Measurement knob of the two-level variants: poses per interior domain of the nested dissection
+ * (0 = library default: a domain is one wave of strip stages, 80 poses for d = 3).  Larger domains mean
+ * fewer separator poses and larger interior inverses; max_domain_poses >= n gives a single domain and no
+ * separator, i.e. the full dense inverse applied by the one-CTA-per-SM strip kernel (strips then take
+ * several waves).  Takes effect at the next preconditioner build. */
+int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses);
 /* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
 int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,

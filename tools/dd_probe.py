@@ -3,7 +3,7 @@
 Prints, per problem and configuration, the stand-alone apply time, the fused-solver time of one
 optimize() and the in-kernel phase clocks (dpgo_ropt_result.phase_ms), as JSON lines.
 
-    python tools/dd_probe.py [--quick] > gpurun_out/dd_probe.jsonl
+    python tools/dd_probe.py [--quick | --forms] > gpurun_out/dd_probe.jsonl
 """
 import json
 import os
@@ -24,11 +24,11 @@ def fixture(name):
     return dict(z), int(z["d"]), int(z["n"]), z["T_chordal"]
 
 
-def run(tag, z, d, n, T0, r, mode, tuning=None, reps=3):
+def run(tag, z, d, n, T0, r, mode, tuning=None, reps=3, domain_size=None):
     X0 = np.asfortranarray(lifting_matrix(d, r) @ T0)
     t0 = time.time()
     gp = dpgo_b200.problem_from_measurements(z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"], n, d, r,
-                                             precon_mode=mode, precon_tuning=tuning)
+                                             precon_mode=mode, precon_tuning=tuning, domain_size=domain_size)
     setup = time.time() - t0
     gp.slot_set(0, X0)
     us = gp.time_precon(20, False)
@@ -39,7 +39,8 @@ def run(tag, z, d, n, T0, r, mode, tuning=None, reps=3):
         if best is None or res["elapsed_ms"] < best["elapsed_ms"]:
             best = res
     ph = best["phase_ms"]
-    print(json.dumps({"problem": tag, "n": n, "d": d, "mode": mode, "tuning": tuning, "setup_s": round(setup, 2),
+    print(json.dumps({"problem": tag, "n": n, "d": d, "mode": mode, "tuning": tuning, "domain_size": domain_size,
+                      "setup_s": round(setup, 2),
                       "apply_us": round(us, 1), "apply_bytes": by, "optimize_ms": round(best["elapsed_ms"], 3),
                       "outer": best["outer_iters"], "tcg": best["inner_iters"], "n_precon": best["n_precon"],
                       "two_f": 2 * best["f_opt"], "barriers": best["n_barriers"],
@@ -47,7 +48,27 @@ def run(tag, z, d, n, T0, r, mode, tuning=None, reps=3):
     gp.close()
 
 
+def forms():
+    """--forms: the five-phase form against the three-phase forms (modes 3 / 4) and the domain-size knob
+    (one domain = the dense inverse through the strip kernel), on the bench problem and on agent-sized
+    grids (512 / 1000 / 1728 poses: torus3D/8-, grid3D/8-sized agents)."""
+    z, d, n, T0 = fixture("sphere2500")
+    for mode, tuning, dom in [(2, None, None), (3, None, None), (3, (2, 0, -1), None), (4, None, None),
+                              (4, (2, 0, -1), None), (2, None, 160), (4, None, 160), (4, None, 40)]:
+        run("sphere2500", z, d, n, T0, 5, mode, tuning, domain_size=dom)
+    for L in (8, 10, 12):
+        g = synthetic.grid3d(L, seed=1)
+        T = g["T_true"] if "T_true" in g else g["T0"]
+        for mode, dom in [(0, None), (2, None), (3, None), (4, None), (2, L ** 3), (4, 160)]:
+            run(f"grid3d_L{L}", g, 3, L ** 3, T, 5, mode, domain_size=dom)
+    z, d, n, T0 = fixture("city10000")
+    for mode in (2, 3):
+        run("city10000", z, d, n, T0, 3, mode, reps=2)
+
+
 def main():
+    if "--forms" in sys.argv:
+        return forms()
     quick = "--quick" in sys.argv
     z, d, n, T0 = fixture("sphere2500")
     run("sphere2500", z, d, n, T0, 5, 0)
