@@ -46,6 +46,8 @@ def _replay(meas, n, max_poses, V, split=0, r=3, seed=0, affine=0):
     ("smallGrid3D", 20, 7, 0),        # several strips per virtual CTA
     ("smallGrid3D", 0, 148, 0),       # the library's domain size, one B200 worth of CTAs
     ("smallGrid3D", 10, 16, 3),       # forced inner split of the Schur strips
+    ("smallGrid3D", 200, 16, 0),      # one domain, no separator: strips longer than one wave of stages
+    ("smallGrid3D", 60, 16, 0),       # two large domains: multi-wave interior strips and a separator
 ])
 def test_three_phase_replay_is_exact(datasets, name, max_poses, V, split):
     meas, n, _ = datasets(name)
