@@ -108,6 +108,9 @@ class DeviceProblem:
     def set_precon_tuning(self, split_interior=0, split_schur=0, prefetch=-1):
         check(lib.dpgo_set_precon_tuning(self._h, int(split_interior), int(split_schur), int(prefetch)))
 
+    def set_qx_variant(self, variant=0, prefetch_distance=0):
+        check(lib.dpgo_set_qx_variant(self._h, int(variant), int(prefetch_distance)))
+
     def set_two_level_domain_size(self, max_domain_poses=0):
         check(lib.dpgo_set_two_level_domain_size(self._h, int(max_domain_poses)))
 

@@ -86,6 +86,12 @@ __global__ void __launch_bounds__(kBlock) k_qx(BsrView Q, const double *X, const
 }
 
 template <int R, int D>
+__global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const double *X, const double *G,
+                                                        double *out, int n, int dist) {
+  phase_qx_prefetch<R, D>(make_ctx(), Q, X, G, out, n, dist);
+}
+
+template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_fgrad(BsrView Q, const double *X, const double *G,
                                                   double *EG, double *grad, double *S, int n,
                                                   double *partials) {
@@ -419,6 +425,24 @@ int read_partials(dpgo_dev *h, int nblocks, int K, double *out) { return read_sc
 int op_qx(dpgo_dev *h, const BsrView &Q, const double *X, const double *G, double *out) {
   const int grid = pose_grid(h, h->d + 1);
   DPGO_DISPATCH(h, k_qx<R, D><<<grid, kBlock, 0, h->stream>>>(Q, X, G, out, h->n));
+  LAUNCH_CHECK(h);
+  return DPGO_OK;
+}
+// the stand-alone Q*X of dpgo_qx / dpgo_time_qx, in the variant chosen with dpgo_set_qx_variant
+template <int R, int D>
+static int qx_prefetch_distance(dpgo_dev *h) {
+  // poses covered by the CTAs that are resident together: the row a newly scheduled CTA starts with
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_qx_prefetch<R, D>, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+  return h->num_sms * occ * kWarpsPerBlock * (32 / (D + 1));
+}
+int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
+  if (h->qx_variant == 0) return op_qx(h, qview(h), X, G, out);
+  const int grid = pose_grid(h, h->d + 1);
+  DPGO_DISPATCH(h, {
+    const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : qx_prefetch_distance<R, D>(h);
+    k_qx_prefetch<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
+  });
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }
@@ -1254,6 +1278,13 @@ int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, i
   return DPGO_OK;
 }
 
+int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance) {
+  CHECK_ARG(h != nullptr && (variant == 0 || variant == 1) && prefetch_distance >= 0);
+  h->qx_variant = variant;
+  h->qx_prefetch_dist = prefetch_distance;
+  return DPGO_OK;
+}
+
 int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses) {
   CHECK_ARG(h != nullptr && max_domain_poses >= 0);
   h->dd_max_domain = max_domain_poses;
@@ -1354,7 +1385,7 @@ int dpgo_qx(dpgo_handle h, const double *X, double *out) {
   H_CHECK(h); NEED_FINAL(h);
   CHECK_ARG(X && out);
   DPGO_TRY(h2d(h, h->d_t0, X));
-  DPGO_TRY(op_qx(h, qview(h), h->d_t0, nullptr, h->d_t1));
+  DPGO_TRY(op_qx_main(h, h->d_t0, nullptr, h->d_t1));
   return d2h(h, out, h->d_t1);
 }
 
@@ -1719,7 +1750,7 @@ extern "C" {
 int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec) {
   H_CHECK(h); NEED_FINAL(h);
   return time_launches(h, reps, flush_l2,
-                       [&]() { return op_qx(h, qview(h), h->d_slot[0], nullptr, h->d_t1); }, usec);
+                       [&]() { return op_qx_main(h, h->d_slot[0], nullptr, h->d_t1); }, usec);
 }
 
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {

@@ -100,6 +100,7 @@ struct dpgo_dev {
   void *dd = nullptr;           // dpgo::DdState (precon_mode >= 2)
   int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
   int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
+  int qx_variant = 0, qx_prefetch_dist = 0;   // dpgo_set_qx_variant (stand-alone Q*X only)
   int dd_max_domain = 0;              // poses per interior domain (0 = one wave of strip stages)
   int *d_public_idx = nullptr;
   int num_public = 0;

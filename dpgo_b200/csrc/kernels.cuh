@@ -263,6 +263,54 @@ __device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const
   }
 }
 
+// TMA bulk prefetch into L2 (no destination in the SM, no registers held): `bytes` from a 16-byte aligned
+// address, a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Measurement variant of phase_qx for problems that stream from HBM (dpgo_set_qx_variant(h, 1)): the same
+// product, plus a software prefetch -- one lane of every warp asks the L2 for the Q blocks, the column
+// indices and the own X tiles of the block rows `dist` poses further on (the rows a CTA that becomes
+// resident when this one retires will read), one bulk prefetch each.  The dependent chain rowptr -> colidx -> X
+// otherwise leaves only the loads of one block row per lane group in flight.
+template <int R, int D>
+__device__ __forceinline__ void phase_qx_prefetch(const Ctx &ctx, const BsrView &Q, const double *X,
+                                                  const double *G, double *out, int n, int dist) {
+  using Gm = Geo<R, D>;
+  constexpr int BLK = Gm::DH * Gm::DH;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    // one lane per warp: the GPW block rows `dist` poses ahead are contiguous in the block-CSR, so their
+    // Q blocks, their column indices and their own X tiles are one contiguous span each
+    const int ip0 = base + dist;
+    if (ctx.lane == 0 && ip0 < n) {
+      const int ip1 = min(ip0 + Gm::GPW, n);
+      const int f0 = __ldg(Q.rowptr + ip0), f1 = __ldg(Q.rowptr + ip1);
+      if constexpr ((BLK * 8) % 16 == 0) {
+        if (f1 > f0) bulk_prefetch_l2(Q.blocks + (size_t)f0 * BLK, (uint32_t)(f1 - f0) * (BLK * 8));
+      }
+      if constexpr ((Gm::TILE * 8) % 16 == 0)
+        bulk_prefetch_l2(X + (size_t)ip0 * Gm::TILE, (uint32_t)(ip1 - ip0) * (Gm::TILE * 8));
+      // colidx entries are 4 bytes: prefetch the 16-byte aligned span that covers the rows
+      const size_t a0 = ((size_t)f0 * 4) & ~(size_t)15, a1 = (((size_t)f1 * 4) + 15) & ~(size_t)15;
+      if (a1 > a0) bulk_prefetch_l2(reinterpret_cast<const char *>(Q.colidx) + a0, (uint32_t)(a1 - a0));
+    }
+    if (lp.ok && i < n) {
+      double acc[R];
+      const size_t off = ((size_t)i * Gm::DH + lp.c) * R;
+      if (G) load_col<R>(G + off, acc);
+      else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) acc[q] = 0.0;
+      }
+      spmm_col<R, D>(Q, X, i, lp.c, acc);
+      store_col<R>(out + off, acc);
+    }
+  }
+}
+
 // Cost, Euclidean gradient, Riemannian gradient and the per-pose S = sym(Y^T EG_Y) in one pass:
 //   EG = X Q + G; f = 0.5 <EG + G, X>; grad = Proj_X(EG); acc = {f, <grad,grad>}
 // ref: QuadraticProblem::f / EucGrad / RieGrad, src/QuadraticProblem.cpp:29-47,71-83.

@@ -265,6 +265,11 @@ int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double 
  * (outside the timed intervals).  Returns mean microseconds per launch. */
 int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec);
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
+/* Measurement knob for the stand-alone Q*X (dpgo_qx, dpgo_time_qx; the solver's fused passes are not
+ * affected): variant 0 = the default kernel; 1 = the same product with a software prefetch -- every pose
+ * group asks the L2 (cp.async.bulk.prefetch.L2) for the Q blocks, column indices and X tile of the pose
+ * `prefetch_distance` rows further on (0 = the poses covered by the CTAs that are resident together). */
+int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance);
 /* Measurement builds only (library compiled with -DDPGO_TRACE, `python dpgo_b200/build.py --trace`;
  * otherwise DPGO_ESTATE): how long every CTA of the last fused solve worked in each phase before
  * reaching the phase's grid barrier, busy_ms[cta * 16 + phase] with the phase ids of

@@ -39,6 +39,19 @@ def main():
                    back_to_back_us=warm, back_to_back_gbs=nbytes / warm / 1e3,
                    flushed_us=cold, flushed_gbs=nbytes / cold / 1e3,
                    frac_of_measured_peak=nbytes / cold / 1e3 / peak, peak_gbs=peak)
+        # measurement variant 1 (dpgo_set_qx_variant): software prefetch into L2, a few distances;
+        # its product must equal the default kernel's bit for bit (same arithmetic)
+        Xh = rng.standard_normal((5, 4 * g["n"]))
+        ref = gp.qx(Xh)
+        rec["prefetch_variant"] = []
+        for dist in (0, 4096, 16384, 65536):
+            gp.set_qx_variant(1, dist)
+            same = bool(np.array_equal(gp.qx(Xh), ref))
+            w1, c1 = gp.time_qx(20, False), gp.time_qx(10, True)
+            rec["prefetch_variant"].append(dict(distance=dist, identical=same, back_to_back_us=w1, flushed_us=c1,
+                                                flushed_gbs=nbytes / c1 / 1e3,
+                                                frac_of_measured_peak=nbytes / c1 / 1e3 / peak))
+        gp.set_qx_variant(0, 0)
         print(json.dumps(rec), flush=True)
         out.append(rec)
         gp.close()
