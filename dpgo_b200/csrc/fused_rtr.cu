@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   // poses: packed is 8 % faster)
   const Ctx ctx = ((p.n + Geo<R, D>::GPW - 1) / Geo<R, D>::GPW >= (int)gridDim.x) ? make_ctx_spread() : make_ctx();
   const int n = p.n;
-  GemvPipe pipe = gemv_pipe_init<(MODE >= 2 ? kDdStages : kStages), (MODE >= 2 ? kDdVecChunks : kStages)>(dsm);
+  GemvPipe pipe = gemv_pipe_init<(MODE >= 3 ? kDd3Stages : (MODE == 2 ? kDdStages : kStages)),
+                                 (MODE >= 3 ? kDd3Stages : (MODE == 2 ? kDdVecChunks : kStages))>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
   GridReducer red;
   red.buf[0] = p.partials;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
-      constexpr int ST = kDdStages;
+      constexpr int ST = kDd3Stages;
       phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
       if (dd.nS > 0) {
         if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
-      constexpr int ST = kDdStages;
+      constexpr int ST = kDd3Stages;
       phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
       if (dd.nS > 0) {
         if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
 
 template <int R, int D, int MODE>
 static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
-  constexpr int smem = (MODE >= 2) ? kDdDynSmem : kGemvDynSmem;
+  constexpr int smem = (MODE >= 3) ? kDd3DynSmem : ((MODE == 2) ? kDdDynSmem : kGemvDynSmem);
   // the shared-memory attribute and the occupancy belong to the device (one handle = one device; a
   // process may hold handles on several): cached per device
   static int occ_by_device[64];

@@ -863,6 +863,13 @@ constexpr int kDdScratch = kWarpsPerBlock * kGemvMaxR * kGemvCols * 8;
 constexpr int kDdDynSmem =
     kDdStages * kStageDoubles * 8 + kDdStages * 8 + kDdVecChunks * kStageK * kGemvMaxR * 8 + kDdScratch;
 static_assert(kDdDynSmem <= 227 * 1024, "two-level pipeline does not fit in shared memory");
+// the fused solver of the three-phase forms runs an 11-stage ring: the Schur strips of sphere2500 are 11
+// chunks long (54 chunks in 5 inner splits) and become a single wave; the partition (domains of at most
+// kDdStages chunks) is the same as for the five-phase form
+constexpr int kDd3Stages = 11;
+constexpr int kDd3DynSmem =
+    kDd3Stages * kStageDoubles * 8 + kDd3Stages * 8 + kDd3Stages * kStageK * kGemvMaxR * 8 + kDdScratch;
+static_assert(kDd3DynSmem + 4096 <= 227 * 1024, "three-phase pipeline (+ static shared memory) does not fit");
 
 struct DdStrip {
   int cb, kc0, nchunks, slot;   // output column block, first inner chunk, #chunks, partial slot
