@@ -529,7 +529,7 @@ int dd3_build(dpgo_dev *h) {
   const int V = std::max(1, h->num_sms);
   const ThreePhasePlan pl = build_three_phase_plan(n, h->rowptr.data(), h->colidx.data(), dh,
                                                    h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh),
-                                                   V, h->dd_split3, kDdStages,
+                                                   V, h->dd_split3, kDd3Stages /* wave of the fused solver */,
                                                    /*affine=*/h->dd_split1 == 2);
   const int K = pl.K;
   s->K = K; s->nS = pl.nS; s->V = V;
