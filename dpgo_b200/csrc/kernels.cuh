@@ -8,7 +8,12 @@
 // "lane group" of D+1 adjacent lanes of a warp, lane c owning column c of the tile (R doubles in
 // registers); d x d cross-column quantities are exchanged with warp shuffles.
 #pragma once
+// DPGO_CPU_EMU: tests/native/cuda_emu.h has defined the CUDA keywords, builtins and the PTX helpers below
+// for a host build that runs ONE CTA with real threads (a CPU test of the device functions of the
+// three-phase preconditioner; never part of the product libraries)
+#ifndef DPGO_CPU_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "dd_stage.h"
@@ -265,9 +270,11 @@ __device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const
 
 // TMA bulk prefetch into L2 (no destination in the SM, no registers held): `bytes` from a 16-byte aligned
 // address, a multiple of 16
+#ifndef DPGO_CPU_EMU
 __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+#endif
 
 // Measurement variant of phase_qx for problems that stream from HBM (dpgo_set_qx_variant(h, 1)): the same
 // product, plus a software prefetch -- one lane of every warp asks the L2 for the Q blocks, the column
@@ -414,6 +421,7 @@ __device__ __forceinline__ void phase_tangent(const Ctx &ctx, const double *X, c
 }
 
 // ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
+#ifndef DPGO_CPU_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -443,6 +451,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#endif  // DPGO_CPU_EMU
 
 constexpr int kStageK = 32;                                  // inner indices per pipeline stage
 constexpr int kStages = 4;                                   // stages in flight per CTA

@@ -262,3 +262,108 @@ def test_kernel_layout_arithmetic_matches_the_replay(datasets, host_arith):
             assert np.array_equal(got2, want)
             checked += 1
     assert checked >= 4
+
+
+# ---- the device functions themselves, executed on the host (tests/native/cuda_emu.h) -----------------------
+@pytest.fixture(scope="module")
+def device_emu(tmp_path_factory):
+    """kernels.cuh compiled with g++ against a minimal CUDA execution model (one CTA, 256 real threads)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path_factory.mktemp("native") / "libthree_phase_device_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                           os.path.join(root, "tests", "native", "three_phase_device_emu.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.tp_apply_device_emu.restype = C.c_int
+    return lib
+
+
+STRIP_DT = np.dtype([("cb", np.int32), ("kc0", np.int32), ("nchunks", np.int32), ("slot", np.int32),
+                     ("data_off", np.int64)])
+
+
+def _device_apply(lib, plan, bufs, R, d, Y, rvec, fused, prefetch):
+    """One application through phase_strip_gemv<SRC 1 / 2 / 3> (+ fused finish) / phase_dd_finish(_sep)."""
+    assert STRIP_DT.itemsize == 24
+    keep = []                                               # buffers must outlive the call
+
+    def strips(ph):
+        st = plan["strips" + ph]
+        a = np.zeros(max(len(st), 1), dtype=STRIP_DT)
+        for k, name in enumerate(("cb", "kc0", "nchunks", "slot", "data_off")):
+            a[name][:len(st)] = st[:, k]
+        cta = np.ascontiguousarray(plan["cta" + ph], dtype=np.int32)
+        chunks = np.array([st[cta[v]:cta[v + 1], 2].sum() for v in range(plan["V"])], dtype=np.int32)
+        M = np.ascontiguousarray(bufs[ph].reshape(-1)) if bufs[ph].size else np.zeros(1)
+        keep.extend([a, cta, chunks, M])
+        return [_dp(M), a.ctypes.data_as(C.c_void_p), _ip(cta), _ip(chunks)]
+
+    i32 = lambda name: np.ascontiguousarray(plan[name], dtype=np.int32)
+    gidx, icol, tptr, tcol, pcol, srow = (i32(k) for k in ("gidx", "icol", "tptr", "tcol", "pcol", "srow"))
+    if not len(gidx):
+        gidx = np.zeros(1, dtype=np.int32)
+    if not len(tcol):
+        tcol = np.zeros(1, dtype=np.int32)
+    if not len(srow):
+        srow = np.zeros(1, dtype=np.int32)
+    N = rvec.shape[1]
+    col = lambda A: np.ascontiguousarray(A.T).reshape(-1)   # column-major R x N, as on the device
+    y = np.zeros(R * plan["ycols"]); zs = np.zeros(plan["nsplit3"] * R * plan["pcols"]); w = np.zeros(R * plan["pcols"])
+    Yc, rc = col(Y), col(rvec)
+    z = np.full(R * N, np.nan); neg = np.full(R * N, np.nan); zr = np.zeros(1)
+    rc_ = lib.tp_apply_device_emu(R, d, plan["n"], plan["V"], plan["nS"], plan["nsplit3"], plan["sep_col0"],
+                                  plan["pcols"], prefetch, *strips("1"), *strips("3"), *strips("5"),
+                                  _ip(gidx), _ip(icol), _ip(tptr), _ip(tcol), _ip(pcol), _ip(srow),
+                                  _dp(y), _dp(zs), _dp(w), _dp(Yc), _dp(rc), _dp(z), _dp(neg), _dp(zr), int(fused))
+    assert rc_ == 0
+    return z.reshape(N, R).T, neg.reshape(N, R).T, float(zr[0])
+
+
+@pytest.mark.parametrize("name,max_poses,V,R,fused,prefetch,split", [
+    ("smallGrid3D", 12, 5, 5, 0, 1, 2),       # mode 3: separate finish
+    ("smallGrid3D", 12, 5, 5, 1, 1, 2),       # mode 4: finish in the epilogue of the last strip phase
+    ("smallGrid3D", 12, 3, 3, 1, 0, 0),       # r = d, no prefetch before the barriers
+    ("smallGrid3D", 60, 4, 5, 1, 1, 0),       # domains longer than one wave of stages
+    ("smallGrid3D", 200, 2, 5, 1, 1, 0),      # one domain, no separator
+    ("tinyGrid3D", 3, 2, 5, 1, 1, 0),
+])
+def test_device_functions_on_the_host(datasets, device_emu, name, max_poses, V, R, fused, prefetch, split):
+    """z = Proj_Y(r (Q + 0.1 I)^-1), <z, r> and -z from the CUDA device functions run on the host, against
+    the oracle's exact preconditioner (src/QuadraticProblem.cpp:56-69)."""
+    meas, n, _ = datasets(name)
+    d, dh = meas.d, meas.d + 1
+    G = _pose_graph(meas.p1, meas.p2, n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split)
+    Q = pgo.connection_laplacian(meas, n)
+    A = (Q + 0.1 * sp.identity(dh * n)).tocsc()
+    bufs = emu.fill_stage_buffers(plan, *emu.dense_blocks(A, plan))
+    rng = np.random.default_rng(7)
+    Y = pgo.manifold_project(rng.standard_normal((R, dh * n)), d)
+    rvec = pgo.tangent_project(Y, rng.standard_normal((R, dh * n)), d)
+    ref = pgo.QuadraticProblem(Q, np.zeros((R, dh * n)), d).precondition(Y, rvec)
+    z, neg, zr = _device_apply(device_emu, plan, bufs, R, d, Y, rvec, fused, prefetch)
+    assert np.linalg.norm(z - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert np.array_equal(neg, -z)
+    assert abs(zr - float(np.sum(ref * rvec))) <= 1e-10 * abs(float(np.sum(ref * rvec)))
+
+
+def test_device_functions_on_the_host_2d(datasets, device_emu):
+    """d = 2 (pose tiles of 3 columns straddle the 64-wide strips: separate finish only)."""
+    meas, n, _ = datasets("city10000")
+    keep = (meas.p1 < 300) & (meas.p2 < 300)
+    sub = pgo.make_measurements(meas.d, meas.p1[keep], meas.p2[keep], meas.R[keep], meas.t[keep],
+                                meas.kappa[keep], meas.tau[keep])
+    n, d, dh, R = 300, 2, 3, 3
+    G = _pose_graph(sub.p1, sub.p2, n)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, 30, 6)
+    Q = pgo.connection_laplacian(sub, n)
+    A = (Q + 0.1 * sp.identity(dh * n)).tocsc()
+    bufs = emu.fill_stage_buffers(plan, *emu.dense_blocks(A, plan))
+    rng = np.random.default_rng(9)
+    Y = pgo.manifold_project(rng.standard_normal((R, dh * n)), d)
+    rvec = pgo.tangent_project(Y, rng.standard_normal((R, dh * n)), d)
+    ref = pgo.QuadraticProblem(Q, np.zeros((R, dh * n)), d).precondition(Y, rvec)
+    z, neg, zr = _device_apply(device_emu, plan, bufs, R, d, Y, rvec, 0, 1)
+    assert np.linalg.norm(z - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert np.array_equal(neg, -z)
