@@ -74,3 +74,18 @@ inline void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar
   emu::mbar_done[emu::mbar_slot(bar)].fetch_add(1, std::memory_order_release);
 }
 inline void bulk_prefetch_l2(const void *, uint32_t) {}
+
+// ---- what the fused solver kernel (fused_kernel.cuh) needs on top -------------------------------------------
+#include <chrono>
+#define __launch_bounds__(...)
+#define DPGO_DYNAMIC_SMEM(name) unsigned char *name = emu::dsm
+namespace cg {
+struct grid_group {
+  void sync() const { __syncthreads(); }   // one CTA: the grid barrier is the CTA barrier
+};
+inline grid_group this_grid() { return {}; }
+}  // namespace cg
+inline unsigned long long gtimer() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}

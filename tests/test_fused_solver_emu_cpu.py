@@ -1,0 +1,162 @@
+"""CPU test of the persistent fused RTR solver kernel itself: k_rtr_fused<R, D, MODE>
+(dpgo_b200/csrc/fused_kernel.cuh, the source nvcc compiles for the product) is built with g++ against
+tests/native/cuda_emu.h -- one CTA of 256 real threads, CTA barriers for __syncthreads and grid.sync, warp
+shuffles, TMA bulk copies completing emulated mbarriers -- and must reproduce the oracle's
+QuadraticOptimizer::optimize (ref: src/QuadraticOptimizer.cpp:26-108): same outer / tCG iteration counts,
+same objective, same iterate.  MODE 0 = dense inverse (the default below 3000 scalars), MODE 3 / 4 = the
+three-phase forms of the two-level preconditioner, whose first run on a device is still pending.
+What the emulation cannot show: timing, the asynchrony of real TMA copies, memory-model effects across SMs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import three_phase_emu as emu
+from oracle import pgo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_dp, _ip, _vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+
+
+class EmuProblem(C.Structure):
+    _fields_ = ([("mode", C.c_int), ("R", C.c_int), ("d", C.c_int), ("n", C.c_int),
+                 ("rowptr", _ip), ("colidx", _ip), ("blocks", _dp), ("G", _dp),
+                 ("Pinv", _dp), ("ld", C.c_int), ("KT", C.c_int), ("nsplit", C.c_int)] +
+                [(k, C.c_int) for k in ("V", "nS", "nsplit3", "sep_col0", "pcols", "ycols", "prefetch")] +
+                [("M1", _dp), ("M3", _dp), ("M5", _dp), ("strips1", _vp), ("strips3", _vp), ("strips5", _vp)] +
+                [(k, _ip) for k in ("cta1", "chunks1", "cta3", "chunks3", "cta5", "chunks5",
+                                    "gidx", "icol", "tptr", "tcol", "pcol", "srow")] +
+                [(k, C.c_double) for k in ("gradnorm_tol", "init_radius", "theta", "kappa", "accept_rho", "shrink",
+                                           "magnify")] +
+                [("max_outer", C.c_int), ("max_inner", C.c_int), ("x_in", _dp), ("x_out", _dp), ("result", _dp)])
+
+
+STRIP_DT = np.dtype([("cb", np.int32), ("kc0", np.int32), ("nchunks", np.int32), ("slot", np.int32),
+                     ("data_off", np.int64)])
+
+
+@pytest.fixture(scope="module")
+def solver_emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("native") / "libfused_solver_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                           os.path.join(ROOT, "tests", "native", "fused_solver_emu.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.fused_solve_emu.restype = C.c_int
+    lib.fused_solve_emu.argtypes = [C.POINTER(EmuProblem)]
+    return lib
+
+
+def _dense_tiling(N, num_sms=148):
+    """ld, KT, nsplit as dpgo_create chooses them (dpgo_b200/csrc/device_lib.cu)."""
+    ld = -(-N // 128) * 128
+    ncb, wave = ld // 64, num_sms * 2
+    best, KT_best, ns_best = -1.0, 0, 0
+    for ns in range(6, 25):
+        KT = -(-(-(-ld // ns)) // 32) * 32
+        KT = max(KT, 256)
+        nsp = -(-ld // KT)
+        tiles = ncb * nsp
+        rounds = -(-tiles // wave)
+        eff = (tiles / (rounds * wave)) * (ld / (nsp * KT))
+        score = 0.5 * eff if tiles < wave else eff
+        if score > best + 1e-9:
+            best, KT_best, ns_best = score, KT, nsp
+    return ld, KT_best, ns_best
+
+
+def _solve(lib, meas, n, R, mode, X0, max_poses=12, V=5, prefetch=1):
+    d, dh = meas.d, meas.d + 1
+    N = dh * n
+    keep = []
+    hold = lambda a: (keep.append(a), a)[1]
+    Q = pgo.connection_laplacian(meas, n)
+    B = sp.bsr_matrix(Q, blocksize=(dh, dh))
+    B.sort_indices()
+    e = EmuProblem()
+    e.mode, e.R, e.d, e.n = mode, R, d, n
+    e.rowptr = _ip_of(hold(np.ascontiguousarray(B.indptr, dtype=np.int32)))
+    e.colidx = _ip_of(hold(np.ascontiguousarray(B.indices, dtype=np.int32)))
+    e.blocks = _dp_of(hold(np.ascontiguousarray(B.data, dtype=np.float64)))
+    e.G = _dp_of(hold(np.zeros(R * N)))
+    A = (Q + 0.1 * sp.identity(N)).tocsc()
+    if mode == 0:
+        ld, KT, nsplit = _dense_tiling(N)
+        ldk = KT * nsplit
+        P = np.zeros((ld, ldk))
+        P[:N, :N] = np.linalg.inv(A.toarray())
+        ncb = ld // 64
+        # T[((kc * ncb + cb) * 32 + kk) * 64 + jj] = P[cb * 64 + jj, kc * 32 + kk]
+        T = P.reshape(ncb, 64, ldk // 32, 32).transpose(2, 0, 3, 1)
+        e.Pinv = _dp_of(hold(np.ascontiguousarray(T).reshape(-1)))
+        e.ld, e.KT, e.nsplit = ld, KT, nsplit
+    else:
+        from dpgo_b200 import _lib
+        G = sp.coo_matrix((np.ones(len(meas.p1)), (meas.p1, meas.p2)), shape=(n, n))
+        G = (G + G.T + sp.identity(n)).tocsr()
+        G.sort_indices()
+        plan = emu.fetch_plan(_lib.lib.dpgo_three_phase_plan, n, G.indptr, G.indices, dh, max_poses, V)
+        bufs = emu.fill_stage_buffers(plan, *emu.dense_blocks(A, plan))
+        for ph in ("1", "3", "5"):
+            st = plan["strips" + ph]
+            a = hold(np.zeros(max(len(st), 1), dtype=STRIP_DT))
+            for k, name in enumerate(("cb", "kc0", "nchunks", "slot", "data_off")):
+                a[name][:len(st)] = st[:, k]
+            cta = hold(np.ascontiguousarray(plan["cta" + ph], dtype=np.int32))
+            chunks = hold(np.array([st[cta[v]:cta[v + 1], 2].sum() for v in range(plan["V"])], dtype=np.int32))
+            M = hold(np.ascontiguousarray(bufs[ph].reshape(-1)) if bufs[ph].size else np.zeros(1))
+            setattr(e, "M" + ph, _dp_of(M))
+            setattr(e, "strips" + ph, a.ctypes.data_as(_vp))
+            setattr(e, "cta" + ph, _ip_of(cta))
+            setattr(e, "chunks" + ph, _ip_of(chunks))
+        for name in ("gidx", "icol", "tptr", "tcol", "pcol", "srow"):
+            arr = np.ascontiguousarray(plan[name], dtype=np.int32)
+            setattr(e, name, _ip_of(hold(arr if len(arr) else np.zeros(1, dtype=np.int32))))
+        for name in ("V", "nS", "nsplit3", "sep_col0", "pcols", "ycols"):
+            setattr(e, name, plan[name])
+        e.prefetch = prefetch
+    prm = pgo.ROptParameters()
+    e.gradnorm_tol, e.init_radius = prm.gradnorm_tol, prm.RTR_initial_radius
+    e.theta, e.kappa, e.accept_rho, e.shrink, e.magnify = 1.0, 0.1, 0.1, 0.25, 2.0     # ROPTLIB defaults (rtr_logic.h)
+    e.max_outer, e.max_inner = prm.RTR_iterations, prm.RTR_tCG_iterations
+    xin = hold(np.ascontiguousarray(X0.T).reshape(-1))
+    xout = hold(np.zeros(R * N))
+    res = hold(np.zeros(16))
+    e.x_in, e.x_out, e.result = _dp_of(xin), _dp_of(xout), _dp_of(res)
+    assert lib.fused_solve_emu(C.byref(e)) == 0
+    names = ["f_init", "gn_init", "f_opt", "gn_opt", "outer", "inner", "accepted", "rejected", "tcg_status",
+             "returned_initial", "n_qx", "n_precon", "n_sweeps", "n_barriers"]
+    return xout.reshape(N, R).T.copy(), dict(zip(names, res[:14]))
+
+
+def _dp_of(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ip_of(a):
+    return a.ctypes.data_as(_ip)
+
+
+@pytest.mark.parametrize("name,R,mode,max_poses,V,prefetch", [
+    ("tinyGrid3D", 5, 0, 0, 0, 1),
+    ("smallGrid3D", 5, 0, 0, 0, 1),          # the product's default path for this size (dense inverse)
+    ("smallGrid3D", 5, 3, 12, 5, 1),         # three-phase form, separate finish
+    ("smallGrid3D", 5, 4, 12, 5, 1),         # finish fused into the last strip phase
+    ("smallGrid3D", 5, 4, 12, 5, 0),         # the same without the pre-barrier prefetch
+    ("smallGrid3D", 3, 4, 60, 3, 1),         # r = d, domains longer than one wave
+    ("smallGrid3D", 5, 4, 200, 2, 1),        # a single domain, no separator
+])
+def test_fused_solver_kernel_matches_the_oracle(datasets, solver_emu, name, R, mode, max_poses, V, prefetch):
+    meas, n, z = datasets(name)
+    d = meas.d
+    X0 = pgo.lifting_matrix(d, R) @ z["T_chordal"]
+    Xg, res = _solve(solver_emu, meas, n, R, mode, X0, max_poses, V, prefetch)
+    op = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((R, (d + 1) * n)), d)
+    Xo, ro = pgo.optimize(op, X0)
+    assert (int(res["outer"]), int(res["inner"])) == (ro.outer, ro.inner_total)
+    assert abs(res["f_init"] - ro.fInit) <= 1e-10 * abs(ro.fInit)
+    assert abs(res["f_opt"] - ro.fOpt) <= 1e-9 * abs(ro.fOpt)
+    assert np.linalg.norm(Xg - Xo) <= 1e-6 * np.linalg.norm(Xo)
+    assert res["n_precon"] >= res["inner"] and res["n_barriers"] > 0
