@@ -1,8 +1,20 @@
 import os
 import sys
 
-import numpy as np
+# Single-threaded BLAS for the whole suite, set before numpy loads: a multi-threaded OpenBLAS call made after
+# tests/test_exchange_gloo.py has forked its multiprocessing manager can deadlock in this process (seen as
+# np.linalg.inv never returning); nothing here is large enough to need the threads.
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
 import pytest
+
+try:    # numpy may have been imported by a pytest plugin before this file: cap the live pools as well
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=1)
+except Exception:   # pragma: no cover
+    pass
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -3,6 +3,9 @@
 // the host through tests/native/cuda_emu.h and run as ONE CTA of 256 real threads (grid barriers become CTA
 // barriers; every phase walks all tiles / virtual CTAs).  tests/test_fused_solver_emu_cpu.py compares its
 // iterates, iteration counts and objective with the oracle's optimize().
+// built with -fvisibility=hidden -Wl,-Bsymbolic: the product library exports host stubs with the same mangled
+// names as the kernels compiled here, and must not interpose them when both are loaded in one process
+#define TP_EXPORT __attribute__((visibility("default")))
 #include "cuda_emu.h"
 
 #include <vector>
@@ -116,7 +119,7 @@ int by_mode(const EmuProblem &e) {
 
 }  // namespace
 
-extern "C" int fused_solve_emu(const EmuProblem *e) {
+extern "C" TP_EXPORT int fused_solve_emu(const EmuProblem *e) {
   if (e->R == 5 && e->d == 3) return by_mode<5, 3>(*e);
   if (e->R == 3 && e->d == 3) return by_mode<3, 3>(*e);
   if (e->R == 3 && e->d == 2) return by_mode<3, 2>(*e);

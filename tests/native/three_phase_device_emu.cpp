@@ -3,6 +3,9 @@
 // (phase_strip_gemv with its staging modes and its fused-finish epilogue, phase_dd_finish,
 // phase_dd_finish_sep, block_reduce_store), compiled for the host through tests/native/cuda_emu.h and
 // run as one CTA of 256 real threads that walks every virtual CTA of the plan.
+// built with -fvisibility=hidden -Wl,-Bsymbolic: the product library exports host stubs with the same mangled
+// names as the kernels compiled here, and must not interpose them when both are loaded in one process
+#define TP_EXPORT __attribute__((visibility("default")))
 #include "cuda_emu.h"
 
 #include <vector>
@@ -78,7 +81,7 @@ extern "C" {
 
 // strips*: arrays of DdStrip {int cb, kc0, nchunks, slot; long long data_off}; y / zs / w: zero-initialised work
 // arrays of R*ycols, nsplit3*R*pcols, R*pcols doubles.  (R, d) in {(5,3), (3,3), (3,2)}.
-int tp_apply_device_emu(int R, int d, int n, int V, int nS, int nsplit3, int sep_col0, int pcols, int prefetch,
+TP_EXPORT int tp_apply_device_emu(int R, int d, int n, int V, int nS, int nsplit3, int sep_col0, int pcols, int prefetch,
                         const double *M1, const void *strips1, const int *cta1, const int *chunks1,
                         const double *M3, const void *strips3, const int *cta3, const int *chunks3,
                         const double *M5, const void *strips5, const int *cta5, const int *chunks5,

@@ -10,14 +10,19 @@ import ctypes as C
 import os
 import subprocess
 
+import sys
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
-import three_phase_emu as emu
-from oracle import pgo
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests")):       # also when run as a script (one case per process)
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import three_phase_emu as emu  # noqa: E402
+from oracle import pgo  # noqa: E402
 _dp, _ip, _vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
 
 
@@ -39,10 +44,15 @@ STRIP_DT = np.dtype([("cb", np.int32), ("kc0", np.int32), ("nchunks", np.int32),
 
 
 @pytest.fixture(scope="module")
-def solver_emu(tmp_path_factory):
+def solver_emu_so(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("native") / "libfused_solver_emu.so")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                           "-fvisibility=hidden", "-fno-gnu-unique", "-Wl,-Bsymbolic",
                            os.path.join(ROOT, "tests", "native", "fused_solver_emu.cpp"), "-o", so])
+    return so
+
+
+def _load(so):
     lib = C.CDLL(so)
     lib.fused_solve_emu.restype = C.c_int
     lib.fused_solve_emu.argtypes = [C.POINTER(EmuProblem)]
@@ -139,7 +149,7 @@ def _ip_of(a):
     return a.ctypes.data_as(_ip)
 
 
-@pytest.mark.parametrize("name,R,mode,max_poses,V,prefetch", [
+CASES = [
     ("tinyGrid3D", 5, 0, 0, 0, 1),
     ("smallGrid3D", 5, 0, 0, 0, 1),          # the product's default path for this size (dense inverse)
     ("smallGrid3D", 5, 3, 12, 5, 1),         # three-phase form, separate finish
@@ -147,16 +157,37 @@ def _ip_of(a):
     ("smallGrid3D", 5, 4, 12, 5, 0),         # the same without the pre-barrier prefetch
     ("smallGrid3D", 3, 4, 60, 3, 1),         # r = d, domains longer than one wave
     ("smallGrid3D", 5, 4, 200, 2, 1),        # a single domain, no separator
-])
-def test_fused_solver_kernel_matches_the_oracle(datasets, solver_emu, name, R, mode, max_poses, V, prefetch):
-    meas, n, z = datasets(name)
+]
+
+
+def _run_case(so, name, R, mode, max_poses, V, prefetch):
+    from conftest import load_dataset
+    meas, n, z = load_dataset(name)
     d = meas.d
     X0 = pgo.lifting_matrix(d, R) @ z["T_chordal"]
-    Xg, res = _solve(solver_emu, meas, n, R, mode, X0, max_poses, V, prefetch)
+    Xg, res = _solve(_load(so), meas, n, R, mode, X0, max_poses, V, prefetch)
     op = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((R, (d + 1) * n)), d)
     Xo, ro = pgo.optimize(op, X0)
-    assert (int(res["outer"]), int(res["inner"])) == (ro.outer, ro.inner_total)
+    assert (int(res["outer"]), int(res["inner"])) == (ro.outer, ro.inner_total), (res, ro.outer, ro.inner_total)
     assert abs(res["f_init"] - ro.fInit) <= 1e-10 * abs(ro.fInit)
     assert abs(res["f_opt"] - ro.fOpt) <= 1e-9 * abs(ro.fOpt)
     assert np.linalg.norm(Xg - Xo) <= 1e-6 * np.linalg.norm(Xo)
     assert res["n_precon"] >= res["inner"] and res["n_barriers"] > 0
+
+
+@pytest.mark.parametrize("name,R,mode,max_poses,V,prefetch", CASES)
+def test_fused_solver_kernel_matches_the_oracle(solver_emu_so, name, R, mode, max_poses, V, prefetch):
+    """Each case in a fresh interpreter: the emulation runs 256 OS threads that meet at barriers thousands of
+    times, and must not share a process with whatever thread pools earlier tests have started."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.abspath(__file__),
+                          json.dumps([solver_emu_so, name, R, mode, max_poses, V, prefetch])],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    _run_case(*json.loads(sys.argv[1]))

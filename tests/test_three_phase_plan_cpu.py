@@ -5,14 +5,21 @@ three strip phases with the kernels' staging rules, the finish) and must reprodu
 (Q + 0.1 I)^-1 -- the reference's preconditioner (src/QuadraticProblem.cpp:56-69).  What this does
 not cover is the CUDA code itself; that is tests/test_gpu_zzz_three_phase.py."""
 import ctypes as C
+import os
+import sys
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spl
 
-import three_phase_emu as emu
-from oracle import pgo
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests")):       # also when run as a script (one emulation case per process)
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import three_phase_emu as emu  # noqa: E402
+from oracle import pgo  # noqa: E402
 
 
 def _fn():
@@ -156,7 +163,8 @@ def host_arith(tmp_path_factory):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = str(tmp_path_factory.mktemp("native") / "libthree_phase_host.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fvisibility=hidden", "-fno-gnu-unique",
+                           "-Wl,-Bsymbolic",
                            os.path.join(root, "tests", "native", "three_phase_host.cpp"), "-o", so])
     return C.CDLL(so)
 
@@ -266,17 +274,30 @@ def test_kernel_layout_arithmetic_matches_the_replay(datasets, host_arith):
 
 # ---- the device functions themselves, executed on the host (tests/native/cuda_emu.h) -----------------------
 @pytest.fixture(scope="module")
-def device_emu(tmp_path_factory):
+def device_emu_so(tmp_path_factory):
     """kernels.cuh compiled with g++ against a minimal CUDA execution model (one CTA, 256 real threads)."""
-    import os
     import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = str(tmp_path_factory.mktemp("native") / "libthree_phase_device_emu.so")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-                           os.path.join(root, "tests", "native", "three_phase_device_emu.cpp"), "-o", so])
+                           "-fvisibility=hidden", "-fno-gnu-unique", "-Wl,-Bsymbolic",
+                           os.path.join(ROOT, "tests", "native", "three_phase_device_emu.cpp"), "-o", so])
+    return so
+
+
+def _load_device_emu(so):
     lib = C.CDLL(so)
     lib.tp_apply_device_emu.restype = C.c_int
     return lib
+
+
+def _in_fresh_interpreter(case, *args):
+    """The emulation runs 256 OS threads that meet at barriers thousands of times; it must not share a process
+    with whatever thread pools earlier tests have started (it crawls there), so every case gets its own."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), case, json.dumps(args)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 STRIP_DT = np.dtype([("cb", np.int32), ("kc0", np.int32), ("nchunks", np.int32), ("slot", np.int32),
@@ -328,10 +349,16 @@ def _device_apply(lib, plan, bufs, R, d, Y, rvec, fused, prefetch):
     ("smallGrid3D", 200, 2, 5, 1, 1, 0),      # one domain, no separator
     ("tinyGrid3D", 3, 2, 5, 1, 1, 0),
 ])
-def test_device_functions_on_the_host(datasets, device_emu, name, max_poses, V, R, fused, prefetch, split):
+def test_device_functions_on_the_host(device_emu_so, name, max_poses, V, R, fused, prefetch, split):
     """z = Proj_Y(r (Q + 0.1 I)^-1), <z, r> and -z from the CUDA device functions run on the host, against
     the oracle's exact preconditioner (src/QuadraticProblem.cpp:56-69)."""
-    meas, n, _ = datasets(name)
+    _in_fresh_interpreter("3d", device_emu_so, name, max_poses, V, R, fused, prefetch, split)
+
+
+def _device_case(so, name, max_poses, V, R, fused, prefetch, split):
+    from conftest import load_dataset
+    device_emu = _load_device_emu(so)
+    meas, n, _ = load_dataset(name)
     d, dh = meas.d, meas.d + 1
     G = _pose_graph(meas.p1, meas.p2, n)
     plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split)
@@ -348,9 +375,15 @@ def test_device_functions_on_the_host(datasets, device_emu, name, max_poses, V, 
     assert abs(zr - float(np.sum(ref * rvec))) <= 1e-10 * abs(float(np.sum(ref * rvec)))
 
 
-def test_device_functions_on_the_host_2d(datasets, device_emu):
+def test_device_functions_on_the_host_2d(device_emu_so):
     """d = 2 (pose tiles of 3 columns straddle the 64-wide strips: separate finish only)."""
-    meas, n, _ = datasets("city10000")
+    _in_fresh_interpreter("2d", device_emu_so)
+
+
+def _device_case_2d(so):
+    from conftest import load_dataset
+    device_emu = _load_device_emu(so)
+    meas, n, _ = load_dataset("city10000")
     keep = (meas.p1 < 300) & (meas.p2 < 300)
     sub = pgo.make_measurements(meas.d, meas.p1[keep], meas.p2[keep], meas.R[keep], meas.t[keep],
                                 meas.kappa[keep], meas.tau[keep])
@@ -367,3 +400,8 @@ def test_device_functions_on_the_host_2d(datasets, device_emu):
     z, neg, zr = _device_apply(device_emu, plan, bufs, R, d, Y, rvec, 0, 1)
     assert np.linalg.norm(z - ref) <= 1e-10 * np.linalg.norm(ref)
     assert np.array_equal(neg, -z)
+
+
+if __name__ == "__main__":
+    import json
+    {"3d": _device_case, "2d": _device_case_2d}[sys.argv[1]](*json.loads(sys.argv[2]))
