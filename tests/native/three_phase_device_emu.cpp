@@ -108,4 +108,31 @@ TP_EXPORT int tp_apply_device_emu(int R, int d, int n, int V, int nS, int nsplit
   return 0;
 }
 
+// The RGD step's fused kernel (phase_retract_impl<R, D, true>: Xout = Retraction_X(s * Dir)) beside the
+// two-pass form it replaces (Eta = s * Dir rounded, then phase_retract): both outputs, to be compared bit for bit.
+TP_EXPORT int emu_retract_scaled(int R, int d, int n, const double *X, const double *Dir, double s, double *out_fused,
+                                 double *out_two_pass) {
+  if (!(R == 5 && d == 3) && !(R == 3 && d == 2)) return -1;
+  const size_t len = (size_t)R * (d + 1) * n;
+  std::vector<double> eta(len);
+  for (size_t k = 0; k < len; ++k) eta[k] = s * Dir[k];
+  for (int wv = 0; wv < emu::kWarps; ++wv) emu::warp_barrier[wv] = new std::barrier<>(32);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < (unsigned)emu::kThreads; ++t)
+    th.emplace_back([=, &eta]() {
+      threadIdx.x = t;
+      const Ctx ctx = make_ctx();
+      if (R == 5) {
+        phase_retract_impl<5, 3, true>(ctx, X, Dir, out_fused, n, s);
+        phase_retract<5, 3>(ctx, X, eta.data(), out_two_pass, n);
+      } else {
+        phase_retract_impl<3, 2, true>(ctx, X, Dir, out_fused, n, s);
+        phase_retract<3, 2>(ctx, X, eta.data(), out_two_pass, n);
+      }
+    });
+  for (auto &t : th) t.join();
+  for (int wv = 0; wv < emu::kWarps; ++wv) delete emu::warp_barrier[wv];
+  return 0;
+}
+
 }  // extern "C"

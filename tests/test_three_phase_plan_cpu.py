@@ -402,6 +402,33 @@ def _device_case_2d(so):
     assert np.array_equal(neg, -z)
 
 
+def test_rgd_scaled_retraction_on_the_host(device_emu_so):
+    """k_retract_scaled (gradient scale applied inside the QF retraction, the RGD step of
+    QuadraticOptimizer::gradientDescent, ref: src/QuadraticOptimizer.cpp:133-134) gives the same bits as
+    scaling into a separate array and retracting, and a point on the manifold."""
+    _in_fresh_interpreter("retract", device_emu_so)
+
+
+def _retract_case(so):
+    lib = _load_device_emu(so)
+    lib.emu_retract_scaled.restype = C.c_int
+    for R, d, n in ((5, 3, 700), (3, 2, 333)):
+        rng = np.random.default_rng(R)
+        dh = d + 1
+        X = pgo.manifold_project(rng.standard_normal((R, dh * n)), d)
+        Dir = rng.standard_normal((R, dh * n))
+        col = lambda A: np.ascontiguousarray(A.T).reshape(-1)
+        Xc, Dc = col(X), col(Dir)
+        a, b = np.zeros(R * dh * n), np.zeros(R * dh * n)
+        assert lib.emu_retract_scaled(R, d, n, _dp(Xc), _dp(Dc), C.c_double(-1e-3), _dp(a), _dp(b)) == 0
+        assert np.array_equal(a, b)
+        out = a.reshape(dh * n, R).T
+        ref = pgo.retract_qf(X, -1e-3 * Dir, d)
+        assert np.linalg.norm(out - ref) <= 1e-12 * np.linalg.norm(ref)
+        T = out.T.reshape(n, dh, R)[:, :d, :]                     # Stiefel blocks: Y^T Y = I
+        assert np.abs(np.einsum("nar,nbr->nab", T, T) - np.eye(d)).max() < 1e-12
+
+
 if __name__ == "__main__":
     import json
-    {"3d": _device_case, "2d": _device_case_2d}[sys.argv[1]](*json.loads(sys.argv[2]))
+    {"3d": _device_case, "2d": _device_case_2d, "retract": _retract_case}[sys.argv[1]](*json.loads(sys.argv[2]))
