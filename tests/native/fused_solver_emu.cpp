@@ -30,6 +30,11 @@ struct EmuProblem {
   const void *strips1, *strips3, *strips5;
   const int *cta1, *chunks1, *cta3, *chunks3, *cta5, *chunks5;
   const int *gidx, *icol, *tptr, *tcol, *pcol, *srow;
+  // mode 2 (five-phase form): sparse couplings A_SI (rows = separator positions) and A_BS (rows = interior
+  // poses with a separator neighbour), block-CSR with permuted scalar columns; bcol = permuted column per row
+  const int *si_rowptr, *si_colidx, *bs_rowptr, *bs_colidx, *bcol;
+  const double *si_blocks, *bs_blocks;
+  int nB;
   // solver parameters (dpgo_ropt_params)
   double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
   int max_outer, max_inner;
@@ -71,6 +76,19 @@ int run(const EmuProblem &e) {
   fp.ld = e.ld; fp.KT = e.KT; fp.nsplit = e.nsplit; fp.n = e.n;
   fp.zstride = len;
   fp.precon_mode = MODE;
+  std::vector<double> tt((size_t)R * std::max(e.pcols, 64), 0.0), uu(tt);
+  if (MODE == 2) {
+    DdView &dd = fp.dd;
+    dd.P1 = DdStripSet{e.M1, (const DdStrip *)e.strips1, e.cta1, e.chunks1, nullptr};
+    dd.P3 = DdStripSet{e.M3, (const DdStrip *)e.strips3, e.cta3, e.chunks3, nullptr};
+    dd.V = e.V; dd.nsplit1 = 1; dd.nsplit3 = e.nsplit3; dd.nS = e.nS; dd.nB = e.nB;
+    dd.A_SI = BsrView{e.si_rowptr, e.si_colidx, e.si_blocks};
+    dd.A_BS = BsrView{e.bs_rowptr, e.bs_colidx, e.bs_blocks};
+    dd.pcol = e.pcol; dd.srow = e.srow; dd.bcol = e.bcol; dd.icol = e.icol;
+    dd.sep_col0 = e.sep_col0; dd.pcols = e.pcols;
+    dd.y = y.data(); dd.t = tt.data(); dd.zs = zs.data(); dd.u = uu.data(); dd.w = w.data();
+    dd.prefetch = e.prefetch;
+  }
   if (MODE >= 3) {
     DdView &dd = fp.dd;
     dd.P1 = DdStripSet{e.M1, (const DdStrip *)e.strips1, e.cta1, e.chunks1, nullptr};
@@ -110,6 +128,7 @@ int run(const EmuProblem &e) {
 template <int R, int D>
 int by_mode(const EmuProblem &e) {
   if (e.mode == 0) return run<R, D, 0>(e);
+  if (e.mode == 2) return run<R, D, 2>(e);
   if (e.mode == 3) return run<R, D, 3>(e);
   if constexpr (D == 3) {
     if (e.mode == 4) return run<R, D, 4>(e);
