@@ -342,6 +342,7 @@ def _device_apply(lib, plan, bufs, R, d, Y, rvec, fused, prefetch):
 
 
 @pytest.mark.parametrize("name,max_poses,V,R,fused,prefetch,split", [
+    ("smallGrid3D", 12, 24, 5, 1, 1, -1),     # split -1: domain-affine placement (strips of a domain stage once)
     ("smallGrid3D", 12, 5, 5, 0, 1, 2),       # mode 3: separate finish
     ("smallGrid3D", 12, 5, 5, 1, 1, 2),       # mode 4: finish in the epilogue of the last strip phase
     ("smallGrid3D", 12, 3, 3, 1, 0, 0),       # r = d, no prefetch before the barriers
@@ -361,7 +362,10 @@ def _device_case(so, name, max_poses, V, R, fused, prefetch, split):
     meas, n, _ = load_dataset(name)
     d, dh = meas.d, meas.d + 1
     G = _pose_graph(meas.p1, meas.p2, n)
-    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, split)
+    plan = emu.fetch_plan(_fn(), n, G.indptr, G.indices, dh, max_poses, V, max(split, 0), 1 if split < 0 else 0)
+    if split < 0:   # the reuse path must actually occur: the one emulated CTA walks the virtual CTAs in order,
+        st = plan["strips1"]                     # so consecutive strips of one domain share their staged slice
+        assert sum(tuple(st[i, 1:3]) == tuple(st[i + 1, 1:3]) for i in range(len(st) - 1)) >= 3
     Q = pgo.connection_laplacian(meas, n)
     A = (Q + 0.1 * sp.identity(dh * n)).tocsc()
     bufs = emu.fill_stage_buffers(plan, *emu.dense_blocks(A, plan))
