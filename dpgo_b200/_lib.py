@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpgo_b200.so")
+# DPGO_B200_LIB: measurement builds of the same library (tools/phase_trace.py loads the -DDPGO_TRACE one)
+LIB_PATH = os.environ.get("DPGO_B200_LIB") or os.path.join(_HERE, "libdpgo_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libdpgo_b200.so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
-CU_SOURCES = ["device_lib.cu", "fused_rtr.cu", "precon_dd.cu"]
+CU_SOURCES = ["device_lib.cu", "fused_rtr.cu", "precon_dd.cu", "dense_la.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-cudart", "shared", "-diag-suppress", "177"]
 
@@ -23,33 +23,34 @@ def _stale(target, deps):
 
 def build_device_lib(force=False, verbose=False, trace=False):
     """trace=True: measurement build (-DDPGO_TRACE: per-CTA phase times in the fused solver, read with
-    dpgo_phase_trace); always rebuilt, and the next normal build replaces it."""
+    dpgo_phase_trace) into libdpgo_b200_trace.so beside the product library (own object files); it is loaded
+    only when DPGO_B200_LIB points at it (tools/phase_trace.py)."""
     flags = FLAGS + (["-DDPGO_TRACE"] if trace else [])
-    marker = os.path.join(CSRC, ".trace_build")
-    if trace or os.path.exists(marker):
-        force = True
-    if trace:
-        open(marker, "w").close()
-    elif os.path.exists(marker):
-        os.remove(marker)
+    suffix = ".trace.o" if trace else ".o"
+    out = LIB.replace(".so", "_trace.so") if trace else LIB
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith(".") and not f.endswith(".o")]
     deps.append(os.path.join(HERE, "..", "include", "dpgo_b200.h"))
     objs = []
+    procs = []
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", suffix))
         if force or _stale(o, deps):
             cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             print(" ".join(cmd), flush=True)
-            subprocess.check_call(cmd)
+            procs.append((cmd, subprocess.Popen(cmd)))     # the translation units compile side by side
         objs.append(o)
-    if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB] + objs + [
-            "-L" + os.path.join(CUDA_HOME, "lib64"), "-lcusolver", "-lcublas",
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    if force or _stale(out, objs):
+        # no library on the link line but the CUDA runtime: the dense factorizations of the set-up are in-tree
+        # (dense_la.cu); libcusolver / libcublas / libcublasLt (1.2 GB, minutes to page in on a fresh box) are gone
+        cmd = [NVCC, "-shared", "-cudart", "shared", "-o", out] + objs + [
             "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 HOST = os.path.join(HERE, "host")
@@ -75,21 +76,62 @@ def build_host(force=False):
     bindir = os.path.join(HOST, "bin")
     os.makedirs(bindir, exist_ok=True)
     targets = [(os.path.join(HOST, "tests", "host_tests.cpp"), "host_tests"),
-               (os.path.join(HOST, "tests", "robust_pgo_test.cpp"), "robust_pgo_test")]
+               (os.path.join(HOST, "tests", "robust_pgo_test.cpp"), "robust_pgo_test"),
+               (os.path.join(HOST, "tests", "host_cli.cpp"), "host_cli")]
     if os.path.isdir(REFERENCE_EXAMPLES):
         targets += [(os.path.join(REFERENCE_EXAMPLES, "MultiRobotExample.cpp"), "multi-robot-example"),
                     (os.path.join(REFERENCE_EXAMPLES, "SingleRobotExample.cpp"), "single-robot-example"),
                     (os.path.join(REFERENCE_EXAMPLES, "ChordalInitializationExample.cpp"),
                      "chordal-initialization-example")]
+    stamp = host_abi_stamp()
     for src, name in targets:
         out = os.path.join(bindir, name)
-        if force or _stale(out, [src, lib] + hdrs):
+        if force or _stale(out, [src, lib] + hdrs) or _read(out + ".abi") != stamp:
             cmd = ["g++", "-std=c++17", "-O2", "-I" + inc, src, "-L" + HOST, "-lDPGO"] + link + ["-o", out]
             print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
+            with open(out + ".abi", "w") as f:
+                f.write(stamp)
     return lib
+
+
+def _read(path):
+    try:
+        with open(path) as f:
+            return f.read()
+    except OSError:
+        return None
+
+
+def host_abi_stamp():
+    """Hash of everything a driver binary in host/bin compiles in or links against by layout: the drop-in
+    headers (inline code, class layouts), the C-ABI header and the sources of libDPGO.  A binary whose
+    recorded stamp differs is stale (the reference's example drivers can only be rebuilt where the reference
+    tree is present, so they travel to the GPU box as built files): tests refuse to run it."""
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(HERE, "..", "include", "dpgo_b200.h")]
+    for root in (os.path.join(HOST, "include"), os.path.join(HOST, "src")):
+        for r, _, fs in os.walk(root):
+            files += [os.path.join(r, f) for f in fs]
+    for f in sorted(os.path.abspath(x) for x in files):
+        h.update(os.path.relpath(f, HERE).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def host_binary(name):
+    """Path of a driver binary in host/bin, or raises when it is missing or stale against the drop-in sources."""
+    out = os.path.join(HOST, "bin", name)
+    if not os.path.exists(out):
+        raise FileNotFoundError(f"{out} not built: run __graft_entry__.build() where the sources are present")
+    if _read(out + ".abi") != host_abi_stamp():
+        raise RuntimeError(f"{out} is stale against dpgo_b200/host (headers or sources changed since it was built)")
+    return out
 
 
 if __name__ == "__main__":
     build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
-    build_host(force="--force" in sys.argv)
+    if "--trace" not in sys.argv:
+        build_host(force="--force" in sys.argv)

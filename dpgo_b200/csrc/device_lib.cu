@@ -1,9 +1,8 @@
 // C-ABI implementation: handle lifecycle, host-side construction of the block-CSR connection
-// Laplacian, dense preconditioner build (cuSOLVER potrf/potri, set-up path only), stand-alone
+// Laplacian, dense preconditioner build (in-tree Cholesky / inverse of dense_la.cu, set-up path only), stand-alone
 // kernels (one launch per op) and the host-driven RTR/RGD solver built from them.  The
 // persistent single-kernel solver lives in fused_rtr.cu.
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -13,6 +12,7 @@
 #include <vector>
 
 #include "dd_plan.h"
+#include "dense_la.h"
 #include "device_state.h"
 #include "dissect.h"
 #include "kernels.cuh"
@@ -35,15 +35,6 @@ void set_error(const char *fmt, ...) {
     if (_e != cudaSuccess) {                                                             \
       dpgo::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,              \
                       cudaGetErrorString(_e));                                           \
-      return DPGO_ECUDA;                                                                 \
-    }                                                                                    \
-  } while (0)
-
-#define CUSOLVER_TRY(expr)                                                               \
-  do {                                                                                   \
-    cusolverStatus_t _s = (expr);                                                        \
-    if (_s != CUSOLVER_STATUS_SUCCESS) {                                                 \
-      dpgo::set_error("%s:%d cuSOLVER error %d in %s", __FILE__, __LINE__, (int)_s, #expr); \
       return DPGO_ECUDA;                                                                 \
     }                                                                                    \
   } while (0)
@@ -884,36 +875,19 @@ static int build_precon(dpgo_dev *h) {
                                                  0.1 /* ref: src/PoseGraph.cpp:603 */, A, ld);
     LAUNCH_CHECK(h);
   }
-  if (!h->cusolver) {
-    CUSOLVER_TRY(cusolverDnCreate(&h->cusolver));
-    CUSOLVER_TRY(cusolverDnSetStream(h->cusolver, h->stream));
-  }
-  int lw1 = 0, lw2 = 0;
-  CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, &lw1));
-  CUSOLVER_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, &lw2));
-  const int lw = std::max(lw1, lw2);
-  double *work = nullptr;
-  int *info = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&work, (size_t)std::max(lw, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
-  int hinfo = 0;
-  CUSOLVER_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, work, lw, info));
-  CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (hinfo != 0) {
-    cudaFree(work); cudaFree(info); cudaFree(A);
-    set_error("Cholesky of Q + 0.1 I failed (potrf info = %d)", hinfo);
-    return DPGO_ENUMERIC;
-  }
-  CUSOLVER_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, N, A, ld, work, lw, info));
-  CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  CUDA_TRY(cudaFree(work));
-  CUDA_TRY(cudaFree(info));
-  if (hinfo != 0) {
-    cudaFree(A);
-    set_error("inverse of Q + 0.1 I failed (potri info = %d)", hinfo);
-    return DPGO_ENUMERIC;
+  {
+    // in-tree blocked Cholesky + triangular inverse + W^T W (dense_la.cu); lower triangle of A <- inverse
+    const dla::SpdItem item{A, N, ld};
+    const int rc = dla::spd_inverse_batched(h->stream, &item, 1, false);
+    if (rc != 0) {
+      cudaFree(A);
+      if (rc > 0) {
+        set_error("Cholesky of Q + 0.1 I failed (matrix not positive definite)");
+        return DPGO_ENUMERIC;
+      }
+      set_error("%s", dla::last_error());
+      return DPGO_ECUDA;
+    }
   }
   if (h->d_Pinv) { CUDA_TRY(cudaFree(h->d_Pinv)); h->d_Pinv = nullptr; }
   if (h->d_zpart) { CUDA_TRY(cudaFree(h->d_zpart)); h->d_zpart = nullptr; }
@@ -1076,6 +1050,16 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
   h->N = (d + 1) * n;
   h->ld = ((h->N + kSymB - 1) / kSymB) * kSymB;  // multiple of 128 (and of 64): both apply variants
   h->vlen = (size_t)r * h->N;
+  {
+    int sms = 0;   // needed by the tiling below
+    cudaError_t ea = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (ea != cudaSuccess || sms <= 0) {
+      delete h;
+      set_error("cannot read the SM count of device %d (%s)", device, cudaGetErrorString(ea));
+      return DPGO_ECUDA;
+    }
+    h->num_sms = sms;
+  }
   // tiling of the dense preconditioner apply: tiles of 64 output columns x KT inner indices.
   // Pick the number of inner splits (6..24) whose tile count balances best over one wave of
   // 2 CTAs per SM, counting the zero padding to ldk = nsplit * KT columns as waste.
@@ -1096,9 +1080,6 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
     h->ldk = h->nsplit * h->KT;
   }
   h->vpad = (size_t)r * h->ldk;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  h->num_sms = prop.multiProcessorCount;
   if (stream) {
     h->stream = (cudaStream_t)stream;
   } else {
@@ -1136,7 +1117,6 @@ int dpgo_destroy(dpgo_handle h) {
     if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_fused) cudaFreeHost(h->h_fused);
-  if (h->cusolver) cusolverDnDestroy(h->cusolver);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->stream);

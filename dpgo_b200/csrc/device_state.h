@@ -1,7 +1,6 @@
 // Internal state behind a dpgo_handle (not part of the C-ABI).
 #pragma once
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <stdint.h>
 
 #include <string>
@@ -82,7 +81,6 @@ struct dpgo_dev {
   int symv_occ = 0;
   int partial_blocks = 0;  // CTAs the partials buffer can serve (8 doubles each)
   bool finalized = false, has_precon = false;
-  cusolverDnHandle_t cusolver = nullptr;
 
   // lifted pose arrays
   double *d_slot[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -5,13 +5,13 @@
 //   1. nested dissection of the pose graph on the host (BFS level-set vertex separators) ->
 //      interior domains D_1..D_K with no edges between them and a separator S;
 //   2. dense inverses A_k^-1 of every interior block and Sigma^-1 of the Schur complement
-//      Sigma = A_SS - sum_k A_Sk A_k^-1 A_kS (cuSOLVER potrf/potri + cuBLAS GEMMs, set-up only);
+//      Sigma = A_SS - sum_k A_Sk A_k^-1 A_kS (in-tree batched Cholesky / inverse / tile GEMM of
+//      dense_la.cu, all domains in lockstep, couplings restricted to the separator columns S_k
+//      each domain touches; set-up only);
 //   3. application = 3 streamed dense block products + 2 tiny sparse products (kernels.cuh).
 // Bytes per application: sum_k 2 (n_k(d+1))^2 8 + (|S|(d+1))^2 8  (58 MB instead of 800 MB on
 // sphere2500, L2-resident).
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <stdio.h>
 
 #include <algorithm>
@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "dd_plan.h"
+#include "dense_la.h"
 #include "device_state.h"
 #include "dissect.h"
 #include "kernels.cuh"
@@ -31,14 +32,6 @@ namespace dpgo {
     if (_e != cudaSuccess) {                                                             \
       dpgo::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,              \
                       cudaGetErrorString(_e));                                           \
-      return DPGO_ECUDA;                                                                 \
-    }                                                                                    \
-  } while (0)
-#define LIB_TRY(expr)                                                                    \
-  do {                                                                                   \
-    int _s = (int)(expr);                                                                \
-    if (_s != 0) {                                                                       \
-      dpgo::set_error("%s:%d library error %d in %s", __FILE__, __LINE__, _s, #expr);    \
       return DPGO_ECUDA;                                                                 \
     }                                                                                    \
   } while (0)
@@ -67,7 +60,6 @@ struct DdState {
   int *cta5 = nullptr, *chunks5 = nullptr, *tptr = nullptr, *tcol = nullptr, *gidx = nullptr;
   bool configured = false;
   unsigned configured3 = 0;        // bit SRC: k_strip_gemv3<R, SRC> has its shared-memory attribute set
-  cublasHandle_t cublas = nullptr;
 };
 
 namespace {
@@ -83,24 +75,6 @@ int upload_vec(T **dptr, const std::vector<T> &v) {
 }  // namespace
 
 // ---- set-up kernels ---------------------------------------------------------------------------------
-// dense block of A = Q + shift I restricted to rows with group[i] == grow and columns with group[j] == gcol
-__global__ void k_dd_scatter(const int *browidx, const int *colidx, const double *blocks, int nnzb, int dh,
-                             const int *group, const int *lpos, int grow, int gcol, double shift, double *A,
-                             int lda) {
-  const size_t total = (size_t)nnzb * dh * dh;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int e = (int)(t / (dh * dh));
-    const int ab = (int)(t % (dh * dh));
-    const int a = ab / dh, b = ab % dh;
-    const int i = browidx[e], j = colidx[e];
-    if (group[i] != grow || group[j] != gcol) continue;
-    const size_t row = (size_t)lpos[i] * dh + a, col = (size_t)lpos[j] * dh + b;
-    double v = blocks[t];
-    if (grow == gcol && row == col) v += shift;
-    A[row + col * (size_t)lda] = v;
-  }
-}
-
 // stage-major strips of a symmetric m x m block (lower triangle of col-major A valid), zero padded to
 // pad x pad: dst[((cb * (pad/32) + chunk) * 32 + kk) * 64 + jj] = A(cb*64 + jj, chunk*32 + kk)
 __global__ void k_dd_layout(const double *A, int m, int lda, int pad, double *dst) {
@@ -133,15 +107,6 @@ __global__ void k_dd_layout_rect(const double *C, int m, int ldc, const int *col
     dst[t] = layout_rect_value(C, m, ldc, colmap, ncomp, form, nch, t);
 }
 
-// Bc(:, i) = B(:, colmap[i]) : the columns of A_kS that belong to S_k (all others are zero)
-__global__ void k_dd_gather_cols(const double *B, int m, int ldb, const int *colmap, int ncomp, double *Bc) {
-  const size_t total = (size_t)m * ncomp;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)(t % m), i = (int)(t / m);
-    Bc[t] = B[(size_t)row + (size_t)colmap[i] * ldb];
-  }
-}
-
 // Sigma(colmap[i], colmap[j]) -= W(i, j) : the Schur update of one domain touches only S_k x S_k
 __global__ void k_dd_scatter_sub(double *Sg, int ldS, const int *colmap, const double *W, int ncomp) {
   const size_t total = (size_t)ncomp * ncomp;
@@ -150,6 +115,178 @@ __global__ void k_dd_scatter_sub(double *Sg, int ldS, const int *colmap, const d
     Sg[(size_t)colmap[i] + (size_t)colmap[j] * ldS] -= W[t];
   }
 }
+
+// All dense blocks of the block elimination in one pass over the block-CSR entries of Q:
+//   interior x interior (same domain k)  -> A_k   (m_k x m_k at a_off[k], + shift on the diagonal)
+//   interior k x separator               -> B_k   (m_k x tm_k at b_off[k]; column = position of the separator
+//                                                  pose in the ascending list S_k, found by bisection)
+//   separator x separator                -> Sigma (mS x mS, + shift on the diagonal)
+struct ElimView {
+  const int *group, *lpos;       // per pose: domain (-1 = separator), position inside it
+  const int *dom_m;              // scalars per domain
+  const long long *a_off, *b_off;
+  const int *sk_ptr, *sk;        // S_k as separator positions, CSR over the domains
+  double *A, *B, *Sg;
+  int mS;
+};
+
+__global__ void k_dd_scatter_all(const int *browidx, const int *colidx, const double *blocks, int nnzb, int dh,
+                                 double shift, ElimView v) {
+  const size_t total = (size_t)nnzb * dh * dh;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t / (dh * dh));
+    const int ab = (int)(t % (dh * dh));
+    const int a = ab / dh, b = ab % dh;
+    const int i = browidx[e], j = colidx[e];
+    const int gi = v.group[i], gj = v.group[j];
+    const double val = blocks[t];
+    if (gi < 0) {
+      if (gj >= 0) continue;                       // separator x interior: the transpose of a B_k entry
+      const size_t row = (size_t)v.lpos[i] * dh + a, col = (size_t)v.lpos[j] * dh + b;
+      v.Sg[row + col * (size_t)v.mS] = val + (row == col ? shift : 0.0);
+    } else if (gj == gi) {
+      const size_t m = (size_t)v.dom_m[gi];
+      const size_t row = (size_t)v.lpos[i] * dh + a, col = (size_t)v.lpos[j] * dh + b;
+      v.A[v.a_off[gi] + row + col * m] = val + (row == col ? shift : 0.0);
+    } else if (gj < 0) {
+      int lo = v.sk_ptr[gi], hi = v.sk_ptr[gi + 1] - 1;
+      const int want = v.lpos[j];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (v.sk[mid] < want) lo = mid + 1; else hi = mid;
+      }
+      const size_t m = (size_t)v.dom_m[gi];
+      const size_t row = (size_t)v.lpos[i] * dh + a, col = (size_t)(lo - v.sk_ptr[gi]) * dh + b;
+      v.B[v.b_off[gi] + row + col * m] = val;
+    }
+  }
+}
+
+namespace {
+
+// Device results of the elimination of every interior domain (released by the destructor)
+struct Elimination {
+  int K = 0;
+  std::vector<int> m, tm;                    // scalars per domain, scalars of S_k
+  std::vector<long long> a_off, b_off, w_off;
+  std::vector<int> cmap_off;                 // offsets of the per-domain separator scalar lists in d_cmap
+  double *Ainv = nullptr;                    // A_k^-1, full symmetric m_k x m_k
+  double *B = nullptr, *C = nullptr;         // A_kS[:, S_k] and C_k = A_k^-1 A_kS[:, S_k]  (m_k x tm_k)
+  double *W = nullptr;                       // B_k^T C_k (tm_k x tm_k)
+  int *d_cmap = nullptr;
+  std::vector<void *> aux;
+  ~Elimination() {
+    void *p[] = {Ainv, B, C, W, d_cmap};
+    for (void *q : p) if (q) cudaFree(q);
+    for (void *q : aux) if (q) cudaFree(q);
+  }
+};
+
+// A_k^-1 for every domain, C_k on the columns of S_k, and Sigma = A_SS - sum_k B_k^T C_k accumulated into Sg
+// (mS x mS, zeroed here).  sk lists separator POSITIONS (ascending per domain).
+int eliminate_domains(dpgo_dev *h, const std::vector<int> &group, const std::vector<int> &lpos,
+                      const std::vector<int> &dom_m, const std::vector<int> &sk_ptr, const std::vector<int> &sk,
+                      double *Sg, int mS, Elimination &E) {
+  const int K = (int)dom_m.size(), dh = h->d + 1;
+  E.K = K;
+  E.m = dom_m;
+  E.tm.resize(K); E.a_off.resize(K); E.b_off.resize(K); E.w_off.resize(K); E.cmap_off.assign(K + 1, 0);
+  long long na = 0, nb = 0, nw = 0;
+  std::vector<int> cmap;
+  for (int k = 0; k < K; ++k) {
+    E.tm[k] = (sk_ptr[k + 1] - sk_ptr[k]) * dh;
+    E.a_off[k] = na; E.b_off[k] = nb; E.w_off[k] = nw;
+    na += (long long)dom_m[k] * dom_m[k];
+    nb += (long long)dom_m[k] * E.tm[k];
+    nw += (long long)E.tm[k] * E.tm[k];
+    for (int a = sk_ptr[k]; a < sk_ptr[k + 1]; ++a)
+      for (int c = 0; c < dh; ++c) cmap.push_back(sk[a] * dh + c);
+    E.cmap_off[k + 1] = (int)cmap.size();
+  }
+  auto dalloc = [&](double **p, long long count) -> int {
+    const size_t bytes = (size_t)std::max<long long>(count, 1) * sizeof(double);
+    CUDA_TRY(cudaMalloc((void **)p, bytes));
+    CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, h->stream));
+    return DPGO_OK;
+  };
+  DPGO_TRY(dalloc(&E.Ainv, na));
+  DPGO_TRY(dalloc(&E.B, nb));
+  DPGO_TRY(dalloc(&E.C, nb));
+  DPGO_TRY(dalloc(&E.W, nw));
+  DPGO_TRY(upload_vec(&E.d_cmap, cmap));
+  int *d_group = nullptr, *d_lpos = nullptr, *d_m = nullptr, *d_skptr = nullptr, *d_sk = nullptr;
+  long long *d_aoff = nullptr, *d_boff = nullptr;
+  DPGO_TRY(upload_vec(&d_group, group)); E.aux.push_back(d_group);
+  DPGO_TRY(upload_vec(&d_lpos, lpos)); E.aux.push_back(d_lpos);
+  DPGO_TRY(upload_vec(&d_m, dom_m)); E.aux.push_back(d_m);
+  DPGO_TRY(upload_vec(&d_skptr, sk_ptr)); E.aux.push_back(d_skptr);
+  DPGO_TRY(upload_vec(&d_sk, sk)); E.aux.push_back(d_sk);
+  DPGO_TRY(upload_vec(&d_aoff, E.a_off)); E.aux.push_back(d_aoff);
+  DPGO_TRY(upload_vec(&d_boff, E.b_off)); E.aux.push_back(d_boff);
+  if (mS > 0) CUDA_TRY(cudaMemsetAsync(Sg, 0, (size_t)mS * mS * sizeof(double), h->stream));
+  {
+    const size_t total = (size_t)h->nnzb * dh * dh;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8));
+    const ElimView v{d_group, d_lpos, d_m, d_aoff, d_boff, d_skptr, d_sk, E.Ainv, E.B, Sg, mS};
+    k_dd_scatter_all<<<grid, 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
+                                                  0.1 /* ref: src/PoseGraph.cpp:603 */, v);
+    CUDA_TRY(cudaPeekAtLastError());
+  }
+  // ---- A_k^-1, all domains in lockstep
+  {
+    std::vector<dla::SpdItem> items(K);
+    for (int k = 0; k < K; ++k) items[k] = dla::SpdItem{E.Ainv + E.a_off[k], dom_m[k], std::max(dom_m[k], 1)};
+    const int rc = dla::spd_inverse_batched(h->stream, items.data(), K, /*symmetrize=*/true);
+    if (rc > 0) {
+      set_error("interior block %d of Q + 0.1 I is not positive definite", rc - 1);
+      return DPGO_ENUMERIC;
+    }
+    if (rc < 0) {
+      set_error("%s", dla::last_error());
+      return DPGO_ECUDA;
+    }
+  }
+  // ---- C_k = A_k^-1 B_k and the Schur updates W_k = B_k^T C_k
+  std::vector<dla::GemmDesc> gc, gw;
+  for (int k = 0; k < K; ++k) {
+    if (E.tm[k] <= 0) continue;
+    const int m = dom_m[k], tm = E.tm[k];
+    gc.push_back(dla::GemmDesc{E.Ainv + E.a_off[k], E.B + E.b_off[k], E.C + E.b_off[k], m, tm, m, m, m, m});
+    gw.push_back(dla::GemmDesc{E.B + E.b_off[k], E.C + E.b_off[k], E.W + E.w_off[k], tm, tm, m, m, m, tm});
+  }
+  if (!gc.empty()) {
+    if (dla::gemm_batched(h->stream, gc.data(), (int)gc.size(), dla::GemmFlags{0, 0, 0, dla::K_FULL, 1.0, 0.0}) != 0 ||
+        dla::gemm_batched(h->stream, gw.data(), (int)gw.size(), dla::GemmFlags{1, 0, 0, dla::K_FULL, 1.0, 0.0}) != 0) {
+      set_error("%s", dla::last_error());
+      return DPGO_ECUDA;
+    }
+  }
+  // domains share separator poses: the updates of Sigma are applied one domain after the other (fixed order)
+  for (int k = 0; k < K; ++k) {
+    const int tm = E.tm[k];
+    if (tm <= 0) continue;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(((size_t)tm * tm + 255) / 256, (size_t)h->num_sms * 8));
+    k_dd_scatter_sub<<<grid, 256, 0, h->stream>>>(Sg, mS, E.d_cmap + E.cmap_off[k], E.W + E.w_off[k], tm);
+  }
+  CUDA_TRY(cudaPeekAtLastError());
+  return DPGO_OK;
+}
+
+int invert_schur(dpgo_dev *h, double *Sg, int mS) {
+  const dla::SpdItem item{Sg, mS, mS};
+  const int rc = dla::spd_inverse_batched(h->stream, &item, 1, false);
+  if (rc > 0) {
+    set_error("Schur complement of Q + 0.1 I is not positive definite");
+    return DPGO_ENUMERIC;
+  }
+  if (rc < 0) {
+    set_error("%s", dla::last_error());
+    return DPGO_ECUDA;
+  }
+  return DPGO_OK;
+}
+
+}  // namespace
 
 // ---- application kernels -----------------------------------------------------------------------------
 template <int R>
@@ -227,7 +364,6 @@ void dd_free(dpgo_dev *h) {
                   s->y, s->t, s->zs, s->u, s->w, s->M5, s->strips5, s->cta5, s->chunks5, s->tptr, s->tcol, s->gidx};
   for (void *p : ptrs)
     if (p) cudaFree(p);
-  if (s->cublas) cublasDestroy(s->cublas);
   delete s;
   h->dd = nullptr;
 }
@@ -432,84 +568,47 @@ int dd_build(dpgo_dev *h) {
   CUDA_TRY(cudaMalloc((void **)&s->zs, wlen * nsplit3 * sizeof(double)));
   CUDA_TRY(cudaMemset(s->zs, 0, wlen * nsplit3 * sizeof(double)));
   // ---- dense blocks on the device
-  int *d_group = nullptr, *d_lpos = nullptr;
-  DPGO_TRY(upload_vec(&d_group, group));
-  DPGO_TRY(upload_vec(&d_lpos, lpos));
   CUDA_TRY(cudaMalloc((void **)&s->M1, std::max<size_t>((size_t)stages1 * kStageDoubles, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s->M3, std::max<size_t>((size_t)padS * padS, 1) * sizeof(double)));
-  if (!h->cusolver) {
-    LIB_TRY(cusolverDnCreate(&h->cusolver));
-    LIB_TRY(cusolverDnSetStream(h->cusolver, h->stream));
-  }
-  LIB_TRY(cublasCreate(&s->cublas));
-  LIB_TRY(cublasSetStream(s->cublas, h->stream));
-  int maxm = std::max(mS, 1);
-  for (int k = 0; k < K; ++k) maxm = std::max(maxm, dom_m[k]);
-  double *A = nullptr, *Sg = nullptr, *B = nullptr, *C = nullptr, *work = nullptr;
-  int *info = nullptr;
-  int maxdom = 1;
-  for (int k = 0; k < K; ++k) maxdom = std::max(maxdom, dom_m[k]);
-  CUDA_TRY(cudaMalloc((void **)&A, (size_t)maxdom * maxdom * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&B, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&C, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
-  int lwork = 0;
+  // S_k: separator positions with a neighbour in domain k (ascending); the coupling A_kS is non-zero only there
+  std::vector<int> sk_ptr(K + 1, 0), sk;
   {
-    int l1 = 0, l2 = 0;
-    LIB_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l1));
-    LIB_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l2));
-    lwork = std::max(std::max(l1, l2), 1);
-  }
-  CUDA_TRY(cudaMalloc((void **)&work, (size_t)lwork * sizeof(double)));
-  const int sgrid = (int)std::min<size_t>(((size_t)h->nnzb * bs + 255) / 256, (size_t)h->num_sms * 8);
-  auto invert = [&](double *Mx, int m) -> int {
-    int hinfo = 0;
-    LIB_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
-    LIB_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
-    CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (hinfo != 0) {
-      set_error("dense block of Q + 0.1 I is not positive definite (info %d)", hinfo);
-      return DPGO_ENUMERIC;
+    std::vector<std::vector<int>> Sk(K);
+    for (int j = 0; j < s->nS; ++j) {
+      const int i = srow[j];
+      for (int e = h->rowptr[i]; e < h->rowptr[i + 1]; ++e) {
+        const int g = group[h->colidx[e]];
+        if (g >= 0 && (Sk[g].empty() || Sk[g].back() != j)) Sk[g].push_back(j);
+      }
     }
-    return DPGO_OK;
-  };
-  if (mS > 0) {
-    CUDA_TRY(cudaMemsetAsync(Sg, 0, (size_t)mS * mS * sizeof(double), h->stream));
-    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                          d_group, d_lpos, -1, -1, 0.1, Sg, mS);
-  }
-  for (int k = 0; k < K; ++k) {
-    const int m = dom_m[k];
-    CUDA_TRY(cudaMemsetAsync(A, 0, (size_t)m * m * sizeof(double), h->stream));
-    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                          d_group, d_lpos, k, k, 0.1, A, m);
-    DPGO_TRY(invert(A, m));
-    if (mS > 0) {
-      // Sigma -= A_kS^T (A_k^-1 A_kS)
-      CUDA_TRY(cudaMemsetAsync(B, 0, (size_t)m * mS * sizeof(double), h->stream));
-      k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                            d_group, d_lpos, k, -1, 0.0, B, m);
-      const double one = 1.0, zero = 0.0, mone = -1.0;
-      LIB_TRY(cublasDsymm(s->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, m, mS, &one, A, m, B, m, &zero, C, m));
-      LIB_TRY(cublasDgemm(s->cublas, CUBLAS_OP_T, CUBLAS_OP_N, mS, mS, m, &mone, B, m, C, m, &one, Sg, mS));
+    for (int k = 0; k < K; ++k) {
+      sk.insert(sk.end(), Sk[k].begin(), Sk[k].end());
+      sk_ptr[k + 1] = (int)sk.size();
     }
-    const size_t total = (size_t)dom_pad[k] * dom_pad[k];
-    const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(A, m, m, dom_pad[k], s->M1 + (size_t)dom_base[k] * kStageDoubles);
-    CUDA_TRY(cudaPeekAtLastError());
   }
-  if (mS > 0) {
-    DPGO_TRY(invert(Sg, mS));
-    const size_t total = (size_t)padS * padS;
-    const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-    k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
-    CUDA_TRY(cudaPeekAtLastError());
+  double *Sg = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
+  {
+    Elimination E;
+    int rc = eliminate_domains(h, group, lpos, dom_m, sk_ptr, sk, Sg, mS, E);
+    for (int k = 0; k < K && rc == DPGO_OK; ++k) {
+      const size_t total = (size_t)dom_pad[k] * dom_pad[k];
+      const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+      k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(E.Ainv + E.a_off[k], dom_m[k], dom_m[k], dom_pad[k],
+                                                           s->M1 + (size_t)dom_base[k] * kStageDoubles);
+    }
+    if (rc == DPGO_OK && mS > 0) rc = invert_schur(h, Sg, mS);
+    if (rc == DPGO_OK && mS > 0) {
+      const size_t total = (size_t)padS * padS;
+      const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+      k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
+    }
+    const cudaError_t e1 = cudaPeekAtLastError(), e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(Sg);
+    DPGO_TRY(rc);
+    CUDA_TRY(e1);
+    CUDA_TRY(e2);
   }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(A); cudaFree(Sg); cudaFree(B); cudaFree(C); cudaFree(work); cudaFree(info);
-  cudaFree(d_group); cudaFree(d_lpos);
   return DPGO_OK;
 }
 
@@ -561,12 +660,6 @@ int dd3_build(dpgo_dev *h) {
     if (pl.tiles1[i].blk == 0) (pl.tiles1[i].kind == 0 ? baseM : baseG)[pl.tiles1[i].k] = pl.strips1[i].data_off;
   for (size_t i = 0; i < pl.strips5.size(); ++i)
     if (pl.tiles5[i].blk == 0) baseW[pl.tiles5[i].k] = pl.strips5[i].data_off;
-  std::vector<int> cmap, cmap_off(K + 1, 0);
-  for (int k = 0; k < K; ++k) {
-    for (int a = pl.sk_ptr[k]; a < pl.sk_ptr[k + 1]; ++a)
-      for (int c = 0; c < dh; ++c) cmap.push_back(pl.sk[a] * dh + c);
-    cmap_off[k + 1] = (int)cmap.size();
-  }
   // ---- work arrays: y over the y space (interior results + the g_k segments), z_S partial slots, w
   const size_t wlen = (size_t)R * s->pcols;
   CUDA_TRY(cudaMalloc((void **)&s->y, (size_t)R * s->ycols * sizeof(double)));
@@ -576,112 +669,54 @@ int dd3_build(dpgo_dev *h) {
   CUDA_TRY(cudaMalloc((void **)&s->zs, wlen * s->nsplit3 * sizeof(double)));
   CUDA_TRY(cudaMemset(s->zs, 0, wlen * s->nsplit3 * sizeof(double)));
   // ---- dense blocks on the device
-  int *d_group = nullptr, *d_lpos = nullptr, *d_cmap = nullptr;
-  DPGO_TRY(upload_vec(&d_group, pl.group));
-  DPGO_TRY(upload_vec(&d_lpos, pl.lpos));
-  DPGO_TRY(upload_vec(&d_cmap, cmap));
   const int mS = pl.nS * dh, padS = s->pcols - s->sep_col0;
   CUDA_TRY(cudaMalloc((void **)&s->M1, std::max<size_t>((size_t)pl.stages1 * kStageDoubles, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s->M3, std::max<size_t>((size_t)pl.stages3 * kStageDoubles, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s->M5, std::max<size_t>((size_t)pl.stages5 * kStageDoubles, 1) * sizeof(double)));
-  if (!h->cusolver) {
-    LIB_TRY(cusolverDnCreate(&h->cusolver));
-    LIB_TRY(cusolverDnSetStream(h->cusolver, h->stream));
-  }
-  LIB_TRY(cublasCreate(&s->cublas));
-  LIB_TRY(cublasSetStream(s->cublas, h->stream));
-  int maxdom = 1;
-  for (int k = 0; k < K; ++k) maxdom = std::max(maxdom, pl.dom_m[k]);
-  const int maxm = std::max(std::max(mS, 1), maxdom);
-  int maxt = 1;
-  for (int k = 0; k < K; ++k) maxt = std::max(maxt, pl.t_m[k]);
-  // A: one interior block; B: A_kS over all separator columns (zero outside S_k); Bc / Cc: A_kS and
-  // C_k = A_k^-1 A_kS restricted to the columns of S_k; W: the domain's Schur update on S_k x S_k
-  double *A = nullptr, *Sg = nullptr, *B = nullptr, *Bc = nullptr, *C = nullptr, *W = nullptr, *work = nullptr;
-  int *info = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&A, (size_t)maxdom * maxdom * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&B, (size_t)maxdom * std::max(mS, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&Bc, (size_t)maxdom * maxt * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&C, (size_t)maxdom * maxt * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&W, (size_t)maxt * maxt * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&info, sizeof(int)));
-  int lwork = 0;
-  {
-    int l1 = 0, l2 = 0;
-    LIB_TRY(cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l1));
-    LIB_TRY(cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, maxm, A, maxm, &l2));
-    lwork = std::max(std::max(l1, l2), 1);
-  }
-  CUDA_TRY(cudaMalloc((void **)&work, (size_t)lwork * sizeof(double)));
-  const int bs = dh * dh;
-  const int sgrid = (int)std::min<size_t>(((size_t)h->nnzb * bs + 255) / 256, (size_t)h->num_sms * 8);
-  auto invert = [&](double *Mx, int m) -> int {
-    int hinfo = 0;
-    LIB_TRY(cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
-    LIB_TRY(cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, m, Mx, m, work, lwork, info));
-    CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (hinfo != 0) {
-      set_error("dense block of Q + 0.1 I is not positive definite (info %d)", hinfo);
-      return DPGO_ENUMERIC;
-    }
-    return DPGO_OK;
-  };
-  auto lgrid = [&](size_t total) { return std::max(1, (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8)); };
-  if (mS > 0) {
-    CUDA_TRY(cudaMemsetAsync(Sg, 0, (size_t)mS * mS * sizeof(double), h->stream));
-    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                          d_group, d_lpos, -1, -1, 0.1, Sg, mS);
-  }
   for (int k = 0; k < K; ++k) {
-    const int m = pl.dom_m[k];
-    CUDA_TRY(cudaMemsetAsync(A, 0, (size_t)m * m * sizeof(double), h->stream));
-    k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                          d_group, d_lpos, k, k, 0.1, A, m);
-    DPGO_TRY(invert(A, m));
     if (baseM[k] < 0) {
       set_error("three-phase plan has no interior strips for domain %d", k);
       return DPGO_EINVAL;
     }
-    k_dd_layout<<<lgrid((size_t)pl.dom_pad[k] * pl.dom_pad[k]), 256, 0, h->stream>>>(
-        A, m, m, pl.dom_pad[k], s->M1 + (size_t)baseM[k] * kStageDoubles);
-    CUDA_TRY(cudaPeekAtLastError());
-    const int tm = pl.t_m[k];
-    if (tm > 0) {
-      // A_kS is non-zero only in the columns of S_k: C = A_k^-1 A_kS[:, S_k] (m x tm) and the Schur
-      // update Sigma[S_k, S_k] -= A_kS[:, S_k]^T C (tm x tm) are formed on those columns only
-      if (baseG[k] < 0 || baseW[k] < 0) {
-        set_error("three-phase plan has no coupling strips for domain %d", k);
-        return DPGO_EINVAL;
+    if (pl.t_m[k] > 0 && (baseG[k] < 0 || baseW[k] < 0)) {
+      set_error("three-phase plan has no coupling strips for domain %d", k);
+      return DPGO_EINVAL;
+    }
+  }
+  auto lgrid = [&](size_t total) { return std::max(1, (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8)); };
+  double *Sg = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
+  {
+    // A_kS is non-zero only in the columns of S_k: C_k = A_k^-1 A_kS[:, S_k] (m x tm) and the Schur update
+    // Sigma[S_k, S_k] -= A_kS[:, S_k]^T C_k (tm x tm) are formed on those columns only, all domains batched
+    Elimination E;
+    int rc = eliminate_domains(h, pl.group, pl.lpos, pl.dom_m, pl.sk_ptr, pl.sk, Sg, mS, E);
+    for (int k = 0; k < K && rc == DPGO_OK; ++k) {
+      const int m = pl.dom_m[k], tm = pl.t_m[k];
+      k_dd_layout<<<lgrid((size_t)pl.dom_pad[k] * pl.dom_pad[k]), 256, 0, h->stream>>>(
+          E.Ainv + E.a_off[k], m, m, pl.dom_pad[k], s->M1 + (size_t)baseM[k] * kStageDoubles);
+      if (tm <= 0) continue;
+      if (tm != E.tm[k]) {
+        set_error("three-phase plan and elimination disagree on |S_%d|", k);
+        rc = DPGO_EINVAL;
+        break;
       }
-      const int *cm = d_cmap + cmap_off[k];
-      CUDA_TRY(cudaMemsetAsync(B, 0, (size_t)m * mS * sizeof(double), h->stream));
-      k_dd_scatter<<<std::max(sgrid, 1), 256, 0, h->stream>>>(h->d_browidx, h->d_colidx, h->d_blocks, h->nnzb, dh,
-                                                            d_group, d_lpos, k, -1, 0.0, B, m);
-      k_dd_gather_cols<<<lgrid((size_t)m * tm), 256, 0, h->stream>>>(B, m, m, cm, tm, Bc);
-      CUDA_TRY(cudaPeekAtLastError());
-      const double one = 1.0, zero = 0.0;
-      LIB_TRY(cublasDsymm(s->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, m, tm, &one, A, m, Bc, m, &zero, C, m));
-      LIB_TRY(cublasDgemm(s->cublas, CUBLAS_OP_T, CUBLAS_OP_N, tm, tm, m, &one, Bc, m, C, m, &zero, W, tm));
-      k_dd_scatter_sub<<<lgrid((size_t)tm * tm), 256, 0, h->stream>>>(Sg, mS, cm, W, tm);
+      const double *C = E.C + E.b_off[k];
       const int nobG = pl.t_pad[k] / kGemvCols, nchG = pl.dom_pad[k] / kStageK;
       k_dd_layout_rect<<<lgrid((size_t)nobG * nchG * kStageDoubles), 256, 0, h->stream>>>(
           C, m, m, nullptr, tm, 0, nobG, nchG, s->M1 + (size_t)baseG[k] * kStageDoubles);
       const int nobW = pl.dom_pad[k] / kGemvCols, nchW = (tm + kStageK - 1) / kStageK;
       k_dd_layout_rect<<<lgrid((size_t)nobW * nchW * kStageDoubles), 256, 0, h->stream>>>(
           C, m, m, nullptr, tm, 1, nobW, nchW, s->M5 + (size_t)baseW[k] * kStageDoubles);
-      CUDA_TRY(cudaPeekAtLastError());
     }
+    if (rc == DPGO_OK && mS > 0) rc = invert_schur(h, Sg, mS);
+    if (rc == DPGO_OK && mS > 0) k_dd_layout<<<lgrid((size_t)padS * padS), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
+    const cudaError_t e1 = cudaPeekAtLastError(), e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(Sg);
+    DPGO_TRY(rc);
+    CUDA_TRY(e1);
+    CUDA_TRY(e2);
   }
-  if (mS > 0) {
-    DPGO_TRY(invert(Sg, mS));
-    k_dd_layout<<<lgrid((size_t)padS * padS), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
-    CUDA_TRY(cudaPeekAtLastError());
-  }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(A); cudaFree(Sg); cudaFree(B); cudaFree(Bc); cudaFree(C); cudaFree(W); cudaFree(work); cudaFree(info);
-  cudaFree(d_group); cudaFree(d_lpos); cudaFree(d_cmap);
   return DPGO_OK;
 }
 

@@ -221,6 +221,11 @@ class PGOAgent {
   void uploadState();              // host X -> device slots (after setX / re-initialisation)
   void downloadX();
   void downloadY();
+  // host mirrors X / Y of the device iterates, fetched on demand (iterate() marks them stale); a subclass that
+  // reads the protected members X / Y directly must go through these instead
+  LiftedPoseArray &hostX();
+  LiftedPoseArray &hostY();
+  bool mHostXStale = false, mHostYStale = false;
 };
 
 }  // namespace DPGO

@@ -37,18 +37,33 @@ void PGOAgent::uploadState() {
   const Matrix Xm = X.getData();
   DPGO_DEVICE_CALL(dpgo_slot_set(h, DPGO_SLOT_X, Xm.data()));
   mDeviceStateValid = true;
+  mHostXStale = false;
 }
 
 void PGOAgent::downloadX() {
   Matrix M(r, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
   DPGO_DEVICE_CALL(dpgo_slot_get(mPoseGraph->deviceHandle(), DPGO_SLOT_X, M.data()));
   X.setData(M);
+  mHostXStale = false;
 }
 
 void PGOAgent::downloadY() {
   Matrix M(r, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
   DPGO_DEVICE_CALL(dpgo_slot_get(mPoseGraph->deviceHandle(), DPGO_SLOT_Y, M.data()));
   Y.setData(M);
+  mHostYStale = false;
+}
+
+// The iterates live on the device; iterate() only marks the host mirrors stale and the first reader fetches
+// them (callers hold mPosesMutex).  A round in which nobody reads the poses on the host moves no pose data.
+LiftedPoseArray &PGOAgent::hostX() {
+  if (mHostXStale) downloadX();
+  return X;
+}
+
+LiftedPoseArray &PGOAgent::hostY() {
+  if (mHostYStale) downloadY();
+  return Y;
 }
 
 // ---- state -------------------------------------------------------------------------------------
@@ -74,7 +89,7 @@ void PGOAgent::setXToInitialGuess() {
 
 bool PGOAgent::getX(Matrix &Mout) {
   lock_guard<mutex> lock(mPosesMutex);
-  Mout = X.getData();
+  Mout = hostX().getData();
   return true;
 }
 
@@ -82,7 +97,7 @@ bool PGOAgent::getSharedPose(unsigned index, Matrix &Mout) {
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
   if (index >= num_poses()) return false;
-  Mout = X.pose(index);
+  Mout = hostX().pose(index);
   return true;
 }
 
@@ -91,7 +106,7 @@ bool PGOAgent::getAuxSharedPose(unsigned index, Matrix &Mout) {
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
   if (index >= num_poses()) return false;
-  Mout = Y.pose(index);
+  Mout = hostY().pose(index);
   return true;
 }
 
@@ -101,7 +116,7 @@ bool PGOAgent::getSharedPoseDict(PoseDict &map) {  // reference :97-110
   lock_guard<mutex> lock(mPosesMutex);
   for (const auto &pid : mPoseGraph->myPublicPoseIDs()) {
     DPGO_CHECK(pid.robot_id == getID());
-    map.emplace(pid, LiftedPose(X.pose(pid.frame_id)));
+    map.emplace(pid, LiftedPose(hostX().pose(pid.frame_id)));
   }
   return true;
 }
@@ -112,7 +127,7 @@ bool PGOAgent::getSharedPoseDictWithNeighbor(PoseDict &map, unsigned neighborID)
   lock_guard<mutex> lock(mPosesMutex);
   for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
     const PoseID pid(getID(), static_cast<unsigned>(m.r1 == getID() ? m.p1 : m.p2));
-    map.emplace(pid, LiftedPose(X.pose(pid.frame_id)));
+    map.emplace(pid, LiftedPose(hostX().pose(pid.frame_id)));
   }
   return true;
 }
@@ -124,7 +139,7 @@ bool PGOAgent::getAuxSharedPoseDict(PoseDict &map) {  // :132-146
   lock_guard<mutex> lock(mPosesMutex);
   for (const auto &pid : mPoseGraph->myPublicPoseIDs()) {
     DPGO_CHECK(pid.robot_id == getID());
-    map.emplace(pid, LiftedPose(Y.pose(pid.frame_id)));
+    map.emplace(pid, LiftedPose(hostY().pose(pid.frame_id)));
   }
   return true;
 }
@@ -136,7 +151,7 @@ bool PGOAgent::getAuxSharedPoseDictWithNeighbor(PoseDict &map, unsigned neighbor
   lock_guard<mutex> lock(mPosesMutex);
   for (const auto &m : mPoseGraph->sharedLoopClosuresWithRobot(neighborID)) {
     const PoseID pid(getID(), static_cast<unsigned>(m.r1 == getID() ? m.p1 : m.p2));
-    map.emplace(pid, LiftedPose(Y.pose(pid.frame_id)));
+    map.emplace(pid, LiftedPose(hostY().pose(pid.frame_id)));
   }
   return true;
 }
@@ -196,10 +211,29 @@ void PGOAgent::initialize(const PoseArray *TInitPtr) {  // reference :199-306
     switch (mParams.localInitializationMethod) {
       case InitializationMethod::Odometry: T = odometryInitialization(mPoseGraph->odometry()); break;
       case InitializationMethod::Chordal: T = chordalInitialization(mPoseGraph->localMeasurements()); break;
-      case InitializationMethod::GNC_TLS:
-        // robust single-robot initialisation is outside this build: fall back to the chordal one
-        T = chordalInitialization(mPoseGraph->localMeasurements());
+      case InitializationMethod::GNC_TLS: {   // reference :233-262
+        // robust single-robot solve from the odometry guess; local loop closures it rejects get weight 0
+        solveRobustPGOParams rp;
+        rp.verbose = mParams.verbose;
+        rp.opt_params.verbose = false;
+        rp.opt_params.gradnorm_tol = 1;
+        rp.opt_params.RTR_iterations = 20;
+        rp.robust_params.costType = RobustCostParameters::Type::GNC_TLS;
+        rp.robust_params.GNCMaxNumIters = 10;
+        rp.robust_params.GNCBarc = 5.0;
+        rp.robust_params.GNCMuStep = 1.4;
+        const PoseArray TOdom = odometryInitialization(mPoseGraph->odometry());
+        std::vector<RelativeSEMeasurement> local = mPoseGraph->localMeasurements();
+        T = solveRobustPGO(local, rp, &TOdom);
+        int rejected = 0;
+        for (const RelativeSEMeasurement &m : local)
+          if (m.weight < 1e-8) {
+            setMeasurementWeight(PoseID(m.r1, m.p1), PoseID(m.r2, m.p2), 0);
+            rejected++;
+          }
+        if (mParams.verbose) std::printf("GNC_TLS initialization: rejected %d local loop closure(s)\n", rejected);
         break;
+      }
     }
     DPGO_CHECK(T.d() == dimension());
     TLocalInit.emplace(T);
@@ -272,8 +306,8 @@ bool PGOAgent::iterate(bool doOptimization) {  // reference :376-432
   }
   {
     lock_guard<mutex> lock(mPosesMutex);
-    downloadX();
-    if (mParams.acceleration) downloadY();
+    mHostXStale = true;
+    if (mParams.acceleration) mHostYStale = true;
   }
   if (doOptimization) {
     mStatus.agentID = getID();
@@ -362,7 +396,12 @@ void PGOAgent::initializeAcceleration() {
   DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_XPREV, DPGO_SLOT_X));
   DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_V, DPGO_SLOT_X));
   DPGO_DEVICE_CALL(dpgo_slot_copy(h, DPGO_SLOT_Y, DPGO_SLOT_X));
-  Y = X;
+  if (mHostXStale) {
+    mHostYStale = true;
+  } else {
+    Y = X;
+    mHostYStale = false;
+  }
   gamma = 0;
   alpha = 0;
 }
@@ -526,7 +565,7 @@ bool PGOAgent::getTrajectoryInLocalFrame(Matrix &Trajectory) {
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
   PoseArray T(d, num_poses());
-  T.setData(X.rotation(0).transpose() * X.getData());
+  T.setData(hostX().rotation(0).transpose() * hostX().getData());
   const Matrix t0 = T.translation(0);
   for (unsigned i = 0; i < num_poses(); ++i) {
     T.rotation(i) = projectToRotationGroup(T.rotation(i));
@@ -543,7 +582,7 @@ bool PGOAgent::getTrajectoryInGlobalFrame(PoseArray &Trajectory) {
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
   PoseArray T(d, num_poses());
-  T.setData(Xa.rotation().transpose() * X.getData());
+  T.setData(Xa.rotation().transpose() * hostX().getData());
   const Matrix t0 = Xa.rotation().transpose() * Xa.translation();
   for (unsigned i = 0; i < num_poses(); ++i) {
     T.rotation(i) = projectToRotationGroup(T.rotation(i));
@@ -568,7 +607,7 @@ bool PGOAgent::getPoseInGlobalFrame(unsigned poseID, Matrix &T) {
   if (poseID >= num_poses()) return false;
   const Matrix Ya = Xa.rotation();
   const Matrix t0 = Ya.transpose() * Xa.translation();
-  Matrix Ti = Ya.transpose() * X.pose(poseID);
+  Matrix Ti = Ya.transpose() * hostX().pose(poseID);
   Ti.block(0, d, d, 1) -= t0;
   T = Ti;
   return true;
@@ -612,36 +651,39 @@ bool PGOAgent::shouldTerminate() {  // reference :844-878
   return true;
 }
 
-void PGOAgent::reset() {  // reference :434-473
+// End of one optimization instance (reference :434-473): stop the worker thread, leave the logs of the finished
+// instance, then return to WAIT_FOR_DATA under the next instance number with nothing carried over.
+void PGOAgent::reset() {
   endOptimizationLoop();
-  if (mParams.logData) {  // measurements with their final weights, rounded trajectory, raw X (:437-452)
-    std::vector<RelativeSEMeasurement> measurements = mPoseGraph->measurements();
-    mLogger.logMeasurements(measurements, "measurements.csv");
-    Matrix T;
-    if (getTrajectoryInGlobalFrame(T)) {
-      mLogger.logTrajectory(dimension(), num_poses(), T, "trajectory_optimized.csv");
-      std::cout << "Saved optimized trajectory to " << mParams.logDirectory << std::endl;
+  if (mParams.logData) {
+    const std::string &dir = mParams.logDirectory;
+    std::vector<RelativeSEMeasurement> weighted = mPoseGraph->measurements();   // with their final GNC weights
+    mLogger.logMeasurements(weighted, "measurements.csv");
+    Matrix rounded;
+    if (getTrajectoryInGlobalFrame(rounded)) {
+      mLogger.logTrajectory(dimension(), num_poses(), rounded, "trajectory_optimized.csv");
+      std::cout << "Saved optimized trajectory to " << dir << std::endl;
     }
-    writeMatrixToFile(X.getData(), mParams.logDirectory + "X.txt");
+    writeMatrixToFile(hostX().getData(), dir + "X.txt");
   }
-  mInstanceNumber++;
-  mIterationNumber = 0;
-  mLatestWeightUpdateIteration = 0;
-  mRobustOptInnerIter = 0;
-  mWeightUpdateCount = 0;
-  mTrajectoryResetCount = 0;
-  mState = PGOAgentState::WAIT_FOR_DATA;
-  mStatus = PGOAgentStatus(getID(), mState, mInstanceNumber, mIterationNumber, false, 0);
+
+  // what the agent knew about this instance: frames, initial guesses, neighbours, measurements, device state
+  globalAnchor.reset();
+  XInit.reset();
+  TLocalInit.reset();
+  clearNeighborPoses();
+  mPoseGraph->reset();
+  mDeviceStateValid = false;
   mTeamStatus.clear();
   mTeamRobotActive.assign(mParams.numRobots, false);
-  globalAnchor.reset();
-  TLocalInit.reset();
-  XInit.reset();
-  mPublishPublicPosesRequested = false;
-  mPublishAsynchronousRequested = false;
-  mPoseGraph->reset();
-  clearNeighborPoses();
-  mDeviceStateValid = false;
+  mPublishPublicPosesRequested = mPublishAsynchronousRequested = false;
+
+  // counters of the new instance
+  ++mInstanceNumber;
+  mIterationNumber = mLatestWeightUpdateIteration = 0;
+  mRobustOptInnerIter = mWeightUpdateCount = mTrajectoryResetCount = 0;
+  mState = PGOAgentState::WAIT_FOR_DATA;
+  mStatus = PGOAgentStatus(getID(), mState, mInstanceNumber, mIterationNumber, false, 0);
 }
 
 // ---- asynchronous mode (reference :475-513) ------------------------------------------------------------
@@ -701,18 +743,19 @@ void PGOAgent::initializeRobustOptimization() {  // :1048-1060
 bool PGOAgent::computeMeasurementResidual(const RelativeSEMeasurement &m, double *residual) const {  // :1062-1102
   if (mState != PGOAgentState::INITIALIZED) return false;
   DPGO_CHECK(residual != nullptr);
-  // X is the host mirror of the device iterate (refreshed at the end of every iterate())
+  // host mirror of the device iterate, fetched if iterate() ran since the last read
+  const LiftedPoseArray &Xh = const_cast<PGOAgent *>(this)->hostX();
   Matrix Y1, p1, Y2, p2;
   if (m.r1 == m.r2) {
-    Y1 = X.rotation(m.p1); p1 = X.translation(m.p1);
-    Y2 = X.rotation(m.p2); p2 = X.translation(m.p2);
+    Y1 = Xh.rotation(m.p1); p1 = Xh.translation(m.p1);
+    Y2 = Xh.rotation(m.p2); p2 = Xh.translation(m.p2);
   } else if (m.r1 == getID()) {
-    Y1 = X.rotation(m.p1); p1 = X.translation(m.p1);
+    Y1 = Xh.rotation(m.p1); p1 = Xh.translation(m.p1);
     const auto it = neighborPoseDict.find(PoseID(m.r2, m.p2));
     if (it == neighborPoseDict.end()) return false;
     Y2 = it->second.rotation(); p2 = it->second.translation();
   } else {
-    Y2 = X.rotation(m.p2); p2 = X.translation(m.p2);
+    Y2 = Xh.rotation(m.p2); p2 = Xh.translation(m.p2);
     const auto it = neighborPoseDict.find(PoseID(m.r1, m.p1));
     if (it == neighborPoseDict.end()) return false;
     Y1 = it->second.rotation(); p1 = it->second.translation();
@@ -779,7 +822,7 @@ size_t PGOAgent::numActiveRobots() const {
 bool PGOAgent::anchorFirstPose() {
   if (num_poses() == 0) return false;
   LiftedPose prior(relaxation_rank(), dimension());
-  prior.setData(X.pose(0));
+  prior.setData(hostX().pose(0));
   mPoseGraph->setPrior(0, prior);
   return true;
 }

@@ -14,6 +14,14 @@ PoseGraph::PoseGraph(unsigned int id, unsigned int r, unsigned int d)
     : id_(id), r_(r), d_(d), n_(0), use_inactive_neighbors_(false), prior_kappa_(10000), prior_tau_(100),
       dev_(nullptr), dev_n_(0), q_valid_(false), g_valid_(false), precon_valid_(false) {
   DPGO_CHECK(r >= d);  // reference: src/PoseGraph.cpp:19
+  DPGO_CHECK(d == 2 || d == 3);
+  if (r > d + 3) {
+    // the register-resident pose tiles of the CUDA kernels are instantiated for d <= r <= d + 3 (the reference
+    // accepts any r >= d; its examples and dpgo_ros use r = d .. 5): refuse here, not at the first device call
+    std::fprintf(stderr, "[DPGO] relaxation rank r = %u is not supported by the CUDA path (d = %u: %u <= r <= %u)\n",
+                 r, d, d, d + 3);
+    std::abort();
+  }
   empty();
 }
 

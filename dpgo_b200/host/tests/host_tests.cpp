@@ -264,6 +264,8 @@ static void testRobustWeights() {
 }
 
 int main() {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);   // a test killed on a timeout still shows where it was
+
   testPosesAndUtils();
   testTriangleGraph();
   testPrior();

@@ -10,8 +10,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_robust_pgo_rejects_the_wrong_loop_closure():
-    exe = os.path.join(ROOT, "dpgo_b200", "host", "bin", "robust_pgo_test")
-    if not os.path.exists(exe):
-        pytest.skip("host binaries not built (run __graft_entry__.build())")
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    from test_gpu_z_host import _need, _run
+    out = _run([_need("robust_pgo_test")], 120)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]

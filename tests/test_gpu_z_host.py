@@ -13,19 +13,35 @@ from util_g2o import write_g2o
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "dpgo_b200", "host", "bin")
 
 
 def _need(name):
-    p = os.path.join(BIN, name)
-    if not os.path.exists(p):
-        pytest.skip(f"{name} not built (reference tree absent at build time)")
-    return p
+    """Built by __graft_entry__.build(); the reference's example drivers only where the reference tree is
+    present (they travel to the GPU box as built files).  A stale binary (drop-in headers or sources changed
+    since) is an error, not a skip."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_dpgo_build", os.path.join(ROOT, "dpgo_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    try:
+        return b.host_binary(name)
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+def _run(cmd, timeout):
+    """Subprocess with a timeout that reports what the child printed before it was killed."""
+    try:
+        return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired as e:
+        so = (e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        se = (e.stderr or b"").decode(errors="replace") if isinstance(e.stderr, bytes) else (e.stderr or "")
+        pytest.fail(f"{cmd[0]} timed out after {timeout} s; partial stdout:\n{so[-3000:]}\nstderr:\n{se[-2000:]}")
 
 
 def test_host_acceptance_suite():
     """Restated reference gtests (triangle graph, prior, line graph, poses, utils, thread)."""
-    out = subprocess.run([_need("host_tests")], capture_output=True, text=True, timeout=300)
+    out = _run([_need("host_tests")], 120)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "all host tests passed" in out.stdout
 
@@ -37,7 +53,7 @@ def test_multi_robot_example_matches_oracle(datasets, tmp_path):
     meas, n, z = datasets("smallGrid3D")
     path = str(tmp_path / "smallGrid3D.g2o")
     write_g2o(path, meas.d, meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau)
-    out = subprocess.run([exe, "5", path], capture_output=True, text=True, timeout=600)
+    out = _run([exe, "5", path], 120)
     assert out.returncode == 0, out.stderr[-2000:]
     rows = re.findall(r"Iter = (\d+) \| robot = (\d+) \| cost = ([-+.\deE]+) \| gradnorm = ([-+.\deE]+)", out.stdout)
     assert len(rows) >= 30
@@ -61,11 +77,11 @@ def test_chordal_and_single_robot_examples(datasets, tmp_path):
     m2, n2 = pgo.read_g2o(path)
     prob = pgo.QuadraticProblem(pgo.connection_laplacian(m2, n2), np.zeros((3, 4 * n2)), 3)
     T0 = pgo.chordal_initialization(m2, n2)
-    out = subprocess.run([_need("chordal-initialization-example"), path], capture_output=True, text=True, timeout=300)
+    out = _run([_need("chordal-initialization-example"), path], 120)
     assert out.returncode == 0, out.stderr[-2000:]
     cost = float(re.search(r"Chordal initialization cost: ([-+.\deE]+)", out.stdout).group(1))
     assert abs(cost - 2 * prob.f(T0)) <= 1e-4 * cost
-    out = subprocess.run([_need("single-robot-example"), path], capture_output=True, text=True, timeout=300)
+    out = _run([_need("single-robot-example"), path], 120)
     assert out.returncode == 0, out.stderr[-2000:]
     cost = float(re.search(r"Cost = ([-+.\deE]+)", out.stdout).group(1))
     Y, res = pgo.optimize(prob, T0)       # solvePGO: chordal init + RTR at r = d (src/DPGO_solver.cpp:305-333)

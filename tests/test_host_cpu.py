@@ -19,13 +19,7 @@ def host_built():
     from dpgo_b200 import build
     build.build_device_lib()
     build.build_host()
-    cli = os.path.join(HOST, "bin", "host_cli")
-    if not os.path.exists(cli) or os.path.getmtime(cli) < os.path.getmtime(os.path.join(HOST, "libDPGO.so")):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(HOST, "include"),
-                               os.path.join(HOST, "tests", "host_cli.cpp"), "-L" + HOST, "-lDPGO",
-                               "-L" + os.path.join(ROOT, "dpgo_b200"), "-ldpgo_b200",
-                               "-Wl,-rpath," + HOST, "-Wl,-rpath," + os.path.join(ROOT, "dpgo_b200"),
-                               "-pthread", "-o", cli])
+    cli = build.host_binary("host_cli")
     return cli
 
 
