@@ -21,13 +21,16 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_device_lib(force=False, verbose=False, trace=False):
-    """trace=True: measurement build (-DDPGO_TRACE: per-CTA phase times in the fused solver, read with
-    dpgo_phase_trace) into libdpgo_b200_trace.so beside the product library (own object files); it is loaded
-    only when DPGO_B200_LIB points at it (tools/phase_trace.py)."""
-    flags = FLAGS + (["-DDPGO_TRACE"] if trace else [])
-    suffix = ".trace.o" if trace else ".o"
-    out = LIB.replace(".so", "_trace.so") if trace else LIB
+def build_device_lib(force=False, verbose=False, trace=False, variant=None, defines=()):
+    """The product library libdpgo_b200.so, or a measurement build beside it (own object files, loaded only
+    when DPGO_B200_LIB points at it): trace=True -> libdpgo_b200_trace.so with -DDPGO_TRACE (per-CTA phase
+    times in the fused solver, tools/phase_trace.py); variant="name", defines=["X=1", ...] ->
+    libdpgo_b200_<name>.so with -DX=1 ... (A/B runs of compile-time choices on one box)."""
+    if trace:
+        variant, defines = "trace", ["DPGO_TRACE"]
+    flags = FLAGS + ["-D" + d for d in defines]
+    suffix = f".{variant}.o" if variant else ".o"
+    out = LIB.replace(".so", f"_{variant}.so") if variant else LIB
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith(".") and not f.endswith(".o")]
     deps.append(os.path.join(HERE, "..", "include", "dpgo_b200.h"))
     objs = []
@@ -132,6 +135,10 @@ def host_binary(name):
 
 
 if __name__ == "__main__":
-    build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
-    if "--trace" not in sys.argv:
-        build_host(force="--force" in sys.argv)
+    if "--variant" in sys.argv:    # python build.py --variant name -DX=1 -DY ...
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        build_device_lib(variant=name, defines=[a[2:] for a in sys.argv if a.startswith("-D")])
+    else:
+        build_device_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
+        if "--trace" not in sys.argv:
+            build_host(force="--force" in sys.argv)

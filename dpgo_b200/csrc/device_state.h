@@ -98,7 +98,9 @@ struct dpgo_dev {
   void *dd = nullptr;           // dpgo::DdState (precon_mode >= 2)
   int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
   int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
-  int qx_variant = 0, qx_prefetch_dist = 0;   // dpgo_set_qx_variant (stand-alone Q*X only)
+  // stand-alone Q*X (dpgo_set_qx_variant): -1 = automatic (staged kernel when Q and X stream from HBM),
+  // 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch, 2 = shared-memory staged kernel
+  int qx_variant = -1, qx_prefetch_dist = 0;
   int dd_max_domain = 0;              // poses per interior domain (0 = one wave of strip stages)
   int *d_public_idx = nullptr;
   int num_public = 0;

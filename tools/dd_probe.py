@@ -66,9 +66,23 @@ def forms():
         run("city10000", z, d, n, T0, 3, mode, reps=2)
 
 
+def barrier_ab():
+    """--barrier-ab: the solves whose time is barrier / latency bound, for A/B runs of library builds that differ
+    in the grid barrier (DPGO_B200_LIB=...): bench problem in the two-level forms and with the dense inverse,
+    one grid3D-agent-sized problem."""
+    z, d, n, T0 = fixture("sphere2500")
+    for mode in (2, 4, 0):
+        run("sphere2500", z, d, n, T0, 5, mode, reps=5)
+    g = synthetic.grid3d(10, seed=1)
+    for mode in (0, 2):
+        run("grid3d_L10", g, 3, 1000, g["T_true"], 5, mode, reps=5)
+
+
 def main():
     if "--forms" in sys.argv:
         return forms()
+    if "--barrier-ab" in sys.argv:
+        return barrier_ab()
     quick = "--quick" in sys.argv
     z, d, n, T0 = fixture("sphere2500")
     run("sphere2500", z, d, n, T0, 5, 0)

@@ -33,25 +33,22 @@ def main():
         rng = np.random.default_rng(0)
         gp.slot_set(0, rng.standard_normal((5, 4 * g["n"])))
         nbytes = gp.bytes_qx()
-        warm = gp.time_qx(20, False)
-        cold = gp.time_qx(10, True)
-        rec = dict(L=L, n=g["n"], m=len(g["p1"]), bytes=nbytes, gen_s=tg, build_s=tb,
-                   back_to_back_us=warm, back_to_back_gbs=nbytes / warm / 1e3,
-                   flushed_us=cold, flushed_gbs=nbytes / cold / 1e3,
-                   frac_of_measured_peak=nbytes / cold / 1e3 / peak, peak_gbs=peak)
-        # measurement variant 1 (dpgo_set_qx_variant): software prefetch into L2, a few distances;
-        # its product must equal the default kernel's bit for bit (same arithmetic)
         Xh = rng.standard_normal((5, 4 * g["n"]))
-        ref = gp.qx(Xh)
-        rec["prefetch_variant"] = []
-        for dist in (0, 4096, 16384, 65536):
-            gp.set_qx_variant(1, dist)
-            same = bool(np.array_equal(gp.qx(Xh), ref))
+        rec = dict(L=L, n=g["n"], m=len(g["p1"]), bytes=nbytes, gen_s=tg, build_s=tb, peak_gbs=peak, variants=[])
+        ref = None
+        # 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch (distance 4096), 2 = shared-memory staged
+        # kernel (qx_staged.cuh; the automatic choice at this size)
+        for variant, dist in ((0, 0), (1, 4096), (2, 0)):
+            gp.set_qx_variant(variant, dist)
+            out = gp.qx(Xh)
+            if ref is None:
+                ref = out
+            err = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
             w1, c1 = gp.time_qx(20, False), gp.time_qx(10, True)
-            rec["prefetch_variant"].append(dict(distance=dist, identical=same, back_to_back_us=w1, flushed_us=c1,
-                                                flushed_gbs=nbytes / c1 / 1e3,
-                                                frac_of_measured_peak=nbytes / c1 / 1e3 / peak))
-        gp.set_qx_variant(0, 0)
+            rec["variants"].append(dict(variant=variant, distance=dist, rel_diff_vs_variant0=err,
+                                        back_to_back_us=w1, back_to_back_gbs=nbytes / w1 / 1e3, flushed_us=c1,
+                                        flushed_gbs=nbytes / c1 / 1e3, frac_of_measured_peak=nbytes / c1 / 1e3 / peak))
+        gp.set_qx_variant(-1, 0)
         print(json.dumps(rec), flush=True)
         out.append(rec)
         gp.close()
