@@ -44,6 +44,15 @@ _ip = C.POINTER(C.c_int32)
 _bp = C.POINTER(C.c_uint8)
 H = C.c_void_p
 
+class Message(C.Structure):
+    """dpgo_message: one public-pose message of an exchange (include/dpgo_b200.h)."""
+    _fields_ = [("src", H), ("dst", H), ("peer", C.c_int), ("slot", C.c_int), ("aux", C.c_int),
+                ("count", C.c_int), ("d_frames", C.c_void_p), ("dst_offset", C.c_int)]
+
+
+COMM = C.c_void_p
+COMM_ID_BYTES = 128
+
 # name -> (restype, argtypes); every symbol declared in include/dpgo_b200.h
 SIGNATURES = {
     "dpgo_default_params": (None, [C.POINTER(RoptParams)]),
@@ -92,6 +101,13 @@ SIGNATURES = {
     "dpgo_set_public_indices": (C.c_int, [H, C.c_int, _ip]),
     "dpgo_pack_public_dev": (C.c_int, [H, C.c_int, C.c_void_p]),
     "dpgo_gather_tiles_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dpgo_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "dpgo_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.POINTER(COMM)]),
+    "dpgo_comm_destroy": (C.c_int, [COMM]),
+    "dpgo_comm_launch_count": (C.c_int, [COMM, C.POINTER(C.c_int64)]),
+    "dpgo_neighbor_buffer": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p)]),
+    "dpgo_use_neighbor_poses": (C.c_int, [H, C.c_int]),
+    "dpgo_exchange": (C.c_int, [COMM, C.POINTER(Message), C.c_int]),
     "dpgo_measurement_errors": (C.c_int, [H, C.c_int, C.c_void_p, _dp, _dp]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),

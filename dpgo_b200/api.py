@@ -108,6 +108,15 @@ class DeviceProblem:
     def set_precon_tuning(self, split_interior=0, split_schur=0, prefetch=-1):
         check(lib.dpgo_set_precon_tuning(self._h, int(split_interior), int(split_schur), int(prefetch)))
 
+    def neighbor_buffer(self, aux):
+        """Device address of the handle's neighbour pose buffer (aux = 0: X, 1: auxiliary Y)."""
+        p = C.c_void_p()
+        check(lib.dpgo_neighbor_buffer(self._h, int(aux), C.byref(p)))
+        return p.value
+
+    def use_neighbor_poses(self, aux):
+        check(lib.dpgo_use_neighbor_poses(self._h, int(aux)))
+
     def set_qx_variant(self, variant=0, prefetch_distance=0):
         check(lib.dpgo_set_qx_variant(self._h, int(variant), int(prefetch_distance)))
 

@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libdpgo_b200.so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
-CU_SOURCES = ["device_lib.cu", "fused_rtr.cu", "precon_dd.cu", "dense_la.cu"]
+CU_SOURCES = ["device_lib.cu", "fused_rtr.cu", "precon_dd.cu", "dense_la.cu", "exchange.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-cudart", "shared", "-diag-suppress", "177"]
 
@@ -50,7 +50,7 @@ def build_device_lib(force=False, verbose=False, trace=False, variant=None, defi
         # no library on the link line but the CUDA runtime: the dense factorizations of the set-up are in-tree
         # (dense_la.cu); libcusolver / libcublas / libcublasLt (1.2 GB, minutes to page in on a fresh box) are gone
         cmd = [NVCC, "-shared", "-cudart", "shared", "-o", out] + objs + [
-            "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
+            "-ldl", "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     return out

@@ -77,6 +77,13 @@ __global__ void __launch_bounds__(kBlock) k_qx(BsrView Q, const double *X, const
   phase_qx<R, D>(make_ctx(), Q, X, G, out, n);
 }
 
+// lane-group kernel, two blocks per step (spmm_col2): 3 CTAs / SM
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock, 3) k_qx_pipe(BsrView Q, const double *X, const double *G,
+                                                       double *out, int n) {
+  phase_qx<R, D, true>(make_ctx(), Q, X, G, out, n);
+}
+
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const double *X, const double *G,
                                                         double *out, int n, int dist) {
@@ -474,6 +481,12 @@ int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
     return DPGO_OK;
   }
   if (variant == 0) return op_qx(h, qview(h), X, G, out);
+  if (variant == 3) {
+    const int grid = pose_grid(h, h->d + 1);
+    DPGO_DISPATCH(h, k_qx_pipe<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    LAUNCH_CHECK(h);
+    return DPGO_OK;
+  }
   const int grid = pose_grid(h, h->d + 1);
   DPGO_DISPATCH(h, {
     const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : qx_prefetch_distance<R, D>(h);
@@ -1157,7 +1170,7 @@ int dpgo_destroy(dpgo_handle h) {
                   h->d_slot[1], h->d_slot[2], h->d_slot[3], h->d_xa, h->d_xb, h->d_EG, h->d_EG2,
                   h->d_grad, h->d_grad2, h->d_S, h->d_S2, h->d_eta, h->d_r, h->d_z, h->d_delta,
                   h->d_Hd, h->d_t0, h->d_t1, h->d_t2, h->d_partials, h->d_scalars, h->d_fused,
-                  h->d_public_idx, h->d_flush, h->d_zT, h->d_sym_items, h->d_trace};
+                  h->d_public_idx, h->d_flush, h->d_zT, h->d_sym_items, h->d_trace, h->d_nbr_xy[0], h->d_nbr_xy[1]};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -1304,7 +1317,7 @@ int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, i
 }
 
 int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance) {
-  CHECK_ARG(h != nullptr && variant >= -1 && variant <= 2 && prefetch_distance >= 0);
+  CHECK_ARG(h != nullptr && variant >= -1 && variant <= 3 && prefetch_distance >= 0);
   h->qx_variant = variant;
   h->qx_prefetch_dist = prefetch_distance;
   return DPGO_OK;

@@ -64,6 +64,7 @@ struct dpgo_dev {
   int *d_crowptr = nullptr, *d_ccolidx = nullptr;
   double *d_cblocks = nullptr;
   double *d_Gconst = nullptr, *d_G = nullptr, *d_nbr = nullptr;
+  double *d_nbr_xy[2] = {nullptr, nullptr};   // dpgo_neighbor_buffer: neighbours' X / auxiliary Y (exchange.cu)
 
   // dense preconditioner
   double *d_Pinv = nullptr, *d_zpart = nullptr;

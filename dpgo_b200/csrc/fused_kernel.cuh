@@ -116,6 +116,21 @@ struct GridReducer {
       } while ((int)(v - epoch) < 0);
     }
     __syncthreads();
+#elif DPGO_GRID_BARRIER == 2
+    // same counter, fences outside the spin: fence -> relaxed arrive -> relaxed polls -> fence
+    (void)grid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      epoch += gridDim.x;
+      __threadfence();
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+      unsigned v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      } while ((int)(v - epoch) < 0);
+      __threadfence();
+    }
+    __syncthreads();
 #else
 #ifdef DPGO_BARRIER_PRESYNC
     __syncthreads();
@@ -125,7 +140,7 @@ struct GridReducer {
   }
   // after the last barrier of the kernel: the CTA that arrives last puts the counter back to zero
   __device__ __forceinline__ void exit_kernel() {
-#if DPGO_GRID_BARRIER == 1
+#if DPGO_GRID_BARRIER >= 1
     if (threadIdx.x == 0) {
       const unsigned old = atomicAdd(bar, 1u);
       if (old + 1u == epoch + gridDim.x) atomicExch(bar, 0u);

@@ -201,6 +201,74 @@ __device__ __forceinline__ void spmm_col(const BsrView &Q, const double *X, int 
   }
 }
 
+// Same sum in the same order (bit-identical), two blocks per step: the loads of blocks e and e + 1 (Q rows and
+// X tiles) are all issued before the first FMA, and the column indices of the next step are fetched during
+// the current one, so a step costs one memory latency instead of the dependent chain colidx -> X tile, and a
+// lane group keeps two blocks' loads in flight.  Used where the row walk is latency bound: Q*X streaming from
+// HBM (stand-alone kernel at scale) -- more registers than spmm_col (two tiles live).
+template <int R, int D>
+__device__ __forceinline__ void spmm_col2(const BsrView &Q, const double *X, int i, int c, double (&acc)[R]) {
+  constexpr int DH = D + 1, TILE = R * DH;
+  const int e0 = __ldg(Q.rowptr + i), e1 = __ldg(Q.rowptr + i + 1);
+  auto load_m = [&](int e, double (&mk)[DH]) {
+    const double *m = Q.blocks + (size_t)e * (DH * DH) + c * DH;
+    if constexpr (DH % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < DH / 2; ++k) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
+        mk[2 * k] = v.x;
+        mk[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
+    }
+  };
+  auto load_x = [&](int j, double (&x)[TILE]) {
+    const double *xj = X + (size_t)j * TILE;
+    if constexpr (TILE % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < TILE / 2; ++k) {
+        const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) x[k] = xj[k];
+    }
+  };
+  auto fmas = [&](const double (&x)[TILE], const double (&mk)[DH]) {
+#pragma unroll
+    for (int k = 0; k < DH; ++k) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = fma(x[k * R + q], mk[k], acc[q]);
+    }
+  };
+  int e = e0;
+  int ja = (e < e1) ? __ldg(Q.colidx + e) : 0;
+  int jb = (e + 1 < e1) ? __ldg(Q.colidx + e + 1) : 0;
+  while (e + 1 < e1) {
+    const int j0 = ja, j1 = jb;
+    ja = (e + 2 < e1) ? __ldg(Q.colidx + e + 2) : 0;
+    jb = (e + 3 < e1) ? __ldg(Q.colidx + e + 3) : 0;
+    double m0[DH], m1[DH], x0[TILE], x1[TILE];
+    load_m(e, m0);
+    load_m(e + 1, m1);
+    load_x(j0, x0);
+    load_x(j1, x1);
+    fmas(x0, m0);
+    fmas(x1, m1);
+    e += 2;
+  }
+  if (e < e1) {
+    double m0[DH], x0[TILE];
+    load_m(e, m0);
+    load_x(ja, x0);
+    fmas(x0, m0);
+  }
+}
+
 // Stiefel tangent projection of one pose, column-distributed over the lane group:
 //   w_Y <- w_Y - Y sym(Y^T w_Y), translation column untouched.
 // Every lane of the warp must call this (shuffles); `valid` guards memory access only.
@@ -246,8 +314,8 @@ __device__ __forceinline__ void group_tangent(const double *Ytile, double (&w)[R
 // ---------------------------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------------------------
-// out = X * Q (+ G if G != nullptr)
-template <int R, int D>
+// out = X * Q (+ G if G != nullptr).  PIPE: walk the block row two blocks per step (spmm_col2, same bits)
+template <int R, int D, bool PIPE = false>
 __device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const double *X,
                                          const double *G, double *out, int n) {
   using Gm = Geo<R, D>;
@@ -262,7 +330,8 @@ __device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const
 #pragma unroll
         for (int q = 0; q < R; ++q) acc[q] = 0.0;
       }
-      spmm_col<R, D>(Q, X, i, lp.c, acc);
+      if constexpr (PIPE) spmm_col2<R, D>(Q, X, i, lp.c, acc);
+      else spmm_col<R, D>(Q, X, i, lp.c, acc);
       store_col<R>(out + off, acc);
     }
   }

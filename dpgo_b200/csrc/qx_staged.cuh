@@ -22,6 +22,8 @@ namespace dpgo {
 
 constexpr int kQxDepth = 2;              // steps in flight ahead of the computed one
 constexpr int kQxBufs = kQxDepth + 1;
+constexpr int kQxIdxAhead = 2;           // steps whose column indices are loaded ahead of their copies
+constexpr int kQxWindow = kQxDepth + 1 + kQxIdxAhead;
 
 template <int R, int D>
 struct QxGeo {
@@ -134,10 +136,10 @@ __device__ __forceinline__ void phase_qx_staged(const BsrView &Q, const double *
   };
 
   // ---- pipeline: steps t+1 .. t+kQxDepth are in flight while step t is computed; the column indices of
-  // step t+kQxDepth+1 are being loaded
-  QxStep st[kQxDepth + 2];
+  // steps up to t+kQxDepth+kQxIdxAhead are being loaded
+  QxStep st[kQxWindow];
 #pragma unroll
-  for (int i = 0; i < kQxDepth + 2; ++i) st[i] = generate();
+  for (int i = 0; i < kQxWindow; ++i) st[i] = generate();
 #pragma unroll
   for (int i = 0; i <= kQxDepth; ++i) issue(st[i], i);    // steps 0 .. kQxDepth (uses their indices)
   double acc[R];
@@ -206,8 +208,8 @@ __device__ __forceinline__ void phase_qx_staged(const BsrView &Q, const double *
     __syncwarp();                                         // every lane has read buffer `buf`: it may be refilled
     // shift the window, start the copies of the step that enters it
 #pragma unroll
-    for (int i = 0; i < kQxDepth + 1; ++i) st[i] = st[i + 1];
-    st[kQxDepth + 1] = generate();
+    for (int i = 0; i < kQxWindow - 1; ++i) st[i] = st[i + 1];
+    st[kQxWindow - 1] = generate();
     issue(st[kQxDepth], buf);                             // step t + kQxDepth + 1 reuses the buffer just read
     buf = (buf + 1 == kQxBufs) ? 0 : buf + 1;
   }

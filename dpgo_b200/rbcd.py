@@ -104,6 +104,8 @@ class DeviceAgent:
         self.nbr = torch.zeros(nslots * tile, dtype=torch.float64, device=dev)       # neighbours' X
         self.nbr_aux = torch.zeros(nslots * tile, dtype=torch.float64, device=dev)   # neighbours' Y
         self.tile = tile
+        # native exchange (dpgo_exchange): neighbour poses live in the handle's own buffers
+        self.native = False
         self.iteration = 0
         self.gamma = self.alpha = 0.0
         self.last_result = None
@@ -150,8 +152,11 @@ class DeviceAgent:
             if acceleration:
                 self.prob.slot_copy(SLOT_X, SLOT_Y)
             return
-        buf = self.nbr_aux if acceleration else self.nbr
-        self.prob.set_neighbor_poses_dev(buf.data_ptr())   # setNeighborPoses + constructG on device
+        if self.native:
+            self.prob.use_neighbor_poses(1 if acceleration else 0)   # setNeighborPoses + constructG on device
+        else:
+            buf = self.nbr_aux if acceleration else self.nbr
+            self.prob.set_neighbor_poses_dev(buf.data_ptr())
         src = SLOT_Y if acceleration else SLOT_X
         if self.async_solve:
             self.prob.optimize_slot_async(src, self.params)
@@ -171,7 +176,8 @@ class DeviceAgent:
         residual of every loop closure at X and the neighbours' X by one device pass
         (dpgo_measurement_errors), new weights for the edges whose weight is not fixed, GNC
         schedule step, Q and preconditioner rebuilt on the device, acceleration restarted."""
-        ep, es = self.prob.measurement_errors(SLOT_X, self.nbr.data_ptr())
+        ep, es = self.prob.measurement_errors(SLOT_X, self.prob.neighbor_buffer(0) if self.native
+                                              else self.nbr.data_ptr())
         wp = np.where(self.spec.priv_fixed, self.w_private, robust.weights(np.sqrt(ep)))
         ws = np.where(self.spec.shared_fixed, self.w_shared, robust.weights(np.sqrt(es)))
         self.w_private, self.w_shared = wp, ws
@@ -232,6 +238,84 @@ def exchange_poses(agents, specs, owner, rank, active, acceleration):
             req.wait()
 
 
+class NativeExchange:
+    """The public-pose exchange inside the C-ABI (dpgo_exchange, csrc/exchange.cu): per round one call that packs
+    on the device, moves the cross-rank messages with one NCCL group on the rank's stream and gathers the
+    same-device ones straight into the receiver's buffer.  The message list of an active set is built once.
+    The communicator is the library's own (ncclCommInitRank from an id rank 0 creates and torch.distributed
+    only broadcasts)."""
+
+    def __init__(self, team, device, stream):
+        import ctypes as C
+        from ._lib import COMM, COMM_ID_BYTES, check, lib
+        self.team, self._plans = team, {}
+        ident = None
+        if team.world > 1:
+            import torch.distributed as dist
+            box = [None]
+            if team.rank == 0:
+                buf = C.create_string_buffer(COMM_ID_BYTES)
+                check(lib.dpgo_comm_unique_id(buf))
+                box[0] = buf.raw
+            dist.broadcast_object_list(box, src=0)
+            ident = box[0]
+        self._comm = COMM()
+        check(lib.dpgo_comm_create(int(device), team.rank, team.world, ident, C.c_void_p(stream) if stream else None,
+                                   C.byref(self._comm)))
+        for ag in team.agents.values():
+            ag.native = True
+            ag.prob.neighbor_buffer(0)
+            ag.prob.neighbor_buffer(1)
+
+    def plan(self, active):
+        from ._lib import Message
+        key = (tuple(active), self.team.acceleration)
+        if key in self._plans:
+            return self._plans[key]
+        t = self.team
+        msgs = []
+        for a in active:
+            for b in t.specs[a].neighbors:
+                src = t.agents[b] if t.owner[b] == t.rank else None
+                dst = t.agents[a] if t.owner[a] == t.rank else None
+                if src is None and dst is None:
+                    continue
+                lo, hi = t.specs[a].nbr_range[b]
+                for aux in ((0, 1) if t.acceleration else (0,)):
+                    m = Message()
+                    m.src = src.prob._h.value if src is not None else None
+                    m.dst = dst.prob._h.value if dst is not None else None
+                    m.peer = t.owner[a] if dst is None else t.owner[b]
+                    m.slot = SLOT_Y if aux else SLOT_X
+                    m.aux = aux
+                    m.count = hi - lo
+                    m.d_frames = src.send_idx[a].data_ptr() if src is not None else None
+                    m.dst_offset = lo
+                    msgs.append(m)
+        arr = (Message * max(len(msgs), 1))(*msgs)
+        self._plans[key] = (arr, len(msgs))
+        return self._plans[key]
+
+    def exchange(self, active):
+        from ._lib import check, lib
+        arr, n = self.plan(active)
+        if n:
+            check(lib.dpgo_exchange(self._comm, arr, n))
+
+    def launch_count(self):
+        import ctypes as C
+        from ._lib import check, lib
+        v = C.c_int64()
+        check(lib.dpgo_comm_launch_count(self._comm, C.byref(v)))
+        return v.value
+
+    def close(self):
+        from ._lib import lib
+        if self._comm:
+            lib.dpgo_comm_destroy(self._comm)
+            self._comm = None
+
+
 def block_owner(num_robots, world):
     """Block distribution of agents over ranks (keeps both colours of a chain on every rank)."""
     per_rank = (num_robots + world - 1) // world
@@ -251,7 +335,7 @@ class DeviceTeam:
     (block distribution: agent a lives on rank a // (A / world))."""
 
     def __init__(self, p1, p2, R, t, kappa, tau, n, d, r, num_robots, device=0, stream=None,
-                 rank=0, world=1, acceleration=True, params=None, restart_interval=30):
+                 rank=0, world=1, acceleration=True, params=None, restart_interval=30, native_exchange=False):
         self.d, self.r, self.n, self.A = d, r, n, num_robots
         self.rank, self.world = rank, world
         self.acceleration = acceleration
@@ -272,6 +356,9 @@ class DeviceTeam:
                 # what b needs from a = the frames of a listed in b's neighbour slots for robot a
                 ag.prepare_send(b, self.specs[b].nbr_frames[a])
         self.round = 0
+        # native_exchange: pack / NCCL send-recv / gather inside the C-ABI on the rank's stream (GPU runs);
+        # otherwise torch.distributed P2P ops issued from here (also what the gloo CPU tests drive)
+        self.native = NativeExchange(self, device, stream) if native_exchange else None
 
     def set_async(self, on):
         """Stream-ordered rounds: no host wait inside a round (see DeviceAgent.async_solve)."""
@@ -286,7 +373,10 @@ class DeviceTeam:
 
     # -- public-pose exchange towards the agents in `active` (ref: MultiRobotExample.cpp:183-204)
     def exchange(self, active):
-        exchange_poses(self.agents, self.specs, self.owner, self.rank, active, self.acceleration)
+        if self.native is not None:
+            self.native.exchange(active)
+        else:
+            exchange_poses(self.agents, self.specs, self.owner, self.rank, active, self.acceleration)
 
     def step_colored(self):
         """One round of the coloured parallel schedule: the agents of the current colour optimize,
@@ -367,5 +457,7 @@ class DeviceTeam:
         return X
 
     def close(self):
+        if self.native is not None:
+            self.native.close()
         for ag in self.agents.values():
             ag.prob.close()

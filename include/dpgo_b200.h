@@ -244,6 +244,40 @@ int dpgo_pack_public_dev(dpgo_handle h, int slot, double *tiles_dev);
  * ref: src/PGOAgent.cpp:112-130) straight into the NCCL send buffer. */
 int dpgo_gather_tiles_dev(dpgo_handle h, int slot, int num, const int32_t *idx_dev,
                           double *tiles_dev);
+/* ---- public-pose exchange between agents, inside the library ------------------------------------
+ * What PGOAgent::getSharedPoseDict / getAuxSharedPoseDict hand out (ref: src/PGOAgent.cpp:97-146) and
+ * updateNeighborPoses / updateAuxNeighborPoses take in (:650-702), as the reference's driver moves them
+ * every iteration (examples/MultiRobotExample.cpp:183-204): packed device tiles, NCCL send/recv between
+ * ranks (one process per GPU), gathered straight into the receiver's buffer when both agents share a
+ * device.  A communicator is bound to one device + stream; all handles it serves use that stream, so a
+ * round (solve -> pack -> send/recv -> G -> solve) is ordered by the stream alone. */
+typedef struct dpgo_comm_s *dpgo_comm;
+#define DPGO_COMM_ID_BYTES 128
+int dpgo_comm_unique_id(unsigned char *id);                       /* rank 0 creates it, every rank gets a copy */
+int dpgo_comm_create(int device, int rank, int world, const unsigned char *id, void *stream, dpgo_comm *out);
+int dpgo_comm_destroy(dpgo_comm c);
+int dpgo_comm_launch_count(dpgo_comm c, int64_t *n);              /* kernels + NCCL groups queued so far */
+/* Neighbour pose buffers owned by the handle (num_nbr_slots tiles): aux = 0 the neighbours' X
+ * (neighborPoseDict), aux = 1 their auxiliary Y (neighborAuxPoseDict). */
+int dpgo_neighbor_buffer(dpgo_handle h, int aux, double **dev_ptr);
+/* G from one of them: setNeighborPoses + constructG (ref: src/PoseGraph.cpp:183-186, :493-580). */
+int dpgo_use_neighbor_poses(dpgo_handle h, int aux);
+/* One message: the `count` tiles of slot `slot` of agent `src` listed in the device array d_frames go to
+ * neighbour slots [dst_offset, dst_offset + count) of agent `dst` (buffer `aux`).  src == NULL: the sender
+ * lives on rank `peer` (receive); dst == NULL: the receiver lives on rank `peer` (send).  Both sides list
+ * the messages between a pair of ranks in the same order. */
+typedef struct dpgo_message {
+  dpgo_handle src;
+  dpgo_handle dst;
+  int peer;
+  int slot;
+  int aux;
+  int count;
+  const int32_t *d_frames;
+  int dst_offset;
+} dpgo_message;
+int dpgo_exchange(dpgo_comm c, const dpgo_message *msgs, int n);
+
 /* Squared residual of every measurement of this agent at the poses in `slot`:
  *   err = kappa |Y1 R~ - Y2|_F^2 + tau |p2 - p1 - Y1 t~|^2
  * (ref: computeMeasurementError, src/DPGO_utils.cpp:501-507; PGOAgent::computeMeasurementResidual,

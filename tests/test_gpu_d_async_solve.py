@@ -62,3 +62,46 @@ def test_stream_ordered_rounds_equal_blocking_rounds(datasets, acceleration):
     for a in out[False][1]:
         assert out[True][1][a]["f_opt"] == out[False][1][a]["f_opt"]
         assert out[True][1][a]["inner_iters"] == out[False][1][a]["inner_iters"]
+
+
+@pytest.mark.parametrize("schedule", ["colored", "all"])
+def test_native_exchange_equals_python_exchange(datasets, schedule):
+    """dpgo_exchange (pack / gather inside the C-ABI, csrc/exchange.cu) against the exchange issued from Python
+    (the path the oracle-parity tests of the team use): identical poses after rounds that cross the Nesterov
+    restart, on one device (same-device messages; the NCCL messages are covered by tests/gpu_native_exchange_2gpu.py
+    under torchrun)."""
+    from dpgo_b200 import rbcd
+    meas, n, z = datasets("smallGrid3D")
+    d, r, A = meas.d, 5, 5
+    X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
+    out = {}
+    for native in (False, True):
+        team = rbcd.DeviceTeam(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r, A,
+                               acceleration=(schedule == "colored"), native_exchange=native)
+        team.set_async(True)
+        team.set_X(X0)
+        for _ in range(33 if schedule == "colored" else 6):
+            (team.step_colored if schedule == "colored" else team.step_all)()
+        out[native] = team.assemble()
+        if native:
+            assert team.native.launch_count() > 0
+        team.close()
+    assert np.array_equal(out[True], out[False])
+
+
+def test_native_exchange_across_ranks():
+    """Two ranks, two GPUs (skipped on a one-GPU box): the NCCL messages of dpgo_exchange give the same poses as
+    one rank holding all agents."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(root, "tests", "gpu_native_exchange_2gpu.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "native exchange ok" in out.stdout

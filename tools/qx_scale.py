@@ -37,13 +37,13 @@ def main():
         rec = dict(L=L, n=g["n"], m=len(g["p1"]), bytes=nbytes, gen_s=tg, build_s=tb, peak_gbs=peak, variants=[])
         ref = None
         # 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch (distance 4096), 2 = shared-memory staged
-        # kernel (qx_staged.cuh; the automatic choice at this size)
-        for variant, dist in ((0, 0), (1, 4096), (2, 0)):
+        # kernel (qx_staged.cuh), 3 = lane-group kernel, two blocks per step with the column indices one step ahead
+        for variant, dist in ((0, 0), (1, 4096), (2, 0), (3, 0)):
             gp.set_qx_variant(variant, dist)
-            out = gp.qx(Xh)
+            prod = gp.qx(Xh)
             if ref is None:
-                ref = out
-            err = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
+                ref = prod
+            err = float(np.linalg.norm(prod - ref) / np.linalg.norm(ref))
             w1, c1 = gp.time_qx(20, False), gp.time_qx(10, True)
             rec["variants"].append(dict(variant=variant, distance=dist, rel_diff_vs_variant0=err,
                                         back_to_back_us=w1, back_to_back_gbs=nbytes / w1 / 1e3, flushed_us=c1,
