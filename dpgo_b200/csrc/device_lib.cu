@@ -16,7 +16,6 @@
 #include "device_state.h"
 #include "dissect.h"
 #include "kernels.cuh"
-#include "qx_staged.cuh"
 #include "rtr_logic.h"
 
 namespace dpgo {
@@ -88,15 +87,6 @@ template <int R, int D>
 __global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const double *X, const double *G,
                                                         double *out, int n, int dist) {
   phase_qx_prefetch<R, D>(make_ctx(), Q, X, G, out, n, dist);
-}
-
-// Q*X with shared-memory staging (qx_staged.cuh): persistent, one block row per warp, 3 CTAs per SM
-template <int R, int D>
-__global__ void __launch_bounds__(kBlock, 3) k_qx_staged(BsrView Q, const double *X, const double *G,
-                                                         double *out, int n) {
-  extern __shared__ __align__(128) unsigned char qx_dsm[];
-  phase_qx_staged<R, D>(Q, X, G, out, n, qx_dsm, (int)(blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)),
-                        (int)(gridDim.x * kWarpsPerBlock));
 }
 
 template <int R, int D>
@@ -444,42 +434,8 @@ static int qx_prefetch_distance(dpgo_dev *h) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_qx_prefetch<R, D>, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
   return h->num_sms * occ * kWarpsPerBlock * (32 / (D + 1));
 }
-template <int R, int D>
-static int launch_qx_staged(dpgo_dev *h, const double *X, const double *G, double *out) {
-  constexpr int smem = QxGeo<R, D>::CTA_BYTES;
-  static int occ_by_device[64];
-  if (h->device < 0 || h->device >= 64) {
-    set_error("device ordinal %d not supported by the staged Q*X", h->device);
-    return DPGO_EINVAL;
-  }
-  int &occ = occ_by_device[h->device];
-  if (occ <= 0) {
-    int o = 0;
-    if (cudaFuncSetAttribute(k_qx_staged<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_qx_staged<R, D>, kBlock, smem) != cudaSuccess || o < 1) {
-      set_error("staged Q*X kernel does not fit on the device");
-      return DPGO_ECUDA;
-    }
-    occ = o;
-  }
-  // persistent: every resident warp takes rows warp, warp + W, ... ; never more CTAs than rows / 8
-  const long want = ((long)h->n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int grid = (int)std::max(1L, std::min(want, (long)h->num_sms * occ));
-  k_qx_staged<R, D><<<grid, kBlock, smem, h->stream>>>(qview(h), X, G, out, h->n);
-  return DPGO_OK;
-}
-
-// rows from which the stand-alone Q*X streams from HBM and the staged kernel is the default
-// (qx_variant -1 = automatic): Q + X beyond the L2
-static const int kAutoStagedQxMinPoses = 100000;
-
 int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
-  const int variant = h->qx_variant >= 0 ? h->qx_variant : (h->n >= kAutoStagedQxMinPoses ? 2 : 0);
-  if (variant == 2) {
-    DPGO_DISPATCH(h, DPGO_TRY((launch_qx_staged<R, D>(h, X, G, out))));
-    LAUNCH_CHECK(h);
-    return DPGO_OK;
-  }
+  const int variant = h->qx_variant > 0 ? h->qx_variant : 0;
   if (variant == 0) return op_qx(h, qview(h), X, G, out);
   if (variant == 3) {
     const int grid = pose_grid(h, h->d + 1);
@@ -1317,7 +1273,7 @@ int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, i
 }
 
 int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance) {
-  CHECK_ARG(h != nullptr && variant >= -1 && variant <= 3 && prefetch_distance >= 0);
+  CHECK_ARG(h != nullptr && (variant == -1 || variant == 0 || variant == 1 || variant == 3) && prefetch_distance >= 0);
   h->qx_variant = variant;
   h->qx_prefetch_dist = prefetch_distance;
   return DPGO_OK;

@@ -99,8 +99,8 @@ struct dpgo_dev {
   void *dd = nullptr;           // dpgo::DdState (precon_mode >= 2)
   int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
   int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
-  // stand-alone Q*X (dpgo_set_qx_variant): -1 = automatic (staged kernel when Q and X stream from HBM),
-  // 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch, 2 = shared-memory staged kernel
+  // stand-alone Q*X (dpgo_set_qx_variant; measurement variants): -1 / 0 = lane-group kernel (default),
+  // 1 = + L2 prefetch hints, 3 = two blocks per step
   int qx_variant = -1, qx_prefetch_dist = 0;
   int dd_max_domain = 0;              // poses per interior domain (0 = one wave of strip stages)
   int *d_public_idx = nullptr;

@@ -39,7 +39,6 @@ struct FusedParams {
   double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
   double *partials;  // [2][gridDim.x][4]
   FusedOut *out;
-  unsigned *barrier_counter;   // grid barrier arrival counter (zero between launches)
   unsigned long long *trace;   // -DDPGO_TRACE builds: [gridDim.x][16] ns each CTA worked in a phase before its barrier
   double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
   int max_outer, max_inner;
@@ -83,69 +82,20 @@ struct PhaseClock {
   }
 };
 
-// Grid-wide barrier of the persistent solver.  DPGO_GRID_BARRIER == 1 (default): one monotonic arrival counter in
-// global memory -- thread 0 of every CTA arrives with red.release.gpu and spins on ld.acquire.gpu until the
-// counter reaches gridDim.x * (number of barriers so far); the CTA barriers on either side order the other
-// threads, the acquire invalidates the SM's L1 so the plain loads of the next phase see the other CTAs' writes.
-// The last CTA to leave the kernel resets the counter (grid_barrier_exit), so launches need no memset.
-// DPGO_GRID_BARRIER == 0: cooperative-groups grid.sync() (the round-1 form; also what the CPU emulation uses).
-#ifndef DPGO_GRID_BARRIER
-#define DPGO_GRID_BARRIER 1
-#endif
-#if defined(DPGO_CPU_EMU)
-#undef DPGO_GRID_BARRIER
-#define DPGO_GRID_BARRIER 0
-#endif
-
+// Grid-wide barrier of the persistent solver: cooperative-groups grid.sync() behind a CTA barrier.  Measured on
+// B200 (sphere2500, 302 barriers per solve, two A/B runs each on one box, profiles/r02_barrier_ab.json):
+//   grid.sync() alone                                   1.993 ms per solve
+//   __syncthreads(); grid.sync()                        1.423 ms   <- this form (1.9 us less per barrier)
+//   own counter, red.release.gpu + ld.acquire.gpu spin  1.51  ms
+//   own counter, fence + relaxed add / polls + fence    1.63  ms
+// The hand-rolled counters lost and are gone.
 struct GridReducer {
   double *buf[2];
   int flip;
   int barriers;
-  unsigned *bar;      // arrival counter (zero between launches)
-  unsigned epoch;     // arrivals that complete the current barrier
   __device__ __forceinline__ void sync(cg::grid_group &grid) {
-#if DPGO_GRID_BARRIER == 1
-    (void)grid;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      epoch += gridDim.x;
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-      unsigned v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      } while ((int)(v - epoch) < 0);
-    }
-    __syncthreads();
-#elif DPGO_GRID_BARRIER == 2
-    // same counter, fences outside the spin: fence -> relaxed arrive -> relaxed polls -> fence
-    (void)grid;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      epoch += gridDim.x;
-      __threadfence();
-      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-      unsigned v;
-      do {
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      } while ((int)(v - epoch) < 0);
-      __threadfence();
-    }
-    __syncthreads();
-#else
-#ifdef DPGO_BARRIER_PRESYNC
-    __syncthreads();
-#endif
     grid.sync();
-#endif
-  }
-  // after the last barrier of the kernel: the CTA that arrives last puts the counter back to zero
-  __device__ __forceinline__ void exit_kernel() {
-#if DPGO_GRID_BARRIER >= 1
-    if (threadIdx.x == 0) {
-      const unsigned old = atomicAdd(bar, 1u);
-      if (old + 1u == epoch + gridDim.x) atomicExch(bar, 0u);
-    }
-#endif
   }
 #ifdef DPGO_TRACE
   unsigned long long t_rel, pending;   // thread 0: release time of the last barrier, own work before this one
@@ -196,8 +146,6 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   red.buf[1] = p.partials + (size_t)gridDim.x * 4;
   red.flip = 0;
   red.barriers = 0;
-  red.bar = p.barrier_counter;
-  red.epoch = 0;
 
   double *x1 = p.xa, *x2 = p.xb, *EG = p.EG, *EG2 = p.EG2, *grad = p.grad, *grad2 = p.grad2;
   double *S = p.S, *S2 = p.S2;
@@ -466,7 +414,6 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   }
 
   phase_copy(ctx, x1, p.x_out, len);
-  red.exit_kernel();
 #ifdef DPGO_TRACE
   if (threadIdx.x == 0 && p.trace) {
 #pragma unroll

@@ -82,9 +82,7 @@ static int launch_fused(dpgo_dev *h, FusedParams &fp) {
 // are queued on the handle's stream; nothing waits.  solve_fused_collect() is the other half.
 int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_in, double *x_out) {
   if (!h->d_fused) {
-    // result block, followed (at a 128-byte offset) by the arrival counter of the grid barrier
-    if (cudaMalloc(&h->d_fused, sizeof(FusedOut) + 256) != cudaSuccess ||
-        cudaMemset(h->d_fused, 0, sizeof(FusedOut) + 256) != cudaSuccess ||
+    if (cudaMalloc(&h->d_fused, sizeof(FusedOut)) != cudaSuccess ||
         cudaMallocHost(&h->h_fused, sizeof(FusedOut)) != cudaSuccess) {
       set_error("allocation of the fused result block failed");
       return DPGO_ECUDA;
@@ -106,7 +104,6 @@ int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_i
   fp.eta = h->d_eta; fp.r = h->d_r; fp.z = h->d_z; fp.delta = h->d_delta; fp.Hd = h->d_Hd;
   fp.partials = h->d_partials;
   fp.out = (FusedOut *)h->d_fused;
-  fp.barrier_counter = (unsigned *)((char *)h->d_fused + ((sizeof(FusedOut) + 127) / 128) * 128);
   fp.trace = nullptr;
 #ifdef DPGO_TRACE
   if (!h->d_trace) {

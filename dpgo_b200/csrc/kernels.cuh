@@ -158,6 +158,61 @@ __device__ __forceinline__ double dot_col(const double (&a)[R], const double (&b
   return s;
 }
 
+// 256-bit global loads (sm_100: SASS LDG.E.256): one instruction per 32-byte sector.  The lane-group SpMM is bound
+// by L1 sector traffic when it streams from HBM (ncu: L1/TEX throughput 78 %, 15.5 of 32 bytes used per sector with
+// 128-bit loads: every sector of a Q row or of an X tile was requested twice); with whole sectors per instruction the
+// sectors per block drop from ~22 to ~12.  `p` must be 32-byte aligned.
+#ifndef DPGO_CPU_EMU
+__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) {       // coherent (data written by other CTAs)
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld256_nc(const double *p, double (&v)[4]) {    // read-only path (Q blocks)
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+#else
+inline void ld256(const double *p, double (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = p[k]; }
+inline void ld256_nc(const double *p, double (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = p[k]; }
+#endif
+
+// row c of block e of Q (DH doubles) and the pose tile j of X (TILE doubles), widest loads the shape allows
+template <int DH>
+__device__ __forceinline__ void load_q_row(const double *m, double (&mk)[DH]) {
+  if constexpr (DH == 4) {                // 32-byte row: one 256-bit read-only load
+    ld256_nc(m, mk);
+  } else if constexpr (DH % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < DH / 2; ++k) {
+      const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
+      mk[2 * k] = v.x;
+      mk[2 * k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
+  }
+}
+template <int TILE>
+__device__ __forceinline__ void load_x_tile(const double *xj, double (&x)[TILE]) {
+  if constexpr (TILE % 4 == 0) {          // whole 32-byte sectors (d = 3: the tile is r sectors)
+#pragma unroll
+    for (int k = 0; k < TILE / 4; ++k) {
+      double v[4];
+      ld256(xj + 4 * k, v);
+      x[4 * k] = v[0]; x[4 * k + 1] = v[1]; x[4 * k + 2] = v[2]; x[4 * k + 3] = v[3];
+    }
+  } else if constexpr (TILE % 2 == 0) {   // 16-byte aligned tile: 128-bit loads
+#pragma unroll
+    for (int k = 0; k < TILE / 2; ++k) {
+      const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
+      x[2 * k] = v.x;
+      x[2 * k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TILE; ++k) x[k] = xj[k];
+  }
+}
+
 // One column (c) of (X * Q) for pose i: sum over the block row of Q.
 //   out[:, (i,c)] = sum_j sum_k X_j[:, k] * Q_ij[c][k]        (Q symmetric)
 // X tiles are gathered with plain (coherent) loads; Q blocks / indices through the read-only path.
@@ -171,28 +226,8 @@ __device__ __forceinline__ void spmm_col(const BsrView &Q, const double *X, int 
     const double *m = Q.blocks + (size_t)e * (DH * DH) + c * DH;
     const double *xj = X + (size_t)j * TILE;
     double mk[DH], x[TILE];
-    if constexpr (DH % 2 == 0) {  // row c of the block is 16-byte aligned: 128-bit read-only loads
-#pragma unroll
-      for (int k = 0; k < DH / 2; ++k) {
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
-        mk[2 * k] = v.x;
-        mk[2 * k + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
-    }
-    if constexpr (TILE % 2 == 0) {  // pose tile is 16-byte aligned: gather it with 128-bit loads
-#pragma unroll
-      for (int k = 0; k < TILE / 2; ++k) {
-        const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
-        x[2 * k] = v.x;
-        x[2 * k + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < TILE; ++k) x[k] = xj[k];
-    }
+    load_q_row<DH>(m, mk);
+    load_x_tile<TILE>(xj, x);
 #pragma unroll
     for (int k = 0; k < DH; ++k) {
 #pragma unroll
@@ -210,34 +245,8 @@ template <int R, int D>
 __device__ __forceinline__ void spmm_col2(const BsrView &Q, const double *X, int i, int c, double (&acc)[R]) {
   constexpr int DH = D + 1, TILE = R * DH;
   const int e0 = __ldg(Q.rowptr + i), e1 = __ldg(Q.rowptr + i + 1);
-  auto load_m = [&](int e, double (&mk)[DH]) {
-    const double *m = Q.blocks + (size_t)e * (DH * DH) + c * DH;
-    if constexpr (DH % 2 == 0) {
-#pragma unroll
-      for (int k = 0; k < DH / 2; ++k) {
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
-        mk[2 * k] = v.x;
-        mk[2 * k + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < DH; ++k) mk[k] = __ldg(m + k);
-    }
-  };
-  auto load_x = [&](int j, double (&x)[TILE]) {
-    const double *xj = X + (size_t)j * TILE;
-    if constexpr (TILE % 2 == 0) {
-#pragma unroll
-      for (int k = 0; k < TILE / 2; ++k) {
-        const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
-        x[2 * k] = v.x;
-        x[2 * k + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < TILE; ++k) x[k] = xj[k];
-    }
-  };
+  auto load_m = [&](int e, double (&mk)[DH]) { load_q_row<DH>(Q.blocks + (size_t)e * (DH * DH) + c * DH, mk); };
+  auto load_x = [&](int j, double (&x)[TILE]) { load_x_tile<TILE>(X + (size_t)j * TILE, x); };
   auto fmas = [&](const double (&x)[TILE], const double (&mk)[DH]) {
 #pragma unroll
     for (int k = 0; k < DH; ++k) {

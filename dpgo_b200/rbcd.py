@@ -142,6 +142,15 @@ class DeviceAgent:
         if self.acceleration:
             self.prob.gather_tiles_dev(SLOT_Y, idx.numel(), idx.data_ptr(), self.send_buf_aux[b].data_ptr())
 
+    def host_buffer(self, key, numel):
+        """Pinned host staging buffer of the host-staged exchange (allocated at first use)."""
+        import torch
+        if not hasattr(self, "_host"):
+            self._host = {}
+        if key not in self._host:
+            self._host[key] = torch.empty(numel, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+        return self._host[key]
+
     def recv_view(self, b, aux):
         lo, hi = self.spec.nbr_range[b]
         buf = self.nbr_aux if aux else self.nbr
@@ -236,6 +245,53 @@ def exchange_poses(agents, specs, owner, rank, active, acceleration):
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+def exchange_poses_host(agents, specs, owner, rank, active, acceleration, group=None, stats=None):
+    """The exchange as a deployment of the reference performs it (one process per robot, public poses as
+    messages between processes): the poses leave the sender's device into pinned host memory (D2H), travel
+    between ranks as HOST buffers (torch.distributed on CPU tensors: gloo), and enter the receiver's device
+    from pinned host memory (H2D).  Same walk over (active agent, neighbour) pairs as exchange_poses.
+    stats (dict) accumulates the bytes copied each way."""
+    import torch
+    import torch.distributed as dist
+    auxes = (False, True) if acceleration else (False,)
+    staged = []                                        # (a, b, aux, host tensor) of the messages this rank holds
+    for a in active:
+        for b in specs[a].neighbors:
+            if owner[b] != rank:
+                continue
+            agents[b].pack_for(a)
+            for aux in auxes:
+                src = agents[b].send_buf_aux[a] if aux else agents[b].send_buf[a]
+                host = agents[b].host_buffer(("send", a, aux), src.numel())
+                host.copy_(src, non_blocking=True)
+                staged.append((a, b, aux, host))
+                if stats is not None:
+                    stats["d2h"] = stats.get("d2h", 0) + host.numel() * 8
+    if staged and staged[0][3].is_pinned():
+        torch.cuda.current_stream().synchronize()      # the host buffers are complete
+    ops, arrived = [], []
+    for a in active:
+        for b in specs[a].neighbors:
+            ob, oa = owner[b], owner[a]
+            for aux in auxes:
+                if ob == rank and oa == rank:
+                    arrived.append((a, b, aux, agents[b].host_buffer(("send", a, aux), 0)))
+                elif ob == rank:
+                    ops.append(dist.P2POp(dist.isend, agents[b].host_buffer(("send", a, aux), 0), oa, group))
+                elif oa == rank:
+                    lo, hi = specs[a].nbr_range[b]
+                    host = agents[a].host_buffer(("recv", b, aux), (hi - lo) * agents[a].tile)
+                    ops.append(dist.P2POp(dist.irecv, host, ob, group))
+                    arrived.append((a, b, aux, host))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for a, b, aux, host in arrived:
+        agents[a].recv_view(b, aux).copy_(host, non_blocking=True)
+        if stats is not None:
+            stats["h2d"] = stats.get("h2d", 0) + host.numel() * 8
 
 
 class NativeExchange:
@@ -335,7 +391,8 @@ class DeviceTeam:
     (block distribution: agent a lives on rank a // (A / world))."""
 
     def __init__(self, p1, p2, R, t, kappa, tau, n, d, r, num_robots, device=0, stream=None,
-                 rank=0, world=1, acceleration=True, params=None, restart_interval=30, native_exchange=False):
+                 rank=0, world=1, acceleration=True, params=None, restart_interval=30, native_exchange=False,
+                 host_exchange=False):
         self.d, self.r, self.n, self.A = d, r, n, num_robots
         self.rank, self.world = rank, world
         self.acceleration = acceleration
@@ -359,6 +416,14 @@ class DeviceTeam:
         # native_exchange: pack / NCCL send-recv / gather inside the C-ABI on the rank's stream (GPU runs);
         # otherwise torch.distributed P2P ops issued from here (also what the gloo CPU tests drive)
         self.native = NativeExchange(self, device, stream) if native_exchange else None
+        # host_exchange: the poses travel through pinned host memory and a CPU process group (the end-to-end
+        # form: what the reference-facing host API does with them); bytes copied are counted in host_stats
+        self.host_exchange = bool(host_exchange)
+        self.host_stats = {"d2h": 0, "h2d": 0}
+        self.host_group = None
+        if self.host_exchange and world > 1:
+            import torch.distributed as dist
+            self.host_group = dist.new_group(backend="gloo")
 
     def set_async(self, on):
         """Stream-ordered rounds: no host wait inside a round (see DeviceAgent.async_solve)."""
@@ -375,6 +440,9 @@ class DeviceTeam:
     def exchange(self, active):
         if self.native is not None:
             self.native.exchange(active)
+        elif self.host_exchange:
+            exchange_poses_host(self.agents, self.specs, self.owner, self.rank, active, self.acceleration,
+                                self.host_group, self.host_stats)
         else:
             exchange_poses(self.agents, self.specs, self.owner, self.rank, active, self.acceleration)
 

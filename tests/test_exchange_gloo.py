@@ -37,6 +37,13 @@ class _CpuAgent:
         lo, hi = self.spec.nbr_range[b]
         return (self.nbr_aux if aux else self.nbr)[lo * self.tile:hi * self.tile]
 
+    def host_buffer(self, key, numel):
+        if not hasattr(self, "_host"):
+            self._host = {}
+        if key not in self._host:
+            self._host[key] = torch.empty(numel, dtype=torch.float64)
+        return self._host[key]
+
 
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
@@ -81,6 +88,23 @@ def _worker(rank, world, port, ret):
         for slot, (b, f) in enumerate(specs[a].nbr_keys):
             ok &= bool(torch.equal(agents[a].nbr[slot * tile:(slot + 1) * tile], Xs[b][f]))
         ok &= bool(torch.count_nonzero(agents[a].nbr_aux) == 0)
+    # the host-staged form of the same exchange (end-to-end series of bench.py): identical deliveries, and the
+    # bytes it reports are the tiles this rank sent (D2H) and received (H2D)
+    stats = {}
+    for active, acc in [(c, True) for c in colors] + [(everyone, False)]:
+        for ag in agents.values():
+            ag.nbr.zero_(); ag.nbr_aux.zero_()
+        rbcd.exchange_poses_host(agents, specs, owner, rank, active, acc, None, stats)
+        for a in active:
+            if owner[a] != rank:
+                continue
+            for slot, (b, f) in enumerate(specs[a].nbr_keys):
+                ok &= bool(torch.equal(agents[a].nbr[slot * tile:(slot + 1) * tile], Xs[b][f]))
+                if acc:
+                    ok &= bool(torch.equal(agents[a].nbr_aux[slot * tile:(slot + 1) * tile], Ys[b][f]))
+    want_h2d = sum((2 if acc else 1) * len(specs[a].nbr_keys) * tile * 8
+                   for active, acc in [(c, True) for c in colors] + [(everyone, False)] for a in active if owner[a] == rank)
+    ok &= stats.get("h2d", 0) == want_h2d and stats.get("d2h", 0) > 0
     ret[rank] = (ok, owner, colors)
     dist.barrier()
     dist.destroy_process_group()

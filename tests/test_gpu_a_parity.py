@@ -214,11 +214,11 @@ def test_linearity_and_symmetry_at_scale(datasets):
 
 
 @pytest.mark.parametrize("name,r", [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 5), ("city10000", 3),
-                                    ("grid3D", 5)])
-def test_qx_staged_parity(datasets, name, r):
-    """The shared-memory staged Q*X (qx_staged.cuh; dpgo_set_qx_variant(h, 2, 0), the automatic choice once Q and X
-    stream from HBM) against the oracle's X Q (1e-12), with and without the linear term path, and against the
-    lane-group kernel (different summation order: 1e-13)."""
+                                    ("grid3D", 5), ("grid3D", 4), ("grid3D", 6)])
+def test_qx_variants_parity(datasets, name, r):
+    """The stand-alone Q*X against the oracle's X Q (1e-12) for every tile shape the kernels are instantiated for
+    (256-bit loads of whole 32-byte sectors for d = 3, 128- / 64-bit loads for d = 2), and the measurement variants
+    (L2 prefetch hints, two blocks per step): same sums in the same order, bit for bit."""
     meas, n, _ = datasets(name)
     d = meas.d
     gp = make_problem(meas, n, r, build_precon=False)
@@ -227,18 +227,17 @@ def test_qx_staged_parity(datasets, name, r):
     ref = X @ pgo.connection_laplacian(meas, n)
     gp.set_qx_variant(0, 0)
     base = gp.qx(X)
-    gp.set_qx_variant(2, 0)
-    got = gp.qx(X)
-    assert rel(got, ref) < 1e-12
-    assert rel(got, base) < 1e-13
+    assert rel(base, ref) < 1e-12
+    for variant, dist in ((1, 64), (3, 0)):
+        gp.set_qx_variant(variant, dist)
+        assert np.array_equal(gp.qx(X), base), variant
     gp.set_qx_variant(-1, 0)
     gp.close()
 
 
-def test_qx_staged_properties_beyond_l2():
-    """Size-independent properties at roofline scale (synthetic 3-D grid, 125 000 poses, Q + X = 150 MB > L2; the
-    staged kernel is the automatic choice there): linearity, symmetry, translation gauge in the null space, and
-    agreement with the lane-group kernel."""
+def test_qx_properties_beyond_l2():
+    """Size-independent properties at roofline scale (synthetic 3-D grid, 125 000 poses, Q + X = 150 MB > L2):
+    linearity, symmetry, translation gauge in the null space."""
     import dpgo_b200
     from dpgo_b200 import synthetic
     g = synthetic.grid3d(50)
@@ -247,13 +246,11 @@ def test_qx_staged_properties_beyond_l2():
                                              build_precon=False)
     rng = np.random.default_rng(23)
     U = rng.standard_normal((r, 4 * n)); V = rng.standard_normal((r, 4 * n))
-    QU, QV = gp.qx(U), gp.qx(V)                      # automatic variant
+    QU, QV = gp.qx(U), gp.qx(V)
     assert rel(gp.qx(2.5 * U - 0.5 * V), 2.5 * QU - 0.5 * QV) < 1e-12
     assert abs(np.sum(U * QV) - np.sum(V * QU)) <= 1e-11 * abs(np.sum(U * QV))
     gauge = np.zeros((r, 4 * n)); gauge[:, 3::4] = rng.standard_normal((r, 1))
     assert np.linalg.norm(gp.qx(gauge)) <= 1e-9 * np.linalg.norm(QU)
-    gp.set_qx_variant(0, 0)
-    assert rel(gp.qx(U), QU) < 1e-13
     gp.close()
 
 
