@@ -339,10 +339,7 @@ def bench_single(args):
             if traffic is not None:
                 break
     pre_kernel = {0: "k_precon_gemv<5> (full dense inverse, 800 MB)",
-                  1: "k_precon_symv<5> (symmetric half storage)",
-                  2: "k_strip_gemv<5> x3 + k_dd_sep_rhs + k_dd_back_rhs (two-level, 58 MB, L2 resident)",
-                  3: "k_strip_gemv3<5,*> x3 (two-level, three-phase form, L2 resident)",
-                  4: "k_strip_gemv3<5,*> x3 (two-level, three-phase form, L2 resident)"}[mode]
+                  2: "k_strip_gemv<5> x3 + k_dd_sep_rhs + k_dd_back_rhs (two-level, 55 MB, L2 resident)"}[mode]
     roofline = {"bound": "hbm",
                 "kernel": "k_rtr_fused<5,3,%d> (whole optimize() = 1 launch; dominated by the (Q+0.1I)^-1 apply)" % mode,
                 "achieved": step_gbs, "peak": peak, "unit": "GB/s",
@@ -393,10 +390,8 @@ def bench_single(args):
         "config": single_config(),
         "details": {"n": n, "d": d, "r": r, "solver": "fused persistent kernel" if args.fused else "one launch per op",
                     "l2": "flushed between timed steps (256 MB device write outside the per-step CUDA-event pairs)",
-                    "preconditioner": {0: "full dense inverse", 1: "symmetric half storage",
-                                       2: "two-level (nested dissection + Schur complement)",
-                                       3: "two-level, three-phase form (couplings folded into the strips)",
-                                       4: "two-level, three-phase form with the finish fused into the last phase"}[mode],
+                    "preconditioner": {0: "full dense inverse",
+                                       2: "two-level (nested dissection + Schur complement)"}[mode],
                     "outer_iters": res["outer_iters"], "tcg_iters": res["inner_iters"],
                     "qx_per_step": nq / K, "precon_per_step": npc / K},
         "clocks": clocks,
@@ -422,6 +417,13 @@ def bench_single(args):
                    "rel_gap": gap, "e2e_result_matches": bool(abs(2 * rr.f_opt - 2 * res["f_opt"]) < 1e-9),
                    "x_finite": bool(np.isfinite(Xg).all())},
     }
+    if args.example:
+        # the reference's own acceptance driver (examples/MultiRobotExample.cpp, unmodified) through the C++ drop-in
+        try:
+            from tools import bench_example
+            line["multi_robot_example"] = bench_example.measure()
+        except Exception as exc:
+            line["multi_robot_example"] = {"error": repr(exc)}
     if args.team_steps > 0:
         # 1-GPU anchors of the strong-scaling series (BASELINE configs[2]): the rows the N > 1 lines divide by
         if gp is not None:
@@ -455,14 +457,16 @@ def main():
                          "this picks the headline)")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--precon-mode", type=int, default=None,
-                    help="storage of the exact preconditioner: 0 dense inverse, 1 symmetric half, 2 two-level, "
-                         "3 two-level in three phases (default: the library's choice by size)")
+                    help="storage of the exact preconditioner: 0 dense inverse, 2 two-level (default: the library's "
+                         "choice by size)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--team-dataset", default="grid3D", help="multi-agent series (N > 1): fixture in tests/golden")
     ap.add_argument("--team-agents", type=int, default=8)
     ap.add_argument("--team-r", type=int, default=5)
     ap.add_argument("--team-steps", type=int, default=10,
                     help="rounds of the multi-agent 1-GPU anchors appended to the N=1 line (0 = skip)")
+    ap.add_argument("--example", type=int, default=1,
+                    help="N = 1: also time the reference's MultiRobotExample driver through the C++ drop-in (0 = skip)")
     ap.add_argument("--gnc-interval", type=int, default=0,
                     help="multi-agent series: GNC_TLS robust weight update of all loop closures every this many "
                          "rounds inside the timed rounds (BASELINE configs[4]: --team-dataset city10000 --team-agents 4 "

@@ -53,7 +53,7 @@ class Message(C.Structure):
 COMM = C.c_void_p
 COMM_ID_BYTES = 128
 
-# name -> (restype, argtypes); every symbol declared in include/dpgo_b200.h
+# name -> (restype, argtypes); every symbol declared in include/dpgo_b200.h and include/dpgo_b200_dev.h
 SIGNATURES = {
     "dpgo_default_params": (None, [C.POINTER(RoptParams)]),
     "dpgo_last_error": (C.c_char_p, []),
@@ -69,8 +69,6 @@ SIGNATURES = {
     "dpgo_finalize": (C.c_int, [H, C.c_int]),
     "dpgo_set_precon_mode": (C.c_int, [H, C.c_int]),
     "dpgo_two_level_partition": (C.c_int, [C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, C.POINTER(C.c_int)]),
-    "dpgo_three_phase_plan": (C.c_int, [C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]),
     "dpgo_get_precon_mode": (C.c_int, [H, C.POINTER(C.c_int)]),
     "dpgo_set_precon_tuning": (C.c_int, [H, C.c_int, C.c_int, C.c_int]),
     "dpgo_set_two_level_domain_size": (C.c_int, [H, C.c_int]),

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/dpgo_b200.h"
+#include "../../include/dpgo_b200_dev.h"
 
 namespace dpgo {
 
@@ -27,7 +28,6 @@ namespace dpgo {
 int read_partials(dpgo_dev *h, int nblocks, int K, double *out);
 // precon_dd.cu: two-level (domain decomposition) exact preconditioner, precon_mode == 2
 int dd_build(dpgo_dev *h);
-int dd3_build(dpgo_dev *h);               // three-phase form of the same preconditioner, precon_mode == 3
 void dd_free(dpgo_dev *h);
 int op_precon_dd(dpgo_dev *h, const double *Y, const double *rvec, double *z, double *neg_out, double *z_r);
 int dd_time_apply(dpgo_dev *h, const double *vec);   // the streaming phases only (no finish)
@@ -75,11 +75,7 @@ struct dpgo_dev {
   // precon_request is what the caller asked for (-1 = choose by size at build time)
   int precon_mode = 0;
   int precon_request = -1;
-  int symT = 0, symNG = 0, sym_nitems = 0;
-  void *d_sym_items = nullptr;
-  double *d_zT = nullptr;
   int gemv_occ = 0;
-  int symv_occ = 0;
   int partial_blocks = 0;  // CTAs the partials buffer can serve (8 doubles each)
   bool finalized = false, has_precon = false;
 

@@ -30,9 +30,7 @@ struct FusedParams {
   double *zpart;
   int ld, KT, nsplit, n;
   size_t zstride;
-  int precon_mode, symT, symNG, nitems;   // symmetric half-storage variant
-  const SymItem *items;
-  double *zT;
+  int precon_mode;
   DdView dd;                              // two-level variant (precon_mode == 2)
   const double *x_in;
   double *x_out;
@@ -130,7 +128,7 @@ struct GridReducer {
 };
 
 template <int R, int D, int MODE>
-__global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedParams p) {
   DPGO_DYNAMIC_SMEM(dsm);
   cg::grid_group grid = cg::this_grid();
   // per-pose phases: deal the warps over every CTA once there is at least one warp of poses per CTA
@@ -138,8 +136,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   // poses: packed is 8 % faster)
   const Ctx ctx = ((p.n + Geo<R, D>::GPW - 1) / Geo<R, D>::GPW >= (int)gridDim.x) ? make_ctx_spread() : make_ctx();
   const int n = p.n;
-  GemvPipe pipe = gemv_pipe_init<(MODE >= 3 ? kDd3Stages : (MODE == 2 ? kDdStages : kStages)),
-                                 (MODE >= 3 ? kDd3Stages : (MODE == 2 ? kDdVecChunks : kStages))>(dsm);
+  GemvPipe pipe = gemv_pipe_init<(MODE == 2 ? kDdStages : kStages), (MODE == 2 ? kDdVecChunks : kStages)>(dsm);
   const size_t len = (size_t)R * (D + 1) * n;
   GridReducer red;
   red.buf[0] = p.partials;
@@ -164,65 +161,14 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
   clk.busy = s_busy;
   clk.pending = &red.pending;
 #endif
-  __shared__ StripPlanStore s_plan[MODE >= 3 ? 3 : (MODE == 2 ? 2 : 1)];   // two-level variants: this CTA's strips
-  if constexpr (MODE >= 2) {
+  __shared__ StripPlanStore s_plan[MODE == 2 ? 2 : 1];   // two-level variant: this CTA's strips
+  if constexpr (MODE == 2) {
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
-  if constexpr (MODE >= 3) strip_plan_fill(&s_plan[2], p.dd.P5, p.dd.V);
-  // the three variants of the exact preconditioner (compile-time: one per kernel instantiation)
-  // MODE 4 = the three-phase form with the finish of the interior poses in the epilogue of the last strip
-  // phase and the separator poses right after it: one application = 3 grid phases, the third one ending in
-  // the <z, r> reduction (d = 3 only: 64-column strips hold whole poses)
-  auto precon_fused = [&](const double *v, const double *Ycur, double *neg_out, double (&a1)[1]) {
-    if constexpr (MODE == 4) {
-      const DdView &dd = p.dd;
-      const size_t zs = (size_t)dd.pcols * R;
-      const bool pf = dd.prefetch != 0;
-      constexpr int ST = kDd3Stages;
-      phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
-      if (dd.nS > 0) {
-        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
-        red.barrier(grid);
-        clk.lap(8);
-        const StageAux a3{dd.y, dd.tptr, dd.tcol, dd.sep_col0, 0, 0};
-        phase_strip_gemv<R, ST, 2>(pipe, dd.P3, dd.V, &s_plan[1], v, dd.icol, dd.zs, zs, pf, &a3);
-        if (pf) strip_prefetch<ST>(pipe, dd.P5, dd.V, &s_plan[2]);
-        red.barrier(grid);
-        clk.lap(10);
-        const StageAux a5{nullptr, nullptr, nullptr, 0, dd.nsplit3, zs};
-        StripFinish fin{dd.y, dd.icol, Ycur, v, p.z, neg_out, 0.0};
-        phase_strip_gemv<R, ST, 3, D>(pipe, dd.P5, dd.V, &s_plan[2], dd.zs, nullptr, dd.w, 0, pf, &a5, &fin);
-        a1[0] += fin.acc;
-        phase_dd_finish_sep<R, D>(ctx, dd, Ycur, v, p.z, neg_out, a1);
-      } else {   // a single domain: z = Proj(y)
-        red.barrier(grid);
-        clk.lap(8);
-        phase_dd_finish<R, D>(ctx, dd, Ycur, v, p.z, neg_out, n, a1);
-      }
-    }
-  };
+  // the two forms of the exact preconditioner (compile-time: one kernel instantiation each)
   auto precon_stream = [&](const double *v) {
-    if constexpr (MODE == 3) {
-      // three-phase form: [M_k | C_k] strips -> Sigma^-1 strips (t_S formed while staged) -> C_k^T strips
-      const DdView &dd = p.dd;
-      const size_t zs = (size_t)dd.pcols * R;
-      const bool pf = dd.prefetch != 0;
-      constexpr int ST = kDd3Stages;
-      phase_strip_gemv<R, ST, 1>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, 0);
-      if (dd.nS > 0) {
-        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
-        red.barrier(grid);
-        clk.lap(8);
-        const StageAux a3{dd.y, dd.tptr, dd.tcol, dd.sep_col0, 0, 0};
-        phase_strip_gemv<R, ST, 2>(pipe, dd.P3, dd.V, &s_plan[1], v, dd.icol, dd.zs, zs, pf, &a3);
-        if (pf) strip_prefetch<ST>(pipe, dd.P5, dd.V, &s_plan[2]);
-        red.barrier(grid);
-        clk.lap(10);
-        const StageAux a5{nullptr, nullptr, nullptr, 0, dd.nsplit3, zs};
-        phase_strip_gemv<R, ST, 3>(pipe, dd.P5, dd.V, &s_plan[2], dd.zs, nullptr, dd.w, 0, pf, &a5);
-      }
-    } else if constexpr (MODE == 2) {
+    if constexpr (MODE == 2) {
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
@@ -245,18 +191,13 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
         phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.u, nullptr, dd.w, zs, pf);
       }
       // no separator (a single domain): z = y, w stays zero
-    } else if constexpr (MODE == 1) {
-      phase_precon_symv<R>(pipe, p.Pinv, p.symT, p.items, p.nitems, v, p.zpart, p.zT, p.zstride);
     } else {
       phase_precon_gemv<R>(pipe, p.Pinv, p.ld, v, p.zpart, p.zstride, p.KT, p.nsplit);
     }
   };
   auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
-    if constexpr (MODE >= 2)   // (MODE 4 finishes inside precon_fused)
+    if constexpr (MODE == 2)
       phase_dd_finish<R, D>(ctx, p.dd, Ycur, rvec, p.z, neg_out, n, a1);
-    else if constexpr (MODE == 1)
-      phase_precon_finish_sym<R, D>(pipe.scratch, p.zpart, p.zT, p.zstride, p.symNG, Ycur, rvec, p.z,
-                                    neg_out, n, a1);
     else
       phase_precon_finish<R, D>(ctx, p.zpart, p.zstride, p.nsplit, Ycur, rvec, p.z, neg_out, n, a1);
   };
@@ -296,32 +237,13 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
     bool first = true;
     for (int j = 0;; ++j) {
       const double *pvec = first ? grad : p.r;
-      if constexpr (MODE == 4) {
-        double acc[1] = {0.0}, sc[1];
-        precon_fused(pvec, x1, first ? p.delta : nullptr, acc);    // first: delta = -z
-        if (first) {
-          phase_copy(ctx, grad, p.r, len);
-          phase_zero(ctx, p.eta, len);
-        }
-        red.reduce<1>(grid, acc, sc);
-        clk.lap(12);
-        n_precon++;
-        if (first) {
-          tcg_begin(s, gn2, sc[0]);
-        } else {
-          const double beta = tcg_direction(s, sc[0]);
-          phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
-          red.barrier(grid);
-          clk.lap(5);
-        }
-      } else {
       precon_stream(pvec);
       if (first) {
         phase_copy(ctx, grad, p.r, len);
         phase_zero(ctx, p.eta, len);
       }
       red.barrier(grid);
-      clk.lap(MODE >= 2 ? 12 : 1);
+      clk.lap(MODE == 2 ? 12 : 1);
       {
         double acc[1] = {0.0}, sc[1];
         precon_finish(x1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
@@ -336,7 +258,6 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
           red.barrier(grid);
           clk.lap(5);
         }
-      }
       }
       first = false;
       if (j >= p.max_inner) break;
@@ -428,7 +349,7 @@ __global__ void __launch_bounds__(kBlock, MODE >= 2 ? 1 : 2) k_rtr_fused(FusedPa
     o.n_qx = n_qx; o.n_precon = n_precon; o.n_sweeps = n_sweeps; o.n_barriers = red.barriers;
 #pragma unroll
     for (int i = 0; i < 16; ++i) o.phase_ms[i] = (double)clk.acc[i] * 1e-6;
-    if (MODE >= 2) {
+    if (MODE == 2) {
 #pragma unroll
       for (int i = 8; i <= 12; ++i) o.phase_ms[1] += o.phase_ms[i];
     }

@@ -23,7 +23,7 @@ DdView dd_view(const dpgo_dev *h);  // precon_dd.cu
 
 template <int R, int D, int MODE>
 static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
-  constexpr int smem = (MODE >= 3) ? kDd3DynSmem : ((MODE == 2) ? kDdDynSmem : kGemvDynSmem);
+  constexpr int smem = (MODE == 2) ? kDdDynSmem : kGemvDynSmem;
   // the shared-memory attribute and the occupancy belong to the device (one handle = one device; a
   // process may hold handles on several): cached per device
   static int occ_by_device[64];
@@ -45,7 +45,6 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
   const long cap = (long)h->num_sms * occ_cache;
   // enough CTAs for the widest phase, never more than can be co-resident
   long tiles = (long)(h->ld / kGemvCols) * h->nsplit;
-  if (h->precon_mode == 1) tiles = h->sym_nitems;
   if (h->precon_mode >= 2) tiles = fp.dd.V;
   const int gpw = 32 / (h->d + 1);
   const long pose_blocks = (((long)h->n + gpw - 1) / gpw + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -69,12 +68,7 @@ static int launch_fused_v(dpgo_dev *h, FusedParams &fp) {
 
 template <int R, int D>
 static int launch_fused(dpgo_dev *h, FusedParams &fp) {
-  if constexpr (D == 3) {
-    if (h->precon_mode == 4) return launch_fused_v<R, D, 4>(h, fp);
-  }
-  if (h->precon_mode >= 3) return launch_fused_v<R, D, 3>(h, fp);
   if (h->precon_mode == 2) return launch_fused_v<R, D, 2>(h, fp);
-  if (h->precon_mode == 1) return launch_fused_v<R, D, 1>(h, fp);
   return launch_fused_v<R, D, 0>(h, fp);
 }
 
@@ -95,8 +89,7 @@ int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_i
   fp.zpart = h->d_zpart;
   fp.ld = h->ld; fp.KT = h->KT; fp.nsplit = h->nsplit; fp.n = h->n;
   fp.zstride = h->vpad;
-  fp.precon_mode = h->precon_mode; fp.symT = h->symT; fp.symNG = h->symNG; fp.nitems = h->sym_nitems;
-  fp.items = (const SymItem *)h->d_sym_items; fp.zT = h->d_zT;
+  fp.precon_mode = h->precon_mode;
   if (h->precon_mode >= 2) fp.dd = dd_view(h); else memset(&fp.dd, 0, sizeof(fp.dd));
   fp.x_in = x_in; fp.x_out = x_out;
   fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;

@@ -16,7 +16,6 @@
 #endif
 #include <stdint.h>
 
-#include "dd_stage.h"
 
 namespace dpgo {
 
@@ -158,28 +157,15 @@ __device__ __forceinline__ double dot_col(const double (&a)[R], const double (&b
   return s;
 }
 
-// 256-bit global loads (sm_100: SASS LDG.E.256): one instruction per 32-byte sector.  The lane-group SpMM is bound
-// by L1 sector traffic when it streams from HBM (ncu: L1/TEX throughput 78 %, 15.5 of 32 bytes used per sector with
-// 128-bit loads: every sector of a Q row or of an X tile was requested twice); with whole sectors per instruction the
-// sectors per block drop from ~22 to ~12.  `p` must be 32-byte aligned.
-#ifndef DPGO_CPU_EMU
-__device__ __forceinline__ void ld256(const double *p, double (&v)[4]) {       // coherent (data written by other CTAs)
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void ld256_nc(const double *p, double (&v)[4]) {    // read-only path (Q blocks)
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-#else
-inline void ld256(const double *p, double (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = p[k]; }
-inline void ld256_nc(const double *p, double (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = p[k]; }
-#endif
-
+// Loads of the lane-group SpMM.  At scale the kernel is bound by L1 data-pipe wavefronts (ncu, 262 144-pose grid:
+// l1tex__data_pipe_lsu_wavefronts 72 % of peak, DRAM 47 %): a lane group reads its Q row and the whole X tile, 16
+// bytes per lane and instruction, 8 different lines per warp instruction.  256-bit loads (LDG.E.256, one per
+// 32-byte sector) were measured in round 2 and are not used: 92.3 / 298.3 us against 88.2 / 282.1 us with 128-bit
+// loads on the 262 144- / 1 000 000-pose grids (profiles/r02_qx_scale.md).
 // row c of block e of Q (DH doubles) and the pose tile j of X (TILE doubles), widest loads the shape allows
 template <int DH>
 __device__ __forceinline__ void load_q_row(const double *m, double (&mk)[DH]) {
-  if constexpr (DH == 4) {                // 32-byte row: one 256-bit read-only load
-    ld256_nc(m, mk);
-  } else if constexpr (DH % 2 == 0) {
+  if constexpr (DH % 2 == 0) {            // row c of the block is 16-byte aligned: 128-bit read-only loads
 #pragma unroll
     for (int k = 0; k < DH / 2; ++k) {
       const double2 v = __ldg(reinterpret_cast<const double2 *>(m) + k);
@@ -193,14 +179,7 @@ __device__ __forceinline__ void load_q_row(const double *m, double (&mk)[DH]) {
 }
 template <int TILE>
 __device__ __forceinline__ void load_x_tile(const double *xj, double (&x)[TILE]) {
-  if constexpr (TILE % 4 == 0) {          // whole 32-byte sectors (d = 3: the tile is r sectors)
-#pragma unroll
-    for (int k = 0; k < TILE / 4; ++k) {
-      double v[4];
-      ld256(xj + 4 * k, v);
-      x[4 * k] = v[0]; x[4 * k + 1] = v[1]; x[4 * k + 2] = v[2]; x[4 * k + 3] = v[3];
-    }
-  } else if constexpr (TILE % 2 == 0) {   // 16-byte aligned tile: 128-bit loads
+  if constexpr (TILE % 2 == 0) {          // 16-byte aligned tile: 128-bit loads
 #pragma unroll
     for (int k = 0; k < TILE / 2; ++k) {
       const double2 v = *(reinterpret_cast<const double2 *>(xj) + k);
@@ -691,247 +670,6 @@ __device__ __forceinline__ void phase_precon_gemv(GemvPipe &pp, const double *Pi
   }
 }
 
-// ---- symmetric (half-storage) variant ---------------------------------------------------------
-// Only the blocks (I, K), I >= K, of the symmetric inverse are stored (128 x 128 doubles each,
-// lower-triangular packed, 8 stages of 16 inner indices x 128 columns per block), so one apply
-// streams ~N^2/2 * 8 bytes.  Each streamed stage st[kk][jj] = P[I*128+jj, K*128+16h+kk] is used twice:
-//   direct      z[I-block][jj] += st[kk][jj] * vec[K-block][kk]     (lane-local, like the full variant)
-//   transposed  z[K-block][kk] += st[kk][jj] * vec[I-block][jj]     (off-diagonal blocks; the sum
-//               over jj crosses lanes: 8-slot halving butterfly of warp shuffles per kk)
-// A work item is a kSymS x kSymS group of blocks (ig, kg), ig >= kg: direct sums of a block row
-// live in registers across the item's columns and go to zD[kg]; transposed sums accumulate in
-// shared memory over the item's rows and go to zT[ig].  Every (partial buffer, column) pair is
-// written by exactly one CTA and summed in a fixed order by phase_precon_finish_sym.
-struct SymItem {
-  int ig, kg, ntiles, pad;
-};
-
-struct SymCursor {
-  int item, ig, kg, I, K, h;
-};
-
-template <int R>
-__device__ __forceinline__ void phase_precon_symv(GemvPipe &pp, const double *Psym, int T,
-                                                  const SymItem *items, int nitems, const double *vec,
-                                                  double *zD, double *zT, size_t zstride) {
-  static_assert(R <= kGemvMaxR, "scratch sized for R <= kGemvMaxR");
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double(*sacc)[R][kSymB] = reinterpret_cast<double(*)[R][kSymB]>(pp.scratch);          // [4][R][128]
-  double *accT = pp.scratch + 4 * kGemvMaxR * kSymB;                                     // [kSymS][128][R]
-  int G = 0;
-  for (int it = blockIdx.x; it < nitems; it += gridDim.x) G += items[it].ntiles * kSymStagesPerTile;
-  if (G == 0) return;
-  const uint32_t stage0 = smem_u32(pp.stage);
-
-  auto cur_init = [&](SymCursor &c, int item) {
-    c.item = item;
-    if (item < nitems) {
-      const SymItem d = items[item];
-      c.ig = d.ig; c.kg = d.kg;
-      c.I = d.ig * kSymS; c.K = d.kg * kSymS; c.h = 0;
-    }
-  };
-  auto last_K = [&](const SymCursor &c) { return min(c.kg * kSymS + kSymS - 1, c.I); };
-  auto last_I = [&](const SymCursor &c) { return min(c.ig * kSymS + kSymS - 1, T - 1); };
-  auto cur_next = [&](SymCursor &c) {
-    if (++c.h < kSymStagesPerTile) return;
-    c.h = 0;
-    if (c.K < last_K(c)) { c.K++; return; }
-    c.K = c.kg * kSymS;
-    if (c.I < last_I(c)) { c.I++; return; }
-    cur_init(c, c.item + gridDim.x);
-  };
-  auto produce = [&](const SymCursor &c, uint32_t slot) {
-    if (threadIdx.x == 0) {
-      const uint32_t bar = pp.bar + 8 * slot;
-      mbar_expect_tx(bar, kStageDoubles * 8);
-      const size_t tile = (size_t)c.I * (c.I + 1) / 2 + c.K;
-      bulk_g2s(stage0 + slot * (kStageDoubles * 8),
-               Psym + (tile * kSymStagesPerTile + c.h) * kStageDoubles, kStageDoubles * 8, bar);
-    }
-    if (threadIdx.x < kSymStageK * R)
-      pp.svec[slot * (kStageK * R) + threadIdx.x] =
-          vec[((size_t)c.K * kSymB + c.h * kSymStageK) * R + threadIdx.x];
-  };
-
-  SymCursor ci, cc;
-  cur_init(ci, blockIdx.x);
-  cur_init(cc, blockIdx.x);
-  uint32_t slot_i = pp.slot;
-  int issued = 0;
-  for (; issued < kStages && issued < G; ++issued) {
-    produce(ci, slot_i);
-    cur_next(ci);
-    slot_i = (slot_i + 1 == kStages) ? 0 : slot_i + 1;
-  }
-  __syncthreads();
-
-  const int jj[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 64 + 2 * lane + 1};
-  double a[4][R], rI[4][R];
-  for (int g = 0; g < G; ++g) {
-    const bool row_start = (cc.K == cc.kg * kSymS && cc.h == 0);
-    const bool item_start = row_start && (cc.I == cc.ig * kSymS);
-    if (item_start) {
-      for (int o = threadIdx.x; o < kSymS * kSymB * R; o += kBlock) accT[o] = 0.0;
-      __syncthreads();
-    }
-    if (row_start) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double *rp = vec + ((size_t)cc.I * kSymB + jj[c]) * R;
-#pragma unroll
-        for (int q = 0; q < R; ++q) { rI[c][q] = rp[q]; a[c][q] = 0.0; }
-      }
-    }
-    const bool offdiag = (cc.I != cc.K);
-    const uint32_t slot = pp.slot;
-    mbar_wait(pp.bar + 8 * slot, pp.parity);
-    const double *st = pp.stage + (size_t)slot * kStageDoubles;
-    const double *sv = pp.svec + slot * (kStageK * R);
-    double *aT = accT + ((size_t)(cc.K - cc.kg * kSymS) * kSymB + cc.h * kSymStageK) * R;
-#pragma unroll
-    for (int u = 0; u < kSymStageK / kWarpsPerBlock; ++u) {
-      const int kk = w + u * kWarpsPerBlock;
-      const double2 p0 = *reinterpret_cast<const double2 *>(st + kk * kSymB + 2 * lane);
-      const double2 p1 = *reinterpret_cast<const double2 *>(st + kk * kSymB + 64 + 2 * lane);
-      const double pv[4] = {p0.x, p0.y, p1.x, p1.y};
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = 0.0;
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double x = sv[kk * R + q];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          a[c][q] = fma(pv[c], x, a[c][q]);
-          v[q] = fma(pv[c], rI[c][q], v[q]);
-        }
-      }
-      if (offdiag) {  // warp-uniform
-        // 8 slots over 32 lanes: halve the slot set on lane bits 4, 3, 2, then all-reduce bits 1, 0
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool up = (lane & 16) != 0;
-          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 4], 16);
-          v[i] = (up ? v[i + 4] : v[i]) + recv;
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const bool up = (lane & 8) != 0;
-          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 2], 8);
-          v[i] = (up ? v[i + 2] : v[i]) + recv;
-        }
-        {
-          const bool up = (lane & 4) != 0;
-          const double recv = __shfl_xor_sync(0xffffffffu, up ? v[0] : v[1], 4);
-          v[0] = (up ? v[1] : v[0]) + recv;
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        const int slot_q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        if ((lane & 3) == 0 && slot_q < R) aT[kk * R + slot_q] += v[0];
-      }
-    }
-    const bool row_end = (cc.h == kSymStagesPerTile - 1) && (cc.K == last_K(cc));
-    const bool item_end = row_end && (cc.I == last_I(cc));
-    __syncthreads();  // every warp is done with this stage
-    if (issued < G) {
-      produce(ci, slot);
-      cur_next(ci);
-      ++issued;
-    }
-    if (row_end) {  // combine the 8 warps' direct sums for block row I -> zD[kg]
-      if (w >= 4) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int q = 0; q < R; ++q) sacc[w - 4][q][jj[c]] = a[c][q];
-      }
-      __syncthreads();
-      if (w < 4) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int q = 0; q < R; ++q) sacc[w][q][jj[c]] += a[c][q];
-      }
-      __syncthreads();
-      for (int o = threadIdx.x; o < R * kSymB; o += kBlock) {
-        const int q = o / kSymB, j = o % kSymB;
-        const double x = (sacc[0][q][j] + sacc[1][q][j]) + (sacc[2][q][j] + sacc[3][q][j]);
-        zD[(size_t)cc.kg * zstride + ((size_t)cc.I * kSymB + j) * R + q] = x;
-      }
-      __syncthreads();
-    }
-    if (item_end) {  // transposed sums of this item's block columns -> zT[ig]
-      const int kb0 = cc.kg * kSymS;
-      const int nkb = min(kSymS, T - kb0);
-      for (int o = threadIdx.x; o < nkb * kSymB * R; o += kBlock)
-        zT[(size_t)cc.ig * zstride + (size_t)kb0 * kSymB * R + o] = accT[o];
-      __syncthreads();
-    }
-    cur_next(cc);
-    if (pp.slot + 1 == kStages) { pp.slot = 0; pp.parity ^= 1u; } else { pp.slot += 1; }
-  }
-}
-
-// z = Proj_Y( sum of the NG+1 partials that exist for a column ); acc = {<z, rvec>}.  A CTA takes
-// one warp-row of poses at a time and its 8 warps split the partial buffers, so the ~40 dependent
-// L2/HBM reads per column become 5 per warp.
-template <int R, int D>
-__device__ __forceinline__ void phase_precon_finish_sym(double *scratch, const double *zD, const double *zT,
-                                                        size_t zstride, int NG, const double *Y,
-                                                        const double *rvec, double *z, double *neg_out,
-                                                        int n, double (&acc)[1]) {
-  using Gm = Geo<R, D>;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const LanePos lp = lane_pos<D>(lane);
-  double(*sfin)[32][R] = reinterpret_cast<double(*)[32][R]>(scratch);  // [8][32][R]
-  const int nchunks = (n + Gm::GPW - 1) / Gm::GPW;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int i = chunk * Gm::GPW + lp.grp;
-    const bool valid = lp.ok && i < n;
-    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
-    double part[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) part[q] = 0.0;
-    if (valid) {
-      const int col = i * Gm::DH + lp.c;
-      const int gi = (col / kSymB) / kSymS;
-      for (int s = w; s <= NG; s += kWarpsPerBlock) {
-        const double *zp = (s <= gi) ? zD + (size_t)s * zstride + off : zT + (size_t)(s - 1) * zstride + off;
-#pragma unroll
-        for (int q = 0; q < R; ++q) part[q] += zp[q];
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < R; ++q) sfin[w][lane][q] = part[q];
-    __syncthreads();
-    if (w == 0) {
-      double wv[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        double x = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sfin[ww][lane][q];
-        wv[q] = x;
-      }
-      double sym[D];
-      group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), wv, lp, valid, sym);
-      if (valid) {
-        store_col<R>(z + off, wv);
-        double rr[R];
-        load_col<R>(rvec + off, rr);
-        acc[0] += dot_col<R>(wv, rr);
-        if (neg_out) {
-#pragma unroll
-          for (int q = 0; q < R; ++q) neg_out[off + q] = -wv[q];
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ---- two-level (domain decomposition) exact preconditioner ---------------------------------------
 // Nested dissection of the pose graph gives interior domains D_1..D_K (no edges between them) and a
 // separator S.  With A = Q + 0.1 I permuted to [D_1 .. D_K | S]:
@@ -950,14 +688,6 @@ constexpr int kDdScratch = kWarpsPerBlock * kGemvMaxR * kGemvCols * 8;
 constexpr int kDdDynSmem =
     kDdStages * kStageDoubles * 8 + kDdStages * 8 + kDdVecChunks * kStageK * kGemvMaxR * 8 + kDdScratch;
 static_assert(kDdDynSmem <= 227 * 1024, "two-level pipeline does not fit in shared memory");
-// the fused solver of the three-phase forms runs an 11-stage ring: the Schur strips of sphere2500 are 11
-// chunks long (54 chunks in 5 inner splits) and become a single wave; the partition (domains of at most
-// kDdStages chunks) is the same as for the five-phase form
-constexpr int kDd3Stages = 11;
-constexpr int kDd3DynSmem =
-    kDd3Stages * kStageDoubles * 8 + kDd3Stages * 8 + kDd3Stages * kStageK * kGemvMaxR * 8 + kDdScratch;
-static_assert(kDd3DynSmem + 4096 <= 227 * 1024, "three-phase pipeline (+ static shared memory) does not fit");
-
 struct DdStrip {
   int cb, kc0, nchunks, slot;   // output column block, first inner chunk, #chunks, partial slot
   long long data_off;           // first stage of the strip in the matrix buffer (units of stages)
@@ -970,8 +700,6 @@ struct DdStripSet {
   const DdStrip *strips;
   const int *cta;      // [V + 1]
   const int *chunks;   // [V]
-  const int *gidx;     // three-phase form, phase 5: inner index -> scalar column of the input (-1: padding);
-                       // a strip's kc0 then counts chunks of this list.  nullptr: inner indices are columns
 };
 
 
@@ -990,11 +718,7 @@ struct DdView {
   int sep_col0, pcols;          // first separator column; padded column count
   double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
                                 // nsplit3 partial slots; u is zero outside the boundary rows)
-  int prefetch;                 // issue the first matrix stages of P3 / P5 before the preceding barrier
-  // three-phase form (precon_mode 3): P1 = [M_k | C_k] strips (y holds y_I and, in its T segments, the
-  // g_k), P3 as above with t_S formed while it is staged, P5 = C_k^T strips (result in w)
-  DdStripSet P5;
-  const int *tptr, *tcol;       // scalar column of the S segment -> columns of y to subtract (CSR)
+  int prefetch;                 // issue the first matrix stages of the next strip phase before the preceding barrier
 };
 
 // Per-CTA cache (shared memory, filled once per kernel) of the head of this CTA's strip list of one
@@ -1107,43 +831,26 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
-// FIND > 0 (three-phase form, d + 1 divides 64): the last strip phase also finishes the application for
-// the interior poses -- its epilogue holds w for 64 permuted columns = whole poses, so z = Proj_Y(y - w),
-// <z, r> and the optional -z are produced there instead of in a separate grid phase.
-struct StripFinish {
-  const double *yarr;      // phase-1 results (permuted columns)
-  const int *icol;         // permuted column -> original scalar column (-1: padding)
-  const double *Y;         // current iterate
-  const double *rvec;      // original order
-  double *z, *neg_out;
-  double acc;              // this thread's part of <z, r>
-};
-
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
 // A strip is processed in waves of <= STAGES chunks: thread 0 puts the whole wave in flight (one
 // TMA bulk copy per 16 KB stage, each with its own mbarrier), all threads stage the matching slice
 // of `vec` (one round of global-load latency per wave), then the 8 warps split the wave into
 // (chunk, 8-row) units and each waits only for the stages it reads -- no CTA-wide barrier per
 // stage.  pp.parity is a bit mask here: bit i = phase parity of stage slot i.
-template <int R, int STAGES, int SRC = 0, int FIND = 0>
+template <int R, int STAGES>
 __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
                                                  const double *vec, const int *icol, double *out,
-                                                 size_t outstride, bool prefetched = false,
-                                                 const StageAux *ax = nullptr, StripFinish *fin = nullptr) {
+                                                 size_t outstride, bool prefetched = false) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
-  // is staged (saves a separate permutation pass + grid barrier).  SRC 1: the same with icol required and
-  // the slice reused across consecutive strips that read the same one; SRC 2 / 3: see StageAux.
+  // is staged (saves a separate permutation pass + grid barrier).
   static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const StripPlan pl = strip_plan_load(st);
-  if constexpr (FIND == 0) {
-    if (pl.G == 0) return;       // (with the fused finish even empty strips have poses to complete)
-  }
+  if (pl.G == 0) return;
   StripCursor cu;
   strip_cursor_init(cu, S, V, pl);
   bool in_flight = prefetched;   // first wave of the current strip already issued
-  int staged_kc0 = -1, staged_n = -1;   // SRC != 0: single-wave slice currently in svec (reused by the next strip)
   while (cu.v < V) {
     const DdStrip d = cu.d;
     double a0[R], a1[R];
@@ -1153,17 +860,12 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
       const int nw = min(STAGES, d.nchunks - c0);
       if (!in_flight && threadIdx.x == 0) strip_issue_wave(pp, S, d, c0, nw);
       in_flight = false;
-      bool staged = false;   // strips of one domain placed on this CTA share their input slice: stage it once
-      if constexpr (SRC != 0) staged = (d.nchunks <= STAGES && d.kc0 == staged_kc0 && d.nchunks == staged_n);
-      if (!staged) {  // the slice of vec that goes with the wave
+      {  // the slice of vec that goes with the wave
         const int k0 = (d.kc0 + c0) * kStageK;
         const int cnt = nw * kStageK * R;
         for (int o = threadIdx.x; o < cnt; o += kBlock) {
           double val;
-          if constexpr (SRC != 0) {   // three-phase form: dd_stage.h (shared with the host test)
-            const int k = o / R, q = o - k * R;
-            val = strip_stage_value<SRC>(k0 + k, q, R, vec, icol, S.gidx, ax);
-          } else if (icol) {
+          if (icol) {
             const int k = o / R, q = o - k * R;
             const int oc = __ldg(icol + k0 + k);
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
@@ -1172,10 +874,6 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
           }
           pp.svec[o] = val;
         }
-      }
-      if constexpr (SRC != 0) {
-        staged_kc0 = (d.nchunks <= STAGES) ? d.kc0 : -1;
-        staged_n = d.nchunks;
       }
       __syncthreads();
       for (int u = w; u < 4 * nw; u += kWarpsPerBlock) {
@@ -1209,47 +907,12 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
       sacc[w][q][2 * lane + 1] = a1[q];
     }
     __syncthreads();
-    if constexpr (FIND > 0) {
-      // two full warps: thread jj owns permuted column 64 cb + jj, D + 1 adjacent lanes = one pose
-      constexpr int DH = FIND + 1;
-      static_assert(FIND == 0 || (kGemvCols % (FIND + 1) == 0 && 32 % (FIND + 1) == 0), "poses must not straddle strips");
-      if (threadIdx.x < kGemvCols) {
-        const int jj = threadIdx.x;
-        const int colp = d.cb * kGemvCols + jj;
-        const int oc = __ldg(fin->icol + colp);      // original scalar column = pose * DH + c
-        const bool valid = oc >= 0;
-        double wv[R];
+    for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
+      const int q = o / kGemvCols, jj = o % kGemvCols;
+      double x = 0.0;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          double x = 0.0;
-#pragma unroll
-          for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-          wv[q] = valid ? fin->yarr[(size_t)colp * R + q] - x : 0.0;
-        }
-        const LanePos lp = lane_pos<FIND>(lane);
-        const int pose = valid ? oc / DH : 0;
-        double sym[FIND];
-        group_tangent<R, FIND>(fin->Y + (size_t)pose * (R * DH), wv, lp, valid, sym);
-        if (valid) {
-          const size_t off = (size_t)oc * R;
-          store_col<R>(fin->z + off, wv);
-          double rr[R];
-          load_col<R>(fin->rvec + off, rr);
-          fin->acc += dot_col<R>(wv, rr);
-          if (fin->neg_out) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) fin->neg_out[off + q] = -wv[q];
-          }
-        }
-      }
-    } else {
-      for (int o = threadIdx.x; o < R * kGemvCols; o += kBlock) {
-        const int q = o / kGemvCols, jj = o % kGemvCols;
-        double x = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
-        out[(size_t)d.slot * outstride + ((size_t)d.cb * kGemvCols + jj) * R + q] = x;
-      }
+      for (int ww = 0; ww < kWarpsPerBlock; ++ww) x += sacc[ww][q][jj];
+      out[(size_t)d.slot * outstride + ((size_t)d.cb * kGemvCols + jj) * R + q] = x;
     }
     __syncthreads();
   }
@@ -1391,57 +1054,6 @@ __device__ __forceinline__ void phase_dd_finish(const Ctx &ctx, const DdView &dd
 #pragma unroll
           for (int q = 0; q < R; ++q)
             wv[q] += dd.y[(size_t)s * zstride + poff + q] - dd.w[(size_t)s * zstride + poff + q];
-        }
-      }
-    }
-    double sym[D];
-    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), wv, lp, valid, sym);
-    if (valid) {
-      store_col<R>(z + off, wv);
-      double rr[R];
-      load_col<R>(rvec + off, rr);
-      acc[0] += dot_col<R>(wv, rr);
-      if (neg_out) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) neg_out[off + q] = -wv[q];
-      }
-    }
-  }
-}
-
-// finish of the separator poses only (three-phase form with the interior finished by the last strip phase):
-// z_S = Proj_Y( sum of the zs partial slots ); acc += <z_S, r_S>
-template <int R, int D>
-__device__ __forceinline__ void phase_dd_finish_sep(const Ctx &ctx, const DdView &dd, const double *Y,
-                                                    const double *rvec, double *z, double *neg_out,
-                                                    double (&acc)[1]) {
-  using Gm = Geo<R, D>;
-  const LanePos lp = lane_pos<D>(ctx.lane);
-  const size_t zstride = (size_t)dd.pcols * R;
-  for (int base = ctx.warp * Gm::GPW; base < dd.nS; base += ctx.nwarps * Gm::GPW) {
-    const int sp = base + lp.grp;
-    const bool valid = lp.ok && sp < dd.nS;
-    const int i = valid ? __ldg(dd.srow + sp) : 0;
-    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
-    double wv[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) wv[q] = 0.0;
-    if (valid) {
-      const size_t poff = ((size_t)dd.sep_col0 + (size_t)sp * Gm::DH + lp.c) * R;
-      for (int s = 0; s < dd.nsplit3; s += 4) {   // same order of additions as phase_dd_finish
-        double tq[4][R];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const size_t so = (size_t)min(s + j, dd.nsplit3 - 1) * zstride + poff;
-#pragma unroll
-          for (int q = 0; q < R; ++q) tq[j][q] = dd.zs[so + q];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (s + j < dd.nsplit3) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) wv[q] += tq[j][q];
-          }
         }
       }
     }

@@ -18,7 +18,6 @@
 #include <deque>
 #include <vector>
 
-#include "dd_plan.h"
 #include "dense_la.h"
 #include "device_state.h"
 #include "dissect.h"
@@ -52,14 +51,7 @@ struct DdState {
   int *si_rowptr = nullptr, *si_colidx = nullptr, *bs_rowptr = nullptr, *bs_colidx = nullptr;
   double *si_blocks = nullptr, *bs_blocks = nullptr;
   double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr;
-  // three-phase form (precon_mode 3, plan in dd_plan.h): M1 holds the [M_k | C_k] strips, M5 the C_k^T strips
-  bool three = false;
-  int nstrips5 = 0, ycols = 0;
-  double *M5 = nullptr;
-  DdStrip *strips5 = nullptr;
-  int *cta5 = nullptr, *chunks5 = nullptr, *tptr = nullptr, *tcol = nullptr, *gidx = nullptr;
   bool configured = false;
-  unsigned configured3 = 0;        // bit SRC: k_strip_gemv3<R, SRC> has its shared-memory attribute set
 };
 
 namespace {
@@ -92,19 +84,6 @@ __global__ void k_dd_layout(const double *A, int m, int lda, int pad, double *ds
     if (j < (size_t)m && k < (size_t)m) val = (j >= k) ? A[j + k * (size_t)lda] : A[k + j * (size_t)lda];
     dst[t] = val;
   }
-}
-
-// stage-major strips of a coupling block C = A_k^-1 A_kS (m x mS col-major, leading dimension ldc) restricted to
-// the columns colmap[0 .. ncomp) (the scalars of S_k, in that order), zero padded:
-//   form 0 (phase 1, output = compact column):  stage (ob, c)(kk, jj) = C(32 c + kk, colmap[64 ob + jj])
-//   form 1 (phase 5, output = domain row):      stage (ob, c)(kk, jj) = C(64 ob + jj, colmap[32 c + kk])
-// stage (ob, c) is the (ob * nch + c)-th 16 KB run of dst.
-__global__ void k_dd_layout_rect(const double *C, int m, int ldc, const int *colmap, int ncomp, int form, int nob,
-                                 int nch, double *dst) {
-  static_assert(kGemvCols == 64 && kStageK == 32, "dd_stage.h states the stage shape");
-  const size_t total = (size_t)nob * nch * kStageDoubles;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
-    dst[t] = layout_rect_value(C, m, ldc, colmap, ncomp, form, nch, t);
 }
 
 // Sigma(colmap[i], colmap[j]) -= W(i, j) : the Schur update of one domain touches only S_k x S_k
@@ -298,16 +277,6 @@ __global__ void __launch_bounds__(kBlock, 1) k_strip_gemv(DdStripSet S, int V, c
   strip_plan_fill(&plan, S, V);
   phase_strip_gemv<R, kDdStages>(pp, S, V, &plan, vec, icol, out, outstride);
 }
-// strip phases of the three-phase form (SRC: how the input slice of a wave is produced, see StageAux)
-template <int R, int SRC>
-__global__ void __launch_bounds__(kBlock, 1) k_strip_gemv3(DdStripSet S, int V, const double *vec, const int *icol,
-                                                           double *out, size_t outstride, StageAux ax) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  GemvPipe pp = gemv_pipe_init<kDdStages, kDdVecChunks>(dsm);
-  __shared__ StripPlanStore plan;
-  strip_plan_fill(&plan, S, V);
-  phase_strip_gemv<R, kDdStages, SRC>(pp, S, V, &plan, vec, icol, out, outstride, false, &ax);
-}
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_dd_sep_rhs(DdView dd, const double *rvec) {
   phase_dd_sep_rhs<R, D>(make_ctx(), dd, rvec);
@@ -351,8 +320,6 @@ DdView dd_view(const dpgo_dev *h) {
   v.sep_col0 = s->sep_col0; v.pcols = s->pcols;
   v.y = s->y; v.t = s->t; v.zs = s->zs; v.u = s->u; v.w = s->w;
   v.prefetch = h->dd_prefetch;
-  v.P5 = DdStripSet{s->M5, s->strips5, s->cta5, s->chunks5, s->gidx};
-  v.tptr = s->tptr; v.tcol = s->tcol;
   return v;
 }
 
@@ -361,7 +328,7 @@ void dd_free(dpgo_dev *h) {
   if (!s) return;
   void *ptrs[] = {s->M1, s->M3, s->strips1, s->strips3, s->cta1, s->cta3, s->chunks1, s->chunks3, s->pcol, s->srow,
                   s->bcol, s->icol, s->si_rowptr, s->si_colidx, s->bs_rowptr, s->bs_colidx, s->si_blocks, s->bs_blocks,
-                  s->y, s->t, s->zs, s->u, s->w, s->M5, s->strips5, s->cta5, s->chunks5, s->tptr, s->tcol, s->gidx};
+                  s->y, s->t, s->zs, s->u, s->w};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -612,114 +579,6 @@ int dd_build(dpgo_dev *h) {
   return DPGO_OK;
 }
 
-// ---- three-phase form (precon_mode 3) ------------------------------------------------------------------
-// Same dissection, same dense inverses and Schur complement as dd_build; the index plan (column
-// spaces, strips, gather lists) comes from dd_plan.h, where the algebra is stated.  The couplings
-// C_k = A_k^-1 A_kS, which dd_build only uses to form Sigma, are kept and laid out as strips.
-static_assert(sizeof(PlanStrip) == sizeof(DdStrip) && kPlanCols == kGemvCols && kPlanStageK == kStageK,
-              "dd_plan.h mirrors the strip format of kernels.cuh");
-
-int dd3_build(dpgo_dev *h) {
-  dd_free(h);
-  DdState *s = new DdState();
-  h->dd = s;
-  s->three = true;
-  const int n = h->n, dh = h->d + 1, R = h->r;
-  const int V = std::max(1, h->num_sms);
-  const ThreePhasePlan pl = build_three_phase_plan(n, h->rowptr.data(), h->colidx.data(), dh,
-                                                   h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh),
-                                                   V, h->dd_split3, kDd3Stages /* wave of the fused solver */,
-                                                   /*affine=*/h->dd_split1 == 2);
-  const int K = pl.K;
-  s->K = K; s->nS = pl.nS; s->V = V;
-  s->nI = n - pl.nS;
-  s->sep_col0 = pl.sep_col0; s->pcols = pl.pcols; s->ycols = pl.ycols;
-  s->nsplit1 = 1; s->nsplit3 = pl.nsplit3;
-  s->nstrips1 = (int)pl.strips1.size(); s->nstrips3 = (int)pl.strips3.size(); s->nstrips5 = (int)pl.strips5.size();
-  s->bytes_per_apply = pl.bytes_per_apply + 6.0 * R * h->N * 8;
-  auto to_dd = [](const std::vector<PlanStrip> &v) {
-    std::vector<DdStrip> o(v.size());
-    for (size_t i = 0; i < v.size(); ++i) o[i] = DdStrip{v[i].cb, v[i].kc0, v[i].nchunks, v[i].slot, v[i].data_off};
-    return o;
-  };
-  DPGO_TRY(upload_vec(&s->strips1, to_dd(pl.strips1)));
-  DPGO_TRY(upload_vec(&s->strips3, to_dd(pl.strips3)));
-  DPGO_TRY(upload_vec(&s->strips5, to_dd(pl.strips5)));
-  DPGO_TRY(upload_vec(&s->cta1, pl.cta1)); DPGO_TRY(upload_vec(&s->chunks1, pl.chunks1));
-  DPGO_TRY(upload_vec(&s->cta3, pl.cta3)); DPGO_TRY(upload_vec(&s->chunks3, pl.chunks3));
-  DPGO_TRY(upload_vec(&s->cta5, pl.cta5)); DPGO_TRY(upload_vec(&s->chunks5, pl.chunks5));
-  DPGO_TRY(upload_vec(&s->pcol, pl.pcol));
-  DPGO_TRY(upload_vec(&s->srow, pl.srow));
-  DPGO_TRY(upload_vec(&s->icol, pl.icol));
-  DPGO_TRY(upload_vec(&s->tptr, pl.tptr));
-  DPGO_TRY(upload_vec(&s->tcol, pl.tcol));
-  DPGO_TRY(upload_vec(&s->gidx, pl.gidx));
-  // first stage of every domain's M_k / C_k / C_k^T strips, and its compact column map into C
-  std::vector<long long> baseM(K, -1), baseG(K, -1), baseW(K, -1);
-  for (size_t i = 0; i < pl.strips1.size(); ++i)
-    if (pl.tiles1[i].blk == 0) (pl.tiles1[i].kind == 0 ? baseM : baseG)[pl.tiles1[i].k] = pl.strips1[i].data_off;
-  for (size_t i = 0; i < pl.strips5.size(); ++i)
-    if (pl.tiles5[i].blk == 0) baseW[pl.tiles5[i].k] = pl.strips5[i].data_off;
-  // ---- work arrays: y over the y space (interior results + the g_k segments), z_S partial slots, w
-  const size_t wlen = (size_t)R * s->pcols;
-  CUDA_TRY(cudaMalloc((void **)&s->y, (size_t)R * s->ycols * sizeof(double)));
-  CUDA_TRY(cudaMemset(s->y, 0, (size_t)R * s->ycols * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s->w, wlen * sizeof(double)));
-  CUDA_TRY(cudaMemset(s->w, 0, wlen * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s->zs, wlen * s->nsplit3 * sizeof(double)));
-  CUDA_TRY(cudaMemset(s->zs, 0, wlen * s->nsplit3 * sizeof(double)));
-  // ---- dense blocks on the device
-  const int mS = pl.nS * dh, padS = s->pcols - s->sep_col0;
-  CUDA_TRY(cudaMalloc((void **)&s->M1, std::max<size_t>((size_t)pl.stages1 * kStageDoubles, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s->M3, std::max<size_t>((size_t)pl.stages3 * kStageDoubles, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc((void **)&s->M5, std::max<size_t>((size_t)pl.stages5 * kStageDoubles, 1) * sizeof(double)));
-  for (int k = 0; k < K; ++k) {
-    if (baseM[k] < 0) {
-      set_error("three-phase plan has no interior strips for domain %d", k);
-      return DPGO_EINVAL;
-    }
-    if (pl.t_m[k] > 0 && (baseG[k] < 0 || baseW[k] < 0)) {
-      set_error("three-phase plan has no coupling strips for domain %d", k);
-      return DPGO_EINVAL;
-    }
-  }
-  auto lgrid = [&](size_t total) { return std::max(1, (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8)); };
-  double *Sg = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
-  {
-    // A_kS is non-zero only in the columns of S_k: C_k = A_k^-1 A_kS[:, S_k] (m x tm) and the Schur update
-    // Sigma[S_k, S_k] -= A_kS[:, S_k]^T C_k (tm x tm) are formed on those columns only, all domains batched
-    Elimination E;
-    int rc = eliminate_domains(h, pl.group, pl.lpos, pl.dom_m, pl.sk_ptr, pl.sk, Sg, mS, E);
-    for (int k = 0; k < K && rc == DPGO_OK; ++k) {
-      const int m = pl.dom_m[k], tm = pl.t_m[k];
-      k_dd_layout<<<lgrid((size_t)pl.dom_pad[k] * pl.dom_pad[k]), 256, 0, h->stream>>>(
-          E.Ainv + E.a_off[k], m, m, pl.dom_pad[k], s->M1 + (size_t)baseM[k] * kStageDoubles);
-      if (tm <= 0) continue;
-      if (tm != E.tm[k]) {
-        set_error("three-phase plan and elimination disagree on |S_%d|", k);
-        rc = DPGO_EINVAL;
-        break;
-      }
-      const double *C = E.C + E.b_off[k];
-      const int nobG = pl.t_pad[k] / kGemvCols, nchG = pl.dom_pad[k] / kStageK;
-      k_dd_layout_rect<<<lgrid((size_t)nobG * nchG * kStageDoubles), 256, 0, h->stream>>>(
-          C, m, m, nullptr, tm, 0, nobG, nchG, s->M1 + (size_t)baseG[k] * kStageDoubles);
-      const int nobW = pl.dom_pad[k] / kGemvCols, nchW = (tm + kStageK - 1) / kStageK;
-      k_dd_layout_rect<<<lgrid((size_t)nobW * nchW * kStageDoubles), 256, 0, h->stream>>>(
-          C, m, m, nullptr, tm, 1, nobW, nchW, s->M5 + (size_t)baseW[k] * kStageDoubles);
-    }
-    if (rc == DPGO_OK && mS > 0) rc = invert_schur(h, Sg, mS);
-    if (rc == DPGO_OK && mS > 0) k_dd_layout<<<lgrid((size_t)padS * padS), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
-    const cudaError_t e1 = cudaPeekAtLastError(), e2 = cudaStreamSynchronize(h->stream);
-    cudaFree(Sg);
-    DPGO_TRY(rc);
-    CUDA_TRY(e1);
-    CUDA_TRY(e2);
-  }
-  return DPGO_OK;
-}
-
 template <int R>
 static int strip_setup() {
   return cudaFuncSetAttribute(k_strip_gemv<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdDynSmem) == cudaSuccess
@@ -759,55 +618,6 @@ static int launch_strips(dpgo_dev *h, const DdStripSet &S, int nstrips, const do
   return DPGO_OK;
 }
 
-template <int R, int SRC>
-static int strip3_launch(dpgo_dev *h, const DdStripSet &S, const double *vec, const int *icol, double *out,
-                         size_t outstride, const StageAux &ax) {
-  DdState *s = (DdState *)h->dd;
-  if (!(s->configured3 & (1u << SRC))) {
-    if (cudaFuncSetAttribute(k_strip_gemv3<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdDynSmem) !=
-        cudaSuccess) {
-      set_error("three-phase strip kernel does not fit on the device");
-      return DPGO_ECUDA;
-    }
-    s->configured3 |= 1u << SRC;
-  }
-  k_strip_gemv3<R, SRC><<<s->V, kBlock, kDdDynSmem, h->stream>>>(S, s->V, vec, icol, out, outstride, ax);
-  h->launches++;
-  CUDA_TRY(cudaPeekAtLastError());
-  return DPGO_OK;
-}
-
-template <int SRC>
-static int launch_strips3(dpgo_dev *h, const DdStripSet &S, int nstrips, const double *vec, const int *icol,
-                          double *out, size_t outstride, const StageAux &ax) {
-  if (nstrips <= 0) return DPGO_OK;
-  switch (h->r) {
-    case 2: return strip3_launch<2, SRC>(h, S, vec, icol, out, outstride, ax);
-    case 3: return strip3_launch<3, SRC>(h, S, vec, icol, out, outstride, ax);
-    case 4: return strip3_launch<4, SRC>(h, S, vec, icol, out, outstride, ax);
-    case 5: return strip3_launch<5, SRC>(h, S, vec, icol, out, outstride, ax);
-    case 6: return strip3_launch<6, SRC>(h, S, vec, icol, out, outstride, ax);
-  }
-  set_error("unsupported r=%d", h->r);
-  return DPGO_EINVAL;
-}
-
-// the three strip phases of the three-phase form (everything but the final projection)
-static int dd3_apply(dpgo_dev *h, const double *vec) {
-  DdState *s = (DdState *)h->dd;
-  const DdView dd = dd_view(h);
-  const size_t zstride = (size_t)h->r * s->pcols;
-  const StageAux a1{nullptr, nullptr, nullptr, 0, 0, 0};
-  DPGO_TRY(launch_strips3<1>(h, dd.P1, s->nstrips1, vec, s->icol, s->y, 0, a1));
-  if (s->nS > 0) {
-    const StageAux a3{s->y, s->tptr, s->tcol, s->sep_col0, 0, 0};
-    DPGO_TRY(launch_strips3<2>(h, dd.P3, s->nstrips3, vec, s->icol, s->zs, zstride, a3));
-    const StageAux a5{nullptr, nullptr, nullptr, 0, s->nsplit3, zstride};
-    DPGO_TRY(launch_strips3<3>(h, dd.P5, s->nstrips5, s->zs, nullptr, s->w, 0, a5));
-  }
-  return DPGO_OK;
-}
-
 // grid for the warp-per-row sparse phases
 static inline int warp_rows_grid(const dpgo_dev *h, int rows) {
   long blocks = ((long)rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -826,7 +636,6 @@ static inline int rows_grid(const dpgo_dev *h, int rows) {
 // the five streaming / sparse phases (everything but the final projection)
 int dd_time_apply(dpgo_dev *h, const double *vec) {
   DdState *s = (DdState *)h->dd;
-  if (s->three) return dd3_apply(h, vec);
   const DdView dd = dd_view(h);
   const size_t zstride = (size_t)h->r * s->pcols;
   DPGO_TRY(launch_strips(h, dd.P1, s->nstrips1, vec, s->icol, s->y, zstride));   // gathers vec on the fly

@@ -113,70 +113,11 @@ int dpgo_set_shared_edges(dpgo_handle h, int m, int num_nbr_slots, const int32_t
 int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *poses,
                     double prior_kappa, double prior_tau);
 /* Build the block-CSR Q on the host, upload it, build the cross blocks for G, and build the
- * preconditioner (dense inverse of Q + 0.1 I via cuSOLVER potrf/potri; the reference uses a
- * CHOLMOD factorization, src/PoseGraph.cpp:598-613 -- both are exact solves).
+ * exact preconditioner (Q + 0.1 I)^-1 with the library's own Cholesky / inverse kernels (the reference
+ * uses a CHOLMOD factorization, src/PoseGraph.cpp:598-613 -- both are exact solves; how the inverse is
+ * stored is the library's choice by size, see dpgo_b200_dev.h).
  * build_precon = 0 skips the preconditioner (then only unpreconditioned ops are available). */
 int dpgo_finalize(dpgo_handle h, int build_precon);
-/* How the exact preconditioner (Q + 0.1 I)^{-1} is stored and applied.  All variants give the same
- * operator (up to summation order); they differ in bytes streamed per application:
- *  -1 (default) choose by size when the preconditioner is built: 2 when N = (d+1)n >= 3000, else 0;
- *   0 full dense inverse, N^2*8 bytes per application (one streaming pass, 2 grid phases);
- *   1 symmetric half storage (blocks I >= K only, each streamed block used for both z_I += P_IK r_K
- *     and z_K += P_IK^T r_I): ~N^2/2*8 bytes, half the memory.  On B200 it is FP64-issue/latency
- *     bound at the wall time of the full one, so it is kept only for memory-limited problems;
- *   2 two-level: nested-dissection domains with dense interior inverses A_II^{-1} and a dense
- *     inverse of the separator Schur complement S = A_SS - A_SI A_II^{-1} A_IS; one application is
- *     z_S = S^{-1}(r_S - A_SI A_II^{-1} r_I), z_I = A_II^{-1}(r_I - A_IS z_S): 3 strip GEMVs and 2
- *     sparse couplings, ~N^2*8/5 bytes on sphere2500 (L2 resident), 5 grid phases.
- *   3 (opt-in, never chosen automatically) the same two-level elimination in three grid phases: the
- *     dense couplings C_k = A_k^{-1} A_kS are kept as strips, so that r_S - A_SI A_II^{-1} r_I comes out
- *     of the first strip phase and z_I = y_I - C z_S out of the last; no sparse coupling phases.
- *   4 (opt-in, d = 3 only; d = 2 falls back to 3) mode 3 with the final projection, <z, r> and -z
- *     produced in the epilogue of the last strip phase inside the fused solver (3 grid phases per
- *     application including the reduction); outside the fused solver it is applied like mode 3.
- * Takes effect at the next dpgo_finalize(h, 1) / dpgo_update_weights(..., 1). */
-int dpgo_set_precon_mode(dpgo_handle h, int mode);
-/* The variant in use (0 .. 4) once the preconditioner is built. */
-int dpgo_get_precon_mode(dpgo_handle h, int *mode);
-/* Host-only inspection of the partition the two-level variant is built on (no device needed): the
- * nested dissection of a pose graph given as a block-CSR pattern (n block rows, rowptr[n+1],
- * colidx) into interior domains of at most max_domain_poses poses (<= 0: the library's value for
- * (d+1) = dh scalars per pose) and a vertex separator.  group[i] = domain id of pose i, or -1 for
- * a separator pose; *num_domains = number of domains.  No block of the pattern joins two
- * different domains. */
-int dpgo_two_level_partition(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
-                             int max_domain_poses, int32_t *group, int *num_domains);
-/* Host-only inspection of the index plan of the three-phase form of the two-level variant
- * (precon_mode 3; no device needed): same nested dissection, separator poses ordered by the set of
- * domains they touch, the dense couplings C_k = A_k^{-1} A_kS folded into the strip phases
- * (dpgo_b200/csrc/dd_plan.h states the algebra).  num_ctas = CTAs the strips are balanced over,
- * split_schur <= 0 = library choice, domain_affine != 0 = the strips of one domain share CTAs (they read
- * the same input slice, which is then staged once per CTA) instead of the plain longest-first
- * balancing.  The plan is written to `out` as a flat int64 image:
- * out[0] = S sections, then S pairs (offset, length), then the sections, in this order:
- *   0 scalars {n, dh, K, nS, V, sep_col0, pcols, ycols, nsplit3, stages1, stages3, stages5, bytes_per_apply}
- *   1 group[n]  2 pcol[n]  3 srow[nS]  4 icol[ycols]  5-7 dom_off / dom_m / dom_pad [K]
- *   8-10 t_off / t_m / t_pad [K]  11 sk_ptr[K+1]  12 sk  13 tptr  14 tcol  15 gchunk[K]  16 gidx
- *   17-19 strips of phase 1 / 3 / 5, 8 values each {cb, kc0, nchunks, slot, data_off, kind, k, blk}
- *   20-22 cta1 / cta3 / cta5 [V+1] (strip ranges of the virtual CTAs).
- * *out_len = values needed; nothing is written when out_capacity is smaller (call twice). */
-int dpgo_three_phase_plan(int n, const int32_t *rowptr, const int32_t *colidx, int dh,
-                          int max_domain_poses, int num_ctas, int split_schur, int domain_affine,
-                          int64_t *out, int64_t out_capacity, int64_t *out_len);
-/* Tuning of the two-level variant (measurement knobs; 0 / negative = library default): how many
- * partial slots the inner dimension of the interior strips and of the Schur strips is split into
- * (more splits = more CTAs busy per phase, more partial sums to add), and whether the first
- * pipeline stages of a strip phase are issued before the grid barrier that precedes it
- * (prefetch: 1 on, 0 off, negative = default on).  The three-phase form (mode 3) has whole interior
- * strips; there split_interior == 2 selects the domain-affine balancing of dpgo_three_phase_plan.
- * Takes effect at the next preconditioner build. */
-int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, int prefetch);
-/* Measurement knob of the two-level variants: poses per interior domain of the nested dissection
- * (0 = library default: a domain is one wave of strip stages, 80 poses for d = 3).  Larger domains mean
- * fewer separator poses and larger interior inverses; max_domain_poses >= n gives a single domain and no
- * separator, i.e. the full dense inverse applied by the one-CTA-per-SM strip kernel (strips then take
- * several waves).  Takes effect at the next preconditioner build. */
-int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses);
 /* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
 int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,
@@ -292,27 +233,6 @@ int dpgo_measurement_errors(dpgo_handle h, int slot, const double *nbr_poses_dev
 /* max_i || p_i(a) - p_i(b) ||  (LiftedPoseArray::maxTranslationDistance, used for
  * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
 int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);
-
-/* ---- measurement helpers ----------------------------------------------------------------- */
-/* Time `reps` back-to-back launches of the Q*X kernel / preconditioner kernel on the handle's
- * stream with CUDA events; flush_l2 != 0 streams a >L2-sized buffer between launches
- * (outside the timed intervals).  Returns mean microseconds per launch. */
-int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec);
-int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
-/* Measurement knob for the stand-alone Q*X (dpgo_qx, dpgo_time_qx; the solver's fused passes are not
- * affected): variant 0 = the default kernel; 1 = the same product with a software prefetch -- every pose
- * group asks the L2 (cp.async.bulk.prefetch.L2) for the Q blocks, column indices and X tile of the pose
- * `prefetch_distance` rows further on (0 = the poses covered by the CTAs that are resident together). */
-int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance);
-/* Measurement builds only (library compiled with -DDPGO_TRACE, `python dpgo_b200/build.py --trace`;
- * otherwise DPGO_ESTATE): how long every CTA of the last fused solve worked in each phase before
- * reaching the phase's grid barrier, busy_ms[cta * 16 + phase] with the phase ids of
- * dpgo_ropt_result.phase_ms.  *num_ctas = CTAs of that launch; nothing is written when cap_ctas is
- * smaller. */
-int dpgo_phase_trace(dpgo_handle h, double *busy_ms, int cap_ctas, int *num_ctas);
-/* algorithmic bytes of one Q*X / one preconditioner application (SURVEY 8(d) formula) */
-int dpgo_bytes_qx(dpgo_handle h, double *bytes);
-int dpgo_bytes_precon(dpgo_handle h, double *bytes);
 
 #ifdef __cplusplus
 }

@@ -24,17 +24,6 @@ struct EmuProblem {
   // mode 0: stage-major tiled dense inverse (k_tile_layout format), ld x ldk
   const double *Pinv;
   int ld, KT, nsplit;
-  // modes 3 / 4: three-phase plan (dd_plan.h) and its stage buffers
-  int V, nS, nsplit3, sep_col0, pcols, ycols, prefetch;
-  const double *M1, *M3, *M5;
-  const void *strips1, *strips3, *strips5;
-  const int *cta1, *chunks1, *cta3, *chunks3, *cta5, *chunks5;
-  const int *gidx, *icol, *tptr, *tcol, *pcol, *srow;
-  // mode 2 (five-phase form): sparse couplings A_SI (rows = separator positions) and A_BS (rows = interior
-  // poses with a separator neighbour), block-CSR with permuted scalar columns; bcol = permuted column per row
-  const int *si_rowptr, *si_colidx, *bs_rowptr, *bs_colidx, *bcol;
-  const double *si_blocks, *bs_blocks;
-  int nB;
   // solver parameters (dpgo_ropt_params)
   double gradnorm_tol, init_radius, theta, kappa, accept_rho, shrink, magnify;
   int max_outer, max_inner;
@@ -49,7 +38,7 @@ struct EmuProblem {
 
 namespace {
 
-alignas(128) unsigned char g_dsm[(kDd3DynSmem > kGemvDynSmem ? kDd3DynSmem : kGemvDynSmem)];
+alignas(128) unsigned char g_dsm[kGemvDynSmem];
 
 template <int R, int D, int MODE>
 void thread_main(unsigned tid, FusedParams fp) {
@@ -60,13 +49,11 @@ void thread_main(unsigned tid, FusedParams fp) {
 template <int R, int D, int MODE>
 int run(const EmuProblem &e) {
   const int dh = D + 1, N = dh * e.n;
-  const size_t cols = (size_t)std::max(std::max(e.nsplit * e.KT, N), e.ycols) + 64;
+  const size_t cols = (size_t)std::max(e.nsplit * e.KT, N) + 64;
   const size_t len = (size_t)R * cols;
   std::vector<std::vector<double>> vec(13, std::vector<double>(len, 0.0));
   std::vector<double> S((size_t)e.n * D * D, 0.0), S2(S), partials(64, 0.0);
   std::vector<double> zpart((size_t)std::max(e.nsplit, 1) * len, 0.0);
-  std::vector<double> y((size_t)R * std::max(e.ycols, 64), 0.0), w((size_t)R * std::max(e.pcols, 64), 0.0);
-  std::vector<double> zs((size_t)std::max(e.nsplit3, 1) * R * std::max(e.pcols, 64), 0.0);
   FusedOut out{};
   FusedParams fp{};
   fp.Q = BsrView{e.rowptr, e.colidx, e.blocks};
@@ -76,31 +63,6 @@ int run(const EmuProblem &e) {
   fp.ld = e.ld; fp.KT = e.KT; fp.nsplit = e.nsplit; fp.n = e.n;
   fp.zstride = len;
   fp.precon_mode = MODE;
-  std::vector<double> tt((size_t)R * std::max(e.pcols, 64), 0.0), uu(tt);
-  if (MODE == 2) {
-    DdView &dd = fp.dd;
-    dd.P1 = DdStripSet{e.M1, (const DdStrip *)e.strips1, e.cta1, e.chunks1, nullptr};
-    dd.P3 = DdStripSet{e.M3, (const DdStrip *)e.strips3, e.cta3, e.chunks3, nullptr};
-    dd.V = e.V; dd.nsplit1 = 1; dd.nsplit3 = e.nsplit3; dd.nS = e.nS; dd.nB = e.nB;
-    dd.A_SI = BsrView{e.si_rowptr, e.si_colidx, e.si_blocks};
-    dd.A_BS = BsrView{e.bs_rowptr, e.bs_colidx, e.bs_blocks};
-    dd.pcol = e.pcol; dd.srow = e.srow; dd.bcol = e.bcol; dd.icol = e.icol;
-    dd.sep_col0 = e.sep_col0; dd.pcols = e.pcols;
-    dd.y = y.data(); dd.t = tt.data(); dd.zs = zs.data(); dd.u = uu.data(); dd.w = w.data();
-    dd.prefetch = e.prefetch;
-  }
-  if (MODE >= 3) {
-    DdView &dd = fp.dd;
-    dd.P1 = DdStripSet{e.M1, (const DdStrip *)e.strips1, e.cta1, e.chunks1, nullptr};
-    dd.P3 = DdStripSet{e.M3, (const DdStrip *)e.strips3, e.cta3, e.chunks3, nullptr};
-    dd.P5 = DdStripSet{e.M5, (const DdStrip *)e.strips5, e.cta5, e.chunks5, e.gidx};
-    dd.V = e.V; dd.nsplit1 = 1; dd.nsplit3 = e.nsplit3; dd.nS = e.nS;
-    dd.pcol = e.pcol; dd.srow = e.srow; dd.icol = e.icol;
-    dd.sep_col0 = e.sep_col0; dd.pcols = e.pcols;
-    dd.y = y.data(); dd.zs = zs.data(); dd.w = w.data();
-    dd.prefetch = e.prefetch;
-    dd.tptr = e.tptr; dd.tcol = e.tcol;
-  }
   fp.x_in = e.x_in; fp.x_out = e.x_out;
   double **slots[] = {&fp.xa, &fp.xb, &fp.EG, &fp.EG2, &fp.grad, &fp.grad2, &fp.eta, &fp.r, &fp.z, &fp.delta, &fp.Hd};
   for (int i = 0; i < 11; ++i) *slots[i] = vec[i].data();
@@ -128,11 +90,6 @@ int run(const EmuProblem &e) {
 template <int R, int D>
 int by_mode(const EmuProblem &e) {
   if (e.mode == 0) return run<R, D, 0>(e);
-  if (e.mode == 2) return run<R, D, 2>(e);
-  if (e.mode == 3) return run<R, D, 3>(e);
-  if constexpr (D == 3) {
-    if (e.mode == 4) return run<R, D, 4>(e);
-  }
   return -1;
 }
 

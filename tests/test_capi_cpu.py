@@ -9,10 +9,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "dpgo_b200.h")).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(dpgo_[a-zA-Z0-9_]+)\s*\(", txt)))
+def _declared_symbols(headers=("dpgo_b200.h", "dpgo_b200_dev.h")):
+    found = set()
+    for hname in headers:
+        txt = open(os.path.join(ROOT, "include", hname)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        found |= set(re.findall(r"\b(dpgo_[a-zA-Z0-9_]+)\s*\(", txt))
+    return sorted(found)
 
 
 def test_library_exports_every_declared_symbol():

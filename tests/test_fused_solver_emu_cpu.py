@@ -1,11 +1,10 @@
-"""CPU test of the persistent fused RTR solver kernel itself: k_rtr_fused<R, D, MODE>
+"""CPU test of the persistent fused RTR solver kernel itself: k_rtr_fused<R, D, 0>
 (dpgo_b200/csrc/fused_kernel.cuh, the source nvcc compiles for the product) is built with g++ against
 tests/native/cuda_emu.h -- one CTA of 256 real threads, CTA barriers for __syncthreads and grid.sync, warp
 shuffles, TMA bulk copies completing emulated mbarriers -- and must reproduce the oracle's
 QuadraticOptimizer::optimize (ref: src/QuadraticOptimizer.cpp:26-108): same outer / tCG iteration counts,
-same objective, same iterate.  MODE 0 = dense inverse (the default below 3000 scalars), MODE 2 = the
-five-phase two-level preconditioner (the default above, i.e. the kernel behind the sphere2500 bench line),
-MODE 3 / 4 = its three-phase forms, whose first run on a device is still pending.
+same objective, same iterate.  MODE 0 = dense inverse (the default below 3000 scalars); the two-level form
+(MODE 2) is covered on the device by tests/test_gpu_a_parity.py.
 What the emulation cannot show: timing, the asynchrony of real TMA copies, memory-model effects across SMs."""
 import ctypes as C
 import os
@@ -22,7 +21,6 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):       # also when run as a script
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-import three_phase_emu as emu  # noqa: E402
 from oracle import pgo  # noqa: E402
 _dp, _ip, _vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
 
@@ -31,19 +29,9 @@ class EmuProblem(C.Structure):
     _fields_ = ([("mode", C.c_int), ("R", C.c_int), ("d", C.c_int), ("n", C.c_int),
                  ("rowptr", _ip), ("colidx", _ip), ("blocks", _dp), ("G", _dp),
                  ("Pinv", _dp), ("ld", C.c_int), ("KT", C.c_int), ("nsplit", C.c_int)] +
-                [(k, C.c_int) for k in ("V", "nS", "nsplit3", "sep_col0", "pcols", "ycols", "prefetch")] +
-                [("M1", _dp), ("M3", _dp), ("M5", _dp), ("strips1", _vp), ("strips3", _vp), ("strips5", _vp)] +
-                [(k, _ip) for k in ("cta1", "chunks1", "cta3", "chunks3", "cta5", "chunks5",
-                                    "gidx", "icol", "tptr", "tcol", "pcol", "srow")] +
-                [(k, _ip) for k in ("si_rowptr", "si_colidx", "bs_rowptr", "bs_colidx", "bcol")] +
-                [("si_blocks", _dp), ("bs_blocks", _dp), ("nB", C.c_int)] +
                 [(k, C.c_double) for k in ("gradnorm_tol", "init_radius", "theta", "kappa", "accept_rho", "shrink",
                                            "magnify")] +
                 [("max_outer", C.c_int), ("max_inner", C.c_int), ("x_in", _dp), ("x_out", _dp), ("result", _dp)])
-
-
-STRIP_DT = np.dtype([("cb", np.int32), ("kc0", np.int32), ("nchunks", np.int32), ("slot", np.int32),
-                     ("data_off", np.int64)])
 
 
 @pytest.fixture(scope="module")
@@ -105,33 +93,6 @@ def _solve(lib, meas, n, R, mode, X0, max_poses=12, V=5, prefetch=1):
         T = P.reshape(ncb, 64, ldk // 32, 32).transpose(2, 0, 3, 1)
         e.Pinv = _dp_of(hold(np.ascontiguousarray(T).reshape(-1)))
         e.ld, e.KT, e.nsplit = ld, KT, nsplit
-    else:
-        from dpgo_b200 import _lib
-        G = sp.coo_matrix((np.ones(len(meas.p1)), (meas.p1, meas.p2)), shape=(n, n))
-        G = (G + G.T + sp.identity(n)).tocsr()
-        G.sort_indices()
-        plan = emu.fetch_plan(_lib.lib.dpgo_three_phase_plan, n, G.indptr, G.indices, dh, max_poses, V)
-        bufs = emu.fill_stage_buffers(plan, *emu.dense_blocks(A, plan))
-        for ph in ("1", "3", "5"):
-            st = plan["strips" + ph]
-            a = hold(np.zeros(max(len(st), 1), dtype=STRIP_DT))
-            for k, name in enumerate(("cb", "kc0", "nchunks", "slot", "data_off")):
-                a[name][:len(st)] = st[:, k]
-            cta = hold(np.ascontiguousarray(plan["cta" + ph], dtype=np.int32))
-            chunks = hold(np.array([st[cta[v]:cta[v + 1], 2].sum() for v in range(plan["V"])], dtype=np.int32))
-            M = hold(np.ascontiguousarray(bufs[ph].reshape(-1)) if bufs[ph].size else np.zeros(1))
-            setattr(e, "M" + ph, _dp_of(M))
-            setattr(e, "strips" + ph, a.ctypes.data_as(_vp))
-            setattr(e, "cta" + ph, _ip_of(cta))
-            setattr(e, "chunks" + ph, _ip_of(chunks))
-        for name in ("gidx", "icol", "tptr", "tcol", "pcol", "srow"):
-            arr = np.ascontiguousarray(plan[name], dtype=np.int32)
-            setattr(e, name, _ip_of(hold(arr if len(arr) else np.zeros(1, dtype=np.int32))))
-        for name in ("V", "nS", "nsplit3", "sep_col0", "pcols", "ycols"):
-            setattr(e, name, plan[name])
-        e.prefetch = prefetch
-        if mode == 2:
-            _five_phase(e, plan, B, dh, hold)
     prm = pgo.ROptParameters()
     e.gradnorm_tol, e.init_radius = prm.gradnorm_tol, prm.RTR_initial_radius
     e.theta, e.kappa, e.accept_rho, e.shrink, e.magnify = 1.0, 0.1, 0.1, 0.25, 2.0     # ROPTLIB defaults (rtr_logic.h)
@@ -146,46 +107,6 @@ def _solve(lib, meas, n, R, mode, X0, max_poses=12, V=5, prefetch=1):
     return xout.reshape(N, R).T.copy(), dict(zip(names, res[:14]))
 
 
-def _five_phase(e, plan, B, dh, hold):
-    """The five-phase form (MODE 2) on the same partition and column order: the interior strips are the M_k
-    strips of the three-phase plan, the couplings stay sparse -- A_SI (rows = separator positions) and A_BS
-    (rows = interior poses with a separator neighbour) as block-CSR with permuted scalar columns, which is
-    what the device set-up (dd_build) uploads."""
-    group, pcol, srow = plan["group"], plan["pcol"], plan["srow"]
-    st, cta = plan["strips1"], plan["cta1"]
-    keep_rows, new_cta = [], [0]
-    for v in range(plan["V"]):
-        keep_rows += [i for i in range(cta[v], cta[v + 1]) if st[i, 5] == 0]
-        new_cta.append(len(keep_rows))
-    a = hold(np.zeros(max(len(keep_rows), 1), dtype=STRIP_DT))
-    for k, name in enumerate(("cb", "kc0", "nchunks", "slot", "data_off")):
-        a[name][:len(keep_rows)] = st[keep_rows, k]
-    ncta = hold(np.array(new_cta, dtype=np.int32))
-    chunks = hold(np.array([a["nchunks"][ncta[v]:ncta[v + 1]].sum() for v in range(plan["V"])], dtype=np.int32))
-    e.strips1, e.cta1, e.chunks1 = a.ctypes.data_as(_vp), _ip_of(ncta), _ip_of(chunks)
-
-    def rows(poses, want_sep_cols):
-        rp, ci, bl, used = [0], [], [], []
-        for i in poses:
-            n0 = len(ci)
-            for p in range(B.indptr[i], B.indptr[i + 1]):
-                c = B.indices[p]
-                if (group[c] < 0) == want_sep_cols:
-                    ci.append(pcol[c]); bl.append(B.data[p])
-            if want_sep_cols and len(ci) == n0:
-                continue                                     # interior pose without a separator neighbour: no row
-            rp.append(len(ci)); used.append(i)
-        blocks = np.ascontiguousarray(np.array(bl).reshape(-1)) if bl else np.zeros(1)
-        return (hold(np.array(rp, dtype=np.int32)), hold(np.array(ci if ci else [0], dtype=np.int32)), hold(blocks), used)
-
-    e.si_rowptr, e.si_colidx, e.si_blocks = (lambda r: (_ip_of(r[0]), _ip_of(r[1]), _dp_of(r[2])))(rows(srow, False))
-    interior = [i for k in range(plan["K"]) for i in np.where(group == k)[0]]
-    rp, ci, bl, used = rows(interior, True)
-    e.bs_rowptr, e.bs_colidx, e.bs_blocks = _ip_of(rp), _ip_of(ci), _dp_of(bl)
-    e.bcol = _ip_of(hold(np.array([pcol[i] for i in used] or [0], dtype=np.int32)))
-    e.nB = len(used)
-
-
 def _dp_of(a):
     return a.ctypes.data_as(_dp)
 
@@ -197,13 +118,7 @@ def _ip_of(a):
 CASES = [
     ("tinyGrid3D", 5, 0, 0, 0, 1),
     ("smallGrid3D", 5, 0, 0, 0, 1),          # the product's default path for this size (dense inverse)
-    ("smallGrid3D", 5, 2, 12, 5, 1),         # five-phase form of the two-level preconditioner (sphere2500's default)
-    ("smallGrid3D", 5, 2, 60, 3, 0),         # the same with multi-wave strips, no prefetch
-    ("smallGrid3D", 5, 3, 12, 5, 1),         # three-phase form, separate finish
-    ("smallGrid3D", 5, 4, 12, 5, 1),         # finish fused into the last strip phase
-    ("smallGrid3D", 5, 4, 12, 5, 0),         # the same without the pre-barrier prefetch
-    ("smallGrid3D", 3, 4, 60, 3, 1),         # r = d, domains longer than one wave
-    ("smallGrid3D", 5, 4, 200, 2, 1),        # a single domain, no separator
+    ("smallGrid3D", 3, 0, 0, 0, 1),          # r = d
 ]
 
 

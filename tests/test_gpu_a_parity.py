@@ -256,9 +256,10 @@ def test_qx_properties_beyond_l2():
 
 @pytest.mark.parametrize("name,r", [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 5)])
 def test_precon_storage_variants(datasets, name, r):
-    """The exact preconditioner in its three forms (dpgo_set_precon_mode 0 / 1 / 2): full dense
-    inverse, symmetric half storage, two-level block elimination over a nested dissection -- the
-    same operator (1e-8 vs the oracle's exact solve, 1e-9 against each other) and the same solve."""
+    """The exact preconditioner in its two forms (dpgo_set_precon_mode 0 / 2): full dense inverse and two-level
+    block elimination over a nested dissection, both set up by the in-tree Cholesky / inverse / tile GEMM kernels
+    (dense_la.cu) -- the same operator (1e-8 vs the oracle's exact solve, 1e-9 against each other) and the same
+    solve; the forms removed in round 2 are refused."""
     import dpgo_b200
     meas, n, z = datasets(name)
     d = meas.d
@@ -268,17 +269,20 @@ def test_precon_storage_variants(datasets, name, r):
     ref = op.precondition(X, Vt)
     X0 = pgo.lifting_matrix(d, r) @ z["T_chordal"]
     outs, sols = [], []
-    for mode in (0, 1, 2):
+    for mode in (0, 2):
         gp = dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau,
                                                  n, d, r, precon_mode=mode)
+        assert gp.precon_mode() == mode
         outs.append(gp.precon(X, Vt))
         assert rel(outs[-1], ref) < 1e-8
         for fused in (0, 1):
             Xg, res = gp.optimize(X0, dpgo_b200.default_params(fused=fused))
             sols.append((Xg, res))
         gp.close()
-    assert rel(outs[0], outs[1]) < 1e-10
-    assert rel(outs[0], outs[2]) < 1e-9      # two-level block elimination: same operator
+    assert rel(outs[0], outs[1]) < 1e-9      # two-level block elimination: same operator
+    with pytest.raises(dpgo_b200.DpgoError):
+        dpgo_b200.problem_from_measurements(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r,
+                                            precon_mode=3)
     Xo, ro = pgo.optimize(op, X0)
     for Xg, res in sols:
         assert (res["outer_iters"], res["inner_iters"]) == (ro.outer, ro.inner_total)

@@ -3,7 +3,7 @@
 Prints, per problem and configuration, the stand-alone apply time, the fused-solver time of one
 optimize() and the in-kernel phase clocks (dpgo_ropt_result.phase_ms), as JSON lines.
 
-    python tools/dd_probe.py [--quick | --forms] > gpurun_out/dd_probe.jsonl
+    python tools/dd_probe.py [--quick | --barrier-ab] > gpurun_out/dd_probe.jsonl
 """
 import json
 import os
@@ -48,30 +48,12 @@ def run(tag, z, d, n, T0, r, mode, tuning=None, reps=3, domain_size=None):
     gp.close()
 
 
-def forms():
-    """--forms: the five-phase form against the three-phase forms (modes 3 / 4) and the domain-size knob
-    (one domain = the dense inverse through the strip kernel), on the bench problem and on agent-sized
-    grids (512 / 1000 / 1728 poses: torus3D/8-, grid3D/8-sized agents)."""
-    z, d, n, T0 = fixture("sphere2500")
-    for mode, tuning, dom in [(2, None, None), (3, None, None), (3, (2, 0, -1), None), (4, None, None),
-                              (4, (2, 0, -1), None), (2, None, 160), (4, None, 160), (4, None, 40)]:
-        run("sphere2500", z, d, n, T0, 5, mode, tuning, domain_size=dom)
-    for L in (8, 10, 12):
-        g = synthetic.grid3d(L, seed=1)
-        T = g["T_true"] if "T_true" in g else g["T0"]
-        for mode, dom in [(0, None), (2, None), (3, None), (4, None), (2, L ** 3), (4, 160)]:
-            run(f"grid3d_L{L}", g, 3, L ** 3, T, 5, mode, domain_size=dom)
-    z, d, n, T0 = fixture("city10000")
-    for mode in (2, 3):
-        run("city10000", z, d, n, T0, 3, mode, reps=2)
-
-
 def barrier_ab():
     """--barrier-ab: the solves whose time is barrier / latency bound, for A/B runs of library builds that differ
     in the grid barrier (DPGO_B200_LIB=...): bench problem in the two-level forms and with the dense inverse,
     one grid3D-agent-sized problem."""
     z, d, n, T0 = fixture("sphere2500")
-    for mode in (2, 4, 0):
+    for mode in (2, 0):
         run("sphere2500", z, d, n, T0, 5, mode, reps=5)
     g = synthetic.grid3d(10, seed=1)
     for mode in (0, 2):
@@ -79,8 +61,6 @@ def barrier_ab():
 
 
 def main():
-    if "--forms" in sys.argv:
-        return forms()
     if "--barrier-ab" in sys.argv:
         return barrier_ab()
     quick = "--quick" in sys.argv

@@ -35,7 +35,7 @@ def main():
     from bench import lifting_matrix, load_fixture
     name = sys.argv[1] if len(sys.argv) > 1 else "sphere2500"
     r = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    modes = [int(a) for a in sys.argv[3:]] or [2, 3]
+    modes = [int(a) for a in sys.argv[3:]] or [2, 0]
     z, d, n = load_fixture(name)
     X0 = np.asfortranarray(lifting_matrix(d, r) @ z["T_chordal"])
     for mode in modes:
