@@ -82,6 +82,14 @@ __global__ void __launch_bounds__(kBlock, 3) k_qx_pipe(BsrView Q, const double *
   phase_qx<R, D, true>(make_ctx(), Q, X, G, out, n);
 }
 
+// lane-group kernel with the X tiles of a warp step staged in shared memory (phase_qx_tiles)
+template <int R, int D>
+__global__ void __launch_bounds__(kBlock, 4) k_qx_tiles(BsrView Q, const double *X, const double *G,
+                                                        double *out, int n) {
+  __shared__ __align__(16) unsigned char stage[kWarpsPerBlock][QxTiles<R, D>::WARP_BYTES];
+  phase_qx_tiles<R, D>(make_ctx(), Q, X, G, out, n, stage[threadIdx.x >> 5]);
+}
+
 template <int R, int D>
 __global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const double *X, const double *G,
                                                         double *out, int n, int dist) {
@@ -364,6 +372,12 @@ static int qx_prefetch_distance(dpgo_dev *h) {
 int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
   const int variant = h->qx_variant > 0 ? h->qx_variant : 0;
   if (variant == 0) return op_qx(h, qview(h), X, G, out);
+  if (variant == 2) {
+    const int grid = pose_grid(h, h->d + 1);
+    DPGO_DISPATCH(h, k_qx_tiles<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    LAUNCH_CHECK(h);
+    return DPGO_OK;
+  }
   if (variant == 3) {
     const int grid = pose_grid(h, h->d + 1);
     DPGO_DISPATCH(h, k_qx_pipe<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
@@ -1141,7 +1155,7 @@ int dpgo_set_precon_tuning(dpgo_handle h, int split_interior, int split_schur, i
 }
 
 int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance) {
-  CHECK_ARG(h != nullptr && (variant == -1 || variant == 0 || variant == 1 || variant == 3) && prefetch_distance >= 0);
+  CHECK_ARG(h != nullptr && variant >= -1 && variant <= 3 && prefetch_distance >= 0);
   h->qx_variant = variant;
   h->qx_prefetch_dist = prefetch_distance;
   return DPGO_OK;

@@ -96,7 +96,7 @@ struct dpgo_dev {
   int dd_split1 = 0, dd_split3 = 0;   // inner splits of the interior / Schur strips (0 = by size)
   int dd_prefetch = 1;                // issue the next strip phase's first stages before the barrier
   // stand-alone Q*X (dpgo_set_qx_variant; measurement variants): -1 / 0 = lane-group kernel (default),
-  // 1 = + L2 prefetch hints, 3 = two blocks per step
+  // 1 = + L2 prefetch hints, 2 = X tiles staged in shared memory, 3 = two blocks per step
   int qx_variant = -1, qx_prefetch_dist = 0;
   int dd_max_domain = 0;              // poses per interior domain (0 = one wave of strip stages)
   int *d_public_idx = nullptr;

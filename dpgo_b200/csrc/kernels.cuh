@@ -325,6 +325,109 @@ __device__ __forceinline__ void phase_qx(const Ctx &ctx, const BsrView &Q, const
   }
 }
 
+// Q*X with the gathered pose tiles staged in shared memory (measurement variant 2 of the stand-alone kernel).
+// Same lane-group mapping and the same sums in the same order as phase_qx; what changes is how an X tile reaches
+// the d+1 lanes that need all of it.  In phase_qx every lane loads the whole tile (r(d+1)/2 128-bit loads whose 32
+// lanes touch 8 different lines: the L1 data pipe is the limiter at scale).  Here the 8 tiles of a warp step are
+// fetched ONCE, 16-byte pieces dealt over the 32 lanes (a tile = 10 consecutive lanes = whole lines), written to
+// the warp's staging area and read back by the lane groups as shared-memory broadcasts: about half the L1
+// wavefronts per block.  The fetch of step s+1 is issued before the FMAs of step s, the column index one step
+// earlier still, so a step costs one memory latency.
+template <int R, int D>
+struct QxTiles {
+  static constexpr int DH = D + 1, GPW = 32 / DH, TILE = R * DH;
+  static constexpr int PB = (TILE % 2 == 0) ? 16 : 8;        // bytes per piece
+  static constexpr int NP = TILE * 8 / PB;                   // pieces per tile
+  static constexpr int NPW = (GPW * NP + 31) / 32;           // pieces per lane and step
+  static constexpr int TP = TILE * 8 + 16;                   // tile pitch in the staging area (bank spread)
+  static constexpr int WARP_BYTES = ((GPW * TP + 15) / 16) * 16;
+};
+
+template <int R, int D>
+__device__ __forceinline__ void phase_qx_tiles(const Ctx &ctx, const BsrView &Q, const double *X, const double *G,
+                                               double *out, int n, unsigned char *wsm) {
+  using T = QxTiles<R, D>;
+  constexpr int DH = T::DH, GPW = T::GPW, TILE = T::TILE;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  struct Piece { double a, b; };
+  for (int base = ctx.warp * GPW; base < n; base += ctx.nwarps * GPW) {      // warp-uniform
+    const int i = base + lp.grp;
+    const bool active = lp.ok && i < n;
+    const int e0 = active ? __ldg(Q.rowptr + i) : 0, e1 = active ? __ldg(Q.rowptr + i + 1) : 0;
+    const int len = e1 - e0;
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, (int)__shfl_xor_sync(0xffffffffu, maxlen, o));
+    double acc[R];
+    const size_t off = ((size_t)i * DH + lp.c) * R;
+    if (active && G) load_col<R>(G + off, acc);
+    else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = 0.0;
+    }
+    Piece t[T::NPW];
+    auto fetch = [&](int j) {      // every lane takes part (shuffles); j = this group's column index or -1
+#pragma unroll
+      for (int m = 0; m < T::NPW; ++m) {
+        const int p = ctx.lane + 32 * m;
+        const bool valid = p < GPW * T::NP;
+        const int tile = valid ? p / T::NP : 0, piece = p - tile * T::NP;
+        const int jt = (int)__shfl_sync(0xffffffffu, j, tile * DH);
+        t[m].a = 0.0; t[m].b = 0.0;
+        if (valid && jt >= 0) {
+          const double *src = X + (size_t)jt * TILE + piece * (T::PB / 8);
+          if constexpr (T::PB == 16) {
+            const double2 v = *reinterpret_cast<const double2 *>(src);
+            t[m].a = v.x; t[m].b = v.y;
+          } else {
+            t[m].a = src[0];
+          }
+        }
+      }
+    };
+    int j = (len > 0) ? __ldg(Q.colidx + e0) : -1;
+    fetch(j);
+    for (int s = 0; s < maxlen; ++s) {
+      const int jn = (s + 1 < len) ? __ldg(Q.colidx + e0 + s + 1) : -1;
+      double mk[DH];
+      if (s < len) load_q_row<DH>(Q.blocks + (size_t)(e0 + s) * (DH * DH) + lp.c * DH, mk);
+#pragma unroll
+      for (int m = 0; m < T::NPW; ++m) {
+        const int p = ctx.lane + 32 * m;
+        if (p < GPW * T::NP) {
+          const int tile = p / T::NP, piece = p - tile * T::NP;
+          double *dst = reinterpret_cast<double *>(wsm + tile * T::TP + piece * T::PB);
+          dst[0] = t[m].a;
+          if constexpr (T::PB == 16) dst[1] = t[m].b;
+        }
+      }
+      __syncwarp();
+      fetch(jn);                                   // next step's tiles in flight during the FMAs
+      if (s < len) {
+        const double *xs = reinterpret_cast<const double *>(wsm + lp.grp * T::TP);
+        double x[TILE];
+        if constexpr (TILE % 2 == 0) {
+#pragma unroll
+          for (int k = 0; k < TILE / 2; ++k) {
+            const double2 v = reinterpret_cast<const double2 *>(xs)[k];
+            x[2 * k] = v.x; x[2 * k + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < TILE; ++k) x[k] = xs[k];
+        }
+#pragma unroll
+        for (int k = 0; k < DH; ++k) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) acc[q] = fma(x[k * R + q], mk[k], acc[q]);
+        }
+      }
+      __syncwarp();                                // the staging area may be overwritten
+    }
+    if (active) store_col<R>(out + off, acc);
+  }
+}
+
 // TMA bulk prefetch into L2 (no destination in the SM, no registers held): `bytes` from a 16-byte aligned
 // address, a multiple of 16
 #ifndef DPGO_CPU_EMU

@@ -57,8 +57,8 @@ int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
  * affected): variant -1 / 0 = the default kernel; 1 = the same product with a software prefetch -- every pose
  * group asks the L2 (cp.async.bulk.prefetch.L2) for the Q blocks, column indices and X tile of the pose
  * `prefetch_distance` rows further on (0 = the poses covered by the CTAs that are resident together);
- * 3 = the block row walked two blocks per step with the column indices one step ahead.  All three give
- * the same bits. */
+ * 2 = the X tiles of a warp step fetched once (16-byte pieces dealt over the lanes) and staged in shared memory;
+ * 3 = the block row walked two blocks per step with the column indices one step ahead.  All give the same bits. */
 int dpgo_set_qx_variant(dpgo_handle h, int variant, int prefetch_distance);
 /* Measurement builds only (library compiled with -DDPGO_TRACE, `python dpgo_b200/build.py --trace`;
  * otherwise DPGO_ESTATE): how long every CTA of the last fused solve worked in each phase before

@@ -218,7 +218,7 @@ def test_linearity_and_symmetry_at_scale(datasets):
 def test_qx_variants_parity(datasets, name, r):
     """The stand-alone Q*X against the oracle's X Q (1e-12) for every tile shape the kernels are instantiated for
     (256-bit loads of whole 32-byte sectors for d = 3, 128- / 64-bit loads for d = 2), and the measurement variants
-    (L2 prefetch hints, two blocks per step): same sums in the same order, bit for bit."""
+    (L2 prefetch hints, X tiles staged in shared memory, two blocks per step): same sums in the same order, bit for bit."""
     meas, n, _ = datasets(name)
     d = meas.d
     gp = make_problem(meas, n, r, build_precon=False)
@@ -228,7 +228,7 @@ def test_qx_variants_parity(datasets, name, r):
     gp.set_qx_variant(0, 0)
     base = gp.qx(X)
     assert rel(base, ref) < 1e-12
-    for variant, dist in ((1, 64), (3, 0)):
+    for variant, dist in ((1, 64), (2, 0), (3, 0)):
         gp.set_qx_variant(variant, dist)
         assert np.array_equal(gp.qx(X), base), variant
     gp.set_qx_variant(-1, 0)

@@ -8,7 +8,7 @@ from oracle import pgo, rbcd as orbcd
 pytestmark = pytest.mark.gpu
 
 
-def _teams(datasets, name, A, r, acceleration=True):
+def _teams(datasets, name, A, r, acceleration=True, native=False):
     from dpgo_b200 import rbcd
     meas, n, z = datasets(name)
     d = meas.d
@@ -16,7 +16,7 @@ def _teams(datasets, name, A, r, acceleration=True):
     ot = orbcd.Team(meas, n, A, r, acceleration=acceleration)
     ot.set_X(X0)
     gt = rbcd.DeviceTeam(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, d, r, A,
-                         acceleration=acceleration)
+                         acceleration=acceleration, native_exchange=native)
     gt.set_X(X0)
     return meas, n, d, ot, gt
 
@@ -103,12 +103,14 @@ def test_measurement_errors_parity(datasets):
     gt.close()
 
 
-def test_gnc_weight_update_parity(datasets):
-    """BASELINE config 5: city10000 (2D), 4 agents, r = 3, GNC_TLS loop-closure weights
+@pytest.mark.parametrize("native", [False, True])
+def test_gnc_weight_update_parity(datasets, native):
+    """native = the public poses move through dpgo_exchange (the path bench.py times), else through the Python exchange.
+    BASELINE config 5: city10000 (2D), 4 agents, r = 3, GNC_TLS loop-closure weights
     (PGOAgent::updateMeasurementWeights, src/PGOAgent.cpp:1104-1142; RobustCost defaults): the
     device path (edge-error kernel, Q and two-level preconditioner rebuilt on the device after
     every weight update) follows the oracle's agents through two weight updates."""
-    meas, n, d, ot, gt = _teams(datasets, "city10000", 4, 3, acceleration=False)
+    meas, n, d, ot, gt = _teams(datasets, "city10000", 4, 3, acceleration=False, native=native)
     colors = orbcd.robot_graph_coloring(ot.agents)
     assert colors == gt.colors
     central = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((3, 3 * n)), d)
@@ -134,11 +136,12 @@ def test_gnc_weight_update_parity(datasets):
     gt.close()
 
 
-def test_all_agents_schedule_parity(datasets):
+@pytest.mark.parametrize("native", [False, True])
+def test_all_agents_schedule_parity(datasets, native):
     """BASELINE config 4: torus3D, 8 agents, r = 5, every agent optimizes in every round with the
     poses of the previous round (the equal-rate instance of asynchronous parallel RBCD,
     src/PGOAgent.cpp:486-499; no acceleration)."""
-    meas, n, d, ot, gt = _teams(datasets, "torus3D", 8, 5, acceleration=False)
+    meas, n, d, ot, gt = _teams(datasets, "torus3D", 8, 5, acceleration=False, native=native)
     central = pgo.QuadraticProblem(pgo.connection_laplacian(meas, n), np.zeros((5, 4 * n)), d)
     prev = None
     for k in range(6):

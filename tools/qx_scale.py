@@ -37,7 +37,7 @@ def main():
         rec = dict(L=L, n=g["n"], m=len(g["p1"]), bytes=nbytes, gen_s=tg, build_s=tb, peak_gbs=peak, variants=[])
         ref = None
         # 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch (distance 4096), 2 = shared-memory staged
-        # kernel (qx_staged.cuh), 3 = lane-group kernel, two blocks per step with the column indices one step ahead
+        # X tiles (phase_qx_tiles), 3 = lane-group kernel, two blocks per step with the column indices one step ahead
         for variant, dist in ((0, 0), (1, 4096), (2, 0), (3, 0)):
             gp.set_qx_variant(variant, dist)
             prod = gp.qx(Xh)
