@@ -52,6 +52,8 @@ class Message(C.Structure):
 
 COMM = C.c_void_p
 COMM_ID_BYTES = 128
+MAILBOX = C.c_void_p
+IPC_HANDLE_BYTES = 64
 
 # name -> (restype, argtypes); every symbol declared in include/dpgo_b200.h and include/dpgo_b200_dev.h
 SIGNATURES = {
@@ -106,6 +108,11 @@ SIGNATURES = {
     "dpgo_neighbor_buffer": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p)]),
     "dpgo_use_neighbor_poses": (C.c_int, [H, C.c_int]),
     "dpgo_exchange": (C.c_int, [COMM, C.POINTER(Message), C.c_int]),
+    "dpgo_mailbox_create": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(MAILBOX), C.c_char_p]),
+    "dpgo_mailbox_open": (C.c_int, [C.c_int, C.c_char_p, MAILBOX, C.c_int, C.c_int, C.POINTER(MAILBOX)]),
+    "dpgo_mailbox_close": (C.c_int, [MAILBOX]),
+    "dpgo_publish": (C.c_int, [H, C.c_int, MAILBOX, C.c_void_p]),
+    "dpgo_collect": (C.c_int, [H]),
     "dpgo_measurement_errors": (C.c_int, [H, C.c_int, C.c_void_p, _dp, _dp]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),

@@ -369,8 +369,20 @@ static int qx_prefetch_distance(dpgo_dev *h) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_qx_prefetch<R, D>, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
   return h->num_sms * occ * kWarpsPerBlock * (32 / (D + 1));
 }
+// Automatic choice of the stand-alone Q*X form (qx_variant -1), from the round-2 measurements on the synthetic grids
+// (profiles/r02_summary.md; fraction of the measured HBM peak, L2 flushed):
+//                      lane-group   + L2 prefetch   tiles in smem   two blocks / step
+//   262 144 poses         0.596         0.550           0.548            0.604
+//   1 000 000 poses       0.685         0.720           0.593            0.663
+// below 100 000 poses Q and X are L2 resident and the plain kernel is used.
+static const int kQxPipeMinPoses = 100000, kQxPrefetchMinPoses = 500000, kQxAutoPrefetchDist = 4096;
+
 int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
-  const int variant = h->qx_variant > 0 ? h->qx_variant : 0;
+  int variant = h->qx_variant, auto_dist = 0;
+  if (variant < 0) {
+    variant = h->n >= kQxPrefetchMinPoses ? 1 : (h->n >= kQxPipeMinPoses ? 3 : 0);
+    auto_dist = kQxAutoPrefetchDist;
+  }
   if (variant == 0) return op_qx(h, qview(h), X, G, out);
   if (variant == 2) {
     const int grid = pose_grid(h, h->d + 1);
@@ -386,7 +398,7 @@ int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
   }
   const int grid = pose_grid(h, h->d + 1);
   DPGO_DISPATCH(h, {
-    const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : qx_prefetch_distance<R, D>(h);
+    const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : (auto_dist > 0 ? auto_dist : qx_prefetch_distance<R, D>(h));
     k_qx_prefetch<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
   });
   LAUNCH_CHECK(h);

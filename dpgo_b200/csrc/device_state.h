@@ -9,6 +9,8 @@
 #include "../../include/dpgo_b200.h"
 #include "../../include/dpgo_b200_dev.h"
 
+struct dpgo_mailbox_s;
+
 namespace dpgo {
 
 struct EdgeSet {
@@ -65,6 +67,9 @@ struct dpgo_dev {
   double *d_cblocks = nullptr;
   double *d_Gconst = nullptr, *d_G = nullptr, *d_nbr = nullptr;
   double *d_nbr_xy[2] = {nullptr, nullptr};   // dpgo_neighbor_buffer: neighbours' X / auxiliary Y (exchange.cu)
+  std::vector<dpgo_mailbox_s *> mailboxes;    // receiver-side mailboxes of the asynchronous publication (exchange.cu)
+  void *d_mailbox_views = nullptr;
+  bool mailbox_views_dirty = true;
 
   // dense preconditioner
   double *d_Pinv = nullptr, *d_zpart = nullptr;

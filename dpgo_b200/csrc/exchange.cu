@@ -248,6 +248,193 @@ int dpgo_exchange(dpgo_comm c, const dpgo_message *msgs, int n) {
   return DPGO_OK;
 }
 
+// ---- asynchronous publication through peer memory ----------------------------------------------------------------
+// The reference's asynchronous mode (src/PGOAgent.cpp:475-499) lets every agent iterate at its own rate with whatever
+// neighbour poses have arrived.  Here an agent PUBLISHES its public poses by storing them straight into a mailbox that
+// lives in the memory of the neighbour's GPU (CUDA IPC mapping, NVLink peer stores), and COLLECTS consistent snapshots
+// of its own mailboxes before a solve -- no rendezvous, no collective, no host in between.
+//   mailbox = sequence word + 3 payload slots; message k goes to slot k % 3; the writer stores the payload, fences
+//   (system scope) and then stores k; the reader loads k, copies slot k % 3 and loads the word again: the snapshot is
+//   torn only if the writer has meanwhile started message k + 3, which it can do only after publishing k + 2 -- so a
+//   second reading below k + 2 proves the copy consistent, anything else retries.
+struct dpgo_mailbox_s {
+  int device = 0;
+  int count = 0, tile = 0;          // tiles per message, doubles per tile
+  int dst_offset = 0;               // first neighbour slot of the owner the payload goes to
+  dpgo_handle owner = nullptr;      // receiving agent (null on the sender's mapping)
+  unsigned long long *base = nullptr;   // [16 words header | 3 payload slots]
+  bool mapped = false;              // base comes from cudaIpcOpenMemHandle
+  unsigned long long next_seq = 1;  // sender side: sequence number of the next message
+};
+
+namespace dpgo_mailbox_detail {
+constexpr int kMailboxHeaderWords = 16;   // 128 bytes: the payload stays 128-byte aligned
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// payload of message `seq`: tiles frames[0..count) of `slot` -> slot seq % 3 of the (remote) mailbox
+__global__ void k_mailbox_store(const double *slot, const int *frames, int count, int tile, unsigned long long *mb,
+                                unsigned long long seq) {
+  double *dst = reinterpret_cast<double *>(mb + kMailboxHeaderWords) + (size_t)(seq % 3) * count * tile;
+  const size_t total = (size_t)count * tile;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / tile), q = (int)(t % tile);
+    dst[t] = slot[(size_t)frames[k] * tile + q];
+  }
+}
+// publication: runs after k_mailbox_store on the same stream (all payload stores are complete), makes them visible
+// system-wide, then releases the sequence number
+__global__ void k_mailbox_release(unsigned long long *mb, unsigned long long seq) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(mb), "l"(seq) : "memory");
+}
+
+struct MailboxView {
+  const unsigned long long *mb;
+  double *dst;          // where the snapshot goes (receiver's neighbour buffer)
+  int doubles;          // count * tile
+};
+// one CTA per mailbox: consistent snapshot of the newest message (nothing is copied before the first message)
+__global__ void k_mailbox_collect(const MailboxView *views) {
+  const MailboxView v = views[blockIdx.x];
+  __shared__ unsigned long long s_seq;
+  for (int attempt = 0; attempt < 64; ++attempt) {
+    if (threadIdx.x == 0) s_seq = ld_acquire_sys(v.mb);
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    if (seq == 0) return;                                   // nothing published yet: keep what is there
+    const double *src = reinterpret_cast<const double *>(v.mb + kMailboxHeaderWords) + (size_t)(seq % 3) * v.doubles;
+    for (int t = threadIdx.x; t < v.doubles; t += blockDim.x) {
+      double x;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(src + t) : "memory");
+      v.dst[t] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_seq = ld_acquire_sys(v.mb);
+    __syncthreads();
+    if (s_seq < seq + 2) return;                            // the writer cannot have touched slot seq % 3
+    __syncthreads();
+  }
+}
+}  // namespace dpgo_mailbox_detail
+using namespace dpgo_mailbox_detail;
+
+int dpgo_mailbox_create(dpgo_handle h, int dst_offset, int count, dpgo_mailbox *out, unsigned char *ipc_handle) {
+  if (!h || !out || count < 0 || dst_offset < 0 || dst_offset + count > h->num_nbr_slots) {
+    set_error("dpgo_mailbox_create: bad arguments");
+    return DPGO_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  dpgo_mailbox_s *m = new dpgo_mailbox_s();
+  m->device = h->device; m->count = count; m->tile = h->r * (h->d + 1); m->dst_offset = dst_offset; m->owner = h;
+  const size_t bytes = kMailboxHeaderWords * 8 + (size_t)3 * std::max(count, 1) * m->tile * sizeof(double);
+  if (cudaMalloc((void **)&m->base, bytes) != cudaSuccess || cudaMemset(m->base, 0, bytes) != cudaSuccess) {
+    set_error("dpgo_mailbox_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete m;
+    return DPGO_ECUDA;
+  }
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == DPGO_IPC_HANDLE_BYTES, "DPGO_IPC_HANDLE_BYTES is CUDA's IPC handle size");
+    cudaIpcMemHandle_t ih;
+    if (cudaIpcGetMemHandle(&ih, m->base) != cudaSuccess) {
+      set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+      cudaFree(m->base);
+      delete m;
+      return DPGO_ECUDA;
+    }
+    memcpy(ipc_handle, &ih, sizeof(ih));
+  }
+  h->mailboxes.push_back(m);
+  h->mailbox_views_dirty = true;
+  *out = m;
+  return DPGO_OK;
+}
+
+int dpgo_mailbox_open(int device, const unsigned char *ipc_handle, dpgo_mailbox local, int count, int tile,
+                      dpgo_mailbox *out) {
+  if (!out || (!ipc_handle && !local) || count < 0 || tile <= 0) { set_error("dpgo_mailbox_open: bad arguments"); return DPGO_EINVAL; }
+  CUDA_TRY(cudaSetDevice(device));
+  dpgo_mailbox_s *m = new dpgo_mailbox_s();
+  m->device = device; m->count = count; m->tile = tile;
+  if (local) {                       // the receiver lives in this process: its mailbox is used directly
+    if (local->count != count || local->tile != tile) { delete m; set_error("dpgo_mailbox_open: shape mismatch"); return DPGO_EINVAL; }
+    m->base = local->base;
+  } else {
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, ipc_handle, sizeof(ih));
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+      delete m;
+      return DPGO_ECUDA;
+    }
+    m->base = (unsigned long long *)p;
+    m->mapped = true;
+  }
+  *out = m;
+  return DPGO_OK;
+}
+
+int dpgo_mailbox_close(dpgo_mailbox m) {
+  if (!m) return DPGO_OK;
+  cudaSetDevice(m->device);
+  if (m->owner) {
+    auto &v = m->owner->mailboxes;
+    v.erase(std::remove(v.begin(), v.end(), m), v.end());
+    m->owner->mailbox_views_dirty = true;
+    cudaFree(m->base);
+  } else if (m->mapped) {
+    cudaIpcCloseMemHandle(m->base);
+  }
+  delete m;
+  return DPGO_OK;
+}
+
+int dpgo_publish(dpgo_handle h, int slot, dpgo_mailbox to, const int32_t *d_frames) {
+  if (!h || !to || to->owner || slot < 0 || slot >= 4 || (to->count > 0 && !d_frames) || to->tile != h->r * (h->d + 1)) {
+    set_error("dpgo_publish: bad arguments (the mailbox must be a sender-side mapping of matching tile size)");
+    return DPGO_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned long long seq = to->next_seq++;
+  if (to->count > 0) {
+    const size_t total = (size_t)to->count * to->tile;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 2));
+    k_mailbox_store<<<grid, 256, 0, h->stream>>>(h->d_slot[slot], d_frames, to->count, to->tile, to->base, seq);
+  }
+  k_mailbox_release<<<1, 1, 0, h->stream>>>(to->base, seq);
+  h->launches += 2;
+  CUDA_TRY(cudaPeekAtLastError());
+  return DPGO_OK;
+}
+
+int dpgo_collect(dpgo_handle h) {
+  if (!h) { set_error("dpgo_collect: null handle"); return DPGO_EINVAL; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->mailboxes.empty()) return DPGO_OK;
+  double *buf = nullptr;
+  const int rc = dpgo_neighbor_buffer(h, 0, &buf);
+  if (rc != DPGO_OK) return rc;
+  if (h->mailbox_views_dirty) {
+    std::vector<MailboxView> v;
+    for (dpgo_mailbox m : h->mailboxes)
+      v.push_back(MailboxView{m->base, buf + (size_t)m->dst_offset * m->tile, m->count * m->tile});
+    if (h->d_mailbox_views) CUDA_TRY(cudaFree(h->d_mailbox_views));
+    CUDA_TRY(cudaMalloc(&h->d_mailbox_views, v.size() * sizeof(MailboxView)));
+    CUDA_TRY(cudaMemcpyAsync(h->d_mailbox_views, v.data(), v.size() * sizeof(MailboxView), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // v goes out of scope
+    h->mailbox_views_dirty = false;
+  }
+  k_mailbox_collect<<<(int)h->mailboxes.size(), 256, 0, h->stream>>>((const MailboxView *)h->d_mailbox_views);
+  h->launches++;
+  CUDA_TRY(cudaPeekAtLastError());
+  return DPGO_OK;
+}
+
 int dpgo_use_neighbor_poses(dpgo_handle h, int aux) {
   if (!h) { set_error("dpgo_use_neighbor_poses: null handle"); return DPGO_EINVAL; }
   double *buf = nullptr;

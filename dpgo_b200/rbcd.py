@@ -372,6 +372,65 @@ class NativeExchange:
             self._comm = None
 
 
+class PeerMailboxes:
+    """Asynchronous publication of the public poses through peer memory (dpgo_mailbox_* / dpgo_publish / dpgo_collect,
+    csrc/exchange.cu): every agent owns one mailbox per neighbour in ITS GPU's memory; the neighbour maps it (CUDA IPC
+    across processes, directly inside one process) and stores its poses there after each of its solves; the owner takes a
+    consistent snapshot before each of its own solves.  No rendezvous: the ranks run at their own rates, which is the
+    reference's asynchronous mode (src/PGOAgent.cpp:475-499, no acceleration)."""
+
+    def __init__(self, team, device):
+        import ctypes as C
+        from ._lib import IPC_HANDLE_BYTES, MAILBOX, check, lib
+        if team.acceleration:
+            raise ValueError("the asynchronous mode does not allow acceleration (src/PGOAgent.cpp:477)")
+        self.team, self.inbox, self.outbox = team, {}, {}
+        mine = {}
+        for a, ag in team.agents.items():
+            ag.native = True
+            ag.prob.neighbor_buffer(0)
+            for b in ag.spec.neighbors:
+                lo, hi = ag.spec.nbr_range[b]
+                buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+                mb = MAILBOX()
+                check(lib.dpgo_mailbox_create(ag.prob._h, lo, hi - lo, C.byref(mb), buf))
+                self.inbox[(a, b)] = mb
+                mine[(a, b)] = buf.raw
+        table = [mine]
+        if team.world > 1:
+            import torch.distributed as dist
+            table = [None] * team.world
+            dist.all_gather_object(table, mine)
+        for b, ag in team.agents.items():          # b publishes to every agent a that lists it as a neighbour
+            for a in ag.spec.neighbors:
+                lo, hi = team.specs[a].nbr_range[b]
+                to = MAILBOX()
+                if team.owner[a] == team.rank:
+                    check(lib.dpgo_mailbox_open(int(device), None, self.inbox[(a, b)], hi - lo, ag.tile, C.byref(to)))
+                else:
+                    check(lib.dpgo_mailbox_open(int(device), table[team.owner[a]][(a, b)], None, hi - lo, ag.tile,
+                                                C.byref(to)))
+                self.outbox[(b, a)] = to
+
+    def publish(self, b):
+        from ._lib import check, lib
+        ag = self.team.agents[b]
+        for a in ag.spec.neighbors:
+            check(lib.dpgo_publish(ag.prob._h, SLOT_X, self.outbox[(b, a)], ag.send_idx[a].data_ptr()))
+
+    def collect(self, a):
+        from ._lib import check, lib
+        check(lib.dpgo_collect(self.team.agents[a].prob._h))
+
+    def close(self):
+        from ._lib import lib
+        for mb in self.outbox.values():
+            lib.dpgo_mailbox_close(mb)
+        for mb in self.inbox.values():
+            lib.dpgo_mailbox_close(mb)
+        self.outbox, self.inbox = {}, {}
+
+
 def block_owner(num_robots, world):
     """Block distribution of agents over ranks (keeps both colours of a chain on every rank)."""
     per_rank = (num_robots + world - 1) // world
@@ -392,7 +451,7 @@ class DeviceTeam:
 
     def __init__(self, p1, p2, R, t, kappa, tau, n, d, r, num_robots, device=0, stream=None,
                  rank=0, world=1, acceleration=True, params=None, restart_interval=30, native_exchange=False,
-                 host_exchange=False):
+                 host_exchange=False, peer_mailboxes=False):
         self.d, self.r, self.n, self.A = d, r, n, num_robots
         self.rank, self.world = rank, world
         self.acceleration = acceleration
@@ -416,6 +475,8 @@ class DeviceTeam:
         # native_exchange: pack / NCCL send-recv / gather inside the C-ABI on the rank's stream (GPU runs);
         # otherwise torch.distributed P2P ops issued from here (also what the gloo CPU tests drive)
         self.native = NativeExchange(self, device, stream) if native_exchange else None
+        # peer_mailboxes: asynchronous publication through peer memory (step_async / publish_all)
+        self.mail = PeerMailboxes(self, device) if peer_mailboxes else None
         # host_exchange: the poses travel through pinned host memory and a CPU process group (the end-to-end
         # form: what the reference-facing host API does with them); bytes copied are counted in host_stats
         self.host_exchange = bool(host_exchange)
@@ -483,6 +544,39 @@ class DeviceTeam:
         self.round += 1
         return everyone
 
+    def publish_all(self):
+        """Every local agent stores its public poses into its neighbours' mailboxes (start of an asynchronous run, and
+        after every solve)."""
+        for b in self.agents:
+            self.mail.publish(b)
+
+    def step_async(self):
+        """One asynchronous iteration of every LOCAL agent, no coordination with the other ranks: snapshot of whatever
+        the neighbours have published so far, local solve, publication (PGOAgent::runOptimizationLoop,
+        src/PGOAgent.cpp:486-499, without the Poisson sleep)."""
+        if self.mail is None:
+            raise ValueError("DeviceTeam(peer_mailboxes=True) is required")
+        for a, ag in self.agents.items():
+            self.mail.collect(a)
+            ag.iterate(True)
+            self.mail.publish(a)
+        self.round += 1
+        return list(self.agents)
+
+    def step_async_lockstep(self, barrier):
+        """The same three operations with every rank in step (`barrier()` = device sync + process barrier): all
+        snapshots, then all solves, then all publications -- which is exactly step_all, message for message.  Used to
+        check the mailboxes against the NCCL exchange."""
+        for a in self.agents:
+            self.mail.collect(a)
+        barrier()
+        for ag in self.agents.values():
+            ag.iterate(True)
+        self.publish_all()
+        barrier()
+        self.round += 1
+        return list(range(self.A))
+
     def update_weights(self, robust=None):
         """All agents refresh their neighbours' X and re-weight their loop closures (one RobustCost
         per agent, as every PGOAgent owns one).  Returns {agent: (w_private, w_shared)} for the
@@ -525,6 +619,8 @@ class DeviceTeam:
         return X
 
     def close(self):
+        if self.mail is not None:
+            self.mail.close()
         if self.native is not None:
             self.native.close()
         for ag in self.agents.values():

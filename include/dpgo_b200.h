@@ -219,6 +219,25 @@ typedef struct dpgo_message {
 } dpgo_message;
 int dpgo_exchange(dpgo_comm c, const dpgo_message *msgs, int n);
 
+/* ---- asynchronous publication of public poses through peer memory ---------------------------------
+ * The reference's asynchronous mode (PGOAgent::startOptimizationLoop / runOptimizationLoop,
+ * src/PGOAgent.cpp:475-499) lets every agent iterate at its own rate with whatever neighbour poses have
+ * arrived (updateNeighborPoses from another thread, :650-678).  Here the sender stores its public poses
+ * straight into a mailbox in the RECEIVER's GPU memory (CUDA IPC mapping, NVLink peer stores) and the
+ * receiver takes consistent snapshots before a solve: no rendezvous, no collective, no host in between.
+ *   receiver:  dpgo_mailbox_create(h_a, first_slot_of_b, count, &mb, ipc)   one per neighbour b; send `ipc` to b's process
+ *   sender:    dpgo_mailbox_open(device, ipc, NULL, count, tile, &to)       (or local = mb when a and b share a process)
+ *   sender, after every solve:   dpgo_publish(h_b, DPGO_SLOT_X, to, frames_a_needs_dev)
+ *   receiver, before every solve: dpgo_collect(h_a); dpgo_use_neighbor_poses(h_a, 0)                              */
+typedef struct dpgo_mailbox_s *dpgo_mailbox;
+#define DPGO_IPC_HANDLE_BYTES 64
+int dpgo_mailbox_create(dpgo_handle h, int dst_offset, int count, dpgo_mailbox *out, unsigned char *ipc_handle);
+int dpgo_mailbox_open(int device, const unsigned char *ipc_handle, dpgo_mailbox local, int count, int tile,
+                      dpgo_mailbox *out);
+int dpgo_mailbox_close(dpgo_mailbox m);
+int dpgo_publish(dpgo_handle h, int slot, dpgo_mailbox to, const int32_t *d_frames);
+int dpgo_collect(dpgo_handle h);
+
 /* Squared residual of every measurement of this agent at the poses in `slot`:
  *   err = kappa |Y1 R~ - Y2|_F^2 + tau |p2 - p1 - Y1 t~|^2
  * (ref: computeMeasurementError, src/DPGO_utils.cpp:501-507; PGOAgent::computeMeasurementResidual,

@@ -38,7 +38,7 @@ def main():
         ref = None
         # 0 = lane-group kernel, 1 = lane-group kernel + L2 prefetch (distance 4096), 2 = shared-memory staged
         # X tiles (phase_qx_tiles), 3 = lane-group kernel, two blocks per step with the column indices one step ahead
-        for variant, dist in ((0, 0), (1, 4096), (2, 0), (3, 0)):
+        for variant, dist in ((0, 0), (1, 4096), (2, 0), (3, 0), (-1, 0)):
             gp.set_qx_variant(variant, dist)
             prod = gp.qx(Xh)
             if ref is None:
