@@ -167,13 +167,15 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
   // the two forms of the exact preconditioner (compile-time: one kernel instantiation each)
-  auto precon_stream = [&](const double *v) {
+  // permuted: v is the tCG residual and its permuted copy dd.rp is current (written by phase_step_perm)
+  auto precon_stream = [&](const double *v, bool permuted) {
     if constexpr (MODE == 2) {
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
       constexpr int ST = kDdStages;
-      phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs);
+      if (permuted) phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.rp, nullptr, dd.y, zs);
+      else phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs);
       if (dd.nS > 0) {
         if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
         red.barrier(grid);
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     bool first = true;
     for (int j = 0;; ++j) {
       const double *pvec = first ? grad : p.r;
-      precon_stream(pvec);
+      precon_stream(pvec, !first);
       if (first) {
         phase_copy(ctx, grad, p.r, len);
         phase_zero(ctx, p.eta, len);
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
       double r_r;
       {
         double acc[1] = {0.0}, sc[1];
-        phase_step(ctx, step, p.delta, p.Hd, p.eta, p.r, len, acc);
+        if constexpr (MODE == 2) phase_step_perm<R, D>(ctx, step, p.delta, p.Hd, p.eta, p.r, p.dd.pcol, p.dd.rp, len, acc);
+        else phase_step(ctx, step, p.delta, p.Hd, p.eta, p.r, len, acc);
         red.reduce<1>(grid, acc, sc);
         clk.lap(4);
         r_r = sc[0];

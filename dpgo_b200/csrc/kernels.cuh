@@ -819,6 +819,7 @@ struct DdView {
   const int *bcol;              // [nB] permuted scalar column of boundary row b
   const int *icol;              // [pcols] original scalar column of a permuted column (-1: padding)
   int sep_col0, pcols;          // first separator column; padded column count
+  double *rp;                   // the tCG residual in permuted order (fused solver, phase_step_perm)
   double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
                                 // nsplit3 partial slots; u is zero outside the boundary rows)
   int prefetch;                 // issue the first matrix stages of the next strip phase before the preceding barrier
@@ -1377,6 +1378,25 @@ __device__ __forceinline__ void phase_step(const Ctx &ctx, double a, const doubl
     eta[k] = fma(a, delta[k], eta[k]);
     const double rn = fma(a, Hd[k], r[k]);
     r[k] = rn;
+    acc[0] = fma(rn, rn, acc[0]);
+  }
+}
+// The same update, and the new residual also written in the PERMUTED column order of the two-level preconditioner
+// (rp, R x pcols, padding columns stay zero): the first strip phase of the next application then stages its input
+// slice with contiguous loads instead of gathering it through icol (measured: the gathering interior phase took
+// 8.9 us per application against 5.5 us for the same strips fed from a permuted array).
+template <int R, int D>
+__device__ __forceinline__ void phase_step_perm(const Ctx &ctx, double a, const double *delta, const double *Hd,
+                                                double *eta, double *r, const int *pcol, double *rp, size_t len,
+                                                double (&acc)[1]) {
+  constexpr int DH = D + 1;
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
+    eta[k] = fma(a, delta[k], eta[k]);
+    const double rn = fma(a, Hd[k], r[k]);
+    r[k] = rn;
+    const int col = (int)(k / R), q = (int)(k - (size_t)col * R);
+    const int pose = col / DH, c = col - pose * DH;
+    rp[(size_t)(__ldg(pcol + pose) + c) * R + q] = rn;
     acc[0] = fma(rn, rn, acc[0]);
   }
 }

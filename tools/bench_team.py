@@ -20,6 +20,9 @@ A step = one round; the metric counts completed agent updates (PGOAgent::iterate
            its ROPTResult is on the host (the reference's updateX).  -> `e2e`
   anchor   the whole workload on rank 0's GPU alone (same schedule, device series) in the same run -> the
            denominator of `speedup_vs_1gpu_same_workload`.
+  async    (reported beside the others) the reference's asynchronous mode proper: no barrier, no collective, every
+           rank iterates its agents at its own rate; public poses are stored into mailboxes in the neighbour's GPU
+           memory (CUDA IPC, NVLink peer stores: dpgo_publish) and read as consistent snapshots (dpgo_collect).
 """
 import json
 import os
@@ -68,8 +71,9 @@ class Series:
         self.team = rbcd.DeviceTeam(z["p1"], z["p2"], z["R"], z["t"], z["kappa"], z["tau"], self.n, self.d, r, agents,
                                     device=local_rank, stream=stream, rank=rank, world=world,
                                     acceleration=(schedule != "all"), native_exchange=(mode == "device"),
-                                    host_exchange=(mode == "host"))
-        self.team.set_async(mode == "device")
+                                    host_exchange=(mode == "host"), peer_mailboxes=(mode == "async"))
+        self.team.set_async(mode in ("device", "async"))
+        self.agents_total = agents
         self.setup_s = time.time() - t0
         self.flush = flush
         self.gnc, self.gnc_on, self.weight_updates = int(gnc), False, 0
@@ -77,6 +81,8 @@ class Series:
 
     def reset(self):
         self.team.set_X(self.X0)
+        if self.mode == "async":
+            self.team.publish_all()          # everybody's initial poses (the callers barrier before the first solve)
         self.team.round = 0
         self.team.host_stats = {"d2h": 0, "h2d": 0}
         for ag in self.team.agents.values():
@@ -86,6 +92,8 @@ class Series:
     def step(self):
         if self.flush is not None:
             self.flush.zero_()
+        if self.mode == "async":
+            return len(self.team.step_async())       # local agents only: no coordination with the other ranks
         active = self.team.step_all() if self.schedule == "all" else self.team.step_colored()
         if self.mode == "host":       # the step's result on the host: every solve's ROPTResult (blocking updateX)
             for a in active:
@@ -135,6 +143,8 @@ class Series:
             ms = max(ms, wall_ms)        # host work is part of the end-to-end round
         launches = self.launches() - l0
         stats = dict(self.team.host_stats)
+        if self.mode == "async":
+            upd = self.agents_total * steps          # every agent of every rank did `steps` solves
         if self.world > 1:
             t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -162,7 +172,7 @@ def measure(steps, warmup, rank=0, world=1, local_rank=0, dataset="grid3D", agen
     if tstream.cuda_stream == 0:         # one explicit stream per rank: library kernels, torch copies, NCCL, events
         tstream = torch.cuda.Stream()
         torch.cuda.set_stream(tstream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if (flush_l2 and mode == "device") else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if (flush_l2 and mode in ("device", "async")) else None
     s = Series(rank, world, local_rank, dataset, agents, r, schedule, mode, tstream.cuda_stream, flush, gnc)
     try:
         out = s.run(steps, max(warmup, 3))
@@ -283,6 +293,12 @@ def run(args, emit=None):
     host = measure(K, W, rank, world, local_rank, schedule=schedule, mode="host", **ds_run)
     other = "colored" if schedule == "all" else "all"
     res2 = measure(K, W, rank, world, local_rank, schedule=other, mode="device", **ds_run)
+    asyn = None
+    if not gnc:       # the asynchronous mode proper (no acceleration, src/PGOAgent.cpp:477)
+        try:
+            asyn = measure(K, W, rank, world, local_rank, schedule="all", mode="async", **ds)
+        except Exception as exc:
+            asyn = {"error": repr(exc)}
     # 1-GPU anchors of both schedules on rank 0's GPU (the other ranks wait), same steps
     anchor = anchor2 = None
     if rank == 0:
@@ -347,6 +363,13 @@ def run(args, emit=None):
             "parity": {"cost2_after_timed_rounds": cost2, "gradnorm": gradnorm,
                        "poses_identical_to_1gpu_run": same_as_anchor,
                        "cpu_cost2_after_its_rounds": cpu_par["cost2"]},
+            "asynchronous_peer_mailboxes": (None if asyn is None else ({"error": asyn["error"]} if "error" in asyn else {
+                "value": asyn["value"], "unit": UNIT, "ms_per_step": asyn["ms_per_step"], "steps": K,
+                "cost2_after_timed_iterations": central_eval(asyn["X"], ds["dataset"], ds["r"], local_rank,
+                                                             tstream.cuda_stream)[0],
+                "note": "every agent does `steps` solves at its own rate, no barrier or collective inside the timed "
+                        "region; poses through dpgo_publish / dpgo_collect (mailboxes in the neighbour's GPU memory); "
+                        "the cost differs from the synchronous series by the staleness of the poses, not by arithmetic"})),
             "other_schedule": {
                 "config": team_config(schedule=other, gnc=gnc, **ds), "value": res2["value"], "unit": UNIT,
                 "ms_per_step": res2["ms_per_step"], "steps": K, "updates": res2["updates"],
