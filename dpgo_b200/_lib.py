@@ -114,6 +114,7 @@ SIGNATURES = {
     "dpgo_publish": (C.c_int, [H, C.c_int, MAILBOX, C.c_void_p]),
     "dpgo_collect": (C.c_int, [H]),
     "dpgo_measurement_errors": (C.c_int, [H, C.c_int, C.c_void_p, _dp, _dp]),
+    "dpgo_round_trajectory": (C.c_int, [H, C.c_int, _dp, _dp]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),

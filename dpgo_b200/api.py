@@ -108,6 +108,13 @@ class DeviceProblem:
     def set_precon_tuning(self, split_interior=0, split_schur=0, prefetch=-1):
         check(lib.dpgo_set_precon_tuning(self._h, int(split_interior), int(split_schur), int(prefetch)))
 
+    def round_trajectory(self, slot=SLOT_X, anchor=None):
+        """d x (d+1)n rounded poses of the slot in the frame of `anchor` (r x (d+1) lifted pose; None: pose 0)."""
+        out = np.zeros((self.d, (self.d + 1) * self.n), order="F")
+        a = None if anchor is None else np.asfortranarray(anchor, dtype=np.float64)
+        check(lib.dpgo_round_trajectory(self._h, int(slot), _d(a) if a is not None else None, _d(out)))
+        return out
+
     def neighbor_buffer(self, aux):
         """Device address of the handle's neighbour pose buffer (aux = 0: X, 1: auxiliary Y)."""
         p = C.c_void_p()

@@ -97,6 +97,11 @@ __global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const doub
 }
 
 template <int R, int D>
+__global__ void __launch_bounds__(kBlock) k_round(const double *X, const double *anchor, double *T, int n) {
+  phase_round<R, D>(make_ctx(), X, anchor, T, n);
+}
+
+template <int R, int D>
 __global__ void __launch_bounds__(kBlock) k_fgrad(BsrView Q, const double *X, const double *G,
                                                   double *EG, double *grad, double *S, int n,
                                                   double *partials) {
@@ -1568,6 +1573,24 @@ int dpgo_measurement_errors(dpgo_handle h, int slot, const double *nbr_poses_dev
     if (!nbr) { set_error("no neighbour poses"); return DPGO_ESTATE; }
     DPGO_TRY(edge_errors(h, h->shared, h->d_slot[slot], nbr, err_shared));
   }
+  return DPGO_OK;
+}
+
+int dpgo_round_trajectory(dpgo_handle h, int slot, const double *anchor_tile, double *T_host) {
+  H_CHECK(h);
+  CHECK_ARG(slot >= 0 && slot < 4 && T_host != nullptr);
+  const int tile = h->r * (h->d + 1), out_tile = h->d * (h->d + 1);
+  // scratch: d_t0 holds the rounded poses (d(d+1) n doubles <= r(d+1) n), d_t1 the anchor tile
+  const double *anchor = h->d_slot[slot];                 // local frame: pose 0 of the slot itself
+  if (anchor_tile) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_t1, anchor_tile, (size_t)tile * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    anchor = h->d_t1;
+  }
+  const int grid = pose_grid(h, 1);
+  DPGO_DISPATCH(h, k_round<R, D><<<grid, kBlock, 0, h->stream>>>(h->d_slot[slot], anchor, h->d_t0, h->n));
+  LAUNCH_CHECK(h);
+  CUDA_TRY(cudaMemcpyAsync(T_host, h->d_t0, (size_t)out_tile * h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return DPGO_OK;
 }
 

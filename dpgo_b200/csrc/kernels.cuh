@@ -1369,6 +1369,125 @@ __device__ __forceinline__ void phase_polar(const Ctx &ctx, double ca, const dou
   }
 }
 
+// Rounding of the lifted iterate to SE(d) poses in the frame of an anchor pose (one thread per pose):
+//   R_i = projectToRotationGroup(Ya^T Y_i),  t_i = Ya^T p_i - Ya^T pa
+// ref: PGOAgent::getTrajectoryInLocalFrame / getTrajectoryInGlobalFrame src/PGOAgent.cpp:718-767,
+//      projectToRotationGroup src/DPGO_utils.cpp:464-478 (SVD, last column of U negated when det U det V < 0 --
+//      the singular values are sorted there, so the negated direction is the one of the smallest singular value).
+// `anchor` is a lifted pose tile r x (d+1) (rotation Ya, translation pa); T is d x (d+1)n, column-major.
+template <int R, int D>
+__device__ __forceinline__ void phase_round(const Ctx &ctx, const double *X, const double *anchor, double *T, int n) {
+  constexpr int DH = D + 1, TILE = R * DH;
+  double ya[D][R], pa[R];
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int q = 0; q < R; ++q) ya[k][q] = anchor[k * R + q];
+#pragma unroll
+  for (int q = 0; q < R; ++q) pa[q] = anchor[D * R + q];
+  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
+    const double *x = X + (size_t)i * TILE;
+    // a[k][l] = (Ya^T Y_i)[l][k]: column k of M as a[k][.]
+    double a[D][D], v[D][D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int l = 0; l < D; ++l) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s = fma(ya[l][q], x[k * R + q], s);
+        a[k][l] = s;
+        v[k][l] = (k == l) ? 1.0 : 0.0;
+      }
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {      // one-sided Jacobi: columns of M V become orthogonal
+      double offmax = 0.0;
+#pragma unroll
+      for (int p = 0; p < D - 1; ++p) {
+#pragma unroll
+        for (int q2 = p + 1; q2 < D; ++q2) {
+          double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+          for (int l = 0; l < D; ++l) {
+            al = fma(a[p][l], a[p][l], al);
+            be = fma(a[q2][l], a[q2][l], be);
+            ga = fma(a[p][l], a[q2][l], ga);
+          }
+          const double lim = sqrt(al * be);
+          const double rel = (lim > 0.0) ? fabs(ga) / lim : 0.0;
+          offmax = fmax(offmax, rel);
+          if (rel > 1e-16) {
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+              const double xp = a[p][l], xq = a[q2][l];
+              a[p][l] = cs * xp - sn * xq;
+              a[q2][l] = sn * xp + cs * xq;
+              const double vp = v[p][l], vq = v[q2][l];
+              v[p][l] = cs * vp - sn * vq;
+              v[q2][l] = sn * vp + cs * vq;
+            }
+          }
+        }
+      }
+      if (offmax <= 1e-15) break;
+    }
+    // a[k] = sigma_k u_k, v[k][l] = V[l][k];  U V^T = sum_k u_k v_k^T
+    double sig[D], rot[D][D];   // rot[c][l] = (U V^T)[l][c]
+    int kmin = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double nn = 0.0;
+#pragma unroll
+      for (int l = 0; l < D; ++l) nn = fma(a[k][l], a[k][l], nn);
+      sig[k] = sqrt(nn);
+      const double inv = (nn > 0.0) ? 1.0 / sig[k] : 0.0;
+#pragma unroll
+      for (int l = 0; l < D; ++l) a[k][l] *= inv;
+      if (sig[k] < sig[kmin]) kmin = k;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int l = 0; l < D; ++l) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(a[k][l], v[k][c], s);
+        rot[c][l] = s;
+      }
+    double det;
+    if constexpr (D == 2) det = rot[0][0] * rot[1][1] - rot[1][0] * rot[0][1];
+    else det = rot[0][0] * (rot[1][1] * rot[2][2] - rot[2][1] * rot[1][2]) -
+               rot[1][0] * (rot[0][1] * rot[2][2] - rot[2][1] * rot[0][2]) +
+               rot[2][0] * (rot[0][1] * rot[1][2] - rot[1][1] * rot[0][2]);
+    if (det < 0.0) {   // reflect the direction of the smallest singular value
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (k == kmin) {
+#pragma unroll
+          for (int c = 0; c < D; ++c)
+#pragma unroll
+            for (int l = 0; l < D; ++l) rot[c][l] = fma(-2.0 * a[k][l], v[k][c], rot[c][l]);
+        }
+      }
+    }
+    double *t = T + (size_t)i * (D * DH);
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int l = 0; l < D; ++l) t[c * D + l] = rot[c][l];
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) s = fma(ya[l][q], x[D * R + q] - pa[q], s);
+      t[D * D + l] = s;
+    }
+  }
+}
+
 // Elementwise phases over the r x N arrays (len = R * N doubles).
 //   eta += a*delta; r += a*Hd; acc = {<r,r>}
 __device__ __forceinline__ void phase_step(const Ctx &ctx, double a, const double *delta,

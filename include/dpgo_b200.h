@@ -249,6 +249,13 @@ int dpgo_collect(dpgo_handle h);
  * given to dpgo_set_neighbor_poses(_dev). */
 int dpgo_measurement_errors(dpgo_handle h, int slot, const double *nbr_poses_dev, double *err_private,
                             double *err_shared);
+/* Rounding of the lifted iterate in `slot` to SE(d) poses in the frame of an anchor pose:
+ *   R_i = projectToRotationGroup(Ya^T Y_i), t_i = Ya^T (p_i - pa), one device thread per pose
+ * (ref: PGOAgent::getTrajectoryInLocalFrame / getTrajectoryInGlobalFrame src/PGOAgent.cpp:718-767,
+ * projectToRotationGroup src/DPGO_utils.cpp:464-478).  anchor_tile = the r x (d+1) lifted anchor pose (host;
+ * the globalAnchor), or NULL for the local frame (pose 0 of the slot).  T_host: d x (d+1)n, column-major
+ * (PoseArray layout). */
+int dpgo_round_trajectory(dpgo_handle h, int slot, const double *anchor_tile, double *T_host);
 /* max_i || p_i(a) - p_i(b) ||  (LiftedPoseArray::maxTranslationDistance, used for
  * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
 int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "cpu_port", "dpgo_cpu.cpp")
 LIB = os.path.join(HERE, "cpu_port", "libdpgo_cpu.so")
-DEPS = [SRC, os.path.join(HERE, "..", "dpgo_b200", "csrc", "rtr_logic.h")]
+DEPS = [SRC]
 
 
 def build(force=False):

@@ -6,7 +6,8 @@
 //   * preconditioner = exact solve with Q + 0.1 I        (ref: src/PoseGraph.cpp:598-613, CHOLMOD
 //     there; here a block sparse Cholesky with a minimum-degree ordering)
 //   * Stiefel tangent projection / QF retraction          (ROPTLIB semantics, restated)
-//   * RTR + Steihaug-Toint tCG with the scalar logic of dpgo_b200/csrc/rtr_logic.h
+//   * RTR + Steihaug-Toint tCG restated here from oracle/pgo.py (tcg / rtr_run); no product header is included:
+//     the port is test infrastructure and is validated against the numpy oracle (tests/test_cpu_port.py)
 //     (ref: src/QuadraticOptimizer.cpp:26-108)
 // It exists so that the "reference CPU" column of bench.py is a compiled implementation and not
 // a Python one.  Validated against oracle/pgo.py by tests/test_cpu_port.py.
@@ -18,7 +19,6 @@
 #include <set>
 #include <vector>
 
-#include "../../dpgo_b200/csrc/rtr_logic.h"
 
 namespace {
 
@@ -377,7 +377,6 @@ void cpu_solve(void *h, const double *V, double *Z) { solve(*(Problem *)h, V, Z)
 // QuadraticOptimizer::optimize with RTR (ref: src/QuadraticOptimizer.cpp:26-108)
 int cpu_optimize(void *h, const double *X0, double *Xout, double gradnorm_tol, int max_outer, int max_inner,
                  double init_radius, cpu_result *res) {
-  using namespace dpgo;
   Problem &P = *(Problem *)h;
   if (!P.factored && !factorize(P, 0.1)) return -1;
   const size_t len = (size_t)P.r * P.N;
@@ -388,53 +387,76 @@ int cpu_optimize(void *h, const double *X0, double *Xout, double gradnorm_tol, i
   res->f_init = s1.f;
   res->gn_init = sqrt(s1.gn2);
   res->outer = res->inner = res->accepted = res->rejected = 0;
-  res->tcg_status = TCG_MAXITER;
-  const bool single = (max_outer == 1);
+  // tCG status codes of the reference's ROPTResult (LCON, SCON, NEGCURVTURE, EXCREGION, MAXITER)
+  enum { kLcon = 0, kScon = 1, kNegCurv = 2, kExcRegion = 3, kMaxIter = 4 };
+  const double theta = 1.0, kappa = 0.1, accept_rho = 0.1, shrink = 0.25, magnify = 2.0;   // ROPTLIB defaults
+  res->tcg_status = kMaxIter;
+  const bool single = (max_outer == 1);                     // src/QuadraticOptimizer.cpp:80-98
   double radius = init_radius, Delta = init_radius, max_Delta = single ? init_radius : 5 * init_radius;
-  int total_steps = 0;
+  int shrinks = 0;
   bool run = sqrt(s1.gn2) >= gradnorm_tol && max_outer > 0;
   std::vector<double> eta(len), r(len), z, delta(len), Hd;
   while (run) {
-    TcgState s;
+    // ---- Steihaug-Toint truncated CG from eta = 0 (oracle/pgo.py: tcg)
     r = s1.grad;
+    const double norm_r0 = sqrt(s1.gn2);
     precondition(P, s1, r, z);
-    tcg_begin(s, s1.gn2, dot(z, r));
+    double z_r = dot(z, r), d_Pd = z_r, e_Pd = 0.0, e_Pe = 0.0;
+    int status = kMaxIter, inner = 0;
     for (size_t k = 0; k < len; ++k) { delta[k] = -z[k]; eta[k] = 0; }
-    int inner = 0;
     for (int j = 0; j < max_inner; ++j) {
       hess(P, s1, delta, Hd);
       inner = j + 1;
-      double step;
-      if (tcg_curvature(s, dot(delta, Hd), Delta, &step)) {
-        for (size_t k = 0; k < len; ++k) eta[k] += step * delta[k];
+      const double d_Hd = dot(delta, Hd);
+      const double alpha = z_r / d_Hd;
+      const double e_Pe_next = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+      if (d_Hd <= 0.0 || e_Pe_next >= Delta * Delta) {      // leave along delta up to the boundary
+        const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
+        for (size_t k = 0; k < len; ++k) eta[k] += tau * delta[k];
+        status = d_Hd <= 0.0 ? kNegCurv : kExcRegion;
         break;
       }
+      e_Pe = e_Pe_next;
       double r_r = 0;
       for (size_t k = 0; k < len; ++k) {
-        eta[k] += step * delta[k];
-        r[k] += step * Hd[k];
+        eta[k] += alpha * delta[k];
+        r[k] += alpha * Hd[k];
         r_r += r[k] * r[k];
       }
-      if (tcg_converged(s, r_r, 1.0, 0.1)) break;
+      const double lim = pow(norm_r0, theta);
+      if (sqrt(r_r) <= norm_r0 * std::min(lim, kappa)) {
+        status = kappa < lim ? kLcon : kScon;
+        break;
+      }
       precondition(P, s1, r, z);
-      const double beta = tcg_direction(s, dot(z, r));
+      const double z_r_prev = z_r;
+      z_r = dot(z, r);
+      const double beta = z_r / z_r_prev;
       for (size_t k = 0; k < len; ++k) delta[k] = -z[k] + beta * delta[k];
+      e_Pd = beta * (e_Pd + alpha * d_Pd);
+      d_Pd = z_r + beta * beta * d_Pd;
     }
     res->inner += inner;
-    res->tcg_status = s.status;
+    res->tcg_status = status;
+    // ---- candidate, ratio test, radius update (oracle/pgo.py: rtr_run)
     s2.x.resize(len);
     retract(P, s1.x.data(), eta.data(), s2.x.data());
     fgrad(P, s2);
     hess(P, s1, eta, Hd);
-    double rho;
-    const bool acc = rtr_accept(s1.f, s2.f, dot(eta, s1.grad), dot(eta, Hd), s.status, 0.1, 0.25, 2.0, max_Delta,
-                                &Delta, &rho);
+    const double rho = (s1.f - s2.f) / (-(dot(eta, s1.grad) + 0.5 * dot(eta, Hd)));
+    if (rho > 0.75) {
+      if (status == kExcRegion || status == kNegCurv) Delta = std::min(magnify * Delta, max_Delta);
+    } else if (rho < 0.25) {
+      Delta = shrink * Delta;
+    }
+    const double sqeps = sqrt(2.220446049250313e-16);
+    const bool acc = rho > accept_rho || (fabs(s1.f - s2.f) / (fabs(s1.f) + 1.0) < sqeps && s2.f < s1.f);
     if (acc) { std::swap(s1, s2); res->accepted++; } else { res->rejected++; }
     res->outer++;
     if (single) {
       if (acc) run = false;
-      else if (total_steps > 10) run = false;
-      else { radius *= 0.25; total_steps++; Delta = radius; max_Delta = radius; }
+      else if (shrinks > 10) run = false;
+      else { radius *= 0.25; shrinks++; Delta = radius; max_Delta = radius; }
     } else {
       run = res->outer < max_outer && !(sqrt(s1.gn2) < gradnorm_tol);
     }
