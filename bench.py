@@ -349,7 +349,9 @@ def bench_single(args):
                                        "us_cold_l2": pre_us_cold,
                                        "achieved": pre_bytes / pre_us / 1e3,
                                        "frac": pre_bytes / pre_us / 1e3 / peak,
-                                       "share_of_step": (npc / K) * pre_us / (ms / K * 1e3)}}
+                                       "share_of_step": (res["phase_ms"][1] + res["phase_ms"][2]) / max(res["elapsed_ms"], 1e-9),
+                                       "share_note": "in-kernel clocks of the last timed step: preconditioner "
+                                                     "phases / kernel time"}}
     if mode >= 2:
         roofline["note"] = ("two-level exact preconditioner: 14x fewer algorithmic bytes than the dense inverse and "
                             "L2 resident within a step, so the step is grid-barrier / latency bound, not HBM bound; "

@@ -5,6 +5,7 @@
 #include <DPGO/QuadraticProblem.h>
 
 #include <cmath>
+#include <cstdio>
 #include <functional>
 #include <vector>
 
@@ -54,6 +55,18 @@ void pcg(const std::function<void(const std::vector<double> &, std::vector<doubl
       else all_done = false;
     }
     if (all_done) break;
+    if (it + 1 == max_iter) {
+      // the reference solves these systems directly (SPQR); an iteration that stops at the cap must say so
+      double worst = 0;
+      for (size_t c = 0; c < cols; ++c) {
+        if (done[c] || b2[c] == 0) continue;
+        double r2 = 0;
+        for (size_t i = 0; i < dim; ++i) r2 += r[c * dim + i] * r[c * dim + i];
+        worst = std::max(worst, std::sqrt(r2 / b2[c]));
+      }
+      std::fprintf(stderr, "[DPGO] chordalInitialization: PCG stopped at %d iterations with relative residual %.3e "
+                           "(tolerance %.1e); the initial guess may be inaccurate\n", max_iter, worst, tol);
+    }
     precond();
     for (size_t c = 0; c < cols; ++c) {
       if (done[c]) {

@@ -561,17 +561,15 @@ bool PGOAgent::isRobotActive(unsigned robot_id) const {
 }
 
 // ---- rounding (reference :718-767) ------------------------------------------------------------------
+// Rounding runs on the device (dpgo_round_trajectory: one thread per pose, anchor rotation applied and the d x d
+// block projected to SO(d) in registers); only the d x (d+1)n result crosses to the host.
 bool PGOAgent::getTrajectoryInLocalFrame(Matrix &Trajectory) {
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
-  PoseArray T(d, num_poses());
-  T.setData(hostX().rotation(0).transpose() * hostX().getData());
-  const Matrix t0 = T.translation(0);
-  for (unsigned i = 0; i < num_poses(); ++i) {
-    T.rotation(i) = projectToRotationGroup(T.rotation(i));
-    T.translation(i) = T.translation(i) - t0;
-  }
-  Trajectory = T.getData();
+  if (!mDeviceStateValid) uploadState();
+  Matrix T(d, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
+  DPGO_DEVICE_CALL(dpgo_round_trajectory(mPoseGraph->deviceHandle(), DPGO_SLOT_X, nullptr, T.data()));
+  Trajectory = T;
   return true;
 }
 
@@ -581,14 +579,13 @@ bool PGOAgent::getTrajectoryInGlobalFrame(PoseArray &Trajectory) {
   DPGO_CHECK(Xa.r() == relaxation_rank() && Xa.d() == dimension());
   if (mState != PGOAgentState::INITIALIZED) return false;
   lock_guard<mutex> lock(mPosesMutex);
-  PoseArray T(d, num_poses());
-  T.setData(Xa.rotation().transpose() * hostX().getData());
-  const Matrix t0 = Xa.rotation().transpose() * Xa.translation();
-  for (unsigned i = 0; i < num_poses(); ++i) {
-    T.rotation(i) = projectToRotationGroup(T.rotation(i));
-    T.translation(i) = T.translation(i) - t0;
-  }
-  Trajectory = T;
+  if (!mDeviceStateValid) uploadState();
+  Matrix T(d, static_cast<std::ptrdiff_t>(d + 1) * num_poses());
+  const Matrix anchor = Xa.getData();      // r x (d+1): rotation block and translation of the anchor
+  DPGO_DEVICE_CALL(dpgo_round_trajectory(mPoseGraph->deviceHandle(), DPGO_SLOT_X, anchor.data(), T.data()));
+  PoseArray out(d, num_poses());
+  out.setData(T);
+  Trajectory = out;
   return true;
 }
 

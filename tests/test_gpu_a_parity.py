@@ -319,3 +319,34 @@ def test_two_level_precon_tuning(datasets, name, r):
         assert ra["inner_iters"] == rb["inner_iters"]
         assert abs(ra["f_opt"] - rb["f_opt"]) <= 1e-10 * abs(rb["f_opt"])
         assert rel(Xa, Xb) < 1e-8
+
+
+@pytest.mark.parametrize("name,r", [("smallGrid3D", 5), ("sphere2500", 5), ("city10000", 3)])
+def test_rounding_parity(datasets, name, r):
+    """dpgo_round_trajectory (one device thread per pose: anchor rotation applied, d x d block projected to SO(d) by
+    a one-sided Jacobi SVD with the reflection of the smallest singular direction) against the oracle's restatement of
+    PGOAgent::getTrajectoryInLocalFrame / projectToRotationGroup (src/PGOAgent.cpp:718-736, src/DPGO_utils.cpp:464-478):
+    on a manifold point, on arbitrary r x d blocks (both signs of the determinant), and in a global anchor's frame."""
+    meas, n, z = datasets(name)
+    d = meas.d
+    gp = make_problem(meas, n, r, build_precon=False)
+    rng = np.random.default_rng(29)
+    X = pgo.manifold_project(rng.standard_normal((r, (d + 1) * n)), d)
+    gp.slot_set(0, X)
+    T = gp.round_trajectory(0)
+    assert rel(T, pgo.round_solution(X, d)) < 1e-12
+    for i in range(0, n, max(1, n // 50)):           # rotations
+        Ri = T[:, i * (d + 1):i * (d + 1) + d]
+        assert np.allclose(Ri.T @ Ri, np.eye(d), atol=1e-12) and np.linalg.det(Ri) > 0
+    W = rng.standard_normal((r, (d + 1) * n))         # not on the manifold: det(Ya^T Y_i) takes both signs
+    gp.slot_set(0, W)
+    Tw, ref = gp.round_trajectory(0), pgo.round_solution(W, d)
+    dets = [np.linalg.det((W[:, :d].T @ W)[:, i * (d + 1):i * (d + 1) + d]) for i in range(n)]
+    assert min(dets) < 0 < max(dets)
+    assert rel(Tw, ref) < 1e-9
+    anchor = pgo.manifold_project(rng.standard_normal((r, d + 1)), d)
+    gp.slot_set(0, X)
+    Tg = gp.round_trajectory(0, anchor)
+    ref = pgo.round_solution(np.hstack([anchor, X]), d)[:, d + 1:]     # the anchor as pose 0 of a longer array
+    assert rel(Tg, ref) < 1e-12
+    gp.close()
