@@ -57,14 +57,16 @@ struct CudaBackend {
     }
     return true;
   }
+  // stream-ordered scratch (the device's default memory pool keeps freed blocks: dpgo_create raises its release
+  // threshold), so a rebuild of the preconditioner at every GNC weight update does not pay for cudaMalloc / cudaFree
   void *alloc(size_t bytes) {
     void *p = nullptr;
-    if (!check(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
+    if (!check(cudaMallocAsync(&p, bytes, st), "cudaMallocAsync")) return nullptr;
     if (!check(cudaMemsetAsync(p, 0, bytes, st), "cudaMemsetAsync")) return nullptr;
     return p;
   }
   void release(void *p) {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
   }
   bool upload(void *dst, const void *src, size_t bytes) {
     // pageable source: the copy has left the host buffer when the call returns

@@ -159,6 +159,10 @@ struct SpdDesc {
 };
 
 // sL, sW: TS x (TS + 1) doubles each.  info: set to 1 + batch index when a pivot is not positive.
+// 256 threads = 64 rows (columns) x 4 parts: a row's dot product is split over 4 adjacent lanes and combined with
+// two shuffles, so a Cholesky column costs two CTA barriers and <= 16 FMAs per thread, and the 64 columns of the
+// triangular inverse advance together one row per step (round 2, first version: rank-1 updates with three barriers
+// per column and a 64-thread triangular inverse, 94 us per block; this form is bound by the 2 x 64 barriers).
 __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int batch, double *sL, double *sW,
                                                int *info) {
   constexpr int P = TS + 1;
@@ -166,43 +170,48 @@ __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int 
   if (j0 >= d.n) return;
   const int nb = min(TS, d.n - j0);
   const int tid = threadIdx.x;
+  const int row = tid >> 2, part = tid & 3;       // 4 adjacent lanes share a row (Cholesky) / a column (inverse)
   double *A = d.A + (size_t)j0 + (size_t)j0 * d.lda;
   for (int e = tid; e < TS * TS; e += kThreads) {
     const int i = e & (TS - 1), j = e >> 6;
     sL[i * P + j] = (i < nb && j < nb && i >= j) ? A[(size_t)i + (size_t)j * d.lda] : 0.0;
     sW[i * P + j] = 0.0;
   }
-  __syncthreads();
   __shared__ int s_bad;
+  __shared__ double s_piv;
   if (tid == 0) s_bad = 0;
+  __syncthreads();
+  // ---- left-looking Cholesky: column j = (A[:, j] - L[:, :j] L[j, :j]^T) / sqrt(pivot)
   for (int j = 0; j < nb; ++j) {
+    double s = 0.0;
+    if (row >= j && row < nb)
+      for (int k = part; k < j; k += 4) s = fma(sL[row * P + k], sL[j * P + k], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const double v = sL[row * P + j] - s;         // unscaled entry (row, j); meaningful for j <= row < nb
+    if (part == 0 && row == j) s_piv = v;
     __syncthreads();
-    const double piv = sL[j * P + j];
-    if (!(piv > 0.0)) {          // same value in every thread: uniform exit
+    const double piv = s_piv;
+    if (!(piv > 0.0)) {                           // the same value in every thread: uniform exit
       if (tid == 0) { s_bad = 1; atomicMax(info, 1 + batch); }
       break;
     }
-    const double dj = sqrt(piv), rinv = 1.0 / dj;
+    if (part == 0 && row >= j && row < nb) sL[row * P + j] = (row == j) ? sqrt(piv) : v / sqrt(piv);
     __syncthreads();
-    if (tid == 0) sL[j * P + j] = dj;
-    for (int i = j + 1 + tid; i < nb; i += kThreads) sL[i * P + j] *= rinv;
-    __syncthreads();
-    // trailing update of the lower triangle: (i, k), j < k <= i < nb
-    const int rem = nb - j - 1;
-    for (int e = tid; e < rem * rem; e += kThreads) {
-      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) sL[i * P + k] -= sL[i * P + j] * sL[k * P + j];
-    }
   }
   __syncthreads();
   if (s_bad) return;
-  // W = L^-1 (lower): thread c solves column c by forward substitution
-  if (tid < nb) {
-    const int c = tid;
-    for (int i = c; i < nb; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) s -= sL[i * P + k] * sW[k * P + c];
-      sW[i * P + c] = s / sL[i * P + i];
+  // ---- W = L^-1 (lower): column c = thread group `row`; x_i = (delta_ic - sum_{c <= k < i} L[i][k] x_k) / L[i][i]
+  {
+    const int c = row;
+    for (int i = 0; i < nb; ++i) {                // all groups step through the rows together (warp-synchronous)
+      double s = 0.0;
+      if (c < nb && i > c)
+        for (int k = c + part; k < i; k += 4) s = fma(sL[i * P + k], sW[k * P + c], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0 && c < nb && i >= c) sW[i * P + c] = (((i == c) ? 1.0 : 0.0) - s) / sL[i * P + i];
+      __syncwarp();                               // x_i of this warp's columns is visible to its 4-lane groups
     }
   }
   __syncthreads();

@@ -653,12 +653,6 @@ int fused_phase_trace(dpgo_dev *h, double *busy_ms, int cap_ctas, int *num_ctas)
 // ---------------------------------------------------------------------------------------------
 // host-side graph -> block-CSR
 // ---------------------------------------------------------------------------------------------
-struct Contribution {
-  int32_t row, col;
-  int32_t src;   // index into the edge set
-  int8_t kind;   // 0: T W T^T, 1: -T W, 2: -W T^T, 3: W   (private) ; 4/5 shared out/in ; 6 prior ; 7 zero
-};
-
 static void edge_T_W(const EdgeSet &E, int k, int d, double *T, double *W) {
   const int dh = d + 1;
   for (int a = 0; a < dh * dh; ++a) T[a] = 0.0;
@@ -688,24 +682,29 @@ static void block_of_kind(int kind, const double *T, const double *W, int dh, do
 
 static int build_Q_host(dpgo_dev *h) {
   const int d = h->d, dh = d + 1, n = h->n, bs = dh * dh;
-  std::vector<Contribution> cs;
-  cs.reserve((size_t)4 * h->priv.m + h->shared.m + h->prior_idx.size() + n);
-  for (int i = 0; i < n; ++i) cs.push_back({i, i, 0, 7});
-  for (int k = 0; k < h->priv.m; ++k) {
-    const int i = h->priv.a[k], j = h->priv.b[k];
-    cs.push_back({i, i, k, 0});
-    cs.push_back({i, j, k, 1});
-    cs.push_back({j, i, k, 2});
-    cs.push_back({j, j, k, 3});
+  // the sorted contribution list is the sparsity pattern: kept across weight-only rebuilds (GNC)
+  const bool reuse = h->weights_only_update && !h->q_contribs.empty();
+  std::vector<Contribution> &cs = h->q_contribs;
+  if (!reuse) {
+    cs.clear();
+    cs.reserve((size_t)4 * h->priv.m + h->shared.m + h->prior_idx.size() + n);
+    for (int i = 0; i < n; ++i) cs.push_back({i, i, 0, 7});
+    for (int k = 0; k < h->priv.m; ++k) {
+      const int i = h->priv.a[k], j = h->priv.b[k];
+      cs.push_back({i, i, k, 0});
+      cs.push_back({i, j, k, 1});
+      cs.push_back({j, i, k, 2});
+      cs.push_back({j, j, k, 3});
+    }
+    for (int k = 0; k < h->shared.m; ++k) {
+      const int i = h->shared.a[k];
+      cs.push_back({i, i, k, (int8_t)(h->shared.outgoing[k] ? 4 : 5)});
+    }
+    for (size_t k = 0; k < h->prior_idx.size(); ++k) cs.push_back({h->prior_idx[k], h->prior_idx[k], (int32_t)k, 6});
+    std::stable_sort(cs.begin(), cs.end(), [](const Contribution &x, const Contribution &y) {
+      return x.row != y.row ? x.row < y.row : x.col < y.col;
+    });
   }
-  for (int k = 0; k < h->shared.m; ++k) {
-    const int i = h->shared.a[k];
-    cs.push_back({i, i, k, (int8_t)(h->shared.outgoing[k] ? 4 : 5)});
-  }
-  for (size_t k = 0; k < h->prior_idx.size(); ++k) cs.push_back({h->prior_idx[k], h->prior_idx[k], (int32_t)k, 6});
-  std::stable_sort(cs.begin(), cs.end(), [](const Contribution &x, const Contribution &y) {
-    return x.row != y.row ? x.row < y.row : x.col < y.col;
-  });
   h->rowptr.assign(n + 1, 0);
   h->colidx.clear();
   h->blocks.clear();
@@ -753,6 +752,12 @@ static int upload(T **dptr, const std::vector<T> &v, size_t min_elems = 1) {
 }
 
 static int upload_Q(dpgo_dev *h) {
+  if (h->weights_only_update && h->d_blocks && h->uploaded_nnzb == h->nnzb) {   // same pattern: values only
+    CUDA_TRY(cudaMemcpyAsync(h->d_blocks, h->blocks.data(), h->blocks.size() * sizeof(double), cudaMemcpyHostToDevice,
+                             h->stream));
+    return DPGO_OK;
+  }
+  h->uploaded_nnzb = h->nnzb;
   DPGO_TRY(upload(&h->d_rowptr, h->rowptr));
   DPGO_TRY(upload(&h->d_colidx, h->colidx));
   DPGO_TRY(upload(&h->d_blocks, h->blocks));
@@ -792,6 +797,11 @@ static int build_cross_host(dpgo_dev *h) {
     blocks.insert(blocks.end(), B, B + bs);
   }
   for (int i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
+  if (h->weights_only_update && h->d_cblocks && h->cnnzb == (int)colidx.size()) {   // same pattern: values only
+    if (!blocks.empty())
+      CUDA_TRY(cudaMemcpy(h->d_cblocks, blocks.data(), blocks.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return DPGO_OK;                                                                  // (priors do not carry weights)
+  }
   h->cnnzb = (int)colidx.size();
   DPGO_TRY(upload(&h->d_crowptr, rowptr));
   DPGO_TRY(upload(&h->d_ccolidx, colidx));
@@ -1013,6 +1023,15 @@ int dpgo_create(int device, int n, int d, int r, void *stream, dpgo_handle *out)
     h->ldk = h->nsplit * h->KT;
   }
   h->vpad = (size_t)r * h->ldk;
+  {
+    // stream-ordered scratch of the preconditioner set-up is kept by the device's default pool instead of going
+    // back to the driver at every synchronization (GNC rebuilds the preconditioner at every weight update)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (stream) {
     h->stream = (cudaStream_t)stream;
   } else {
@@ -1205,7 +1224,10 @@ int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_
   H_CHECK(h);
   if (w_private) h->priv.weight.assign(w_private, w_private + h->priv.m);
   if (w_shared) h->shared.weight.assign(w_shared, w_shared + h->shared.m);
-  return dpgo_finalize(h, build_precon_flag);
+  h->weights_only_update = h->finalized;     // same pattern: the two-level set-up keeps its symbolic part
+  const int rc = dpgo_finalize(h, build_precon_flag);
+  h->weights_only_update = false;
+  return rc;
 }
 
 int dpgo_get_Q_bsr(dpgo_handle h, int *nnzb, int32_t *rowptr, int32_t *colidx, double *blocks) {

@@ -13,6 +13,14 @@ struct dpgo_mailbox_s;
 
 namespace dpgo {
 
+// one edge's contribution to one block of Q (host-side assembly, device_lib.cu)
+struct Contribution {
+  int32_t row, col;
+  int32_t src;   // index into the edge set
+  int8_t kind;   // 0: T W T^T, 1: -T W, 2: -W T^T, 3: W   (private) ; 4/5 shared out/in ; 6 prior ; 7 zero
+};
+
+
 struct EdgeSet {
   int m = 0;
   std::vector<int32_t> a, b;  // private: p1,p2 ; shared: my_idx, nbr_slot
@@ -83,6 +91,9 @@ struct dpgo_dev {
   int gemv_occ = 0;
   int partial_blocks = 0;  // CTAs the partials buffer can serve (8 doubles each)
   bool finalized = false, has_precon = false;
+  bool weights_only_update = false;   // inside dpgo_update_weights: the pattern of Q is unchanged
+  std::vector<dpgo::Contribution> q_contribs;   // sorted contributions of the edges to the blocks of Q (the pattern)
+  int uploaded_nnzb = -1;
 
   // lifted pose arrays
   double *d_slot[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -13,6 +13,7 @@
 // sphere2500, L2-resident).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <deque>
@@ -52,6 +53,12 @@ struct DdState {
   double *si_blocks = nullptr, *bs_blocks = nullptr;
   double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr, *rp = nullptr;
   bool configured = false;
+  // symbolic part kept for weight-only rebuilds (GNC): the dissection, the strip tables and the index lists depend on
+  // the sparsity pattern only, so dpgo_update_weights redoes the numeric part alone (dd_numeric)
+  bool symbolic = false;
+  int sym_n = 0, sym_nnzb = 0, sym_thr = 0, sym_split1 = 0, sym_split3 = 0, mS = 0, padS = 0;
+  std::vector<int> h_group, h_lpos, h_dom_m, h_dom_pad, h_sk_ptr, h_sk, si_src, bs_src;
+  std::vector<long long> h_dom_base;
 };
 
 namespace {
@@ -154,12 +161,21 @@ struct Elimination {
   double *W = nullptr;                       // B_k^T C_k (tm_k x tm_k)
   int *d_cmap = nullptr;
   std::vector<void *> aux;
+  cudaStream_t stream = nullptr;             // everything here is stream-ordered scratch
   ~Elimination() {
     void *p[] = {Ainv, B, C, W, d_cmap};
-    for (void *q : p) if (q) cudaFree(q);
-    for (void *q : aux) if (q) cudaFree(q);
+    for (void *q : p) if (q) cudaFreeAsync(q, stream);
+    for (void *q : aux) if (q) cudaFreeAsync(q, stream);
   }
 };
+
+template <typename T>
+int upload_scratch(T **dptr, const std::vector<T> &v, cudaStream_t st) {
+  const size_t ne = std::max<size_t>(v.size(), 1);
+  CUDA_TRY(cudaMallocAsync((void **)dptr, ne * sizeof(T), st));
+  if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return DPGO_OK;
+}
 
 // A_k^-1 for every domain, C_k on the columns of S_k, and Sigma = A_SS - sum_k B_k^T C_k accumulated into Sg
 // (mS x mS, zeroed here).  sk lists separator POSITIONS (ascending per domain).
@@ -168,6 +184,7 @@ int eliminate_domains(dpgo_dev *h, const std::vector<int> &group, const std::vec
                       double *Sg, int mS, Elimination &E) {
   const int K = (int)dom_m.size(), dh = h->d + 1;
   E.K = K;
+  E.stream = h->stream;
   E.m = dom_m;
   E.tm.resize(K); E.a_off.resize(K); E.b_off.resize(K); E.w_off.resize(K); E.cmap_off.assign(K + 1, 0);
   long long na = 0, nb = 0, nw = 0;
@@ -184,7 +201,7 @@ int eliminate_domains(dpgo_dev *h, const std::vector<int> &group, const std::vec
   }
   auto dalloc = [&](double **p, long long count) -> int {
     const size_t bytes = (size_t)std::max<long long>(count, 1) * sizeof(double);
-    CUDA_TRY(cudaMalloc((void **)p, bytes));
+    CUDA_TRY(cudaMallocAsync((void **)p, bytes, h->stream));
     CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, h->stream));
     return DPGO_OK;
   };
@@ -192,16 +209,16 @@ int eliminate_domains(dpgo_dev *h, const std::vector<int> &group, const std::vec
   DPGO_TRY(dalloc(&E.B, nb));
   DPGO_TRY(dalloc(&E.C, nb));
   DPGO_TRY(dalloc(&E.W, nw));
-  DPGO_TRY(upload_vec(&E.d_cmap, cmap));
+  DPGO_TRY(upload_scratch(&E.d_cmap, cmap, h->stream));
   int *d_group = nullptr, *d_lpos = nullptr, *d_m = nullptr, *d_skptr = nullptr, *d_sk = nullptr;
   long long *d_aoff = nullptr, *d_boff = nullptr;
-  DPGO_TRY(upload_vec(&d_group, group)); E.aux.push_back(d_group);
-  DPGO_TRY(upload_vec(&d_lpos, lpos)); E.aux.push_back(d_lpos);
-  DPGO_TRY(upload_vec(&d_m, dom_m)); E.aux.push_back(d_m);
-  DPGO_TRY(upload_vec(&d_skptr, sk_ptr)); E.aux.push_back(d_skptr);
-  DPGO_TRY(upload_vec(&d_sk, sk)); E.aux.push_back(d_sk);
-  DPGO_TRY(upload_vec(&d_aoff, E.a_off)); E.aux.push_back(d_aoff);
-  DPGO_TRY(upload_vec(&d_boff, E.b_off)); E.aux.push_back(d_boff);
+  DPGO_TRY(upload_scratch(&d_group, group, h->stream)); E.aux.push_back(d_group);
+  DPGO_TRY(upload_scratch(&d_lpos, lpos, h->stream)); E.aux.push_back(d_lpos);
+  DPGO_TRY(upload_scratch(&d_m, dom_m, h->stream)); E.aux.push_back(d_m);
+  DPGO_TRY(upload_scratch(&d_skptr, sk_ptr, h->stream)); E.aux.push_back(d_skptr);
+  DPGO_TRY(upload_scratch(&d_sk, sk, h->stream)); E.aux.push_back(d_sk);
+  DPGO_TRY(upload_scratch(&d_aoff, E.a_off, h->stream)); E.aux.push_back(d_aoff);
+  DPGO_TRY(upload_scratch(&d_boff, E.b_off, h->stream)); E.aux.push_back(d_boff);
   if (mS > 0) CUDA_TRY(cudaMemsetAsync(Sg, 0, (size_t)mS * mS * sizeof(double), h->stream));
   {
     const size_t total = (size_t)h->nnzb * dh * dh;
@@ -340,15 +357,24 @@ int two_level_max_domain_poses(int dh) { return std::max(8, kDdStages * kStageK 
 
 double dd_bytes(const dpgo_dev *h) { return h->dd ? ((const DdState *)h->dd)->bytes_per_apply : 0.0; }
 
+static int dd_numeric(dpgo_dev *h, DdState *s, bool refresh_couplings);
+
 int dd_build(dpgo_dev *h) {
+  const int n = h->n, dh = h->d + 1, R = h->r;
+  // interior blocks of <= 320 scalars (5 column blocks of 64): a strip is one wave of kDdStages chunks
+  const int thr = h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh);
+  {
+    // weight-only update (dpgo_update_weights: same pattern, new values): numeric part only
+    DdState *old = (DdState *)h->dd;
+    if (old && old->symbolic && h->weights_only_update && old->sym_n == n && old->sym_nnzb == h->nnzb &&
+        old->sym_thr == thr && old->sym_split1 == h->dd_split1 && old->sym_split3 == h->dd_split3)
+      return dd_numeric(h, old, true);
+  }
   dd_free(h);
   DdState *s = new DdState();
   h->dd = s;
-  const int n = h->n, dh = h->d + 1, R = h->r;
   // ---- partition
   const std::vector<std::vector<int>> adj = bsr_adjacency(n, h->rowptr.data(), h->colidx.data());
-  // interior blocks of <= 320 scalars (5 column blocks of 64): a strip is one wave of kDdStages chunks
-  const int thr = h->dd_max_domain > 0 ? h->dd_max_domain : two_level_max_domain_poses(dh);
   Dissector ds(adj, thr);
   {
     std::vector<int> all(n);
@@ -397,6 +423,7 @@ int dd_build(dpgo_dev *h) {
       const int c = h->colidx[e];
       if (group[c] < 0) continue;
       si_colidx.push_back(pcol[c]);
+      s->si_src.push_back(e);
       si_blocks.insert(si_blocks.end(), h->blocks.begin() + (size_t)e * bs, h->blocks.begin() + (size_t)(e + 1) * bs);
     }
     si_rowptr[j + 1] = (int)si_colidx.size();
@@ -409,6 +436,7 @@ int dd_build(dpgo_dev *h) {
       const int c = h->colidx[e];
       if (group[c] >= 0) continue;
       bs_colidx.push_back(pcol[c]);
+      s->bs_src.push_back(e);
       bs_blocks.insert(bs_blocks.end(), h->blocks.begin() + (size_t)e * bs, h->blocks.begin() + (size_t)(e + 1) * bs);
     }
     if (bs_colidx.size() > before) {
@@ -555,16 +583,43 @@ int dd_build(dpgo_dev *h) {
       sk_ptr[k + 1] = (int)sk.size();
     }
   }
+  s->h_group = group; s->h_lpos = lpos; s->h_dom_m = dom_m; s->h_dom_pad = dom_pad; s->h_dom_base = dom_base;
+  s->h_sk_ptr = sk_ptr; s->h_sk = sk;
+  s->mS = mS; s->padS = padS;
+  s->sym_n = n; s->sym_nnzb = h->nnzb; s->sym_thr = thr; s->sym_split1 = h->dd_split1; s->sym_split3 = h->dd_split3;
+  s->symbolic = true;
+  return dd_numeric(h, s, false);
+}
+
+// Numeric part of the two-level set-up: dense interior inverses, couplings on S_k, Schur complement and its inverse,
+// strip layouts -- from the current values of Q.  refresh_couplings: also re-read the sparse coupling blocks
+// (weight-only rebuild; the index structure on the device stays).
+static int dd_numeric(dpgo_dev *h, DdState *s, bool refresh_couplings) {
+  const int dh = h->d + 1, bs = dh * dh, K = s->K, mS = s->mS, padS = s->padS;
+  if (refresh_couplings) {
+    std::vector<double> vals;
+    auto regather = [&](const std::vector<int> &src, double *dst) -> int {
+      if (src.empty()) return DPGO_OK;
+      vals.resize(src.size() * (size_t)bs);
+      for (size_t k = 0; k < src.size(); ++k)
+        memcpy(vals.data() + k * bs, h->blocks.data() + (size_t)src[k] * bs, bs * sizeof(double));
+      CUDA_TRY(cudaMemcpyAsync(dst, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));     // vals is reused
+      return DPGO_OK;
+    };
+    DPGO_TRY(regather(s->si_src, s->si_blocks));
+    DPGO_TRY(regather(s->bs_src, s->bs_blocks));
+  }
   double *Sg = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double)));
+  CUDA_TRY(cudaMallocAsync((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double), h->stream));
   {
     Elimination E;
-    int rc = eliminate_domains(h, group, lpos, dom_m, sk_ptr, sk, Sg, mS, E);
+    int rc = eliminate_domains(h, s->h_group, s->h_lpos, s->h_dom_m, s->h_sk_ptr, s->h_sk, Sg, mS, E);
     for (int k = 0; k < K && rc == DPGO_OK; ++k) {
-      const size_t total = (size_t)dom_pad[k] * dom_pad[k];
+      const size_t total = (size_t)s->h_dom_pad[k] * s->h_dom_pad[k];
       const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
-      k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(E.Ainv + E.a_off[k], dom_m[k], dom_m[k], dom_pad[k],
-                                                           s->M1 + (size_t)dom_base[k] * kStageDoubles);
+      k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(E.Ainv + E.a_off[k], s->h_dom_m[k], s->h_dom_m[k], s->h_dom_pad[k],
+                                                           s->M1 + (size_t)s->h_dom_base[k] * kStageDoubles);
     }
     if (rc == DPGO_OK && mS > 0) rc = invert_schur(h, Sg, mS);
     if (rc == DPGO_OK && mS > 0) {
@@ -572,8 +627,8 @@ int dd_build(dpgo_dev *h) {
       const int lgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
       k_dd_layout<<<std::max(lgrid, 1), 256, 0, h->stream>>>(Sg, mS, mS, padS, s->M3);
     }
+    cudaFreeAsync(Sg, h->stream);
     const cudaError_t e1 = cudaPeekAtLastError(), e2 = cudaStreamSynchronize(h->stream);
-    cudaFree(Sg);
     DPGO_TRY(rc);
     CUDA_TRY(e1);
     CUDA_TRY(e2);

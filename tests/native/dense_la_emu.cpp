@@ -11,6 +11,8 @@
 #include <mutex>
 #include <vector>
 
+inline void __syncwarp() { emu::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
+
 inline int atomicMax(int *p, int v) {
   static std::mutex m;
   std::lock_guard<std::mutex> g(m);
@@ -27,6 +29,8 @@ namespace {
 
 // run body(bx, by, bz) for every CTA of the grid, each with 256 threads
 void launch(int gx, int gy, int gz, const std::function<void(int, int, int)> &body) {
+  for (int wv = 0; wv < emu::kWarps; ++wv)
+    if (!emu::warp_barrier[wv]) emu::warp_barrier[wv] = new std::barrier<>(32);
   std::vector<std::thread> th;
   for (unsigned t = 0; t < (unsigned)emu::kThreads; ++t)
     th.emplace_back([&, t]() {
