@@ -161,8 +161,8 @@ struct SpdDesc {
 // sL, sW: TS x (TS + 1) doubles each.  info: set to 1 + batch index when a pivot is not positive.
 // 256 threads = 64 rows (columns) x 4 parts: a row's dot product is split over 4 adjacent lanes and combined with
 // two shuffles, so a Cholesky column costs two CTA barriers and <= 16 FMAs per thread, and the 64 columns of the
-// triangular inverse advance together one row per step (round 2, first version: rank-1 updates with three barriers
-// per column and a 64-thread triangular inverse, 94 us per block; this form is bound by the 2 x 64 barriers).
+// triangular inverse advance together one row per step.  The block is a chain of 2 x 64 latency-bound steps
+// (measured 89-94 us per block with sqrt + divide in every step and a single running sum).
 __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int batch, double *sL, double *sW,
                                                int *info) {
   constexpr int P = TS + 1;
@@ -179,13 +179,26 @@ __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int 
   }
   __shared__ int s_bad;
   __shared__ double s_piv;
+  __shared__ double s_rdiag[TS];                  // 1 / L[i][i]
   if (tid == 0) s_bad = 0;
   __syncthreads();
-  // ---- left-looking Cholesky: column j = (A[:, j] - L[:, :j] L[j, :j]^T) / sqrt(pivot)
+  // ---- left-looking Cholesky: column j = (A[:, j] - L[:, :j] L[j, :j]^T) / sqrt(pivot).  The step is a latency
+  // chain (dot product -> shuffles -> barrier -> reciprocal square root -> barrier): four independent partial sums
+  // per lane and rsqrt instead of sqrt + divide keep it short.
   for (int j = 0; j < nb; ++j) {
-    double s = 0.0;
-    if (row >= j && row < nb)
-      for (int k = part; k < j; k += 4) s = fma(sL[row * P + k], sL[j * P + k], s);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (row >= j && row < nb) {
+      const double *lr = sL + row * P, *lj = sL + j * P;
+      int k = part;
+      for (; k + 12 < j; k += 16) {
+        s0 = fma(lr[k], lj[k], s0);
+        s1 = fma(lr[k + 4], lj[k + 4], s1);
+        s2 = fma(lr[k + 8], lj[k + 8], s2);
+        s3 = fma(lr[k + 12], lj[k + 12], s3);
+      }
+      for (; k < j; k += 4) s0 = fma(lr[k], lj[k], s0);
+    }
+    double s = (s0 + s1) + (s2 + s3);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     const double v = sL[row * P + j] - s;         // unscaled entry (row, j); meaningful for j <= row < nb
@@ -196,7 +209,11 @@ __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int 
       if (tid == 0) { s_bad = 1; atomicMax(info, 1 + batch); }
       break;
     }
-    if (part == 0 && row >= j && row < nb) sL[row * P + j] = (row == j) ? sqrt(piv) : v / sqrt(piv);
+    const double rinv = rsqrt(piv);
+    if (part == 0 && row >= j && row < nb) {
+      sL[row * P + j] = (row == j) ? piv * rinv : v * rinv;
+      if (row == j) s_rdiag[j] = rinv;
+    }
     __syncthreads();
   }
   __syncthreads();
@@ -205,12 +222,20 @@ __device__ __forceinline__ void dla_diag_block(const SpdDesc &d, int panel, int 
   {
     const int c = row;
     for (int i = 0; i < nb; ++i) {                // all groups step through the rows together (warp-synchronous)
-      double s = 0.0;
-      if (c < nb && i > c)
-        for (int k = c + part; k < i; k += 4) s = fma(sL[i * P + k], sW[k * P + c], s);
+      double s0 = 0.0, s1 = 0.0;
+      if (c < nb && i > c) {
+        const double *li = sL + i * P;
+        int k = c + part;
+        for (; k + 4 < i; k += 8) {
+          s0 = fma(li[k], sW[k * P + c], s0);
+          s1 = fma(li[k + 4], sW[(k + 4) * P + c], s1);
+        }
+        for (; k < i; k += 4) s0 = fma(li[k], sW[k * P + c], s0);
+      }
+      double s = s0 + s1;
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && c < nb && i >= c) sW[i * P + c] = (((i == c) ? 1.0 : 0.0) - s) / sL[i * P + i];
+      if (part == 0 && c < nb && i >= c) sW[i * P + c] = (((i == c) ? 1.0 : 0.0) - s) * s_rdiag[i];
       __syncwarp();                               // x_i of this warp's columns is visible to its 4-lane groups
     }
   }

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <vector>
 
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void __syncwarp() { emu::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 
 inline int atomicMax(int *p, int v) {

@@ -60,7 +60,19 @@ def barrier_ab():
         run("grid3d_L10", g, 3, 1000, g["T_true"], 5, mode, reps=5)
 
 
+def strip_tuning():
+    """--strip-tuning: inner splits of the interior / Schur strips (balance over the 148 CTAs against partial sums)."""
+    z, d, n, T0 = fixture("sphere2500")
+    for tuning in [None, (1, 0, -1), (2, 0, -1), (3, 0, -1), (2, 4, -1), (2, 7, -1), (1, 7, -1), (1, 3, -1)]:
+        run("sphere2500", z, d, n, T0, 5, 2, tuning, reps=5)
+    g = synthetic.grid3d(10, seed=1)
+    for tuning in [None, (2, 0, -1), (3, 0, -1)]:
+        run("grid3d_L10", g, 3, 1000, g["T_true"], 5, 2, tuning, reps=5)
+
+
 def main():
+    if "--strip-tuning" in sys.argv:
+        return strip_tuning()
     if "--barrier-ab" in sys.argv:
         return barrier_ab()
     quick = "--quick" in sys.argv
