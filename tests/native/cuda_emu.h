@@ -45,6 +45,7 @@ inline double emu_shfl(double v, int src) {
   emu::warp_barrier[w]->arrive_and_wait();
   return out;
 }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
 inline double __shfl_down_sync(unsigned, double v, int delta) {
   const int lane = threadIdx.x & 31;

@@ -12,7 +12,6 @@
 #include <vector>
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
-inline void __syncwarp() { emu::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 
 inline int atomicMax(int *p, int v) {
   static std::mutex m;

@@ -6,7 +6,6 @@
 
 #include <vector>
 
-inline void __syncwarp() { emu::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 
 #include "../../dpgo_b200/csrc/kernels.cuh"
 
