@@ -118,6 +118,7 @@ SIGNATURES = {
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),
+    "dpgo_time_pose_op": (C.c_int, [H, C.c_int, C.c_int, C.c_int, _dp]),
     "dpgo_set_qx_variant": (C.c_int, [H, C.c_int, C.c_int]),
     "dpgo_phase_trace": (C.c_int, [H, _dp, C.c_int, C.POINTER(C.c_int)]),
     "dpgo_bytes_qx": (C.c_int, [H, _dp]),

@@ -317,6 +317,12 @@ class DeviceProblem:
         check(lib.dpgo_time_qx(self._h, reps, 1 if flush_l2 else 0, C.byref(v)))
         return v.value
 
+    def time_pose_op(self, op, reps=20, flush_l2=False):
+        """op 0 = QF retraction, 1 = polar projection (Nesterov form), 2 = rounding; microseconds per launch"""
+        v = C.c_double()
+        check(lib.dpgo_time_pose_op(self._h, int(op), reps, 1 if flush_l2 else 0, C.byref(v)))
+        return v.value
+
     def time_precon(self, reps=10, flush_l2=False):
         v = C.c_double()
         check(lib.dpgo_time_precon(self._h, reps, 1 if flush_l2 else 0, C.byref(v)))

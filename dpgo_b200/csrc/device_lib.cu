@@ -1706,6 +1706,22 @@ int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec) {
   }, usec);
 }
 
+int dpgo_time_pose_op(dpgo_handle h, int op, int reps, int flush_l2, double *usec) {
+  H_CHECK(h);
+  CHECK_ARG(op >= 0 && op <= 2);
+  if (op == 0)
+    return time_launches(h, reps, flush_l2, [&]() { return op_retract(h, h->d_slot[0], h->d_slot[1], h->d_t2); }, usec);
+  if (op == 1)
+    return time_launches(h, reps, flush_l2, [&]() {
+      return op_polar(h, 0.5, h->d_slot[0], 0.3, h->d_slot[1], 0.2, h->d_slot[2], h->d_t2); }, usec);
+  return time_launches(h, reps, flush_l2, [&]() {
+    const int grid = pose_grid(h, 1);
+    DPGO_DISPATCH(h, k_round<R, D><<<grid, kBlock, 0, h->stream>>>(h->d_slot[0], h->d_slot[0], h->d_t0, h->n));
+    LAUNCH_CHECK(h);
+    return DPGO_OK;
+  }, usec);
+}
+
 int dpgo_phase_trace(dpgo_handle h, double *busy_ms, int cap_ctas, int *num_ctas) {
   H_CHECK(h);
   CHECK_ARG(num_ctas != nullptr && cap_ctas >= 0 && (busy_ms != nullptr || cap_ctas == 0));

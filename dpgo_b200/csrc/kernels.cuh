@@ -519,10 +519,13 @@ __device__ __forceinline__ void phase_fgrad(const Ctx &ctx, const BsrView &Q, co
 // Riemannian Hessian-vector product at Y (S = sym(Y^T EG_Y) cached by phase_fgrad):
 //   HV = Proj_Y( V Q - [V_Y S, 0] );  acc = {<V, HV>, <V, W>}  (W optional)
 // ref: QuadraticProblem::EucHessianEta src/QuadraticProblem.cpp:49-54 + Stiefel EucHvToHv.
+// pcol / HVp (optional): HV is also written in the permuted column order of the two-level preconditioner
+// (tile of pose i at scalar column pcol[i]); the folded tCG update of the fused solver reads it from there.
 template <int R, int D>
 __device__ __forceinline__ void phase_hess(const Ctx &ctx, const BsrView &Q, const double *Y,
                                            const double *S, const double *V, double *HV,
-                                           const double *W, int n, double (&acc)[2]) {
+                                           const double *W, int n, double (&acc)[2],
+                                           const int *pcol = nullptr, double *HVp = nullptr) {
   using Gm = Geo<R, D>;
   const LanePos lp = lane_pos<D>(ctx.lane);
   for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
@@ -550,12 +553,81 @@ __device__ __forceinline__ void phase_hess(const Ctx &ctx, const BsrView &Q, con
     group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), out, lp, valid, sym);
     if (valid) {
       store_col<R>(HV + off, out);
+      if (HVp) store_col<R>(HVp + ((size_t)__ldg(pcol + i) + lp.c) * R, out);
       acc[0] += dot_col<R>(v, out);
       if (W) {
         double w[R];
         load_col<R>(W + off, w);
         acc[1] += dot_col<R>(v, w);
       }
+    }
+  }
+}
+
+// tCG direction update  delta+ = -z + beta delta  (the value phase_axpby(-1, z, beta, delta) writes)
+// (intrinsics: the constant -1 must not let the compiler turn this into fma(beta, d, -z), which rounds differently)
+__device__ __forceinline__ double tcg_dir_val(double z, double beta, double d) {
+  return __fma_rn(-1.0, z, __dmul_rn(beta, d));
+}
+
+// phase_hess on the NEW tCG direction, formed on the fly: V = -Z + beta Dold is computed per gathered tile (same
+// expression, same bits as the separate axpby pass), this lane group writes its own columns of V to Dnew (a second
+// buffer: other groups still gather Dold), and the pass goes on as phase_hess(V).  Saves the direction phase and its
+// grid barrier in the fused solver at the price of a second gathered tile per block (L2 resident there).
+template <int R, int D>
+__device__ __forceinline__ void phase_hess_dir(const Ctx &ctx, const BsrView &Q, const double *Y, const double *S,
+                                               const double *Z, const double *Dold, double beta, double *Dnew,
+                                               double *HV, int n, double (&acc)[2], const int *pcol = nullptr,
+                                               double *HVp = nullptr) {
+  using Gm = Geo<R, D>;
+  constexpr int DH = D + 1, TILE = R * DH;
+  const LanePos lp = lane_pos<D>(ctx.lane);
+  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
+    const int i = base + lp.grp;
+    const bool valid = lp.ok && i < n;
+    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
+    double out[R], v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { out[q] = 0.0; v[q] = 0.0; }
+    if (valid) {
+      const int e0 = __ldg(Q.rowptr + i), e1 = __ldg(Q.rowptr + i + 1);
+      for (int e = e0; e < e1; ++e) {
+        const int j = __ldg(Q.colidx + e);
+        double mk[DH], zt[TILE], dt[TILE];
+        load_q_row<DH>(Q.blocks + (size_t)e * (DH * DH) + lp.c * DH, mk);
+        load_x_tile<TILE>(Z + (size_t)j * TILE, zt);
+        load_x_tile<TILE>(Dold + (size_t)j * TILE, dt);
+#pragma unroll
+        for (int k = 0; k < DH; ++k) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) out[q] = fma(tcg_dir_val(zt[k * R + q], beta, dt[k * R + q]), mk[k], out[q]);
+        }
+      }
+      {
+        double zc[R], dc[R];
+        load_col<R>(Z + off, zc);
+        load_col<R>(Dold + off, dc);
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = tcg_dir_val(zc[q], beta, dc[q]);
+        store_col<R>(Dnew + off, v);
+      }
+      if (lp.c < D) {
+        const double *Zi = Z + (size_t)i * Gm::TILE, *Di = Dold + (size_t)i * Gm::TILE;
+        const double *Si = S + (size_t)i * (D * D) + lp.c * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double sk = Si[k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) out[q] = fma(-tcg_dir_val(Zi[k * R + q], beta, Di[k * R + q]), sk, out[q]);
+        }
+      }
+    }
+    double sym[D];
+    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), out, lp, valid, sym);
+    if (valid) {
+      store_col<R>(HV + off, out);
+      if (HVp) store_col<R>(HVp + ((size_t)__ldg(pcol + i) + lp.c) * R, out);
+      acc[0] += dot_col<R>(v, out);
     }
   }
 }
@@ -820,6 +892,7 @@ struct DdView {
   const int *icol;              // [pcols] original scalar column of a permuted column (-1: padding)
   int sep_col0, pcols;          // first separator column; padded column count
   double *rp;                   // the tCG residual in permuted order (fused solver, phase_step_perm)
+  double *rp2, *hp;             // folded update of the fused solver: second residual buffer, permuted copy of Hd
   double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
                                 // nsplit3 partial slots; u is zero outside the boundary rows)
   int prefetch;                 // issue the first matrix stages of the next strip phase before the preceding barrier
@@ -935,6 +1008,22 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
+// Discard a prefetched first wave that will not be consumed by the phase it was issued for (the tCG loop left
+// before that phase): wait for its copies, flip the stage parities.  S is the strip set the prefetch was for.
+// All threads of the CTA call.
+template <int STAGES>
+__device__ __forceinline__ void strip_drain(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st) {
+  const StripPlan pl = strip_plan_load(st);
+  StripCursor cu;
+  strip_cursor_init(cu, S, V, pl);
+  if (cu.v < V) {
+    const int nw = min(STAGES, cu.d.nchunks);
+    for (int ch = 0; ch < nw; ++ch) mbar_wait(pp.bar + 8 * ch, (pp.parity >> ch) & 1u);
+    pp.parity ^= (1u << nw) - 1u;
+  }
+  __syncthreads();
+}
+
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
 // A strip is processed in waves of <= STAGES chunks: thread 0 puts the whole wave in flight (one
 // TMA bulk copy per 16 KB stage, each with its own mbarrier), all threads stage the matching slice
@@ -944,9 +1033,12 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
 template <int R, int STAGES>
 __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
                                                  const double *vec, const int *icol, double *out,
-                                                 size_t outstride, bool prefetched = false) {
+                                                 size_t outstride, bool prefetched = false,
+                                                 const double *vec2 = nullptr, double a2 = 0.0) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
   // is staged (saves a separate permutation pass + grid barrier).
+  // vec2 != nullptr (permuted arrays only): the staged input is fma(a2, vec2, vec) -- the tCG residual update
+  // r + alpha Hd formed while staging, same expression as phase_step_perm2 (folded update of the fused solver).
   static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -975,6 +1067,7 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
           } else {
             val = vec[(size_t)k0 * R + o];
+            if (vec2) val = fma(a2, vec2[(size_t)k0 * R + o], val);
           }
           pp.svec[o] = val;
         }
@@ -1517,6 +1610,37 @@ __device__ __forceinline__ void phase_step_perm(const Ctx &ctx, double a, const 
     const int pose = col / DH, c = col - pose * DH;
     rp[(size_t)(__ldg(pcol + pose) + c) * R + q] = rn;
     acc[0] = fma(rn, rn, acc[0]);
+  }
+}
+// Out-of-place form for the folded update of the fused solver: while this runs, the first strip phase of the next
+// preconditioner application (same grid phase, other warps / CTAs) forms the same residual from rp_in and the
+// permuted Hd, so r_in / rp_in must stay intact until the next grid barrier.
+template <int R, int D>
+__device__ __forceinline__ void phase_step_perm2(const Ctx &ctx, double a, const double *delta, const double *Hd,
+                                                 double *eta, const double *r_in, double *r_out, const int *pcol,
+                                                 double *rp_out, size_t len, double (&acc)[1]) {
+  constexpr int DH = D + 1;
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
+    eta[k] = fma(a, delta[k], eta[k]);
+    const double rn = fma(a, Hd[k], r_in[k]);
+    r_out[k] = rn;
+    const int col = (int)(k / R), q = (int)(k - (size_t)col * R);
+    const int pose = col / DH, c = col - pose * DH;
+    rp_out[(size_t)(__ldg(pcol + pose) + c) * R + q] = rn;
+    acc[0] = fma(rn, rn, acc[0]);
+  }
+}
+//   y = x, yp = x in the permuted column order
+template <int R, int D>
+__device__ __forceinline__ void phase_copy_perm(const Ctx &ctx, const double *x, double *y, const int *pcol,
+                                                double *yp, size_t len) {
+  constexpr int DH = D + 1;
+  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
+    const double v = x[k];
+    y[k] = v;
+    const int col = (int)(k / R), q = (int)(k - (size_t)col * R);
+    const int pose = col / DH, c = col - pose * DH;
+    yp[(size_t)(__ldg(pcol + pose) + c) * R + q] = v;
   }
 }
 //   y = a*x + b*y

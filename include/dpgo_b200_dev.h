@@ -53,6 +53,10 @@ int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses);
  * (outside the timed intervals).  Returns mean microseconds per launch. */
 int dpgo_time_qx(dpgo_handle h, int reps, int flush_l2, double *usec);
 int dpgo_time_precon(dpgo_handle h, int reps, int flush_l2, double *usec);
+/* Same for the per-pose kernels: op 0 = QF retraction (slot 0 + slot 1), 1 = polar projection of
+ * 0.5 slot0 + 0.3 slot1 + 0.2 slot2 (the Nesterov updateY / updateV form), 2 = rounding of slot 0 in the frame of
+ * its first pose.  Algorithmic bytes: 3, 4 and (r + d)/r tile arrays of r(d+1)n doubles. */
+int dpgo_time_pose_op(dpgo_handle h, int op, int reps, int flush_l2, double *usec);
 /* Measurement knob for the stand-alone Q*X (dpgo_qx, dpgo_time_qx; the solver's fused passes are not
  * affected): variant -1 / 0 = the default kernel; 1 = the same product with a software prefetch -- every pose
  * group asks the L2 (cp.async.bulk.prefetch.L2) for the Q blocks, column indices and X tile of the pose
