@@ -39,6 +39,11 @@ class RoptResult(C.Structure):
         return d
 
 
+class ChordalInfo(C.Structure):
+    _fields_ = [("rotation_iterations", C.c_int32), ("translation_iterations", C.c_int32),
+                ("rotation_residual", C.c_double), ("translation_residual", C.c_double), ("launches", C.c_int64)]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _bp = C.POINTER(C.c_uint8)
@@ -116,6 +121,8 @@ SIGNATURES = {
     "dpgo_measurement_errors": (C.c_int, [H, C.c_int, C.c_void_p, _dp, _dp]),
     "dpgo_round_trajectory": (C.c_int, [H, C.c_int, _dp, _dp]),
     "dpgo_max_translation_distance": (C.c_int, [H, C.c_int, C.c_int, _dp]),
+    "dpgo_chordal_initialization": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp,
+                                              C.POINTER(ChordalInfo)]),
     "dpgo_time_qx": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_precon": (C.c_int, [H, C.c_int, C.c_int, _dp]),
     "dpgo_time_pose_op": (C.c_int, [H, C.c_int, C.c_int, C.c_int, _dp]),

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import RoptParams, RoptResult, check, lib
+from ._lib import ChordalInfo, RoptParams, RoptResult, check, lib
 
 SLOT_X, SLOT_Y, SLOT_V, SLOT_XPREV = 0, 1, 2, 3
 _dp = C.POINTER(C.c_double)
@@ -354,3 +354,17 @@ def problem_from_measurements(p1, p2, R, t, kappa, tau, n, d, r, device=0, strea
         prob.set_two_level_domain_size(domain_size)
     prob.finalize(build_precon)
     return prob
+
+
+def chordal_initialization(p1, p2, R, t, kappa, tau, n, d, device=0):
+    """chordalInitialization (src/DPGO_solver.cpp:220-269) on the device; returns (T, info) with T the
+    d x (d+1)n pose array and info the iteration counts / relative residuals of the two linear solves."""
+    m = len(p1)
+    p1 = np.ascontiguousarray(p1, dtype=np.int32)
+    p2 = np.ascontiguousarray(p2, dtype=np.int32)
+    R, t, kappa, tau, _ = DeviceProblem._edge_arrays(d, R, t, kappa, tau, None, m)
+    T = np.zeros((d, (d + 1) * n), order="F")
+    info = ChordalInfo()
+    check(lib.dpgo_chordal_initialization(device, n, d, m, _i(p1), _i(p2), _d(R), _d(t), _d(kappa), _d(tau), _d(T),
+                                          C.byref(info)))
+    return T, {k: getattr(info, k) for k, _ in ChordalInfo._fields_}

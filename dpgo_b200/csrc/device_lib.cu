@@ -96,9 +96,12 @@ __global__ void __launch_bounds__(kBlock, 5) k_qx_prefetch(BsrView Q, const doub
   phase_qx_prefetch<R, D>(make_ctx(), Q, X, G, out, n, dist);
 }
 
+// per-pose kernels: one thread per pose, tiles staged through shared memory (coalesced global traffic), kPoseBlock
+// threads per CTA
 template <int R, int D>
-__global__ void __launch_bounds__(kBlock) k_round(const double *X, const double *anchor, double *T, int n) {
-  phase_round<R, D>(make_ctx(), X, anchor, T, n);
+__global__ void __launch_bounds__(kPoseBlock) k_round(const double *X, const double *anchor, double *T, int n) {
+  __shared__ double sw[kPoseBlock / 32][PoseStage<R * (D + 1)>::WARP_DOUBLES];
+  round_staged<R, D>(X, anchor, T, n, sw[threadIdx.x >> 5]);
 }
 
 template <int R, int D>
@@ -145,23 +148,26 @@ __global__ void __launch_bounds__(kBlock) k_precon_finish(const double *zpart, s
 }
 
 template <int R, int D>
-__global__ void __launch_bounds__(kBlock) k_retract(const double *X, const double *Eta,
-                                                    double *Xout, int n) {
-  phase_retract<R, D>(make_ctx(), X, Eta, Xout, n);
+__global__ void __launch_bounds__(kPoseBlock) k_retract(const double *X, const double *Eta,
+                                                        double *Xout, int n) {
+  __shared__ double sw[kPoseBlock / 32][PoseStage<R * (D + 1)>::WARP_DOUBLES];
+  retract_staged<R, D, false>(X, Eta, Xout, n, 1.0, sw[threadIdx.x >> 5]);
 }
 
 // RGD step: Xout = Retraction_X(s * Dir) -- gradient scale and QF retraction in one pass
 template <int R, int D>
-__global__ void __launch_bounds__(kBlock) k_retract_scaled(const double *X, const double *Dir, double s,
-                                                           double *Xout, int n) {
-  phase_retract_impl<R, D, true>(make_ctx(), X, Dir, Xout, n, s);
+__global__ void __launch_bounds__(kPoseBlock) k_retract_scaled(const double *X, const double *Dir, double s,
+                                                               double *Xout, int n) {
+  __shared__ double sw[kPoseBlock / 32][PoseStage<R * (D + 1)>::WARP_DOUBLES];
+  retract_staged<R, D, true>(X, Dir, Xout, n, s, sw[threadIdx.x >> 5]);
 }
 
 template <int R, int D>
-__global__ void __launch_bounds__(kBlock) k_polar(double ca, const double *A, double cb,
-                                                  const double *B, double cc, const double *C,
-                                                  double *out, int n) {
-  phase_polar<R, D>(make_ctx(), ca, A, cb, B, cc, C, out, n);
+__global__ void __launch_bounds__(kPoseBlock) k_polar(double ca, const double *A, double cb,
+                                                      const double *B, double cc, const double *C,
+                                                      double *out, int n) {
+  __shared__ double sw[kPoseBlock / 32][PoseStage<R * (D + 1)>::WARP_DOUBLES];
+  polar_staged<R, D>(ca, A, cb, B, cc, C, out, n, sw[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_step(double a, const double *delta, const double *Hd,
@@ -298,6 +304,11 @@ static inline int pose_grid(const dpgo_dev *h, int lanes_per_pose) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+// staged per-pose kernels: one thread per pose, kPoseBlock threads per CTA, one pass over the poses
+static inline int staged_grid(const dpgo_dev *h) {
+  const long blocks = ((long)h->n + kPoseBlock - 1) / kPoseBlock;
+  return (int)std::max(1L, blocks);
 }
 static inline int elem_grid(const dpgo_dev *h, size_t len) {
   long blocks = (long)((len + kBlock - 1) / kBlock);
@@ -464,21 +475,21 @@ int op_precon(dpgo_dev *h, const double *Y, const double *rvec, double *z, doubl
   return DPGO_OK;
 }
 int op_retract(dpgo_dev *h, const double *X, const double *Eta, double *Xout) {
-  const int grid = pose_grid(h, 1);
-  DPGO_DISPATCH(h, k_retract<R, D><<<grid, kBlock, 0, h->stream>>>(X, Eta, Xout, h->n));
+  const int grid = staged_grid(h);
+  DPGO_DISPATCH(h, k_retract<R, D><<<grid, kPoseBlock, 0, h->stream>>>(X, Eta, Xout, h->n));
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }
 int op_retract_scaled(dpgo_dev *h, const double *X, const double *Dir, double s, double *Xout) {
-  const int grid = pose_grid(h, 1);
-  DPGO_DISPATCH(h, k_retract_scaled<R, D><<<grid, kBlock, 0, h->stream>>>(X, Dir, s, Xout, h->n));
+  const int grid = staged_grid(h);
+  DPGO_DISPATCH(h, k_retract_scaled<R, D><<<grid, kPoseBlock, 0, h->stream>>>(X, Dir, s, Xout, h->n));
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }
 int op_polar(dpgo_dev *h, double ca, const double *A, double cb, const double *B, double cc,
              const double *C, double *out) {
-  const int grid = pose_grid(h, 1);
-  DPGO_DISPATCH(h, k_polar<R, D><<<grid, kBlock, 0, h->stream>>>(ca, A, cb, B, cc, C, out, h->n));
+  const int grid = staged_grid(h);
+  DPGO_DISPATCH(h, k_polar<R, D><<<grid, kPoseBlock, 0, h->stream>>>(ca, A, cb, B, cc, C, out, h->n));
   LAUNCH_CHECK(h);
   return DPGO_OK;
 }
@@ -1608,8 +1619,8 @@ int dpgo_round_trajectory(dpgo_handle h, int slot, const double *anchor_tile, do
     CUDA_TRY(cudaMemcpyAsync(h->d_t1, anchor_tile, (size_t)tile * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     anchor = h->d_t1;
   }
-  const int grid = pose_grid(h, 1);
-  DPGO_DISPATCH(h, k_round<R, D><<<grid, kBlock, 0, h->stream>>>(h->d_slot[slot], anchor, h->d_t0, h->n));
+  const int grid = staged_grid(h);
+  DPGO_DISPATCH(h, k_round<R, D><<<grid, kPoseBlock, 0, h->stream>>>(h->d_slot[slot], anchor, h->d_t0, h->n));
   LAUNCH_CHECK(h);
   CUDA_TRY(cudaMemcpyAsync(T_host, h->d_t0, (size_t)out_tile * h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1632,6 +1643,153 @@ int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Chordal initialization on the device.
+// ref: chordalInitialization src/DPGO_solver.cpp:220-269, recoverTranslations src/DPGO_utils.cpp.
+//
+// The reference solves two sparse least-squares problems with SPQR:
+//   rotations     min sum_e kappa_e || R_j - R_i R_ij ||_F^2   with R_0 = I, then every R_i is projected to SO(d)
+//   translations  min sum_e tau_e  || t_j - t_i - R_i t_ij ||^2 with t_0 = 0
+// Both are quadratic forms of connection Laplacians the library already builds: with the rotation-only measurements
+// (tau = 0, t = 0) the cost of X = [R_1 0 | R_2 0 | ...] is tr(X Q_rot X^T); with the full measurements the cost of
+// X = [R_1 t_1 | ...] at fixed rotations is tr(X Q X^T), quadratic in the t_i.  So each stage is a handle at r = d,
+// and the normal equations  P Q P x = -P Q x0  (P = keep the unknown columns: rotation columns / translation column
+// of the poses >= 1) are solved by conjugate gradients preconditioned with P (Q + 0.1 I)^-1 P -- the exact operator
+// the solver uses as its preconditioner -- all on the device: Q*X, the two-level / dense inverse, the update kernels
+// of the tCG loop.  The rows of X are independent right-hand sides of the same system; they are iterated as one
+// vector (one alpha / beta per iteration).
+// ---------------------------------------------------------------------------------------------
+namespace dpgo {
+
+// a <- P a  (zero outside the unknown columns: cls 0 = rotation columns, 1 = translation column, poses >= 1);
+// partials[block] = <P a, b>
+__global__ void k_mask_dot(double *a, const double *b, int r, int dh, int cls, size_t len, double *partials) {
+  double acc[1] = {0.0};
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < len; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t col = k / r;
+    const size_t pose = col / dh;
+    const int c = (int)(col - pose * dh);
+    const bool keep = pose >= 1 && (cls == 0 ? c < dh - 1 : c == dh - 1);
+    const double v = keep ? a[k] : 0.0;
+    a[k] = v;
+    acc[0] = fma(v, b[k], acc[0]);
+  }
+  block_reduce_store<1>(acc, partials + blockIdx.x);
+}
+
+static int mask_dot(dpgo_dev *h, double *a, const double *b, int cls, double *out) {
+  const int grid = elem_grid(h, h->vlen);
+  k_mask_dot<<<grid, kBlock, 0, h->stream>>>(a, b, h->r, h->d + 1, cls, h->vlen, h->d_partials);
+  LAUNCH_CHECK(h);
+  return read_scalars(h, grid, 1, out);
+}
+
+// Solves P Q P x = -g for the unknown columns of class `cls`; g = h->d_r on entry (masked here), x = h->d_eta on
+// exit.  h->d_t2 must be zero (stands in for the base point of the preconditioner's tangent projection, which
+// is the identity there).
+static int chordal_pcg(dpgo_dev *h, int cls, double tol, int max_iter, int *iters, double *relres) {
+  double rr0 = 0.0, z_r = 0.0, r_r = 0.0;
+  CUDA_TRY(cudaMemsetAsync(h->d_eta, 0, h->vpad * sizeof(double), h->stream));
+  DPGO_TRY(mask_dot(h, h->d_r, h->d_r, cls, &rr0));
+  *iters = 0;
+  *relres = 0.0;
+  if (!(rr0 > 0.0)) return DPGO_OK;
+  DPGO_TRY(op_precon(h, h->d_t2, h->d_r, h->d_z, nullptr, nullptr));
+  DPGO_TRY(mask_dot(h, h->d_z, h->d_r, cls, &z_r));
+  DPGO_TRY(op_axpby(h, -1.0, h->d_z, 0.0, h->d_delta));          // delta = -z
+  r_r = rr0;
+  for (int j = 0; j < max_iter; ++j) {
+    double d_Hd = 0.0;
+    DPGO_TRY(op_qx_main(h, h->d_delta, nullptr, h->d_Hd));
+    DPGO_TRY(mask_dot(h, h->d_Hd, h->d_delta, cls, &d_Hd));
+    if (!(d_Hd > 0.0)) break;                                      // null direction (disconnected part): stop
+    const double alpha = z_r / d_Hd;
+    DPGO_TRY(op_step(h, alpha, h->d_delta, h->d_Hd, h->d_eta, h->d_r, &r_r));
+    *iters = j + 1;
+    if (sqrt(r_r) <= tol * sqrt(rr0)) break;
+    double z_r_new = 0.0;
+    DPGO_TRY(op_precon(h, h->d_t2, h->d_r, h->d_z, nullptr, nullptr));
+    DPGO_TRY(mask_dot(h, h->d_z, h->d_r, cls, &z_r_new));
+    const double beta = z_r_new / z_r;
+    z_r = z_r_new;
+    DPGO_TRY(op_axpby(h, -1.0, h->d_z, beta, h->d_delta));
+  }
+  *relres = sqrt(r_r / rr0);
+  return DPGO_OK;
+}
+
+// x0 (slot 0) -> g = P (x0 Q) in d_r; solve; slot 0 += x
+static int chordal_stage(dpgo_dev *h, int cls, double tol, int max_iter, int *iters, double *relres) {
+  CUDA_TRY(cudaMemsetAsync(h->d_t2, 0, h->vpad * sizeof(double), h->stream));
+  DPGO_TRY(op_qx_main(h, h->d_slot[0], nullptr, h->d_r));
+  DPGO_TRY(chordal_pcg(h, cls, tol, max_iter, iters, relres));
+  return op_axpby(h, 1.0, h->d_eta, 1.0, h->d_slot[0]);
+}
+
+}  // namespace dpgo
+
+extern "C" int dpgo_chordal_initialization(int device, int n, int d, int m, const int32_t *p1, const int32_t *p2,
+                                           const double *R, const double *t, const double *kappa, const double *tau,
+                                           double *T_host, dpgo_chordal_info *info) {
+  CHECK_ARG(n >= 1 && (d == 2 || d == 3) && m >= 0 && T_host != nullptr);
+  CHECK_ARG(m == 0 || (p1 && p2 && R && t && kappa && tau));
+  const int dh = d + 1;
+  const size_t len = (size_t)d * dh * n;
+  dpgo_chordal_info inf;
+  memset(&inf, 0, sizeof(inf));
+  // identity poses: the answer for n == 1, and the fixed first pose otherwise
+  std::vector<double> X(len, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < d; ++a) X[((size_t)i * dh + a) * d + a] = (i == 0 || n == 1) ? 1.0 : 0.0;
+  if (n == 1 || m == 0) {
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < d; ++a) X[((size_t)i * dh + a) * d + a] = 1.0;
+    memcpy(T_host, X.data(), len * sizeof(double));
+    if (info) *info = inf;
+    return DPGO_OK;
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  const double tol = 1e-13;
+  const int max_iter = 5000;
+  int rc = DPGO_OK;
+  dpgo_handle hr = nullptr, ht = nullptr;
+  auto done = [&](int code) {
+    if (hr) dpgo_destroy(hr);
+    if (ht) dpgo_destroy(ht);
+    if (info) *info = inf;
+    return code;
+  };
+  // ---- rotations (ref :224-251)
+  {
+    std::vector<double> zt((size_t)m * d, 0.0), ztau((size_t)m, 0.0);
+    if ((rc = dpgo_create(device, n, d, d, nullptr, &hr)) != DPGO_OK) return done(rc);
+    if ((rc = dpgo_set_private_edges(hr, m, p1, p2, R, zt.data(), kappa, ztau.data(), nullptr)) != DPGO_OK) return done(rc);
+    if ((rc = dpgo_finalize(hr, 1)) != DPGO_OK) return done(rc);
+    if ((rc = h2d(hr, hr->d_slot[0], X.data())) != DPGO_OK) return done(rc);
+    if ((rc = chordal_stage(hr, 0, tol, max_iter, &inf.rotation_iterations, &inf.rotation_residual)) != DPGO_OK) return done(rc);
+    // projectToRotationGroup of every block (ref :247-250): the rounding kernel in the frame of the identity pose
+    // (slot 0's first tile is [I 0]); its d x (d+1) output tiles are the r = d pose tiles [R_i 0]
+    const int grid = staged_grid(hr);
+    DPGO_DISPATCH(hr, k_round<R, D><<<grid, kPoseBlock, 0, hr->stream>>>(hr->d_slot[0], hr->d_slot[0], hr->d_t0, hr->n));
+    LAUNCH_CHECK(hr);
+    if ((rc = d2h(hr, X.data(), hr->d_t0)) != DPGO_OK) return done(rc);
+    inf.launches += hr->launches;
+    dpgo_destroy(hr);
+    hr = nullptr;
+  }
+  // ---- translations (ref :253-256, recoverTranslations)
+  {
+    if ((rc = dpgo_create(device, n, d, d, nullptr, &ht)) != DPGO_OK) return done(rc);
+    if ((rc = dpgo_set_private_edges(ht, m, p1, p2, R, t, kappa, tau, nullptr)) != DPGO_OK) return done(rc);
+    if ((rc = dpgo_finalize(ht, 1)) != DPGO_OK) return done(rc);
+    if ((rc = h2d(ht, ht->d_slot[0], X.data())) != DPGO_OK) return done(rc);
+    if ((rc = chordal_stage(ht, 1, tol, max_iter, &inf.translation_iterations, &inf.translation_residual)) != DPGO_OK) return done(rc);
+    if ((rc = d2h(ht, T_host, ht->d_slot[0])) != DPGO_OK) return done(rc);
+    inf.launches += ht->launches;
+  }
+  return done(DPGO_OK);
+}
 
 // ---- measurement helpers -------------------------------------------------------------------
 static int ensure_flush(dpgo_dev *h) {
@@ -1715,8 +1873,8 @@ int dpgo_time_pose_op(dpgo_handle h, int op, int reps, int flush_l2, double *use
     return time_launches(h, reps, flush_l2, [&]() {
       return op_polar(h, 0.5, h->d_slot[0], 0.3, h->d_slot[1], 0.2, h->d_slot[2], h->d_t2); }, usec);
   return time_launches(h, reps, flush_l2, [&]() {
-    const int grid = pose_grid(h, 1);
-    DPGO_DISPATCH(h, k_round<R, D><<<grid, kBlock, 0, h->stream>>>(h->d_slot[0], h->d_slot[0], h->d_t0, h->n));
+    const int grid = staged_grid(h);
+    DPGO_DISPATCH(h, k_round<R, D><<<grid, kPoseBlock, 0, h->stream>>>(h->d_slot[0], h->d_slot[0], h->d_t0, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }, usec);

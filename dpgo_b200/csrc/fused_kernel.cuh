@@ -14,17 +14,6 @@ namespace cg = cooperative_groups;
 #include "kernels.cuh"
 #include "rtr_logic.h"
 
-// folded phases of the two-level form (see k_rtr_fused): all on in the product build
-#ifndef DPGO_FOLD_STEP
-#define DPGO_FOLD_STEP 1
-#endif
-#ifndef DPGO_FOLD_DIR
-#define DPGO_FOLD_DIR 1
-#endif
-#ifndef DPGO_P1_PREFETCH
-#define DPGO_P1_PREFETCH 1
-#endif
-
 namespace dpgo {
 
 struct FusedOut {
@@ -46,7 +35,6 @@ struct FusedParams {
   const double *x_in;
   double *x_out;
   double *xa, *xb, *EG, *EG2, *grad, *grad2, *S, *S2, *eta, *r, *z, *delta, *Hd;
-  double *r2, *delta2;   // second buffers of the folded tCG phases (two-level form)
   double *partials;  // [2][gridDim.x][4]
   FusedOut *out;
   unsigned long long *trace;   // -DDPGO_TRACE builds: [gridDim.x][16] ns each CTA worked in a phase before its barrier
@@ -187,35 +175,20 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
-  // ---- two-level form: folded phases (compile-time switches for A/B builds)
-  //  FS  the tCG update (eta += a delta, r += a Hd, <r,r>) runs in the SAME grid phase as the first strip pass of
-  //      the next preconditioner application, which forms the new residual while it stages its input
-  //      (rp + a hp, permuted copies); the convergence test rides on the barrier that ends that phase
-  //  FD  the direction update delta = -z + beta delta is formed inside the Hessian pass (phase_hess_dir)
-  //  PF1 the first wave of the interior strips of the NEXT application is put in flight as soon as the
-  //      last strip pass of this one has consumed its stages
-  constexpr bool FS = (MODE == 2) && (DPGO_FOLD_STEP != 0);
-  constexpr bool FD = (MODE == 2) && (DPGO_FOLD_DIR != 0);
-  constexpr bool PF1 = (MODE == 2) && (DPGO_P1_PREFETCH != 0);
-  bool rf = false, df = false;
-#define Rc (rf ? p.r2 : p.r)                 // tCG residual (FS: out-of-place update)
-#define Rn (rf ? p.r : p.r2)
-#define RPc (rf ? p.dd.rp2 : p.dd.rp)        // its permuted copy
-#define RPn (rf ? p.dd.rp : p.dd.rp2)
-#define Dc (df ? p.delta2 : p.delta)         // tCG direction (FD: out-of-place update)
-#define Dn (df ? p.delta : p.delta2)
-  bool p1_ready = false;                      // first wave of this CTA's first interior strip is in flight
-
-  // the exact preconditioner, dense form (MODE 0): partial products of v with the stored inverse
-  // two-level form (MODE 2), everything after the first strip pass: t = v_S - A_SI y ; z_S = Sigma^-1 t ;
-  // u = A_BS z_S ; w = A_II^-1 u   (ends WITHOUT the barrier that makes w visible)
-  auto precon_rest = [&](const double *v) {
+  // the two forms of the exact preconditioner (compile-time: one kernel instantiation each)
+  // permuted: v is the tCG residual and its permuted copy dd.rp is current (written by phase_step_perm)
+  auto precon_stream = [&](const double *v, bool permuted) {
     if constexpr (MODE == 2) {
       const DdView &dd = p.dd;
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
       constexpr int ST = kDdStages;
+      if (permuted) phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.rp, nullptr, dd.y, zs);
+      else phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs);
       if (dd.nS > 0) {
+        if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
+        red.barrier(grid);
+        clk.lap(8);
         phase_dd_sep_rhs<R, D>(ctx, dd, v);
         red.barrier(grid);
         clk.lap(9);
@@ -229,10 +202,8 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
         phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.u, nullptr, dd.w, zs, pf);
       }
       // no separator (a single domain): z = y, w stays zero
-      if constexpr (PF1) {
-        strip_prefetch<ST>(pipe, dd.P1, dd.V, &s_plan[0]);
-        p1_ready = true;
-      }
+    } else {
+      phase_precon_gemv<R>(pipe, p.Pinv, p.ld, v, p.zpart, p.zstride, p.KT, p.nsplit);
     }
   };
   auto precon_finish = [&](const double *Ycur, const double *rvec, double *neg_out, double (&a1)[1]) {
@@ -270,123 +241,65 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
 
   while (run) {
     // ------------------------------------------------------------------ truncated CG
-    // One call site per phase: the loop starts with the preconditioner (on GRc the first time,
+    // One call site per phase: the loop starts with the preconditioner (on grad the first time,
     // on the residual r afterwards), then the direction update, then the Hessian product.
     TcgState s;
     int inner = 0;
     bool first = true;
-    double step = 0.0;   // FS: accepted step of the previous tCG iteration, applied in the first phase of this one
     for (int j = 0;; ++j) {
-      const double *pvec = first ? GRc : Rc;
-      if constexpr (MODE == 2) {
-        const DdView &dd = p.dd;
-        const size_t zs = (size_t)dd.pcols * R;
-        const bool pf = dd.prefetch != 0;
-        constexpr int ST = kDdStages;
-        // y = A_II^-1 v_I, and what shares the grid phase with it
-        double acc[1] = {0.0}, sc[1];
-        const bool folded = FS && !first;
-        if (first) {
-          phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], GRc, dd.icol, dd.y, zs, p1_ready);
-          if constexpr (FS) phase_copy_perm<R, D>(ctx, GRc, Rc, dd.pcol, RPc, len);
-          else phase_copy(ctx, GRc, Rc, len);
-          phase_zero(ctx, p.eta, len);
-        } else if (folded) {
-          phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], RPc, nullptr, dd.y, zs, p1_ready, dd.hp, step);
-          phase_step_perm2<R, D>(ctx, step, Dc, p.Hd, p.eta, Rc, Rn, dd.pcol, RPn, len, acc);
-        } else {
-          phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], RPc, nullptr, dd.y, zs, p1_ready);
-        }
-        p1_ready = false;
-        if (dd.nS > 0 && pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
-        if (folded) {
-          red.reduce<1>(grid, acc, sc);
-          clk.lap(8);
-          rf = !rf;
-          pvec = Rc;
-          if (tcg_converged(s, sc[0], p.theta, p.kappa)) {
-            // this pass is not needed: drop the Schur wave that is in flight, keep the stages ready for the next
-            // interior pass (first phase of the next tCG run)
-            if (dd.nS > 0 && pf) strip_drain<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
-            if constexpr (PF1) {
-              strip_prefetch<ST>(pipe, dd.P1, dd.V, &s_plan[0]);
-              p1_ready = true;
-            }
-            break;
-          }
-        } else if (dd.nS > 0) {
-          red.barrier(grid);
-          clk.lap(8);
-        }
-        precon_rest(pvec);
-        if (dd.nS > 0 || !folded) {
-          red.barrier(grid);
-          clk.lap(12);
-        }
-      } else {
-        phase_precon_gemv<R>(pipe, p.Pinv, p.ld, pvec, p.zpart, p.zstride, p.KT, p.nsplit);
-        if (first) {
-          phase_copy(ctx, GRc, Rc, len);
-          phase_zero(ctx, p.eta, len);
-        }
-        red.barrier(grid);
-        clk.lap(1);
+      const double *pvec = first ? GRc : p.r;
+      precon_stream(pvec, !first);
+      if (first) {
+        phase_copy(ctx, GRc, p.r, len);
+        phase_zero(ctx, p.eta, len);
       }
-      double beta = 0.0;
+      red.barrier(grid);
+      clk.lap(MODE == 2 ? 12 : 1);
       {
         double acc[1] = {0.0}, sc[1];
-        precon_finish(X1, pvec, first ? Dc : nullptr, acc);   // first: delta = -z
+        precon_finish(X1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
         red.reduce<1>(grid, acc, sc);
         clk.lap(2);
         n_precon++;
         if (first) {
           tcg_begin(s, gn2, sc[0]);
         } else {
-          beta = tcg_direction(s, sc[0]);
-          if constexpr (!FD) {
-            phase_axpby(ctx, -1.0, p.z, beta, Dc, len);
-            red.barrier(grid);
-            clk.lap(5);
-          }
+          const double beta = tcg_direction(s, sc[0]);
+          phase_axpby(ctx, -1.0, p.z, beta, p.delta, len);
+          red.barrier(grid);
+          clk.lap(5);
         }
       }
-      const bool dir_in_hess = FD && !first;
       first = false;
       if (j >= p.max_inner) break;
       double d_Hd;
       {
         double acc[2] = {0.0, 0.0}, sc[2];
-        const int *pc = FS ? p.dd.pcol : nullptr;
-        double *hp = FS ? p.dd.hp : nullptr;
-        if (dir_in_hess) {
-          phase_hess_dir<R, D>(ctx, p.Q, X1, Sc, p.z, Dc, beta, Dn, p.Hd, n, acc, pc, hp);
-          df = !df;
-        } else {
-          phase_hess<R, D>(ctx, p.Q, X1, Sc, Dc, p.Hd, nullptr, n, acc, pc, hp);
-        }
+        phase_hess<R, D>(ctx, p.Q, X1, Sc, p.delta, p.Hd, nullptr, n, acc);
         red.reduce<2>(grid, acc, sc);
         clk.lap(3);
         d_Hd = sc[0];
         n_qx++;
       }
       inner = j + 1;
+      double step;
       if (tcg_curvature(s, d_Hd, Delta, &step)) {
-        phase_axpby(ctx, step, Dc, 1.0, p.eta, len);
+        phase_axpby(ctx, step, p.delta, 1.0, p.eta, len);
         red.barrier(grid);
         clk.lap(4);
         break;
       }
-      if (!FS || j + 1 >= p.max_inner) {
-        // stand-alone update phase (always in the dense form; in the folded form only when no further
-        // preconditioner application can follow)
+      double r_r;
+      {
         double acc[1] = {0.0}, sc[1];
-        if constexpr (MODE == 2 && !FS) phase_step_perm<R, D>(ctx, step, Dc, p.Hd, p.eta, Rc, p.dd.pcol, RPc, len, acc);
-        else phase_step(ctx, step, Dc, p.Hd, p.eta, Rc, len, acc);
+        if constexpr (MODE == 2) phase_step_perm<R, D>(ctx, step, p.delta, p.Hd, p.eta, p.r, p.dd.pcol, p.dd.rp, len, acc);
+        else phase_step(ctx, step, p.delta, p.Hd, p.eta, p.r, len, acc);
         red.reduce<1>(grid, acc, sc);
         clk.lap(4);
-        if (tcg_converged(s, sc[0], p.theta, p.kappa)) break;
-        if (j + 1 >= p.max_inner) break;   // the reference's loop ends without a further direction
+        r_r = sc[0];
       }
+      if (tcg_converged(s, r_r, p.theta, p.kappa)) break;
+      if (j + 1 >= p.max_inner) break;   // the reference's loop ends without a further direction
     }
     inner_total += inner;
     last_status = s.status;
@@ -430,9 +343,6 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
   }
 
   phase_copy(ctx, X1, p.x_out, len);
-  if constexpr (PF1) {   // no bulk copy may be in flight when the CTA exits
-    if (p1_ready) strip_drain<kDdStages>(pipe, p.dd.P1, p.dd.V, &s_plan[0]);
-  }
 #ifdef DPGO_TRACE
   if (threadIdx.x == 0 && p.trace) {
 #pragma unroll
@@ -461,12 +371,6 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
 #undef GRn
 #undef Sc
 #undef Sn
-#undef Rc
-#undef Rn
-#undef RPc
-#undef RPn
-#undef Dc
-#undef Dn
 }
 
 }  // namespace dpgo

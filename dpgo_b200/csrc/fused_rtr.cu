@@ -95,7 +95,6 @@ int solve_fused_launch(dpgo_dev *h, const dpgo_ropt_params *P, const double *x_i
   fp.xa = h->d_xa; fp.xb = h->d_xb; fp.EG = h->d_EG; fp.EG2 = h->d_EG2;
   fp.grad = h->d_grad; fp.grad2 = h->d_grad2; fp.S = h->d_S; fp.S2 = h->d_S2;
   fp.eta = h->d_eta; fp.r = h->d_r; fp.z = h->d_z; fp.delta = h->d_delta; fp.Hd = h->d_Hd;
-  fp.r2 = h->d_t0; fp.delta2 = h->d_t1;   // second buffers of the folded tCG phases (scratch of the host-facing ops)
   fp.partials = h->d_partials;
   fp.out = (FusedOut *)h->d_fused;
   fp.trace = nullptr;

@@ -519,13 +519,10 @@ __device__ __forceinline__ void phase_fgrad(const Ctx &ctx, const BsrView &Q, co
 // Riemannian Hessian-vector product at Y (S = sym(Y^T EG_Y) cached by phase_fgrad):
 //   HV = Proj_Y( V Q - [V_Y S, 0] );  acc = {<V, HV>, <V, W>}  (W optional)
 // ref: QuadraticProblem::EucHessianEta src/QuadraticProblem.cpp:49-54 + Stiefel EucHvToHv.
-// pcol / HVp (optional): HV is also written in the permuted column order of the two-level preconditioner
-// (tile of pose i at scalar column pcol[i]); the folded tCG update of the fused solver reads it from there.
 template <int R, int D>
 __device__ __forceinline__ void phase_hess(const Ctx &ctx, const BsrView &Q, const double *Y,
                                            const double *S, const double *V, double *HV,
-                                           const double *W, int n, double (&acc)[2],
-                                           const int *pcol = nullptr, double *HVp = nullptr) {
+                                           const double *W, int n, double (&acc)[2]) {
   using Gm = Geo<R, D>;
   const LanePos lp = lane_pos<D>(ctx.lane);
   for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
@@ -553,81 +550,12 @@ __device__ __forceinline__ void phase_hess(const Ctx &ctx, const BsrView &Q, con
     group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), out, lp, valid, sym);
     if (valid) {
       store_col<R>(HV + off, out);
-      if (HVp) store_col<R>(HVp + ((size_t)__ldg(pcol + i) + lp.c) * R, out);
       acc[0] += dot_col<R>(v, out);
       if (W) {
         double w[R];
         load_col<R>(W + off, w);
         acc[1] += dot_col<R>(v, w);
       }
-    }
-  }
-}
-
-// tCG direction update  delta+ = -z + beta delta  (the value phase_axpby(-1, z, beta, delta) writes)
-// (intrinsics: the constant -1 must not let the compiler turn this into fma(beta, d, -z), which rounds differently)
-__device__ __forceinline__ double tcg_dir_val(double z, double beta, double d) {
-  return __fma_rn(-1.0, z, __dmul_rn(beta, d));
-}
-
-// phase_hess on the NEW tCG direction, formed on the fly: V = -Z + beta Dold is computed per gathered tile (same
-// expression, same bits as the separate axpby pass), this lane group writes its own columns of V to Dnew (a second
-// buffer: other groups still gather Dold), and the pass goes on as phase_hess(V).  Saves the direction phase and its
-// grid barrier in the fused solver at the price of a second gathered tile per block (L2 resident there).
-template <int R, int D>
-__device__ __forceinline__ void phase_hess_dir(const Ctx &ctx, const BsrView &Q, const double *Y, const double *S,
-                                               const double *Z, const double *Dold, double beta, double *Dnew,
-                                               double *HV, int n, double (&acc)[2], const int *pcol = nullptr,
-                                               double *HVp = nullptr) {
-  using Gm = Geo<R, D>;
-  constexpr int DH = D + 1, TILE = R * DH;
-  const LanePos lp = lane_pos<D>(ctx.lane);
-  for (int base = ctx.warp * Gm::GPW; base < n; base += ctx.nwarps * Gm::GPW) {
-    const int i = base + lp.grp;
-    const bool valid = lp.ok && i < n;
-    const size_t off = valid ? ((size_t)i * Gm::DH + lp.c) * R : 0;
-    double out[R], v[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) { out[q] = 0.0; v[q] = 0.0; }
-    if (valid) {
-      const int e0 = __ldg(Q.rowptr + i), e1 = __ldg(Q.rowptr + i + 1);
-      for (int e = e0; e < e1; ++e) {
-        const int j = __ldg(Q.colidx + e);
-        double mk[DH], zt[TILE], dt[TILE];
-        load_q_row<DH>(Q.blocks + (size_t)e * (DH * DH) + lp.c * DH, mk);
-        load_x_tile<TILE>(Z + (size_t)j * TILE, zt);
-        load_x_tile<TILE>(Dold + (size_t)j * TILE, dt);
-#pragma unroll
-        for (int k = 0; k < DH; ++k) {
-#pragma unroll
-          for (int q = 0; q < R; ++q) out[q] = fma(tcg_dir_val(zt[k * R + q], beta, dt[k * R + q]), mk[k], out[q]);
-        }
-      }
-      {
-        double zc[R], dc[R];
-        load_col<R>(Z + off, zc);
-        load_col<R>(Dold + off, dc);
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = tcg_dir_val(zc[q], beta, dc[q]);
-        store_col<R>(Dnew + off, v);
-      }
-      if (lp.c < D) {
-        const double *Zi = Z + (size_t)i * Gm::TILE, *Di = Dold + (size_t)i * Gm::TILE;
-        const double *Si = S + (size_t)i * (D * D) + lp.c * D;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          const double sk = Si[k];
-#pragma unroll
-          for (int q = 0; q < R; ++q) out[q] = fma(-tcg_dir_val(Zi[k * R + q], beta, Di[k * R + q]), sk, out[q]);
-        }
-      }
-    }
-    double sym[D];
-    group_tangent<R, D>(Y + (valid ? (size_t)i * Gm::TILE : 0), out, lp, valid, sym);
-    if (valid) {
-      store_col<R>(HV + off, out);
-      if (HVp) store_col<R>(HVp + ((size_t)__ldg(pcol + i) + lp.c) * R, out);
-      acc[0] += dot_col<R>(v, out);
     }
   }
 }
@@ -892,7 +820,6 @@ struct DdView {
   const int *icol;              // [pcols] original scalar column of a permuted column (-1: padding)
   int sep_col0, pcols;          // first separator column; padded column count
   double *rp;                   // the tCG residual in permuted order (fused solver, phase_step_perm)
-  double *rp2, *hp;             // folded update of the fused solver: second residual buffer, permuted copy of Hd
   double *y, *t, *zs, *u, *w;   // permuted work arrays, R x pcols (y, w: nsplit1 partial slots; zs:
                                 // nsplit3 partial slots; u is zero outside the boundary rows)
   int prefetch;                 // issue the first matrix stages of the next strip phase before the preceding barrier
@@ -1008,22 +935,6 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
-// Discard a prefetched first wave that will not be consumed by the phase it was issued for (the tCG loop left
-// before that phase): wait for its copies, flip the stage parities.  S is the strip set the prefetch was for.
-// All threads of the CTA call.
-template <int STAGES>
-__device__ __forceinline__ void strip_drain(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st) {
-  const StripPlan pl = strip_plan_load(st);
-  StripCursor cu;
-  strip_cursor_init(cu, S, V, pl);
-  if (cu.v < V) {
-    const int nw = min(STAGES, cu.d.nchunks);
-    for (int ch = 0; ch < nw; ++ch) mbar_wait(pp.bar + 8 * ch, (pp.parity >> ch) & 1u);
-    pp.parity ^= (1u << nw) - 1u;
-  }
-  __syncthreads();
-}
-
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
 // A strip is processed in waves of <= STAGES chunks: thread 0 puts the whole wave in flight (one
 // TMA bulk copy per 16 KB stage, each with its own mbarrier), all threads stage the matching slice
@@ -1033,12 +944,9 @@ __device__ __forceinline__ void strip_drain(GemvPipe &pp, const DdStripSet &S, i
 template <int R, int STAGES>
 __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st,
                                                  const double *vec, const int *icol, double *out,
-                                                 size_t outstride, bool prefetched = false,
-                                                 const double *vec2 = nullptr, double a2 = 0.0) {
+                                                 size_t outstride, bool prefetched = false) {
   // icol != nullptr: `vec` is in the ORIGINAL column order and is gathered through icol while it
   // is staged (saves a separate permutation pass + grid barrier).
-  // vec2 != nullptr (permuted arrays only): the staged input is fma(a2, vec2, vec) -- the tCG residual update
-  // r + alpha Hd formed while staging, same expression as phase_step_perm2 (folded update of the fused solver).
   static_assert(STAGES <= 32 && kStageK == 32, "wave bookkeeping");
   double(*sacc)[R][kGemvCols] = reinterpret_cast<double(*)[R][kGemvCols]>(pp.scratch);  // [8][R][64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1067,7 +975,6 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
             val = (oc >= 0) ? vec[(size_t)oc * R + q] : 0.0;
           } else {
             val = vec[(size_t)k0 * R + o];
-            if (vec2) val = fma(a2, vec2[(size_t)k0 * R + o], val);
           }
           pp.svec[o] = val;
         }
@@ -1312,20 +1219,15 @@ __device__ __forceinline__ void phase_precon_finish(const Ctx &ctx, const double
 // SCALED: the step is s * Eta (the gradient scale of QuadraticOptimizer::gradientDescent,
 // src/QuadraticOptimizer.cpp:133-134, applied inside the retraction: round(s * e) then the add, i.e. the
 // same bits as scaling into a separate array first).
-template <int R, int D, bool SCALED>
-__device__ __forceinline__ void phase_retract_impl(const Ctx &ctx, const double *X, const double *Eta,
-                                                   double *Xout, int n, double s) {
-  constexpr int TILE = R * (D + 1);
-  auto step = [&](double xv, double ev) { return SCALED ? __dadd_rn(xv, __dmul_rn(s, ev)) : xv + ev; };
-  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
-    const double *x = X + (size_t)i * TILE;
-    const double *e = Eta + (size_t)i * TILE;
-    double *o = Xout + (size_t)i * TILE;
+// one pose: val(k) = entry k of the tile Y + eta (column-major r x (d+1)); o = the retracted tile
+template <int R, int D, class F>
+__device__ __forceinline__ void retract_pose(F val, double *o) {
+  {
     double a[D][R];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
 #pragma unroll
-      for (int q = 0; q < R; ++q) a[k][q] = step(x[k * R + q], e[k * R + q]);
+      for (int q = 0; q < R; ++q) a[k][q] = val(k * R + q);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -1359,7 +1261,18 @@ __device__ __forceinline__ void phase_retract_impl(const Ctx &ctx, const double 
       for (int q = 0; q < R; ++q) o[k * R + q] = a[k][q];
     }
 #pragma unroll
-    for (int q = 0; q < R; ++q) o[D * R + q] = step(x[D * R + q], e[D * R + q]);
+    for (int q = 0; q < R; ++q) o[D * R + q] = val(D * R + q);
+  }
+}
+template <int R, int D, bool SCALED>
+__device__ __forceinline__ void phase_retract_impl(const Ctx &ctx, const double *X, const double *Eta,
+                                                   double *Xout, int n, double s) {
+  constexpr int TILE = R * (D + 1);
+  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
+    const double *x = X + (size_t)i * TILE;
+    const double *e = Eta + (size_t)i * TILE;
+    retract_pose<R, D>([&](int k) { return SCALED ? __dadd_rn(x[k], __dmul_rn(s, e[k])) : x[k] + e[k]; },
+                       Xout + (size_t)i * TILE);
   }
 }
 template <int R, int D>
@@ -1368,29 +1281,81 @@ __device__ __forceinline__ void phase_retract(const Ctx &ctx, const double *X, c
   phase_retract_impl<R, D, false>(ctx, X, Eta, Xout, n, 1.0);
 }
 
+// ---- per-pose kernels at scale: tiles staged through shared memory ------------------------------------------------
+// One thread per pose keeps the arithmetic of a pose in one thread's registers, but its global accesses are 32
+// tiles apart per warp instruction (measured on 262 144 / 1 000 000 poses, profiles/r02_pose_op_scale.jsonl:
+// retraction 0.38 / 0.44, polar projection 0.28 / 0.36, rounding 0.27 / 0.33 of the HBM peak).  The staged forms
+// below move the 32 consecutive tiles of a warp step with coalesced loads / stores (consecutive lanes = consecutive
+// doubles) through a per-warp shared-memory area with an odd pose stride (bank-conflict free), and run the SAME
+// per-pose functions on the staged values: identical bits.  Blocks of kPoseBlock threads.
+constexpr int kPoseBlock = 128;
+template <int TILE>
+struct PoseStage {
+  static constexpr int STRIDE = (TILE % 2) ? TILE : TILE + 1;
+  static constexpr int WARP_DOUBLES = 32 * STRIDE;
+};
+// in(g) = value of global element g of the (combined) input array; pose(sw_tile, lane_valid) transforms the staged
+// tile in place (OUT_TILE <= TILE doubles per pose are written back to out)
+template <int TILE, int OUT_TILE, class In, class Pose>
+__device__ __forceinline__ void pose_staged(int n, double *out, double *sw, In in, Pose pose) {
+  using PS = PoseStage<TILE>;
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int b0 = warp * 32; b0 < n; b0 += nwarps * 32) {
+    const int np = min(32, n - b0);
+    const size_t g0 = (size_t)b0 * TILE;
+    if (np == 32) {
+      double v[TILE];
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) v[k] = in(g0 + lane + 32 * k);      // all loads in flight before the first use
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) {
+        const int e = lane + 32 * k, pl = e / TILE;
+        sw[pl * PS::STRIDE + (e - pl * TILE)] = v[k];
+      }
+    } else {
+      for (int e = lane; e < np * TILE; e += 32) {
+        const int pl = e / TILE;
+        sw[pl * PS::STRIDE + (e - pl * TILE)] = in(g0 + e);
+      }
+    }
+    __syncwarp();
+    if (lane < np) pose(sw + lane * PS::STRIDE);
+    __syncwarp();
+    const size_t o0 = (size_t)b0 * OUT_TILE;
+    for (int e = lane; e < np * OUT_TILE; e += 32) {
+      const int pl = e / OUT_TILE;
+      out[o0 + e] = sw[pl * PS::STRIDE + (e - pl * OUT_TILE)];
+    }
+    __syncwarp();
+  }
+}
+template <int R, int D, bool SCALED>
+__device__ __forceinline__ void retract_staged(const double *X, const double *Eta, double *Xout, int n, double s,
+                                               double *sw) {
+  constexpr int TILE = R * (D + 1);
+  pose_staged<TILE, TILE>(
+      n, Xout, sw, [&](size_t g) { return SCALED ? __dadd_rn(X[g], __dmul_rn(s, Eta[g])) : X[g] + Eta[g]; },
+      [&](double *t) { retract_pose<R, D>([&](int k) { return t[k]; }, t); });
+}
+
 // Polar projection of the Stiefel block (U V^T of the thin SVD) by one-sided Jacobi, one
-// thread per pose, of the combination M = ca*A + cb*B + cc*C (B, C optional); translation is
+// thread per pose (tiles staged through shared memory, polar_staged), of the combination M = ca*A + cb*B + cc*C (B, C optional); translation is
 // the same combination, unprojected.
 // ref: LiftedSEManifold::project src/manifold/LiftedSEManifold.cpp:34-45,
 //      projectToStiefelManifold src/DPGO_utils.cpp:480-486, PGOAgent::updateY/updateV
 //      src/PGOAgent.cpp:922-936.
-template <int R, int D>
-__device__ __forceinline__ void phase_polar(const Ctx &ctx, double ca, const double *A, double cb,
-                                            const double *B, double cc, const double *C,
-                                            double *out, int n) {
-  constexpr int TILE = R * (D + 1);
-  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
-    const size_t o = (size_t)i * TILE;
+// one pose: val(k) = entry k of the tile M; out = [polar factor of the Stiefel block | translation column of M]
+template <int R, int D, class F>
+__device__ __forceinline__ void polar_pose(F val, double *out) {
+  {
+    constexpr size_t o = 0;
     double a[D][R], v[D][D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
 #pragma unroll
-      for (int q = 0; q < R; ++q) {
-        double m = ca * A[o + k * R + q];
-        if (B) m = fma(cb, B[o + k * R + q], m);
-        if (C) m = fma(cc, C[o + k * R + q], m);
-        a[k][q] = m;
-      }
+      for (int q = 0; q < R; ++q) a[k][q] = val(k * R + q);
 #pragma unroll
       for (int l = 0; l < D; ++l) v[k][l] = (k == l) ? 1.0 : 0.0;
     }
@@ -1453,13 +1418,24 @@ __device__ __forceinline__ void phase_polar(const Ctx &ctx, double ca, const dou
       }
     }
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-      double m = ca * A[o + D * R + q];
-      if (B) m = fma(cb, B[o + D * R + q], m);
-      if (C) m = fma(cc, C[o + D * R + q], m);
-      out[o + D * R + q] = m;
-    }
+    for (int q = 0; q < R; ++q) out[o + D * R + q] = val(D * R + q);
   }
+}
+// M = ca*A + cb*B + cc*C, entry g of the arrays (B, C optional)
+__device__ __forceinline__ double polar_combination(double ca, const double *A, double cb, const double *B, double cc,
+                                                    const double *C, size_t g) {
+  double m = ca * A[g];
+  if (B) m = fma(cb, B[g], m);
+  if (C) m = fma(cc, C[g], m);
+  return m;
+}
+template <int R, int D>
+__device__ __forceinline__ void polar_staged(double ca, const double *A, double cb, const double *B, double cc,
+                                             const double *C, double *out, int n, double *sw) {
+  constexpr int TILE = R * (D + 1);
+  pose_staged<TILE, TILE>(
+      n, out, sw, [&](size_t g) { return polar_combination(ca, A, cb, B, cc, C, g); },
+      [&](double *t) { polar_pose<R, D>([&](int k) { return t[k]; }, t); });
 }
 
 // Rounding of the lifted iterate to SE(d) poses in the frame of an anchor pose (one thread per pose):
@@ -1468,18 +1444,16 @@ __device__ __forceinline__ void phase_polar(const Ctx &ctx, double ca, const dou
 //      projectToRotationGroup src/DPGO_utils.cpp:464-478 (SVD, last column of U negated when det U det V < 0 --
 //      the singular values are sorted there, so the negated direction is the one of the smallest singular value).
 // `anchor` is a lifted pose tile r x (d+1) (rotation Ya, translation pa); T is d x (d+1)n, column-major.
+// one pose: x = the lifted tile, (ya, pa) = the anchor; t = the d x (d+1) rounded pose (may alias x: the tile is
+// read into registers first)
 template <int R, int D>
-__device__ __forceinline__ void phase_round(const Ctx &ctx, const double *X, const double *anchor, double *T, int n) {
+__device__ __forceinline__ void round_pose(const double *xin, const double (&ya)[D][R], const double (&pa)[R],
+                                           double *t) {
   constexpr int DH = D + 1, TILE = R * DH;
-  double ya[D][R], pa[R];
+  {
+    double x[TILE];
 #pragma unroll
-  for (int k = 0; k < D; ++k)
-#pragma unroll
-    for (int q = 0; q < R; ++q) ya[k][q] = anchor[k * R + q];
-#pragma unroll
-  for (int q = 0; q < R; ++q) pa[q] = anchor[D * R + q];
-  for (int i = ctx.tid; i < n; i += ctx.nthreads) {
-    const double *x = X + (size_t)i * TILE;
+    for (int k = 0; k < TILE; ++k) x[k] = xin[k];
     // a[k][l] = (Ya^T Y_i)[l][k]: column k of M as a[k][.]
     double a[D][D], v[D][D];
 #pragma unroll
@@ -1566,7 +1540,6 @@ __device__ __forceinline__ void phase_round(const Ctx &ctx, const double *X, con
         }
       }
     }
-    double *t = T + (size_t)i * (D * DH);
 #pragma unroll
     for (int c = 0; c < D; ++c)
 #pragma unroll
@@ -1579,6 +1552,23 @@ __device__ __forceinline__ void phase_round(const Ctx &ctx, const double *X, con
       t[D * D + l] = s;
     }
   }
+}
+template <int R, int D>
+__device__ __forceinline__ void load_anchor(const double *anchor, double (&ya)[D][R], double (&pa)[R]) {
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int q = 0; q < R; ++q) ya[k][q] = anchor[k * R + q];
+#pragma unroll
+  for (int q = 0; q < R; ++q) pa[q] = anchor[D * R + q];
+}
+template <int R, int D>
+__device__ __forceinline__ void round_staged(const double *X, const double *anchor, double *T, int n, double *sw) {
+  constexpr int DH = D + 1, TILE = R * DH;
+  double ya[D][R], pa[R];
+  load_anchor<R, D>(anchor, ya, pa);
+  pose_staged<TILE, D * DH>(
+      n, T, sw, [&](size_t g) { return X[g]; }, [&](double *t) { round_pose<R, D>(t, ya, pa, t); });
 }
 
 // Elementwise phases over the r x N arrays (len = R * N doubles).
@@ -1610,37 +1600,6 @@ __device__ __forceinline__ void phase_step_perm(const Ctx &ctx, double a, const 
     const int pose = col / DH, c = col - pose * DH;
     rp[(size_t)(__ldg(pcol + pose) + c) * R + q] = rn;
     acc[0] = fma(rn, rn, acc[0]);
-  }
-}
-// Out-of-place form for the folded update of the fused solver: while this runs, the first strip phase of the next
-// preconditioner application (same grid phase, other warps / CTAs) forms the same residual from rp_in and the
-// permuted Hd, so r_in / rp_in must stay intact until the next grid barrier.
-template <int R, int D>
-__device__ __forceinline__ void phase_step_perm2(const Ctx &ctx, double a, const double *delta, const double *Hd,
-                                                 double *eta, const double *r_in, double *r_out, const int *pcol,
-                                                 double *rp_out, size_t len, double (&acc)[1]) {
-  constexpr int DH = D + 1;
-  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
-    eta[k] = fma(a, delta[k], eta[k]);
-    const double rn = fma(a, Hd[k], r_in[k]);
-    r_out[k] = rn;
-    const int col = (int)(k / R), q = (int)(k - (size_t)col * R);
-    const int pose = col / DH, c = col - pose * DH;
-    rp_out[(size_t)(__ldg(pcol + pose) + c) * R + q] = rn;
-    acc[0] = fma(rn, rn, acc[0]);
-  }
-}
-//   y = x, yp = x in the permuted column order
-template <int R, int D>
-__device__ __forceinline__ void phase_copy_perm(const Ctx &ctx, const double *x, double *y, const int *pcol,
-                                                double *yp, size_t len) {
-  constexpr int DH = D + 1;
-  for (size_t k = ctx.tid; k < len; k += ctx.nthreads) {
-    const double v = x[k];
-    y[k] = v;
-    const int col = (int)(k / R), q = (int)(k - (size_t)col * R);
-    const int pose = col / DH, c = col - pose * DH;
-    yp[(size_t)(__ldg(pcol + pose) + c) * R + q] = v;
   }
 }
 //   y = a*x + b*y

@@ -51,7 +51,7 @@ struct DdState {
   int *pcol = nullptr, *srow = nullptr, *bcol = nullptr, *icol = nullptr;
   int *si_rowptr = nullptr, *si_colidx = nullptr, *bs_rowptr = nullptr, *bs_colidx = nullptr;
   double *si_blocks = nullptr, *bs_blocks = nullptr;
-  double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr, *rp = nullptr, *rp2 = nullptr, *hp = nullptr;
+  double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr, *rp = nullptr;
   bool configured = false;
   // symbolic part kept for weight-only rebuilds (GNC): the dissection, the strip tables and the index lists depend on
   // the sparsity pattern only, so dpgo_update_weights redoes the numeric part alone (dd_numeric)
@@ -335,7 +335,7 @@ DdView dd_view(const dpgo_dev *h) {
   v.nS = s->nS; v.nB = s->nB;
   v.pcol = s->pcol; v.srow = s->srow; v.bcol = s->bcol; v.icol = s->icol;
   v.sep_col0 = s->sep_col0; v.pcols = s->pcols;
-  v.y = s->y; v.t = s->t; v.zs = s->zs; v.u = s->u; v.w = s->w; v.rp = s->rp; v.rp2 = s->rp2; v.hp = s->hp;
+  v.y = s->y; v.t = s->t; v.zs = s->zs; v.u = s->u; v.w = s->w; v.rp = s->rp;
   v.prefetch = h->dd_prefetch;
   return v;
 }
@@ -345,7 +345,7 @@ void dd_free(dpgo_dev *h) {
   if (!s) return;
   void *ptrs[] = {s->M1, s->M3, s->strips1, s->strips3, s->cta1, s->cta3, s->chunks1, s->chunks3, s->pcol, s->srow,
                   s->bcol, s->icol, s->si_rowptr, s->si_colidx, s->bs_rowptr, s->bs_colidx, s->si_blocks, s->bs_blocks,
-                  s->y, s->t, s->zs, s->u, s->w, s->rp, s->rp2, s->hp};
+                  s->y, s->t, s->zs, s->u, s->w, s->rp};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -562,10 +562,8 @@ int dd_build(dpgo_dev *h) {
   }
   CUDA_TRY(cudaMalloc((void **)&s->zs, wlen * nsplit3 * sizeof(double)));
   CUDA_TRY(cudaMemset(s->zs, 0, wlen * nsplit3 * sizeof(double)));
-  for (double **a : {&s->rp, &s->rp2, &s->hp}) {   // permuted copies used by the fused solver; padding columns stay zero
-    CUDA_TRY(cudaMalloc((void **)a, wlen * sizeof(double)));
-    CUDA_TRY(cudaMemset(*a, 0, wlen * sizeof(double)));
-  }
+  CUDA_TRY(cudaMalloc((void **)&s->rp, wlen * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->rp, 0, wlen * sizeof(double)));
   // ---- dense blocks on the device
   CUDA_TRY(cudaMalloc((void **)&s->M1, std::max<size_t>((size_t)stages1 * kStageDoubles, 1) * sizeof(double)));
   CUDA_TRY(cudaMalloc((void **)&s->M3, std::max<size_t>((size_t)padS * padS, 1) * sizeof(double)));

@@ -1,5 +1,6 @@
 // Chordal / odometry initialization and the single-robot solve (host side, cold path).
 #include <DPGO/DPGO_solver.h>
+#include <DPGO/DPGO_utils.h>
 #include <DPGO/PoseGraph.h>
 #include <DPGO/QuadraticOptimizer.h>
 #include <DPGO/QuadraticProblem.h>
@@ -84,7 +85,43 @@ void pcg(const std::function<void(const std::vector<double> &, std::vector<doubl
 
 }  // namespace
 
+// Device path (dpgo_chordal_initialization: both least-squares problems solved on the GPU with the library's
+// Q*X and exact-preconditioner kernels; the reference factorizes with SPQR, src/DPGO_solver.cpp:220-269).
 PoseArray chordalInitialization(const std::vector<RelativeSEMeasurement> &measurements) {
+  size_t d, n;
+  get_dimension_and_num_poses(measurements, d, n);
+  PoseArray T(static_cast<unsigned>(d), static_cast<unsigned>(n));
+  const size_t m = measurements.size();
+  std::vector<int32_t> p1(m), p2(m);
+  std::vector<double> R(m * d * d), t(m * d), kappa(m), tau(m);
+  for (size_t k = 0; k < m; ++k) {
+    const RelativeSEMeasurement &e = measurements[k];
+    p1[k] = static_cast<int32_t>(e.p1);
+    p2[k] = static_cast<int32_t>(e.p2);
+    for (size_t a = 0; a < d; ++a) {
+      for (size_t b = 0; b < d; ++b) R[(k * d + a) * d + b] = e.R(a, b);
+      t[k * d + a] = e.t(a, 0);
+    }
+    kappa[k] = e.kappa;
+    tau[k] = e.tau;
+  }
+  Matrix Tm(static_cast<std::ptrdiff_t>(d), static_cast<std::ptrdiff_t>(n * (d + 1)));
+  dpgo_chordal_info info;
+  DPGO_DEVICE_CALL(dpgo_chordal_initialization(defaultDevice(), static_cast<int>(n), static_cast<int>(d),
+                                               static_cast<int>(m), p1.data(), p2.data(), R.data(), t.data(),
+                                               kappa.data(), tau.data(), Tm.data(), &info));
+  if (info.rotation_residual > 1e-8 || info.translation_residual > 1e-8)
+    std::fprintf(stderr, "[DPGO] chordalInitialization: linear solves stopped at relative residuals %.3e (rotations, "
+                         "%d iterations) / %.3e (translations, %d iterations); the initial guess may be inaccurate\n",
+                 info.rotation_residual, info.rotation_iterations, info.translation_residual,
+                 info.translation_iterations);
+  T.setData(Tm);
+  return T;
+}
+
+// The same relaxation on the host (Jacobi-preconditioned CG on the normal equations): not called by the library;
+// host_cli uses it to check the host-side measurement handling without a GPU.
+PoseArray chordalInitializationHostCG(const std::vector<RelativeSEMeasurement> &measurements) {
   size_t d, n;
   get_dimension_and_num_poses(measurements, d, n);
   PoseArray T(static_cast<unsigned>(d), static_cast<unsigned>(n));

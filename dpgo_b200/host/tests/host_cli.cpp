@@ -90,8 +90,9 @@ int main(int argc, char **argv) {
     }
     return 0;
   }
-  if (!std::strcmp(argv[1], "chordal")) {
-    const Matrix T = chordalInitialization(ms).getData();
+  if (!std::strcmp(argv[1], "chordal") || !std::strcmp(argv[1], "chordal-device")) {
+    // "chordal": the host CG form (CPU checks); "chordal-device": the library's path (needs a GPU)
+    const Matrix T = (argv[1][7] ? chordalInitialization(ms) : chordalInitializationHostCG(ms)).getData();
     std::printf("%td %td\n", T.rows(), T.cols());
     for (std::ptrdiff_t j = 0; j < T.cols(); ++j)
       for (std::ptrdiff_t i = 0; i < T.rows(); ++i) std::printf("%.17g\n", T(i, j));
@@ -104,7 +105,7 @@ int main(int argc, char **argv) {
     for (size_t k = 0; k < in.size(); ++k) in[k].weight = 1.0 / (1.0 + static_cast<double>(k % 7));
     PGOLogger logger(argv[3]);
     logger.logMeasurements(in, "measurements.csv");
-    const Matrix T = chordalInitialization(ms).getData();
+    const Matrix T = chordalInitializationHostCG(ms).getData();
     logger.logTrajectory(static_cast<unsigned>(d), static_cast<unsigned>(n), T, "trajectory.csv");
     const std::vector<RelativeSEMeasurement> out =
         PGOLogger::loadMeasurements(std::string(argv[3]) + "measurements.csv", true);

@@ -260,6 +260,24 @@ int dpgo_round_trajectory(dpgo_handle h, int slot, const double *anchor_tile, do
  * PGOAgentStatus.relativeChange, src/PGOAgent.cpp:404) */
 int dpgo_max_translation_distance(dpgo_handle h, int slot_a, int slot_b, double *out);
 
+/* ---- chordal initialization (ref: chordalInitialization src/DPGO_solver.cpp:220-269) ------------ */
+/* Relax-and-round initial guess from the measurements alone, on the device: rotations from the linear least-squares
+ * problem min sum kappa ||R_j - R_i R_ij||^2 with R_0 = I (every block then projected to SO(d),
+ * projectToRotationGroup), translations from min sum tau ||t_j - t_i - R_i t_ij||^2 with t_0 = 0
+ * (recoverTranslations).  The reference factorizes with SPQR; here both normal equations are solved by conjugate
+ * gradients on the device with the library's Q*X kernel and its exact (Q + 0.1 I)^-1 as the preconditioner.
+ * Measurement weights are not used (as in the reference).  Edges as in dpgo_set_private_edges.
+ * T_host: d x (d+1)n, column-major (PoseArray layout).  info (optional): iterations and final relative residuals of
+ * the two solves (a residual above ~1e-8 means the graph is badly conditioned or not connected to pose 0). */
+typedef struct {
+  int rotation_iterations, translation_iterations;
+  double rotation_residual, translation_residual;
+  int64_t launches;
+} dpgo_chordal_info;
+int dpgo_chordal_initialization(int device, int n, int d, int m, const int32_t *p1, const int32_t *p2,
+                                const double *R, const double *t, const double *kappa, const double *tau,
+                                double *T_host, dpgo_chordal_info *info);
+
 #ifdef __cplusplus
 }
 #endif

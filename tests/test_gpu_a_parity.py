@@ -350,3 +350,23 @@ def test_rounding_parity(datasets, name, r):
     ref = pgo.round_solution(np.hstack([anchor, X]), d)[:, d + 1:]     # the anchor as pose 0 of a longer array
     assert rel(Tg, ref) < 1e-12
     gp.close()
+
+
+@pytest.mark.parametrize("name", ["tinyGrid3D", "smallGrid3D", "sphere2500", "torus3D", "grid3D", "city10000"])
+def test_chordal_initialization_parity(datasets, name):
+    """chordalInitialization (src/DPGO_solver.cpp:220-269) on the device -- both least-squares problems solved by
+    conjugate gradients with the library's Q*X kernel and its exact (Q + 0.1 I)^-1 as the preconditioner -- against
+    the oracle's sparse direct solves (the golden T_chordal of the fixture, tools/make_fixtures.py).  1e-8 relative:
+    the CG stops at a relative residual of 1e-13, the anchored Laplacians have condition numbers up to ~1e5."""
+    import dpgo_b200
+    meas, n, z = datasets(name)
+    T, info = dpgo_b200.chordal_initialization(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, meas.d)
+    assert info["rotation_residual"] <= 1e-12 and info["translation_residual"] <= 1e-12, info
+    d = meas.d
+    Tr = T.reshape(d, n, d + 1, order="F")
+    for i in (0, n // 2, n - 1):                       # rotations are in SO(d)
+        Ri = Tr[:, i, :d]
+        assert np.allclose(Ri.T @ Ri, np.eye(d), atol=1e-12) and np.linalg.det(Ri) > 0
+    assert np.array_equal(T[:, :d + 1], np.eye(d, d + 1))
+    assert rel(T, z["T_chordal"]) < 1e-8, (rel(T, z["T_chordal"]), info)
+    print(name, info)

@@ -78,37 +78,3 @@ def test_qx_forms_ragged_rows(lib, d, r):
         assert np.allclose(base, X @ dense, rtol=1e-12, atol=1e-11)
         for variant in (2, 3):
             assert np.array_equal(_run(lib, variant, r, d, rowptr, colidx, blocks, X, None, n, ctas), base), variant
-
-
-@pytest.mark.parametrize("name,r", [("smallGrid3D", 5)])
-def test_hessian_pass_with_folded_direction_update(lib, datasets, name, r):
-    """phase_hess_dir (the tCG direction -z + beta delta formed per gathered tile inside the Hessian pass, fused
-    solver) gives the bits of the separate direction pass followed by phase_hess, including the permuted copy"""
-    meas, n, _ = datasets(name)
-    d = meas.d
-    dh = d + 1
-    Qm = pgo.connection_laplacian(meas, n)
-    rowptr, colidx, blocks = bsr_of(Qm, dh)
-    rng = np.random.default_rng(11)
-    shape = (r, dh * n)
-    Y, Z, Dold = (np.asfortranarray(rng.standard_normal(shape)) for _ in range(3))
-    S = np.ascontiguousarray(rng.standard_normal(n * d * d))
-    perm = rng.permutation(n).astype(np.int32) * dh          # permuted tile starts
-    beta = 0.37
-    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
-    res = []
-    for variant in (0, 1):
-        Dnew, HV, HVp = (np.full(shape, np.nan, order="F") for _ in range(3))
-        acc = np.zeros(2)
-        rc = lib.hess_emu(variant, r, d, rowptr.ctypes.data_as(ip), colidx.ctypes.data_as(ip), blocks.ctypes.data_as(dp),
-                          Y.ctypes.data_as(dp), S.ctypes.data_as(dp), Z.ctypes.data_as(dp), Dold.ctypes.data_as(dp),
-                          ctypes.c_double(beta), Dnew.ctypes.data_as(dp), HV.ctypes.data_as(dp), perm.ctypes.data_as(ip),
-                          HVp.ctypes.data_as(dp), acc.ctypes.data_as(dp), n)
-        assert rc == 0
-        res.append((Dnew, HV, HVp, acc))
-    for a, b in zip(res[0], res[1]):
-        assert np.array_equal(a, b)
-    Dnew, HV, HVp, _ = res[1]
-    assert np.array_equal(Dnew, -Z + beta * Dold)
-    for i in range(n):
-        assert np.array_equal(HVp[:, perm[i]:perm[i] + dh], HV[:, i * dh:(i + 1) * dh])

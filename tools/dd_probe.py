@@ -70,21 +70,7 @@ def strip_tuning():
         run("grid3d_L10", g, 3, 1000, g["T_true"], 5, 2, tuning, reps=5)
 
 
-def fold_ab():
-    """--fold-ab: the two-level solves for A/B runs of library builds that differ in the folded phases of the fused
-    solver (DPGO_B200_LIB=...; -DDPGO_FOLD_STEP / DPGO_FOLD_DIR / DPGO_P1_PREFETCH)."""
-    z, d, n, T0 = fixture("sphere2500")
-    run("sphere2500", z, d, n, T0, 5, 2, reps=7)
-    g = synthetic.grid3d(10, seed=1)
-    run("grid3d_L10", g, 3, 1000, g["T_true"], 5, 2, reps=7)
-    for name in ("torus3D", "city10000"):
-        z, d, n, T0 = fixture(name)
-        run(name, z, d, n, T0, 5 if d == 3 else 3, 2, reps=5)
-
-
 def main():
-    if "--fold-ab" in sys.argv:
-        return fold_ab()
     if "--strip-tuning" in sys.argv:
         return strip_tuning()
     if "--barrier-ab" in sys.argv:
