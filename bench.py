@@ -227,8 +227,19 @@ def qx_at_scale(sizes, peak, stream):
         nb = gq.bytes_qx()
         us = gq.time_qx(10, True)
         # the product is checked against linearity on the same handle (size-independent property)
-        out.append({"n": g["n"], "edges": int(len(g["p1"])), "bytes": nb, "flushed_us": us, "gbs": nb / us / 1e3,
-                    "frac": nb / us / 1e3 / peak, "bytes_over_time_le_peak": bool(nb / us / 1e3 <= peak)})
+        rec = {"n": g["n"], "edges": int(len(g["p1"])), "bytes": nb, "flushed_us": us, "gbs": nb / us / 1e3,
+               "frac": nb / us / 1e3 / peak, "bytes_over_time_le_peak": bool(nb / us / 1e3 <= peak)}
+        # the per-pose kernels on the same arrays (QF retraction 3, polar projection 4, rounding (r+d)/r tile arrays)
+        X = np.asfortranarray(lifting_matrix(3, 5) @ g["T_true"])
+        rng = np.random.default_rng(1)
+        for slot in range(3):
+            gq.slot_set(slot, X if slot == 0 else X + 0.05 * rng.standard_normal(X.shape))
+        tile = 5 * 4 * g["n"] * 8.0
+        rec["pose_kernels"] = {}
+        for op, nm, byts in ((0, "qf_retraction", 3 * tile), (1, "polar_projection", 4 * tile), (2, "rounding", 1.6 * tile)):
+            t_us = gq.time_pose_op(op, 10, True)
+            rec["pose_kernels"][nm] = {"bytes": byts, "flushed_us": t_us, "frac": byts / t_us / 1e3 / peak}
+        out.append(rec)
         gq.close()
     return out
 

@@ -30,10 +30,8 @@ void robustSinglePoseAveraging(Matrix &ROpt, Vector &tOpt, std::vector<size_t> &
                                const Vector &kappa = Vector(), const Vector &tau = Vector(),
                                double errorThreshold = 0.1);
 
-/// chordal relaxation (reference: src/DPGO_solver.cpp:220-269)
+/// chordal relaxation (reference: src/DPGO_solver.cpp:220-269), solved on the device (dpgo_chordal_initialization)
 PoseArray chordalInitialization(const std::vector<RelativeSEMeasurement> &measurements);
-/// the same relaxation solved on the host (not part of the reference's interface; CPU checks of the host logic)
-PoseArray chordalInitializationHostCG(const std::vector<RelativeSEMeasurement> &measurements);
 /// compose odometry from the identity or a partial trajectory (reference :271-303)
 PoseArray odometryInitialization(const std::vector<RelativeSEMeasurement> &odometry,
                                  const PoseArray *partial_trajectory = nullptr);

@@ -7,83 +7,11 @@
 
 #include <cmath>
 #include <cstdio>
-#include <functional>
 #include <vector>
 
 #include "check.h"
 
 namespace DPGO {
-
-namespace {
-
-// Conjugate gradients with a diagonal preconditioner for an SPD operator on `cols` right-hand
-// sides stored as a (dim x cols) column-major array.  Stops at relative residual `tol`.
-void pcg(const std::function<void(const std::vector<double> &, std::vector<double> &)> &apply,
-         const std::vector<double> &diag, const std::vector<double> &b, std::vector<double> &x, size_t dim,
-         size_t cols, double tol, int max_iter) {
-  x.assign(dim * cols, 0.0);
-  std::vector<double> r = b, z(dim * cols), p(dim * cols), Ap(dim * cols);
-  std::vector<double> rz(cols), rz_new(cols), b2(cols, 0.0), pAp(cols);
-  std::vector<bool> done(cols, false);
-  for (size_t c = 0; c < cols; ++c)
-    for (size_t i = 0; i < dim; ++i) b2[c] += b[c * dim + i] * b[c * dim + i];
-  auto precond = [&]() {
-    for (size_t c = 0; c < cols; ++c)
-      for (size_t i = 0; i < dim; ++i) z[c * dim + i] = r[c * dim + i] / diag[i];
-  };
-  precond();
-  p = z;
-  for (size_t c = 0; c < cols; ++c) {
-    rz[c] = 0;
-    for (size_t i = 0; i < dim; ++i) rz[c] += r[c * dim + i] * z[c * dim + i];
-    if (b2[c] == 0) done[c] = true;
-  }
-  for (int it = 0; it < max_iter; ++it) {
-    apply(p, Ap);
-    bool all_done = true;
-    for (size_t c = 0; c < cols; ++c) {
-      if (done[c]) continue;
-      pAp[c] = 0;
-      for (size_t i = 0; i < dim; ++i) pAp[c] += p[c * dim + i] * Ap[c * dim + i];
-      const double alpha = rz[c] / pAp[c];
-      double r2 = 0;
-      for (size_t i = 0; i < dim; ++i) {
-        x[c * dim + i] += alpha * p[c * dim + i];
-        r[c * dim + i] -= alpha * Ap[c * dim + i];
-        r2 += r[c * dim + i] * r[c * dim + i];
-      }
-      if (r2 <= tol * tol * b2[c]) done[c] = true;
-      else all_done = false;
-    }
-    if (all_done) break;
-    if (it + 1 == max_iter) {
-      // the reference solves these systems directly (SPQR); an iteration that stops at the cap must say so
-      double worst = 0;
-      for (size_t c = 0; c < cols; ++c) {
-        if (done[c] || b2[c] == 0) continue;
-        double r2 = 0;
-        for (size_t i = 0; i < dim; ++i) r2 += r[c * dim + i] * r[c * dim + i];
-        worst = std::max(worst, std::sqrt(r2 / b2[c]));
-      }
-      std::fprintf(stderr, "[DPGO] chordalInitialization: PCG stopped at %d iterations with relative residual %.3e "
-                           "(tolerance %.1e); the initial guess may be inaccurate\n", max_iter, worst, tol);
-    }
-    precond();
-    for (size_t c = 0; c < cols; ++c) {
-      if (done[c]) {
-        for (size_t i = 0; i < dim; ++i) p[c * dim + i] = 0;
-        continue;
-      }
-      rz_new[c] = 0;
-      for (size_t i = 0; i < dim; ++i) rz_new[c] += r[c * dim + i] * z[c * dim + i];
-      const double beta = rz_new[c] / rz[c];
-      rz[c] = rz_new[c];
-      for (size_t i = 0; i < dim; ++i) p[c * dim + i] = z[c * dim + i] + beta * p[c * dim + i];
-    }
-  }
-}
-
-}  // namespace
 
 // Device path (dpgo_chordal_initialization: both least-squares problems solved on the GPU with the library's
 // Q*X and exact-preconditioner kernels; the reference factorizes with SPQR, src/DPGO_solver.cpp:220-269).
@@ -115,119 +43,6 @@ PoseArray chordalInitialization(const std::vector<RelativeSEMeasurement> &measur
                          "%d iterations) / %.3e (translations, %d iterations); the initial guess may be inaccurate\n",
                  info.rotation_residual, info.rotation_iterations, info.translation_residual,
                  info.translation_iterations);
-  T.setData(Tm);
-  return T;
-}
-
-// The same relaxation on the host (Jacobi-preconditioned CG on the normal equations): not called by the library;
-// host_cli uses it to check the host-side measurement handling without a GPU.
-PoseArray chordalInitializationHostCG(const std::vector<RelativeSEMeasurement> &measurements) {
-  size_t d, n;
-  get_dimension_and_num_poses(measurements, d, n);
-  PoseArray T(static_cast<unsigned>(d), static_cast<unsigned>(n));
-  if (n == 1) return T;
-
-  // ---- rotations: min sum_e kappa_e || R_j - R_i R_ij ||_F^2 with R_0 = I.  The rows of the R_i
-  // decouple: row rho of all poses is the unknown x (1 x d per pose) of one least-squares problem
-  // with the same normal matrix, so the d rows are solved as d right-hand sides.
-  const size_t dim = d * (n - 1);
-  // x layout per rhs: pose i >= 1 at offset (i-1)*d
-  auto applyRot = [&](const std::vector<double> &x, std::vector<double> &y, size_t cols, const double *x0) {
-    std::fill(y.begin(), y.end(), 0.0);
-    std::vector<double> xi(d), xj(d), res(d);
-    for (size_t c = 0; c < cols; ++c) {
-      const double *xc = x.data() + c * dim;
-      double *yc = y.data() + c * dim;
-      for (const auto &m : measurements) {
-        const size_t i = m.p1, j = m.p2;
-        for (size_t a = 0; a < d; ++a) {
-          xi[a] = i == 0 ? (x0 ? x0[c * d + a] : 0.0) : xc[(i - 1) * d + a];
-          xj[a] = j == 0 ? (x0 ? x0[c * d + a] : 0.0) : xc[(j - 1) * d + a];
-        }
-        for (size_t b = 0; b < d; ++b) {  // res = x_j - x_i R
-          double s = 0;
-          for (size_t a = 0; a < d; ++a) s += xi[a] * m.R(a, b);
-          res[b] = m.kappa * (xj[b] - s);
-        }
-        if (j != 0)
-          for (size_t b = 0; b < d; ++b) yc[(j - 1) * d + b] += res[b];
-        if (i != 0)
-          for (size_t a = 0; a < d; ++a) {  // -res R^T
-            double s = 0;
-            for (size_t b = 0; b < d; ++b) s += res[b] * m.R(a, b);
-            yc[(i - 1) * d + a] -= s;
-          }
-      }
-    }
-  };
-  std::vector<double> diag(dim, 0.0);
-  for (const auto &m : measurements) {
-    if (m.p2 != 0)
-      for (size_t a = 0; a < d; ++a) diag[(m.p2 - 1) * d + a] += m.kappa;
-    if (m.p1 != 0)
-      for (size_t a = 0; a < d; ++a) {
-        double s = 0;
-        for (size_t b = 0; b < d; ++b) s += m.R(a, b) * m.R(a, b);
-        diag[(m.p1 - 1) * d + a] += m.kappa * s;
-      }
-  }
-  for (double &v : diag)
-    if (v <= 0) v = 1.0;
-  // right-hand side: - A [e_rho at pose 0; 0 elsewhere]
-  std::vector<double> x0(d * d, 0.0), zero(dim * d, 0.0), b(dim * d);
-  for (size_t c = 0; c < d; ++c) x0[c * d + c] = 1.0;
-  applyRot(zero, b, d, x0.data());
-  for (double &v : b) v = -v;
-  std::vector<double> sol;
-  pcg([&](const std::vector<double> &x, std::vector<double> &y) { applyRot(x, y, d, nullptr); }, diag, b, sol, dim, d,
-      1e-13, 20000);
-  Matrix Rch(static_cast<std::ptrdiff_t>(d), static_cast<std::ptrdiff_t>(d * n));
-  for (size_t a = 0; a < d; ++a) Rch(a, a) = 1.0;
-  for (size_t i = 1; i < n; ++i) {
-    Matrix blk(static_cast<std::ptrdiff_t>(d), static_cast<std::ptrdiff_t>(d));
-    for (size_t rho = 0; rho < d; ++rho)
-      for (size_t a = 0; a < d; ++a) blk(rho, a) = sol[rho * dim + (i - 1) * d + a];
-    Rch.block(0, i * d, d, d) = projectToRotationGroup(blk);
-  }
-
-  // ---- translations: min sum_e tau_e || t_j - t_i - R_i t_ij ||^2 with t_0 = 0
-  const size_t tdim = n - 1;
-  auto applyTr = [&](const std::vector<double> &x, std::vector<double> &y) {
-    std::fill(y.begin(), y.end(), 0.0);
-    for (size_t c = 0; c < d; ++c) {
-      const double *xc = x.data() + c * tdim;
-      double *yc = y.data() + c * tdim;
-      for (const auto &m : measurements) {
-        const double ti = m.p1 == 0 ? 0.0 : xc[m.p1 - 1], tj = m.p2 == 0 ? 0.0 : xc[m.p2 - 1];
-        const double res = m.tau * (tj - ti);
-        if (m.p2 != 0) yc[m.p2 - 1] += res;
-        if (m.p1 != 0) yc[m.p1 - 1] -= res;
-      }
-    }
-  };
-  std::vector<double> tdiag(tdim, 0.0), tb(tdim * d, 0.0);
-  for (const auto &m : measurements) {
-    if (m.p1 != 0) tdiag[m.p1 - 1] += m.tau;
-    if (m.p2 != 0) tdiag[m.p2 - 1] += m.tau;
-    // gradient of the constant part: rhs_j += tau R_i t_ij ; rhs_i -= tau R_i t_ij
-    for (size_t c = 0; c < d; ++c) {
-      double s = 0;
-      for (size_t a = 0; a < d; ++a) s += Rch(c, m.p1 * d + a) * m.t(a, 0);
-      if (m.p2 != 0) tb[c * tdim + m.p2 - 1] += m.tau * s;
-      if (m.p1 != 0) tb[c * tdim + m.p1 - 1] -= m.tau * s;
-    }
-  }
-  for (double &v : tdiag)
-    if (v <= 0) v = 1.0;
-  std::vector<double> tsol;
-  pcg(applyTr, tdiag, tb, tsol, tdim, d, 1e-13, 50000);
-
-  Matrix Tm(static_cast<std::ptrdiff_t>(d), static_cast<std::ptrdiff_t>(n * (d + 1)));
-  for (size_t i = 0; i < n; ++i) {
-    Tm.block(0, i * (d + 1), d, d) = Rch.block(0, i * d, d, d);
-    if (i > 0)
-      for (size_t c = 0; c < d; ++c) Tm(c, i * (d + 1) + d) = tsol[c * tdim + i - 1];
-  }
   T.setData(Tm);
   return T;
 }

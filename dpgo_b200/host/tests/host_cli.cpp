@@ -1,5 +1,5 @@
 // CPU-only command line probe of the host-side (non-CUDA) parts of the drop-in API, used by the
-// "not gpu" tests:  host_cli parse <file.g2o>   |   host_cli chordal <file.g2o>
+// "not gpu" tests:  host_cli parse <file.g2o>   |   host_cli chordal <file.g2o>  (chordal: needs a GPU)
 //                   host_cli logroundtrip <file.g2o> <dir/>  (PGOLogger: write + reload CSV logs)
 //                   host_cli averaging <file>  (robust single rotation / pose averaging of the
 //                                               candidate alignments listed in <file>)
@@ -90,9 +90,8 @@ int main(int argc, char **argv) {
     }
     return 0;
   }
-  if (!std::strcmp(argv[1], "chordal") || !std::strcmp(argv[1], "chordal-device")) {
-    // "chordal": the host CG form (CPU checks); "chordal-device": the library's path (needs a GPU)
-    const Matrix T = (argv[1][7] ? chordalInitialization(ms) : chordalInitializationHostCG(ms)).getData();
+  if (!std::strcmp(argv[1], "chordal")) {   // needs a GPU (the relaxation is solved on the device)
+    const Matrix T = chordalInitialization(ms).getData();
     std::printf("%td %td\n", T.rows(), T.cols());
     for (std::ptrdiff_t j = 0; j < T.cols(); ++j)
       for (std::ptrdiff_t i = 0; i < T.rows(); ++i) std::printf("%.17g\n", T(i, j));
@@ -105,7 +104,13 @@ int main(int argc, char **argv) {
     for (size_t k = 0; k < in.size(); ++k) in[k].weight = 1.0 / (1.0 + static_cast<double>(k % 7));
     PGOLogger logger(argv[3]);
     logger.logMeasurements(in, "measurements.csv");
-    const Matrix T = chordalInitializationHostCG(ms).getData();
+    // a trajectory to log without a GPU: the odometry chain composed from the identity
+    std::vector<RelativeSEMeasurement> odom(n > 0 ? n - 1 : 0);
+    size_t found = 0;
+    for (const auto &e : ms)
+      if (e.p2 == e.p1 + 1 && e.p1 + 1 < n) { odom[e.p1] = e; ++found; }
+    if (found + 1 < n) return 4;
+    const Matrix T = odometryInitialization(odom).getData();
     logger.logTrajectory(static_cast<unsigned>(d), static_cast<unsigned>(n), T, "trajectory.csv");
     const std::vector<RelativeSEMeasurement> out =
         PGOLogger::loadMeasurements(std::string(argv[3]) + "measurements.csv", true);

@@ -363,9 +363,8 @@ def test_chordal_initialization_parity(datasets, name):
     T, info = dpgo_b200.chordal_initialization(meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau, n, meas.d)
     assert info["rotation_residual"] <= 1e-12 and info["translation_residual"] <= 1e-12, info
     d = meas.d
-    Tr = T.reshape(d, n, d + 1, order="F")
     for i in (0, n // 2, n - 1):                       # rotations are in SO(d)
-        Ri = Tr[:, i, :d]
+        Ri = T[:, i * (d + 1):i * (d + 1) + d]
         assert np.allclose(Ri.T @ Ri, np.eye(d), atol=1e-12) and np.linalg.det(Ri) > 0
     assert np.array_equal(T[:, :d + 1], np.eye(d, d + 1))
     assert rel(T, z["T_chordal"]) < 1e-8, (rel(T, z["T_chordal"]), info)

@@ -86,3 +86,20 @@ def test_chordal_and_single_robot_examples(datasets, tmp_path):
     cost = float(re.search(r"Cost = ([-+.\deE]+)", out.stdout).group(1))
     Y, res = pgo.optimize(prob, T0)       # solvePGO: chordal init + RTR at r = d (src/DPGO_solver.cpp:305-333)
     assert abs(cost - 2 * res.fOpt) <= 1e-4 * cost
+
+
+@pytest.mark.parametrize("name", ["smallGrid3D", "sphere2500"])
+def test_host_chordal_initialization_matches_oracle(datasets, tmp_path, name):
+    """DPGO::chordalInitialization of the drop-in (ref: src/DPGO_solver.cpp:220-269; device CG through
+    dpgo_chordal_initialization) on a g2o file == the oracle's sparse direct solves, 1e-8 relative."""
+    meas, n, z = datasets(name)
+    path = str(tmp_path / (name + ".g2o"))
+    write_g2o(path, meas.d, meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau)
+    m2, n2 = pgo.read_g2o(path)
+    out = _run([_need("host_cli"), "chordal", path], 120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    tok = out.stdout.split()
+    r_, c_ = int(tok[0]), int(tok[1])
+    T = np.array([float(v) for v in tok[2:2 + r_ * c_]]).reshape(c_, r_).T
+    To = pgo.chordal_initialization(m2, n2)
+    assert np.linalg.norm(T - To) <= 1e-8 * np.linalg.norm(To)

@@ -1,6 +1,7 @@
 """CPU tests of the C++ drop-in host API: it builds, the reference's example drivers compile
 UNMODIFIED against its headers (when the reference tree is present), and the host-side cold path
-(g2o parser, chordal initialization) matches the oracle / fixtures."""
+(g2o parser, CSV logs, robust averaging) matches the oracle / fixtures; the chordal initialization runs on the
+device and is checked in tests/test_gpu_a_parity.py and tests/test_gpu_z_host.py."""
 import os
 import subprocess
 
@@ -38,7 +39,7 @@ def test_host_library_and_reference_examples_build(host_built):
 
 
 @pytest.mark.parametrize("name", ["tinyGrid3D", "smallGrid3D"])
-def test_g2o_parser_and_chordal_init(host_built, datasets, tmp_path, name):
+def test_g2o_parser(host_built, datasets, tmp_path, name):
     meas, n, z = datasets(name)
     path = str(tmp_path / (name + ".g2o"))
     write_g2o(path, meas.d, meas.p1, meas.p2, meas.R, meas.t, meas.kappa, meas.tau)
@@ -58,12 +59,6 @@ def test_g2o_parser_and_chordal_init(host_built, datasets, tmp_path, name):
     assert np.allclose(rows[:, 3:3 + d * d].reshape(-1, d, d), m2.R, atol=1e-15)
     assert np.allclose(rows[:, 3 + d * d:3 + d * d + d], m2.t, atol=0)
     assert np.allclose(rows[:, -2], m2.kappa, rtol=1e-14) and np.allclose(rows[:, -1], m2.tau, rtol=1e-14)
-    # C++ chordal initialization (CG on the normal equations) == oracle's (sparse LU)
-    out = subprocess.check_output([host_built, "chordal", path], text=True).split()
-    r_, c_ = int(out[0]), int(out[1])
-    T = np.array([float(v) for v in out[2:2 + r_ * c_]]).reshape(c_, r_).T
-    To = pgo.chordal_initialization(m2, n2)
-    assert np.linalg.norm(T - To) <= 1e-8 * np.linalg.norm(To)
 
 
 def test_pgologger_csv_round_trip(host_built, datasets, tmp_path):
