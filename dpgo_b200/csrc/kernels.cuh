@@ -1360,7 +1360,7 @@ __device__ __forceinline__ void polar_pose(F val, double *out) {
       for (int l = 0; l < D; ++l) v[k][l] = (k == l) ? 1.0 : 0.0;
     }
     for (int sweep = 0; sweep < 30; ++sweep) {
-      double offmax = 0.0;
+      bool converged = true;
 #pragma unroll
       for (int p = 0; p < D - 1; ++p) {
 #pragma unroll
@@ -1372,13 +1372,14 @@ __device__ __forceinline__ void polar_pose(F val, double *out) {
             be = fma(a[q2][q], a[q2][q], be);
             ga = fma(a[p][q], a[q2][q], ga);
           }
-          const double lim = sqrt(al * be);
-          const double rel = (lim > 0.0) ? fabs(ga) / lim : 0.0;
-          offmax = fmax(offmax, rel);
-          if (rel > 1e-16) {
+          // |ga| / sqrt(al be) against the two thresholds, as comparisons of squares: the kernel is bound by the
+          // FP64 divide / square-root sequences of this loop, not by memory
+          const double g2 = ga * ga, ab = al * be;
+          if (g2 > 1e-30 * ab) converged = false;          // relative off-diagonal above 1e-15
+          if (g2 > 1e-32 * ab) {                            // above 1e-16: rotate
             const double zeta = (be - al) / (2.0 * ga);
             const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            const double cs = rsqrt(1.0 + t * t), sn = cs * t;
 #pragma unroll
             for (int q = 0; q < R; ++q) {
               const double xp = a[p][q], xq = a[q2][q];
@@ -1394,7 +1395,7 @@ __device__ __forceinline__ void polar_pose(F val, double *out) {
           }
         }
       }
-      if (offmax <= 1e-15) break;
+      if (converged) break;
     }
     // a[k] = sigma_k u_k (column k of A V), v[k][l] = V[l][k];  U V^T = sum_k u_k v_k^T
     double u[D][R];
@@ -1468,7 +1469,7 @@ __device__ __forceinline__ void round_pose(const double *xin, const double (&ya)
       }
     }
     for (int sweep = 0; sweep < 30; ++sweep) {      // one-sided Jacobi: columns of M V become orthogonal
-      double offmax = 0.0;
+      bool converged = true;
 #pragma unroll
       for (int p = 0; p < D - 1; ++p) {
 #pragma unroll
@@ -1480,13 +1481,14 @@ __device__ __forceinline__ void round_pose(const double *xin, const double (&ya)
             be = fma(a[q2][l], a[q2][l], be);
             ga = fma(a[p][l], a[q2][l], ga);
           }
-          const double lim = sqrt(al * be);
-          const double rel = (lim > 0.0) ? fabs(ga) / lim : 0.0;
-          offmax = fmax(offmax, rel);
-          if (rel > 1e-16) {
+          // |ga| / sqrt(al be) against the two thresholds, as comparisons of squares: the kernel is bound by the
+          // FP64 divide / square-root sequences of this loop, not by memory
+          const double g2 = ga * ga, ab = al * be;
+          if (g2 > 1e-30 * ab) converged = false;          // relative off-diagonal above 1e-15
+          if (g2 > 1e-32 * ab) {                            // above 1e-16: rotate
             const double zeta = (be - al) / (2.0 * ga);
             const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            const double cs = rsqrt(1.0 + t * t), sn = cs * t;
 #pragma unroll
             for (int l = 0; l < D; ++l) {
               const double xp = a[p][l], xq = a[q2][l];
@@ -1499,7 +1501,7 @@ __device__ __forceinline__ void round_pose(const double *xin, const double (&ya)
           }
         }
       }
-      if (offmax <= 1e-15) break;
+      if (converged) break;
     }
     // a[k] = sigma_k u_k, v[k][l] = V[l][k];  U V^T = sum_k u_k v_k^T
     double sig[D], rot[D][D];   // rot[c][l] = (U V^T)[l][c]

@@ -57,7 +57,7 @@ template <typename T>
 inline T __ldg(const T *p) { return *p; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
-inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 

@@ -11,7 +11,6 @@
 #include <mutex>
 #include <vector>
 
-inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 
 inline int atomicMax(int *p, int v) {
   static std::mutex m;
