@@ -393,29 +393,48 @@ static int qx_prefetch_distance(dpgo_dev *h) {
 // below 100 000 poses Q and X are L2 resident and the plain kernel is used.
 static const int kQxPipeMinPoses = 100000, kQxPrefetchMinPoses = 500000, kQxAutoPrefetchDist = 4096;
 
+// Grid of the stand-alone Q*X at scale.  One CTA per 8 x GPW poses leaves a tail: a CTA lives ~15 us on the
+// HBM-resident grids (its lane groups walk their block rows through dependent DRAM round trips), so the last
+// partial wave runs at low occupancy.  With DPGO_QX_RESIDENT_WAVES = w > 0 (measurement switch) the grid is capped at
+// w x (SMs x resident CTAs of the kernel) and the CTAs stride over the poses.
+template <typename K>
+static int qx_grid_for(dpgo_dev *h, K kernel) {
+  const int need = pose_grid(h, h->d + 1);
+  static int waves = -1;
+  if (waves < 0) {
+    const char *e = getenv("DPGO_QX_RESIDENT_WAVES");
+    waves = e ? atoi(e) : 0;
+  }
+  if (waves <= 0) return need;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+  return std::min(need, waves * h->num_sms * occ);
+}
+
 int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
   int variant = h->qx_variant, auto_dist = 0;
   if (variant < 0) {
     variant = h->n >= kQxPrefetchMinPoses ? 1 : (h->n >= kQxPipeMinPoses ? 3 : 0);
     auto_dist = kQxAutoPrefetchDist;
   }
-  if (variant == 0) return op_qx(h, qview(h), X, G, out);
+  if (variant == 0) {
+    DPGO_DISPATCH(h, k_qx<R, D><<<qx_grid_for(h, k_qx<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    LAUNCH_CHECK(h);
+    return DPGO_OK;
+  }
   if (variant == 2) {
-    const int grid = pose_grid(h, h->d + 1);
-    DPGO_DISPATCH(h, k_qx_tiles<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    DPGO_DISPATCH(h, k_qx_tiles<R, D><<<qx_grid_for(h, k_qx_tiles<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }
   if (variant == 3) {
-    const int grid = pose_grid(h, h->d + 1);
-    DPGO_DISPATCH(h, k_qx_pipe<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    DPGO_DISPATCH(h, k_qx_pipe<R, D><<<qx_grid_for(h, k_qx_pipe<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }
-  const int grid = pose_grid(h, h->d + 1);
   DPGO_DISPATCH(h, {
     const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : (auto_dist > 0 ? auto_dist : qx_prefetch_distance<R, D>(h));
-    k_qx_prefetch<R, D><<<grid, kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
+    k_qx_prefetch<R, D><<<qx_grid_for(h, k_qx_prefetch<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
   });
   LAUNCH_CHECK(h);
   return DPGO_OK;
