@@ -386,25 +386,30 @@ static int qx_prefetch_distance(dpgo_dev *h) {
   return h->num_sms * occ * kWarpsPerBlock * (32 / (D + 1));
 }
 // Automatic choice of the stand-alone Q*X form (qx_variant -1), from the round-2 measurements on the synthetic grids
-// (profiles/r02_summary.md; fraction of the measured HBM peak, L2 flushed):
-//                      lane-group   + L2 prefetch   tiles in smem   two blocks / step
-//   262 144 poses         0.596         0.550           0.548            0.604
-//   1 000 000 poses       0.685         0.720           0.593            0.663
-// below 100 000 poses Q and X are L2 resident and the plain kernel is used.
-static const int kQxPipeMinPoses = 100000, kQxPrefetchMinPoses = 500000, kQxAutoPrefetchDist = 4096;
+// (profiles/r02_summary.md; fraction of the measured HBM peak, L2 flushed; one CTA per 64 poses / one resident wave):
+//                      lane-group     + L2 prefetch    tiles in smem    two blocks / step
+//   262 144 poses     0.595 / 0.616   0.546 / 0.575    0.547 / 0.580     0.604 / 0.635
+//   1 000 000 poses   0.685 / 0.712   0.720 / 0.624    0.593 / 0.639     0.664 / 0.718
+// from 100 000 poses the two-blocks-per-step form in one resident wave; below, Q and X are L2 resident and the plain
+// kernel is used.
+static const int kQxPipeMinPoses = 100000;
 
-// Grid of the stand-alone Q*X at scale.  One CTA per 8 x GPW poses leaves a tail: a CTA lives ~15 us on the
-// HBM-resident grids (its lane groups walk their block rows through dependent DRAM round trips), so the last
-// partial wave runs at low occupancy.  With DPGO_QX_RESIDENT_WAVES = w > 0 (measurement switch) the grid is capped at
-// w x (SMs x resident CTAs of the kernel) and the CTAs stride over the poses.
+// Grid of the stand-alone Q*X.  One CTA per 8 x GPW poses leaves a tail at scale: a CTA lives ~15 us on the
+// HBM-resident grids (its lane groups walk their block rows through dependent DRAM round trips), so the last partial
+// wave runs at low occupancy.  The lane-group forms therefore run ONE resident wave (SMs x resident CTAs of the
+// kernel) whose CTAs stride over the poses: 262 144 poses 0.604 -> 0.635, 1 000 000 poses 0.664 -> 0.716 of the HBM
+// peak for the two-blocks-per-step form (profiles/r02_qx_resident_waves.jsonl; 2 and 4 waves are in between).  The
+// prefetch form loses with a capped grid (its distance is tuned to the uncapped layout: 0.72 -> 0.62) and keeps one
+// CTA per 64 poses.  DPGO_QX_RESIDENT_WAVES = w overrides (0 = uncapped) for measurements.
 template <typename K>
-static int qx_grid_for(dpgo_dev *h, K kernel) {
+static int qx_grid_for(dpgo_dev *h, K kernel, int default_waves) {
   const int need = pose_grid(h, h->d + 1);
-  static int waves = -1;
-  if (waves < 0) {
+  static int env_waves = -2;
+  if (env_waves == -2) {
     const char *e = getenv("DPGO_QX_RESIDENT_WAVES");
-    waves = e ? atoi(e) : 0;
+    env_waves = e ? atoi(e) : -1;
   }
+  const int waves = env_waves >= 0 ? env_waves : default_waves;
   if (waves <= 0) return need;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
@@ -412,29 +417,28 @@ static int qx_grid_for(dpgo_dev *h, K kernel) {
 }
 
 int op_qx_main(dpgo_dev *h, const double *X, const double *G, double *out) {
-  int variant = h->qx_variant, auto_dist = 0;
+  int variant = h->qx_variant;
   if (variant < 0) {
-    variant = h->n >= kQxPrefetchMinPoses ? 1 : (h->n >= kQxPipeMinPoses ? 3 : 0);
-    auto_dist = kQxAutoPrefetchDist;
+    variant = h->n >= kQxPipeMinPoses ? 3 : 0;
   }
   if (variant == 0) {
-    DPGO_DISPATCH(h, k_qx<R, D><<<qx_grid_for(h, k_qx<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    DPGO_DISPATCH(h, k_qx<R, D><<<qx_grid_for(h, k_qx<R, D>, 1), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }
   if (variant == 2) {
-    DPGO_DISPATCH(h, k_qx_tiles<R, D><<<qx_grid_for(h, k_qx_tiles<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    DPGO_DISPATCH(h, k_qx_tiles<R, D><<<qx_grid_for(h, k_qx_tiles<R, D>, 1), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }
   if (variant == 3) {
-    DPGO_DISPATCH(h, k_qx_pipe<R, D><<<qx_grid_for(h, k_qx_pipe<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
+    DPGO_DISPATCH(h, k_qx_pipe<R, D><<<qx_grid_for(h, k_qx_pipe<R, D>, 1), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n));
     LAUNCH_CHECK(h);
     return DPGO_OK;
   }
   DPGO_DISPATCH(h, {
-    const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : (auto_dist > 0 ? auto_dist : qx_prefetch_distance<R, D>(h));
-    k_qx_prefetch<R, D><<<qx_grid_for(h, k_qx_prefetch<R, D>), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
+    const int dist = h->qx_prefetch_dist > 0 ? h->qx_prefetch_dist : qx_prefetch_distance<R, D>(h);
+    k_qx_prefetch<R, D><<<qx_grid_for(h, k_qx_prefetch<R, D>, 0), kBlock, 0, h->stream>>>(qview(h), X, G, out, h->n, dist);
   });
   LAUNCH_CHECK(h);
   return DPGO_OK;
@@ -1346,7 +1350,7 @@ int dpgo_egrad(dpgo_handle h, const double *X, double *out) {
   H_CHECK(h); NEED_FINAL(h);
   CHECK_ARG(X && out);
   DPGO_TRY(h2d(h, h->d_t0, X));
-  DPGO_TRY(op_qx(h, qview(h), h->d_t0, h->d_G, h->d_t1));
+  DPGO_TRY(op_qx_main(h, h->d_t0, h->d_G, h->d_t1));
   return d2h(h, out, h->d_t1);
 }
 
