@@ -371,6 +371,14 @@ static int read_scalars(dpgo_dev *h, int nblocks, int K, double *out) {
 
 int read_partials(dpgo_dev *h, int nblocks, int K, double *out) { return read_scalars(h, nblocks, K, out); }
 
+int sync_host_blocks(dpgo_dev *h) {
+  if (!h->host_blocks_stale) return DPGO_OK;
+  CUDA_TRY(cudaMemcpyAsync(h->blocks.data(), h->d_blocks, h->blocks.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->host_blocks_stale = false;
+  return DPGO_OK;
+}
+
 // --- op launchers (device pointers) ---
 int op_qx(dpgo_dev *h, const BsrView &Q, const double *X, const double *G, double *out) {
   const int grid = pose_grid(h, h->d + 1);
@@ -774,6 +782,66 @@ static int build_Q_host(dpgo_dev *h) {
   return DPGO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight-only refresh of Q and of the cross blocks on the device (GNC, ref: src/PGOAgent.cpp:1062-1142)
+// ---------------------------------------------------------------------------------------------
+// The kernels restate edge_T_W / block_of_kind / build_cross_host entry by entry with the same operations in the same
+// order and WITHOUT contraction (the host code is compiled for baseline x86-64: separate multiply and add), so a
+// refreshed Q has the bits of a host-assembled one (tests/test_gpu_b_team.py::test_device_weight_refresh_bitwise).
+struct EdgeView { const double *R, *t, *kappa, *tau, *w; };
+__device__ __forceinline__ double edge_T(const EdgeView &E, int k, int d, int a, int b) {   // T = [R t; 0 1]
+  if (a < d) return (b < d) ? E.R[(size_t)k * d * d + a * d + b] : E.t[(size_t)k * d + a];
+  return (b == d) ? 1.0 : 0.0;
+}
+__device__ __forceinline__ double edge_W(const EdgeView &E, int k, int d, int a) {
+  return __dmul_rn(E.w[k], (a < d) ? E.kappa[k] : E.tau[k]);
+}
+__device__ __forceinline__ double block_entry(int kind, const EdgeView &E, int k, int d, int a, int b) {
+  const int dh = d + 1;
+  switch (kind) {
+    case 0: {
+      double v = 0.0;
+      for (int c = 0; c < dh; ++c)
+        v = __dadd_rn(v, __dmul_rn(__dmul_rn(edge_T(E, k, d, a, c), edge_W(E, k, d, c)), edge_T(E, k, d, b, c)));
+      return v;
+    }
+    case 1: return __dmul_rn(-edge_T(E, k, d, a, b), edge_W(E, k, d, b));
+    case 2: return __dmul_rn(-edge_W(E, k, d, a), edge_T(E, k, d, b, a));
+    default: return (a == b) ? edge_W(E, k, d, a) : 0.0;   // 3
+  }
+}
+__global__ void k_refresh_q(int nnzb, int d, const int *cptr, const int *csrc, const signed char *ckind, EdgeView P,
+                            EdgeView S, double prior_kappa, double prior_tau, double *blocks) {
+  const int dh = d + 1, bs = dh * dh;
+  const size_t total = (size_t)nnzb * bs;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx / bs), ab = (int)(idx - (size_t)e * bs), a = ab / dh, b = ab - a * dh;
+    double v = 0.0;
+    for (int c = cptr[e]; c < cptr[e + 1]; ++c) {
+      const int kind = ckind[c], src = csrc[c];
+      double x;
+      if (kind <= 3) x = block_entry(kind, P, src, d, a, b);
+      else if (kind == 4 || kind == 5) x = block_entry(kind == 4 ? 0 : 3, S, src, d, a, b);
+      else if (kind == 6) x = (a == b) ? (a < d ? prior_kappa : prior_tau) : 0.0;
+      else continue;
+      v = __dadd_rn(v, x);
+    }
+    blocks[idx] = v;
+  }
+}
+// cross block p (sorted order) of shared edge k = order[p]:  B[a][b] = -M[b][a], M = W T^T (outgoing) or T W
+__global__ void k_refresh_cross(int m, int d, const int *order, const unsigned char *outgoing, EdgeView S, double *cblocks) {
+  const int dh = d + 1, bs = dh * dh;
+  const size_t total = (size_t)m * bs;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / bs), ab = (int)(idx - (size_t)p * bs), a = ab / dh, b = ab - a * dh;
+    const int k = order[p];
+    const double mv = outgoing[k] ? __dmul_rn(edge_W(S, k, d, b), edge_T(S, k, d, a, b))
+                                  : __dmul_rn(edge_T(S, k, d, b, a), edge_W(S, k, d, a));
+    cblocks[idx] = -mv;
+  }
+}
+
 template <typename T>
 static int upload(T **dptr, const std::vector<T> &v, size_t min_elems = 1) {
   if (*dptr) {
@@ -859,6 +927,73 @@ static int build_cross_host(dpgo_dev *h) {
 // of ~25-30 us (5 grid phases), the full dense apply streams N^2*8 bytes; inside the fused solver
 // the two-level variant is ahead from N = 4000 (1.03 -> 0.87 ms per solve) and behind at N = 500.
 static const int kAutoTwoLevelMinN = 3000;
+
+// Device copy of what the refresh kernels read: uploaded whenever Q is assembled on the host (pattern may have changed).
+static int upload_refresh_plan(dpgo_dev *h) {
+  h->refresh_plan_valid = false;
+  std::vector<int> cptr, csrc;
+  std::vector<signed char> ckind;
+  cptr.reserve(h->nnzb + 1);
+  int cur_row = -1, cur_col = -1;
+  for (const Contribution &c : h->q_contribs) {
+    if (c.row != cur_row || c.col != cur_col) {
+      cptr.push_back((int)csrc.size());
+      cur_row = c.row;
+      cur_col = c.col;
+    }
+    csrc.push_back(c.src);
+    ckind.push_back(c.kind);
+  }
+  cptr.push_back((int)csrc.size());
+  if ((int)cptr.size() != h->nnzb + 1) {
+    set_error("contribution list does not match the pattern of Q");
+    return DPGO_ESTATE;
+  }
+  DPGO_TRY(upload(&h->d_cptr, cptr));
+  DPGO_TRY(upload(&h->d_csrc, csrc));
+  DPGO_TRY(upload(&h->d_ckind, ckind));
+  auto edges = [&](const EdgeSet &E, dpgo_dev::DeviceEdges &D) -> int {
+    DPGO_TRY(upload(&D.R, E.R));
+    DPGO_TRY(upload(&D.t, E.t));
+    DPGO_TRY(upload(&D.kappa, E.kappa));
+    DPGO_TRY(upload(&D.tau, E.tau));
+    return upload(&D.w, E.weight);
+  };
+  DPGO_TRY(edges(h->priv, h->de_priv));
+  DPGO_TRY(edges(h->shared, h->de_shared));
+  std::vector<int> order(h->shared.m);                      // the row order of build_cross_host
+  for (int k = 0; k < h->shared.m; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return h->shared.a[x] < h->shared.a[y]; });
+  DPGO_TRY(upload(&h->d_corder, order));
+  DPGO_TRY(upload(&h->d_sout, h->shared.outgoing));
+  h->refresh_plan_valid = true;
+  return DPGO_OK;
+}
+
+// GNC weight update with an unchanged pattern: new weights up, Q blocks and cross blocks re-weighted in place.
+static int refresh_weights_device(dpgo_dev *h) {
+  auto view = [](const dpgo_dev::DeviceEdges &D) { return EdgeView{D.R, D.t, D.kappa, D.tau, D.w}; };
+  if (h->priv.m > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->de_priv.w, h->priv.weight.data(), (size_t)h->priv.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->shared.m > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->de_shared.w, h->shared.weight.data(), (size_t)h->shared.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int bs = (h->d + 1) * (h->d + 1);
+  {
+    const size_t total = (size_t)h->nnzb * bs;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16));
+    k_refresh_q<<<grid, 256, 0, h->stream>>>(h->nnzb, h->d, h->d_cptr, h->d_csrc, h->d_ckind, view(h->de_priv),
+                                             view(h->de_shared), h->prior_kappa, h->prior_tau, h->d_blocks);
+    LAUNCH_CHECK(h);
+  }
+  if (h->shared.m > 0) {
+    const size_t total = (size_t)h->shared.m * bs;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16));
+    k_refresh_cross<<<grid, 256, 0, h->stream>>>(h->shared.m, h->d, h->d_corder, h->d_sout, view(h->de_shared), h->d_cblocks);
+    LAUNCH_CHECK(h);
+  }
+  h->host_blocks_stale = true;
+  return DPGO_OK;
+}
 
 static int build_precon(dpgo_dev *h) {
   h->precon_mode = (h->precon_request >= 0) ? h->precon_request : (h->N >= kAutoTwoLevelMinN ? 2 : 0);
@@ -1099,7 +1234,9 @@ int dpgo_destroy(dpgo_handle h) {
                   h->d_slot[1], h->d_slot[2], h->d_slot[3], h->d_xa, h->d_xb, h->d_EG, h->d_EG2,
                   h->d_grad, h->d_grad2, h->d_S, h->d_S2, h->d_eta, h->d_r, h->d_z, h->d_delta,
                   h->d_Hd, h->d_t0, h->d_t1, h->d_t2, h->d_partials, h->d_scalars, h->d_fused,
-                  h->d_public_idx, h->d_flush, h->d_trace, h->d_nbr_xy[0], h->d_nbr_xy[1]};
+                  h->d_public_idx, h->d_flush, h->d_trace, h->d_nbr_xy[0], h->d_nbr_xy[1], h->d_cptr, h->d_csrc,
+                  h->d_ckind, h->d_corder, h->d_sout, h->de_priv.R, h->de_priv.t, h->de_priv.kappa, h->de_priv.tau,
+                  h->de_priv.w, h->de_shared.R, h->de_shared.t, h->de_shared.kappa, h->de_shared.tau, h->de_shared.w};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -1241,9 +1378,15 @@ int dpgo_set_two_level_domain_size(dpgo_handle h, int max_domain_poses) {
 
 int dpgo_finalize(dpgo_handle h, int build_precon_flag) {
   H_CHECK(h);
-  DPGO_TRY(build_Q_host(h));
-  DPGO_TRY(upload_Q(h));
-  DPGO_TRY(build_cross_host(h));
+  if (h->weights_only_update && h->refresh_plan_valid && h->cnnzb == h->shared.m) {
+    DPGO_TRY(refresh_weights_device(h));       // GNC: same pattern, values re-weighted on the device
+  } else {
+    DPGO_TRY(build_Q_host(h));
+    h->host_blocks_stale = false;
+    DPGO_TRY(upload_Q(h));
+    DPGO_TRY(build_cross_host(h));
+    DPGO_TRY(upload_refresh_plan(h));
+  }
   // G starts as its constant part (no neighbour poses yet)
   CUDA_TRY(cudaMemcpyAsync(h->d_G, h->d_Gconst, h->vpad * sizeof(double), cudaMemcpyDeviceToDevice,
                            h->stream));
@@ -1271,7 +1414,11 @@ int dpgo_get_Q_bsr(dpgo_handle h, int *nnzb, int32_t *rowptr, int32_t *colidx, d
   if (nnzb) *nnzb = h->nnzb;
   if (rowptr) memcpy(rowptr, h->rowptr.data(), h->rowptr.size() * sizeof(int32_t));
   if (colidx) memcpy(colidx, h->colidx.data(), h->colidx.size() * sizeof(int32_t));
-  if (blocks) memcpy(blocks, h->blocks.data(), h->blocks.size() * sizeof(double));
+  if (blocks) {
+    cudaSetDevice(h->device);
+    DPGO_TRY(sync_host_blocks(h));   // re-weighted on the device since the host assembled them
+    memcpy(blocks, h->blocks.data(), h->blocks.size() * sizeof(double));
+  }
   return DPGO_OK;
 }
 

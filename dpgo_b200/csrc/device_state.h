@@ -36,6 +36,7 @@ struct dpgo_dev;
 namespace dpgo {
 // device_lib.cu
 int read_partials(dpgo_dev *h, int nblocks, int K, double *out);
+int sync_host_blocks(dpgo_dev *h);   // host copy of the Q blocks <- device, when a device-side re-weighting made it stale
 // precon_dd.cu: two-level (domain decomposition) exact preconditioner, precon_mode == 2
 int dd_build(dpgo_dev *h);
 void dd_free(dpgo_dev *h);
@@ -94,6 +95,15 @@ struct dpgo_dev {
   bool weights_only_update = false;   // inside dpgo_update_weights: the pattern of Q is unchanged
   std::vector<dpgo::Contribution> q_contribs;   // sorted contributions of the edges to the blocks of Q (the pattern)
   int uploaded_nnzb = -1;
+  // device copy of what a weight-only refresh (GNC) needs: the contribution lists per block of Q, the sorted shared
+  // edges of the cross blocks, the edge data and the weights; Q and the cross blocks are then re-weighted by kernels
+  // and the host copy of the blocks goes stale until somebody asks for it (dpgo_get_Q_bsr)
+  struct DeviceEdges { double *R = nullptr, *t = nullptr, *kappa = nullptr, *tau = nullptr, *w = nullptr; };
+  DeviceEdges de_priv, de_shared;
+  int *d_cptr = nullptr, *d_csrc = nullptr, *d_corder = nullptr;
+  signed char *d_ckind = nullptr;
+  unsigned char *d_sout = nullptr;
+  bool refresh_plan_valid = false, host_blocks_stale = false;
 
   // lifted pose arrays
   double *d_slot[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -51,6 +51,7 @@ struct DdState {
   int *pcol = nullptr, *srow = nullptr, *bcol = nullptr, *icol = nullptr;
   int *si_rowptr = nullptr, *si_colidx = nullptr, *bs_rowptr = nullptr, *bs_colidx = nullptr;
   double *si_blocks = nullptr, *bs_blocks = nullptr;
+  int *d_si_src = nullptr, *d_bs_src = nullptr;   // block of Q each coupling block is a copy of (weight-only refresh)
   double *y = nullptr, *t = nullptr, *zs = nullptr, *u = nullptr, *w = nullptr, *rp = nullptr;
   bool configured = false;
   // symbolic part kept for weight-only rebuilds (GNC): the dissection, the strip tables and the index lists depend on
@@ -345,7 +346,7 @@ void dd_free(dpgo_dev *h) {
   if (!s) return;
   void *ptrs[] = {s->M1, s->M3, s->strips1, s->strips3, s->cta1, s->cta3, s->chunks1, s->chunks3, s->pcol, s->srow,
                   s->bcol, s->icol, s->si_rowptr, s->si_colidx, s->bs_rowptr, s->bs_colidx, s->si_blocks, s->bs_blocks,
-                  s->y, s->t, s->zs, s->u, s->w, s->rp};
+                  s->y, s->t, s->zs, s->u, s->w, s->rp, s->d_si_src, s->d_bs_src};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -370,6 +371,7 @@ int dd_build(dpgo_dev *h) {
         old->sym_thr == thr && old->sym_split1 == h->dd_split1 && old->sym_split3 == h->dd_split3)
       return dd_numeric(h, old, true);
   }
+  DPGO_TRY(sync_host_blocks(h));   // the couplings below are read from the host copy of Q
   dd_free(h);
   DdState *s = new DdState();
   h->dd = s;
@@ -460,6 +462,8 @@ int dd_build(dpgo_dev *h) {
   DPGO_TRY(upload_vec(&s->bs_rowptr, bs_rowptr));
   DPGO_TRY(upload_vec(&s->bs_colidx, bs_colidx));
   DPGO_TRY(upload_vec(&s->bs_blocks, bs_blocks));
+  DPGO_TRY(upload_vec(&s->d_si_src, s->si_src));
+  DPGO_TRY(upload_vec(&s->d_bs_src, s->bs_src));
   // ---- strip tables.  A strip = 64 output columns x a run of 32-index chunks.  The apply is
   // latency bound (the matrices are L2 resident): one CTA per SM, each with about one pipeline
   // fill of work.  Interior strips are whole (one partial slot) and balanced over the V virtual
@@ -591,24 +595,31 @@ int dd_build(dpgo_dev *h) {
   return dd_numeric(h, s, false);
 }
 
+// coupling block k <- block src[k] of Q
+__global__ void k_dd_regather(const double *blocks, const int *src, int count, int bs, double *dst) {
+  const size_t total = (size_t)count * bs;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = idx / bs;
+    dst[idx] = blocks[(size_t)src[k] * bs + (idx - k * bs)];
+  }
+}
+
 // Numeric part of the two-level set-up: dense interior inverses, couplings on S_k, Schur complement and its inverse,
 // strip layouts -- from the current values of Q.  refresh_couplings: also re-read the sparse coupling blocks
 // (weight-only rebuild; the index structure on the device stays).
 static int dd_numeric(dpgo_dev *h, DdState *s, bool refresh_couplings) {
   const int dh = h->d + 1, bs = dh * dh, K = s->K, mS = s->mS, padS = s->padS;
-  if (refresh_couplings) {
-    std::vector<double> vals;
-    auto regather = [&](const std::vector<int> &src, double *dst) -> int {
-      if (src.empty()) return DPGO_OK;
-      vals.resize(src.size() * (size_t)bs);
-      for (size_t k = 0; k < src.size(); ++k)
-        memcpy(vals.data() + k * bs, h->blocks.data() + (size_t)src[k] * bs, bs * sizeof(double));
-      CUDA_TRY(cudaMemcpyAsync(dst, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      CUDA_TRY(cudaStreamSynchronize(h->stream));     // vals is reused
-      return DPGO_OK;
+  if (refresh_couplings) {    // device copy of the re-weighted blocks of Q (the host copy may be stale)
+    auto regather = [&](const std::vector<int> &src, const int *d_src, double *dst) {
+      if (src.empty()) return;
+      const size_t total = src.size() * (size_t)bs;
+      const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+      k_dd_regather<<<std::max(grid, 1), 256, 0, h->stream>>>(h->d_blocks, d_src, (int)src.size(), bs, dst);
+      h->launches++;
     };
-    DPGO_TRY(regather(s->si_src, s->si_blocks));
-    DPGO_TRY(regather(s->bs_src, s->bs_blocks));
+    regather(s->si_src, s->d_si_src, s->si_blocks);
+    regather(s->bs_src, s->d_bs_src, s->bs_blocks);
+    CUDA_TRY(cudaPeekAtLastError());
   }
   double *Sg = nullptr;
   CUDA_TRY(cudaMallocAsync((void **)&Sg, (size_t)std::max(mS, 1) * std::max(mS, 1) * sizeof(double), h->stream));

@@ -154,3 +154,51 @@ def test_all_agents_schedule_parity(datasets, native):
     Xo = ot.assemble()
     assert np.linalg.norm(Xg - Xo) <= 1e-6 * np.linalg.norm(Xo)
     gt.close()
+
+
+@pytest.mark.parametrize("name,r", [("smallGrid3D", 5), ("city10000", 3)])
+def test_device_weight_refresh_bitwise(datasets, name, r):
+    """dpgo_update_weights with an unchanged pattern re-weights Q and the cross blocks on the device (k_refresh_q /
+    k_refresh_cross restate the host assembly entry by entry, same operations in the same order, no contraction):
+    the refreshed Q, the linear term built from neighbour poses and the preconditioner equal those of a handle whose
+    matrices were assembled on the host from the same weights -- bit for bit.
+    ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142."""
+    import dpgo_b200
+    meas, n, _ = datasets(name)
+    d = meas.d
+    rng = np.random.default_rng(5)
+    m = len(meas.p1)
+    n_a = n // 2                                   # agent = first half of the poses; edges across the cut are shared
+    priv = (meas.p1 < n_a) & (meas.p2 < n_a)
+    cut = (meas.p1 < n_a) != (meas.p2 < n_a)
+    out = meas.p1[cut] < n_a
+    my = np.where(out, meas.p1[cut], meas.p2[cut]).astype(np.int32)
+    slots = np.arange(int(cut.sum()), dtype=np.int32)
+    w1p, w1s = rng.uniform(0.1, 1.0, int(priv.sum())), rng.uniform(0.1, 1.0, int(cut.sum()))
+    w2p, w2s = rng.uniform(0.0, 1.0, int(priv.sum())), rng.uniform(0.0, 1.0, int(cut.sum()))
+    w2p[::7] = 0.0                                 # rejected measurements
+
+    def build(wp, ws):
+        gp = dpgo_b200.DeviceProblem(n_a, d, r)
+        gp.set_private_edges(meas.p1[priv], meas.p2[priv], meas.R[priv], meas.t[priv], meas.kappa[priv], meas.tau[priv], wp)
+        gp.set_shared_edges(my, slots, out.astype(np.uint8), meas.R[cut], meas.t[cut], meas.kappa[cut], meas.tau[cut],
+                            len(slots), ws)
+        gp.finalize(True)
+        return gp
+
+    nbr = rng.standard_normal((len(slots), r, d + 1))
+    V = np.asfortranarray(rng.standard_normal((r, (d + 1) * n_a)))
+    X = pgo.manifold_project(rng.standard_normal((r, (d + 1) * n_a)), d)
+    a = build(w1p, w1s)
+    a.update_weights(w2p, w2s, True)               # device refresh
+    b = build(w2p, w2s)                            # host assembly
+    qa, qb = a.get_Q_bsr(), b.get_Q_bsr()
+    assert all(np.array_equal(x, y) for x, y in zip(qa, qb))
+    a.set_neighbor_poses(nbr); b.set_neighbor_poses(nbr)
+    assert np.array_equal(a.get_G(), b.get_G())
+    assert np.array_equal(a.precon(X, V), b.precon(X, V))
+    a.update_weights(w1p, w1s, True)               # and back: equals the first assembly
+    c = build(w1p, w1s)
+    assert all(np.array_equal(x, y) for x, y in zip(a.get_Q_bsr(), c.get_Q_bsr()))
+    for gp in (a, b, c):
+        gp.close()
