@@ -14,6 +14,7 @@
 #include <DPGO/RelativeSEMeasurement.h>
 #include <DPGO/manifold/Poses.h>
 
+#include <cstdint>
 #include <map>
 #include <memory>
 #include <set>
@@ -132,6 +133,22 @@ class PoseGraph {
   bool q_valid_, g_valid_, precon_valid_;
   std::vector<size_t> q_edges_;     // shared edges included in the current Q
   std::vector<PoseID> q_slots_;     // neighbour poses in slot order
+  // what the device handle was last given, weights aside: when only the measurement weights changed (GNC) the
+  // matrices are re-weighted on the device (dpgo_update_weights) instead of being assembled again
+  struct UploadedGraph {
+    std::vector<int32_t> p1, p2, my, slot, prior_idx;
+    std::vector<uint8_t> outgoing;
+    std::vector<double> Rp, tp, kp, taup, Rs, ts, ks, taus, prior_tiles;
+    double prior_kappa = 0, prior_tau = 0;
+    unsigned generation = 0;
+    bool valid = false, had_precon = false;
+    bool sameStructure(const UploadedGraph &o) const {
+      return valid && o.valid && generation == o.generation && p1 == o.p1 && p2 == o.p2 && my == o.my && slot == o.slot &&
+             prior_idx == o.prior_idx && outgoing == o.outgoing && Rp == o.Rp && tp == o.tp && kp == o.kp &&
+             taup == o.taup && Rs == o.Rs && ts == o.ts && ks == o.ks && taus == o.taus &&
+             prior_tiles == o.prior_tiles && prior_kappa == o.prior_kappa && prior_tau == o.prior_tau;
+    }
+  } uploaded_;
 };
 
 }  // namespace DPGO

@@ -330,55 +330,70 @@ bool PoseGraph::constructQ() {
       w.push_back(m->weight);
     }
   };
+  UploadedGraph g;
+  std::vector<double> wp, ws;
   {  // private edges: odometry + private loop closures
     std::vector<const RelativeSEMeasurement *> ms;
-    std::vector<int32_t> p1, p2;
     for (const auto &m : odometry_) ms.push_back(&m);
     for (const auto &m : private_lcs_) ms.push_back(&m);
     for (const auto *m : ms) {
-      p1.push_back(static_cast<int32_t>(m->p1));
-      p2.push_back(static_cast<int32_t>(m->p2));
+      g.p1.push_back(static_cast<int32_t>(m->p1));
+      g.p2.push_back(static_cast<int32_t>(m->p2));
     }
-    std::vector<double> R, t, kappa, tau, w;
-    pack(ms, R, t, kappa, tau, w);
-    DPGO_DEVICE_CALL(dpgo_set_private_edges(dev_, static_cast<int>(ms.size()), p1.data(), p2.data(), R.data(),
-                                            t.data(), kappa.data(), tau.data(), w.data()));
+    pack(ms, g.Rp, g.tp, g.kp, g.taup, wp);
   }
   {  // shared edges
     std::map<PoseID, int, ComparePoseID> slot_of;
     for (size_t s = 0; s < slots.size(); ++s) slot_of[slots[s]] = static_cast<int>(s);
     std::vector<const RelativeSEMeasurement *> ms;
-    std::vector<int32_t> my, slot;
-    std::vector<uint8_t> outgoing;
     for (size_t k : edges) {
       const auto &m = shared_lcs_[k];
       const bool out = (m.r1 == id_);
       ms.push_back(&m);
-      my.push_back(static_cast<int32_t>(out ? m.p1 : m.p2));
-      slot.push_back(slot_of.at(PoseID(static_cast<unsigned>(out ? m.r2 : m.r1), static_cast<unsigned>(out ? m.p2 : m.p1))));
-      outgoing.push_back(out ? 1 : 0);
+      g.my.push_back(static_cast<int32_t>(out ? m.p1 : m.p2));
+      g.slot.push_back(slot_of.at(PoseID(static_cast<unsigned>(out ? m.r2 : m.r1), static_cast<unsigned>(out ? m.p2 : m.p1))));
+      g.outgoing.push_back(out ? 1 : 0);
     }
-    std::vector<double> R, t, kappa, tau, w;
-    pack(ms, R, t, kappa, tau, w);
-    DPGO_DEVICE_CALL(dpgo_set_shared_edges(dev_, static_cast<int>(ms.size()), static_cast<int>(slots.size()),
-                                           my.data(), slot.data(), outgoing.data(), R.data(), t.data(),
-                                           kappa.data(), tau.data(), w.data()));
+    pack(ms, g.Rs, g.ts, g.ks, g.taus, ws);
   }
-  {  // priors
-    std::vector<int32_t> idx;
-    std::vector<double> tiles;
-    for (const auto &kv : priors_) {
-      idx.push_back(static_cast<int32_t>(kv.first));
-      const Matrix P = kv.second.getData();
-      tiles.insert(tiles.end(), P.data(), P.data() + P.size());
+  for (const auto &kv : priors_) {
+    g.prior_idx.push_back(static_cast<int32_t>(kv.first));
+    const Matrix P = kv.second.getData();
+    g.prior_tiles.insert(g.prior_tiles.end(), P.data(), P.data() + P.size());
+  }
+  g.prior_kappa = prior_kappa_;
+  g.prior_tau = prior_tau_;
+  g.generation = dev_generation_;
+  g.valid = true;
+  bool precon_built = false;
+  if (uploaded_.sameStructure(g) && slots.size() == q_slots_.size()) {
+    // only the weights changed (GNC, ref: src/PGOAgent.cpp:1104-1142): re-weight Q, the cross blocks and -- when the
+    // handle had one -- the preconditioner on the device
+    precon_built = uploaded_.had_precon;
+    const int rc = dpgo_update_weights(dev_, wp.data(), ws.data(), precon_built ? 1 : 0);
+    if (rc == DPGO_ENUMERIC && precon_built) {
+      std::fprintf(stderr, "[PoseGraph] Failed to compute preconditioner: %s\n", dpgo_last_error());
+      precon_built = false;
+      DPGO_DEVICE_CALL(dpgo_update_weights(dev_, wp.data(), ws.data(), 0));
+    } else {
+      DPGO_DEVICE_CALL(rc);
     }
-    DPGO_DEVICE_CALL(dpgo_set_priors(dev_, static_cast<int>(idx.size()), idx.data(), tiles.data(), prior_kappa_, prior_tau_));
+    g.had_precon = uploaded_.had_precon;
+  } else {
+    DPGO_DEVICE_CALL(dpgo_set_private_edges(dev_, static_cast<int>(g.p1.size()), g.p1.data(), g.p2.data(), g.Rp.data(),
+                                            g.tp.data(), g.kp.data(), g.taup.data(), wp.data()));
+    DPGO_DEVICE_CALL(dpgo_set_shared_edges(dev_, static_cast<int>(g.my.size()), static_cast<int>(slots.size()),
+                                           g.my.data(), g.slot.data(), g.outgoing.data(), g.Rs.data(), g.ts.data(),
+                                           g.ks.data(), g.taus.data(), ws.data()));
+    DPGO_DEVICE_CALL(dpgo_set_priors(dev_, static_cast<int>(g.prior_idx.size()), g.prior_idx.data(), g.prior_tiles.data(),
+                                     prior_kappa_, prior_tau_));
+    DPGO_DEVICE_CALL(dpgo_finalize(dev_, 0));
   }
-  DPGO_DEVICE_CALL(dpgo_finalize(dev_, 0));
+  uploaded_ = std::move(g);
   q_edges_ = edges;
   q_slots_ = slots;
   q_valid_ = true;
-  precon_valid_ = false;
+  precon_valid_ = precon_built;
   g_valid_ = false;
   return true;
 }
@@ -419,6 +434,7 @@ bool PoseGraph::hasPreconditioner() {
   }
   DPGO_DEVICE_CALL(rc);
   precon_valid_ = true;
+  uploaded_.had_precon = true;
   g_valid_ = false;  // finalize() re-initialises the linear term
   return true;
 }
