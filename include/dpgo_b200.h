@@ -118,7 +118,10 @@ int dpgo_set_priors(dpgo_handle h, int num, const int32_t *idx, const double *po
  * stored is the library's choice by size, see dpgo_b200_dev.h).
  * build_precon = 0 skips the preconditioner (then only unpreconditioned ops are available). */
 int dpgo_finalize(dpgo_handle h, int build_precon);
-/* Update only the measurement weights (GNC) and rebuild Q / preconditioner.
+/* Update only the measurement weights (GNC): Q, the cross blocks of G and -- when asked for -- the preconditioner
+ * are re-weighted on the device from the new weights (same pattern: no host assembly, the symbolic part of the
+ * preconditioner set-up is kept; the result has the bits of a from-scratch dpgo_finalize with these weights).
+ * NULL keeps the current weights of that edge set.
  * ref: PoseGraph::clearDataMatrices after weight updates, src/PGOAgent.cpp:1062-1142. */
 int dpgo_update_weights(dpgo_handle h, const double *w_private, const double *w_shared,
                         int build_precon);
