@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
   }
+  bool p1_ready = false;   // two-level form: the first wave of this CTA's first interior strip is already in flight
   // the two forms of the exact preconditioner (compile-time: one kernel instantiation each)
   // permuted: v is the tCG residual and its permuted copy dd.rp is current (written by phase_step_perm)
   auto precon_stream = [&](const double *v, bool permuted) {
@@ -183,8 +184,9 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
       const size_t zs = (size_t)dd.pcols * R;
       const bool pf = dd.prefetch != 0;
       constexpr int ST = kDdStages;
-      if (permuted) phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.rp, nullptr, dd.y, zs);
-      else phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs);
+      if (permuted) phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], dd.rp, nullptr, dd.y, zs, p1_ready);
+      else phase_strip_gemv<R, ST>(pipe, dd.P1, dd.V, &s_plan[0], v, dd.icol, dd.y, zs, p1_ready);
+      p1_ready = false;
       if (dd.nS > 0) {
         if (pf) strip_prefetch<ST>(pipe, dd.P3, dd.V, &s_plan[1]);
         red.barrier(grid);
@@ -255,6 +257,15 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
       }
       red.barrier(grid);
       clk.lap(MODE == 2 ? 12 : 1);
+      if constexpr (MODE == 2) {
+        // every stage has been consumed; the interior matrix does not change: the first wave of the next interior pass
+        // (next tCG iteration, or the next tCG run) goes in flight now, issued by the CTA's last warp, which has no
+        // poses in the per-pose phases that follow
+        if (p.dd.prefetch != 0) {
+          strip_prefetch<kDdStages>(pipe, p.dd.P1, p.dd.V, &s_plan[0], kWarpsPerBlock - 1);
+          p1_ready = true;
+        }
+      }
       {
         double acc[1] = {0.0}, sc[1];
         precon_finish(X1, pvec, first ? p.delta : nullptr, acc);   // first: delta = -z
@@ -343,6 +354,9 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
   }
 
   phase_copy(ctx, X1, p.x_out, len);
+  if constexpr (MODE == 2) {   // no bulk copy may be in flight when the CTA exits
+    if (p1_ready) strip_drain<kDdStages>(pipe, p.dd.P1, p.dd.V, &s_plan[0]);
+  }
 #ifdef DPGO_TRACE
   if (threadIdx.x == 0 && p.trace) {
 #pragma unroll

@@ -909,11 +909,13 @@ __device__ __forceinline__ void strip_cursor_next_strip(StripCursor &cu, const D
   strip_cursor_seek(cu, S, V, pl);
 }
 
-// thread 0: put chunks [c0, c0 + nw) of strip d in flight into stage slots 0 .. nw-1
+// one warp (all its lanes call): put chunks [c0, c0 + nw) of strip d in flight into stage slots 0 .. nw-1, lane i
+// issues the copy of stage i (a single thread issuing a 10-stage wave is ~0.4 us on the critical path of a phase)
 __device__ __forceinline__ void strip_issue_wave(const GemvPipe &pp, const DdStripSet &S, const DdStrip &d, int c0,
                                                  int nw) {
-  const uint32_t stage0 = smem_u32(pp.stage);
-  for (int i = 0; i < nw; ++i) {
+  const int i = threadIdx.x & 31;
+  if (i < nw) {
+    const uint32_t stage0 = smem_u32(pp.stage);
     const uint32_t bar = pp.bar + 8 * i;
     mbar_expect_tx(bar, kStageDoubles * 8);
     bulk_g2s(stage0 + i * (kStageDoubles * 8), S.M + (size_t)(d.data_off + c0 + i) * kStageDoubles,
@@ -925,14 +927,31 @@ __device__ __forceinline__ void strip_issue_wave(const GemvPipe &pp, const DdStr
 // does not depend on the phases before it, so this is called BEFORE the grid barrier that makes the
 // input array visible; phase_strip_gemv(..., prefetched = true) then skips that issue.
 // Precondition: every stage has been consumed (true between strip phases).
+// `issuer` = the warp of the CTA that issues (0, or a warp without work in the phase the call sits in).
 template <int STAGES>
 __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStripSet &S, int V,
-                                               const StripPlanStore *st) {
-  if (threadIdx.x != 0) return;
+                                               const StripPlanStore *st, int issuer = 0) {
+  static_assert(STAGES <= 32, "one lane per stage");
+  if ((int)(threadIdx.x >> 5) != issuer) return;
   const StripPlan pl = strip_plan_load(st);
   StripCursor cu;
   strip_cursor_init(cu, S, V, pl);
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
+}
+
+// Wait for a prefetched first wave that no strip pass will consume (end of the kernel) and flip the stage parities.
+// All threads of the CTA call.
+template <int STAGES>
+__device__ __forceinline__ void strip_drain(GemvPipe &pp, const DdStripSet &S, int V, const StripPlanStore *st) {
+  const StripPlan pl = strip_plan_load(st);
+  StripCursor cu;
+  strip_cursor_init(cu, S, V, pl);
+  if (cu.v < V) {
+    const int nw = min(STAGES, cu.d.nchunks);
+    for (int ch = 0; ch < nw; ++ch) mbar_wait(pp.bar + 8 * ch, (pp.parity >> ch) & 1u);
+    pp.parity ^= (1u << nw) - 1u;
+  }
+  __syncthreads();
 }
 
 // out[slot][:, 64 cb + jj] = sum over the strip's chunks of vec[:, k] * M(jj, k)
@@ -962,7 +981,7 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
     for (int q = 0; q < R; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
     for (int c0 = 0; c0 < d.nchunks; c0 += STAGES) {
       const int nw = min(STAGES, d.nchunks - c0);
-      if (!in_flight && threadIdx.x == 0) strip_issue_wave(pp, S, d, c0, nw);
+      if (!in_flight && threadIdx.x < 32) strip_issue_wave(pp, S, d, c0, nw);
       in_flight = false;
       {  // the slice of vec that goes with the wave
         const int k0 = (d.kc0 + c0) * kStageK;
@@ -1002,7 +1021,7 @@ __device__ __forceinline__ void phase_strip_gemv(GemvPipe &pp, const DdStripSet 
     // put the first wave of the next strip in flight, then finish this one
     strip_cursor_next_strip(cu, S, V, pl);
     if (cu.v < V) {
-      if (threadIdx.x == 0) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
+      if (threadIdx.x < 32) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
       in_flight = true;
     }
 #pragma unroll
