@@ -48,3 +48,45 @@ extern "C" QX_EXPORT int qx_emu(int variant, int r, int d, const int *rowptr, co
   if (r == 4 && d == 2) return run<4, 2>(variant, rowptr, colidx, blocks, X, G, out, n, ctas);
   return -1;
 }
+
+namespace {
+// Per-pose kernels: op 0 = QF retraction of X + Eta, 1 = polar projection of 0.5 A + 0.3 B + 0.2 C, 2 = rounding in
+// the frame of pose 0.  staged = 1: the stand-alone form (tiles of a warp step through shared memory, pose_staged);
+// staged = 0: the per-pose function applied to every tile by one host thread.  Same function, same values: same bits.
+template <int R, int D>
+int run_pose_op(int op, int staged, const double *A, const double *B, const double *C, double *out, int n) {
+  constexpr int DH = D + 1, TILE = R * DH;
+  if (!staged) {
+    double ya[D][R], pa[R];
+    load_anchor<R, D>(A, ya, pa);
+    for (int i = 0; i < n; ++i) {
+      const size_t o = (size_t)i * TILE;
+      if (op == 0) retract_pose<R, D>([&](int k) { return A[o + k] + B[o + k]; }, out + o);
+      else if (op == 1) polar_pose<R, D>([&](int k) { return polar_combination(0.5, A, 0.3, B, 0.2, C, o + k); }, out + o);
+      else round_pose<R, D>(A + o, ya, pa, out + (size_t)i * (D * DH));
+    }
+    return 0;
+  }
+  static double sw[emu::kWarps][PoseStage<TILE>::WARP_DOUBLES];
+  for (int wv = 0; wv < emu::kWarps; ++wv) emu::warp_barrier[wv] = new std::barrier<>(32);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < (unsigned)emu::kThreads; ++t)
+    th.emplace_back([&, t]() {
+      threadIdx.x = t;
+      if (op == 0) retract_staged<R, D, false>(A, B, out, n, 1.0, sw[t >> 5]);
+      else if (op == 1) polar_staged<R, D>(0.5, A, 0.3, B, 0.2, C, out, n, sw[t >> 5]);
+      else round_staged<R, D>(A, A, out, n, sw[t >> 5]);
+    });
+  for (auto &x : th) x.join();
+  for (int wv = 0; wv < emu::kWarps; ++wv) delete emu::warp_barrier[wv];
+  return 0;
+}
+}  // namespace
+
+extern "C" QX_EXPORT int pose_op_emu(int op, int staged, int r, int d, const double *A, const double *B, const double *C,
+                                     double *out, int n) {
+  if (r == 5 && d == 3) return run_pose_op<5, 3>(op, staged, A, B, C, out, n);
+  if (r == 3 && d == 2) return run_pose_op<3, 2>(op, staged, A, B, C, out, n);
+  if (r == 4 && d == 2) return run_pose_op<4, 2>(op, staged, A, B, C, out, n);
+  return -1;
+}

@@ -78,3 +78,40 @@ def test_qx_forms_ragged_rows(lib, d, r):
         assert np.allclose(base, X @ dense, rtol=1e-12, atol=1e-11)
         for variant in (2, 3):
             assert np.array_equal(_run(lib, variant, r, d, rowptr, colidx, blocks, X, None, n, ctas), base), variant
+
+
+@pytest.mark.parametrize("d,r,n", [(3, 5, 300), (2, 3, 77), (2, 4, 256)])
+def test_staged_pose_kernels_match_the_per_pose_functions(lib, d, r, n):
+    """The stand-alone QF retraction / polar projection / rounding kernels stage the 32 tiles of a warp step through
+    shared memory (pose_staged: coalesced global traffic at scale) and run the same per-pose function on the staged
+    values: bit-identical to the function applied tile by tile, including a ragged last warp step (n not a multiple
+    of 32) and odd tile sizes; and equal to the oracle (ref: ProductManifold::Retraction, LiftedSEManifold::project
+    src/manifold/LiftedSEManifold.cpp:34-45, projectToRotationGroup src/DPGO_utils.cpp:464-478)."""
+    dh = d + 1
+    rng = np.random.default_rng(100 * d + r)
+    X = pgo.manifold_project(rng.standard_normal((r, dh * n)), d)
+    B = X + 0.05 * rng.standard_normal(X.shape)
+    Cm = X + 0.05 * rng.standard_normal(X.shape)
+    A_, B_, C_ = (np.asfortranarray(a) for a in (X, B, Cm))
+    dp = ctypes.POINTER(ctypes.c_double)
+    outs = {}
+    for op, cols in ((0, r), (1, r), (2, d)):
+        for staged in (0, 1):
+            out = np.full((cols, dh * n), np.nan, order="F")
+            rc = lib.pose_op_emu(op, staged, r, d, A_.ctypes.data_as(dp), B_.ctypes.data_as(dp), C_.ctypes.data_as(dp),
+                                 out.ctypes.data_as(dp), n)
+            assert rc == 0
+            outs[op, staged] = out
+        assert np.array_equal(outs[op, 0], outs[op, 1]), op
+    ref = pgo.manifold_project(0.5 * X + 0.3 * B + 0.2 * Cm, d)
+    assert np.allclose(outs[1, 1], ref, rtol=0, atol=1e-12)
+    ret = outs[0, 1]
+    for i in (0, n // 2, n - 1):
+        Y = ret[:, i * dh:i * dh + d]
+        assert np.allclose(Y.T @ Y, np.eye(d), atol=1e-13)
+        assert np.allclose(ret[:, i * dh + d], X[:, i * dh + d] + B[:, i * dh + d], atol=0)
+    T = outs[2, 1]
+    assert np.allclose(T[:, :dh], np.eye(d, dh), atol=1e-12)          # pose 0 in its own frame
+    for i in (1, n - 1):
+        Ri = T[:, i * dh:i * dh + d]
+        assert np.allclose(Ri.T @ Ri, np.eye(d), atol=1e-12) and np.linalg.det(Ri) > 0
