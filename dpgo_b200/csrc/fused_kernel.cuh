@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(kBlock, MODE == 2 ? 1 : 2) k_rtr_fused(FusedPa
   if constexpr (MODE == 2) {
     strip_plan_fill(&s_plan[0], p.dd.P1, p.dd.V);
     strip_plan_fill(&s_plan[1], p.dd.P3, p.dd.V);
+    if (p.dd.prefetch != 0 && (threadIdx.x >> 5) == kWarpsPerBlock - 1) {   // a warp without poses in the first phases
+      strip_l2_prefetch(p.dd.P1, p.dd.V);
+      strip_l2_prefetch(p.dd.P3, p.dd.V);
+    }
   }
   bool p1_ready = false;   // two-level form: the first wave of this CTA's first interior strip is already in flight
   // the two forms of the exact preconditioner (compile-time: one kernel instantiation each)

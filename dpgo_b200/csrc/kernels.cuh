@@ -939,6 +939,22 @@ __device__ __forceinline__ void strip_prefetch(const GemvPipe &pp, const DdStrip
   if (cu.v < V) strip_issue_wave(pp, S, cu.d, 0, min(STAGES, cu.d.nchunks));
 }
 
+// Ask the L2 for every stage of this CTA's strips of one phase (one warp calls, lane l takes the chunks l, l + 32, ..
+// of each strip): the dense blocks are read from DRAM only by the first application after something else used the
+// L2 (another agent's solve on the same GPU, the flush of the bench); issued at the start of the solver kernel, the
+// fetch runs under the cost / gradient phases instead of in front of the first strip pass.
+__device__ __forceinline__ void strip_l2_prefetch(const DdStripSet &S, int V) {
+  const int lane = threadIdx.x & 31;
+  for (int v = blockIdx.x; v < V; v += gridDim.x) {
+    const int s0 = __ldg(S.cta + v), s1 = __ldg(S.cta + v + 1);
+    for (int si = s0; si < s1; ++si) {
+      const DdStrip d = S.strips[si];
+      for (int c = lane; c < d.nchunks; c += 32)
+        bulk_prefetch_l2(S.M + (size_t)(d.data_off + c) * kStageDoubles, kStageDoubles * 8);
+    }
+  }
+}
+
 // Wait for a prefetched first wave that no strip pass will consume (end of the kernel) and flip the stage parities.
 // All threads of the CTA call.
 template <int STAGES>
